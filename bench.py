@@ -1,0 +1,377 @@
+"""Benchmark of the recurrent hot path (Conv1D -> gate GEMMs -> RG-LRU scan).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
+        --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): one RecurrentGemma-2B-shape recurrent
+block's hot path, random init, bf16, batch 8, seq 2048 prefill, per GPU.  A
+"step" is one pass of that batch through ``Conv1D.forward`` ->
+``RGLRU.forward`` (block-diagonal gate GEMMs in cuBLAS + the fused gate/scan
+kernel).  With N GPUs every rank runs its own batch of 8 (batch-sharded, weak
+scaling, no collective inside the path; the small per-row states are
+all-gathered on a side stream).
+
+Prints ONE JSON line (see the task contract): metric = prefill tokens/s of the
+hot path, with `roofline` for the dominant kernel (RG-LRU gate+scan, 4*s
+algorithmic bytes per element), `cpu_baseline` (the oracle port of the
+reference's eager torch path, timed on this box's host cores) and `e2e` (same
+step driven from pinned HOST buffers, H2D + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(batch=8, seq_len=2048, width=2560, heads=10, temporal_width=4)
+METRIC = "rglru_conv1d_prefill_tokens_per_sec"
+UNIT = "tokens/s"
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=50)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--impl", default="own", choices=["own", "reference"])
+  ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  return ap.parse_args()
+
+
+def measured_peak_gbs():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    with open(path) as f:
+      return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+  return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_host_inputs(dtype, seed=1):
+  """Synthetic config-2 tensors + parameters on the host (deterministic)."""
+  w = WORKLOAD
+  g = torch.Generator().manual_seed(seed)
+  bw = w["width"] // w["heads"]
+  p = {
+      "x_lin": torch.randn((w["batch"], w["seq_len"], w["width"]), generator=g).to(dtype),
+      "segment_pos": torch.arange(w["seq_len"], dtype=torch.int32)[None].repeat(w["batch"], 1),
+      "conv_w": (torch.randn((w["temporal_width"], w["width"]), generator=g) *
+                 (0.01 / w["temporal_width"]) ** 0.5 * 10).to(dtype),
+      "conv_b": (torch.randn((w["width"],), generator=g) * 0.1).to(dtype),
+      "input_gate_w": (torch.randn((w["heads"], bw, bw), generator=g) * bw ** -0.5).to(dtype),
+      "input_gate_b": torch.randn((w["heads"], bw), generator=g).to(dtype),
+      "a_gate_w": (torch.randn((w["heads"], bw, bw), generator=g) * bw ** -0.5).to(dtype),
+      "a_gate_b": torch.randn((w["heads"], bw), generator=g).to(dtype),
+  }
+  # a on the ring [0.9, 0.999] through the softplus parametrisation (layers.py:202-221)
+  u = torch.empty(w["width"]).uniform_(0.9 ** 2 + 1e-8, 0.999 ** 2 + 1e-8, generator=g)
+  p["a_param"] = torch.log(torch.exp(-0.5 * torch.log(u)) - 1.0).to(dtype)
+  return p
+
+
+# ----------------------------------------------------------------------------
+# clocks / throttle sampling during the timed region
+# ----------------------------------------------------------------------------
+class ClockSampler:
+  QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+           "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+           "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index):
+    self.gpu_index, self.proc = gpu_index, None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+           "-lms", "100", "-i", str(self.gpu_index)],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except OSError:
+      self.proc = None
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    try:
+      out, _ = self.proc.communicate(timeout=5)
+    except subprocess.TimeoutExpired:
+      self.proc.kill()
+      out, _ = self.proc.communicate()
+    sm, smax, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for line in out.strip().splitlines():
+      f = [c.strip() for c in line.split(",")]
+      if len(f) < 9:
+        continue
+      try:
+        sm.append(float(f[1])); smax.append(float(f[2]))
+      except ValueError:
+        continue
+      for name, val in zip(names, f[5:9]):
+        if val.lower().startswith("active"):
+          reasons.add(name)
+    return {"sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(smax) if smax else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------
+def run_cpu_port(host, steps, warmup, threads):
+  """The oracle port of the reference's eager torch path on the host cores.
+
+  This is the ONLY place bench.py touches oracle/: as the reported CPU
+  baseline / the `--impl reference` arm, never on the product path.
+  """
+  from oracle import torch_port
+  torch.set_num_threads(threads)
+  params = torch_port.RGLRUParams(host["a_param"], host["input_gate_w"],
+                                  host["input_gate_b"], host["a_gate_w"], host["a_gate_b"])
+  times, out = [], None
+  with torch.no_grad():
+    for i in range(warmup + steps):
+      t0 = time.perf_counter()
+      xc, conv_state = torch_port.conv1d_forward(host["conv_w"], host["conv_b"],
+                                                 host["x_lin"], host["segment_pos"])
+      y, last_h = torch_port.rglru_forward(params, xc, host["segment_pos"])
+      dt = time.perf_counter() - t0
+      if i >= warmup:
+        times.append(dt)
+      out = (y, last_h, conv_state)
+  return times, out
+
+
+def reference_arm(args, dtype):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return   # rank 0 alone runs the CPU reference arm
+  threads = os.cpu_count() or 1
+  host = make_host_inputs(dtype)
+  tokens = WORKLOAD["batch"] * WORKLOAD["seq_len"]
+  times, _ = run_cpu_port(host, args.steps, args.warmup, threads)
+  total = sum(times)
+  value = tokens * len(times) / total
+  sample = (f"full config-2 batch (B={WORKLOAD['batch']}, T={WORKLOAD['seq_len']}, "
+            f"E={WORKLOAD['width']}) per step, {len(times)} steps after {args.warmup} warm-ups")
+  line = {
+      "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+      "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+      "config": config_dict(args, "cpu"),
+      "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                       "sample": sample},
+      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+              "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+def config_dict(args, where):
+  w = WORKLOAD
+  return {"workload": ("BASELINE configs[1]: RecurrentGemma-2B-shape RG-LRU+Conv1D block, "
+                       f"random init, {args.dtype}, batch {w['batch']}, seq {w['seq_len']} prefill"),
+          "batch_per_gpu": w["batch"], "global_batch": w["batch"] * args.gpus,
+          "seq_len": w["seq_len"], "lru_width": w["width"], "num_heads": w["heads"],
+          "conv1d_temporal_width": w["temporal_width"],
+          "parallelism": f"batch-sharded x{args.gpus} (no collective in the path)",
+          "l2": "working set 420 MB per step > 126 MB L2 (no explicit flush)",
+          "device": where}
+
+
+# ----------------------------------------------------------------------------
+def own_arm(args, dtype):
+  import torch.distributed as dist
+  import cadence_gemma_b200 as cg
+  from cadence_gemma_b200 import _abi
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+  _abi.load()
+
+  w = WORKLOAD
+  host = make_host_inputs(dtype, seed=1 + rank)   # every rank its own batch shard
+  conv = cg.Conv1D(w["width"], w["temporal_width"], device=dev, dtype=dtype)
+  lru = cg.RGLRU(w["width"], w["heads"], device=dev, dtype=dtype)
+  conv.load_state_dict({"w": host["conv_w"], "b": host["conv_b"]})
+  lru.load_state_dict({"a_param": host["a_param"], "input_gate.w": host["input_gate_w"],
+                       "input_gate.b": host["input_gate_b"], "a_gate.w": host["a_gate_w"],
+                       "a_gate.b": host["a_gate_b"]})
+  x_dev = host["x_lin"].to(dev)
+  seg_dev = host["segment_pos"].to(dev)
+  tokens = w["batch"] * w["seq_len"]
+  nelem = tokens * w["width"]
+  esize = 2 if dtype == torch.bfloat16 else 4
+
+  # small outputs gathered over NCCL on a side stream (never the activations)
+  comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+  state_numel = w["batch"] * w["width"] * 4   # last_h (1) + conv cache (3 rows) as fp32 words
+  gather_in = torch.empty(state_numel, dtype=torch.float32, device=dev) if world > 1 else None
+  gather_out = (torch.empty(state_numel * world, dtype=torch.float32, device=dev)
+                if world > 1 else None)
+
+  k2_events = []
+
+  def step(x, seg, record=False):
+    xc, conv_state = conv(x, seg)
+    if record:
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      gx = lru.input_gate.gemm(xc)
+      ga = lru.a_gate.gemm(xc)
+      e0.record()
+      y, last_h = _abi.rglru_fwd(xc, gx, ga, lru.input_gate.b, lru.a_gate.b, lru.a_param,
+                                 seg, arith_mode=cg.get_arith_mode())
+      e1.record()
+      k2_events.append((e0, e1))
+    else:
+      y, last_h = lru(xc, seg)
+    if world > 1:
+      gather_in[: last_h.numel()].copy_(last_h.view(-1))
+      gather_in[last_h.numel():].copy_(conv_state.float().view(-1))
+      comm_stream.wait_stream(torch.cuda.current_stream())
+      with torch.cuda.stream(comm_stream):
+        dist.all_gather_into_tensor(gather_out, gather_in)
+    return y, last_h, conv_state
+
+  def sync_all():
+    if world > 1:
+      torch.cuda.current_stream().wait_stream(comm_stream)
+      torch.cuda.synchronize()
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  with torch.no_grad():
+    for _ in range(max(args.warmup, 3)):
+      out = step(x_dev, seg_dev)
+    sync_all()
+
+    # ---------------- device-resident timed region: EXACTLY K steps -------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _abi.launch_count
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+      out = step(x_dev, seg_dev, record=True)
+    if world > 1:
+      torch.cuda.current_stream().wait_stream(comm_stream)
+    t_end.record()
+    sync_all()
+    launches = _abi.launch_count - launches0
+    clocks = sampler.stop()
+    ms_total = t_start.elapsed_time(t_end)
+    k2_us = [a.elapsed_time(b) * 1e3 for a, b in k2_events]
+
+    # ---------------- end to end: pinned host buffers in, results out ------------
+    x_pin = host["x_lin"].pin_memory()
+    seg_pin = host["segment_pos"].pin_memory()
+    y_pin = torch.empty_like(x_pin).pin_memory()
+    h_pin = torch.empty((w["batch"], w["width"]), dtype=torch.float32).pin_memory()
+    c_pin = torch.empty((w["batch"], w["temporal_width"] - 1, w["width"]), dtype=dtype).pin_memory()
+    x_stage, seg_stage = torch.empty_like(x_dev), torch.empty_like(seg_dev)
+    h2d = x_pin.numel() * x_pin.element_size() + seg_pin.numel() * seg_pin.element_size()
+    d2h = (y_pin.numel() * y_pin.element_size() + h_pin.numel() * 4 +
+           c_pin.numel() * c_pin.element_size())
+
+    def e2e_step():
+      x_stage.copy_(x_pin, non_blocking=True)
+      seg_stage.copy_(seg_pin, non_blocking=True)
+      y, last_h, conv_state = step(x_stage, seg_stage)
+      y_pin.copy_(y, non_blocking=True)
+      h_pin.copy_(last_h, non_blocking=True)
+      c_pin.copy_(conv_state, non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for _ in range(3):
+      e2e_step()
+    sync_all()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for _ in range(e2e_steps):
+      e2e_step()
+    if world > 1:
+      torch.cuda.current_stream().wait_stream(comm_stream)
+    e_end.record()
+    sync_all()
+    e2e_ms = e_start.elapsed_time(e_end)
+
+  # max over ranks (device time)
+  t = torch.tensor([ms_total, e2e_ms, statistics.mean(k2_us)], dtype=torch.float64, device=dev)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_total, e2e_ms, k2_mean_us = t.tolist()
+
+  if rank == 0:
+    peak, peak_src = measured_peak_gbs()
+    k2_bytes = 4 * esize * nelem          # read x, gemm_x, gemm_a; write y
+    achieved = k2_bytes / (k2_mean_us * 1e-6) / 1e9
+    value = world * tokens * args.steps / (ms_total * 1e-3)
+    e2e_value = world * tokens * e2e_steps / (e2e_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": config_dict(args, "cuda"),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "ms_per_step": e2e_ms / e2e_steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "cg::scan_kernel (RG-LRU gates + scan; "
+                     "events bracket the C-ABI call incl. its 1-block softplus prologue)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": k2_bytes,
+                     "us_per_launch": k2_mean_us, "traffic": None},
+        "arith_mode": cg.get_arith_mode(),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+      threads = os.cpu_count() or 1
+      host0 = make_host_inputs(dtype, seed=1)
+      times, cpu_out = run_cpu_port(host0, 3, 1, threads)
+      best = min(times)
+      line["cpu_baseline"] = {
+          "value": tokens / best, "unit": UNIT, "cores": threads, "kind": "port",
+          "sample": "full config-2 batch (16384 tokens), best of 3 after 1 warm-up",
+          "ms_per_step": best * 1e3}
+      y_gpu = out[0].float().cpu()
+      y_cpu = cpu_out[0].float()
+      line["parity_vs_cpu_port"] = {
+          "normwise": ((y_gpu - y_cpu).abs().max() / y_cpu.abs().max()).item(),
+          "bit_identical_frac": (out[0].cpu() == cpu_out[0]).float().mean().item()}
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  args = parse_args()
+  dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+  if args.impl == "reference":
+    reference_arm(args, dtype)
+  else:
+    own_arm(args, dtype)
+
+
+if __name__ == "__main__":
+  main()

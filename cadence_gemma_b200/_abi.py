@@ -1,0 +1,235 @@
+"""ctypes binding of ``libcadence_b200.so`` (C ABI in ``include/cadence_b200.h``).
+
+There is no CPU or eager-torch fallback: if the library is missing or a call
+fails, an exception is raised.  PyTorch is used only for device memory and the
+current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcadence_b200.so")
+
+DTYPE_F32, DTYPE_BF16 = 0, 1
+ARITH_REFERENCE, ARITH_FP32, ARITH_FAST, ARITH_STRICT = 0, 1, 2, 4
+MASK_FORK, MASK_UPSTREAM = 0, 1
+
+# Every symbol include/cadence_b200.h declares: (name, restype, argtypes)
+_vp, _i, _ll, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t
+SYMBOLS = {
+    "cg_abi_version": (_i, []),
+    "cg_status_string": (ctypes.c_char_p, [_i]),
+    "cg_scan_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "cg_conv1d_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _i, _i, _i, _i,
+                           _i, _i, _i, _vp]),
+    "cg_conv1d_decode": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i,
+                              _i, _vp]),
+    "cg_rglru_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _ll, _vp,
+                          _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "cg_rnn_scan_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i,
+                             _i, _i, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+launch_count = 0   # kernels launched through this binding (bench bookkeeping)
+
+
+class CadenceAbiError(RuntimeError):
+  pass
+
+
+def load():
+  """Loads the shared library (once).  Raises if it has not been built."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  with _lock:
+    if _lib is None:
+      if not os.path.exists(LIB_PATH):
+        raise CadenceAbiError(
+            f"{LIB_PATH} is missing: run `python -m cadence_gemma_b200.build` "
+            "(there is no CPU / eager fallback for the recurrent hot path)")
+      lib = ctypes.CDLL(LIB_PATH)
+      for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = restype, argtypes
+      if lib.cg_abi_version() != 1:
+        raise CadenceAbiError("libcadence_b200.so ABI version mismatch")
+      _lib = lib
+  return _lib
+
+
+def _check(rc: int, what: str):
+  if rc != 0:
+    msg = load().cg_status_string(rc).decode()
+    if rc < 0:
+      # argument errors mirror the reference's `assert`s
+      raise AssertionError(f"{what}: {msg} (status {rc})")
+    raise CadenceAbiError(f"{what}: CUDA error {rc}: {msg}")
+
+
+def dtype_code(dtype: torch.dtype) -> int:
+  if dtype == torch.float32:
+    return DTYPE_F32
+  if dtype == torch.bfloat16:
+    return DTYPE_BF16
+  raise TypeError(f"cadence_gemma_b200 supports float32/bfloat16, got {dtype}")
+
+
+def _ptr(t):
+  return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor):
+  return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda(*tensors):
+  for t in tensors:
+    if t is not None and not t.is_cuda:
+      raise CadenceAbiError(
+          "the recurrent hot path runs on CUDA only (no CPU fallback); got a "
+          f"{t.device} tensor")
+
+
+def _seg_args(segment_pos: torch.Tensor, batch: int, steps: int):
+  """(tensor kept alive, is_i64, batch stride) for a [B,T] / [1,T] / [T] tensor."""
+  seg = segment_pos
+  if seg.dtype not in (torch.int32, torch.int64):
+    seg = seg.to(torch.int64)
+  if seg.ndim == 1:
+    seg = seg[None, :]
+  assert seg.ndim == 2 and seg.shape[1] == steps, (tuple(seg.shape), steps)
+  assert seg.shape[0] in (1, batch), (tuple(seg.shape), batch)
+  seg = seg.contiguous()
+  stride = 0 if seg.shape[0] == 1 else steps
+  return seg, int(seg.dtype == torch.int64), stride
+
+
+# ---------------------------------------------------------------------------
+_workspaces: dict = {}
+
+
+def scan_workspace(device, batch: int, steps: int, width: int, dtype) -> torch.Tensor:
+  """Cached scratch buffer per (device, stream, shape); never initialised."""
+  key = (device, torch.cuda.current_stream(device).cuda_stream, batch, steps,
+         width, dtype)
+  ws = _workspaces.get(key)
+  if ws is None:
+    nbytes = load().cg_scan_workspace_bytes(batch, steps, width, dtype_code(dtype))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    if len(_workspaces) > 64:
+      _workspaces.clear()
+    _workspaces[key] = ws
+  return ws
+
+
+def conv1d_fwd(x, w, b, segment_pos, return_cache=True, mask_mode=MASK_FORK,
+               arith_mode=ARITH_REFERENCE):
+  global launch_count
+  _require_cuda(x, w, b, segment_pos)
+  bsz, steps, width = x.shape
+  tw = w.shape[0]
+  x, w, b = x.contiguous(), w.contiguous(), b.contiguous()
+  seg, is64, stride = _seg_args(segment_pos, bsz, steps)
+  y = torch.empty_like(x)
+  cache = (torch.empty((bsz, tw - 1, width), dtype=x.dtype, device=x.device)
+           if return_cache else None)
+  with torch.cuda.device(x.device):
+    rc = load().cg_conv1d_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(),
+                              seg.data_ptr(), is64, stride, y.data_ptr(),
+                              _ptr(cache), bsz, steps, width, tw,
+                              dtype_code(x.dtype), mask_mode, arith_mode,
+                              _stream(x))
+  _check(rc, "cg_conv1d_fwd")
+  launch_count += 1
+  return y, cache
+
+
+def conv1d_decode(x, w, b, cache, return_cache=True, arith_mode=ARITH_REFERENCE):
+  global launch_count
+  _require_cuda(x, w, b, cache)
+  bsz, steps, width = x.shape
+  tw = w.shape[0]
+  assert steps == 1, "layers.py:566: decode takes exactly one token"
+  assert cache.shape == (bsz, tw - 1, width), "layers.py:565"
+  x, w, b, cache = x.contiguous(), w.contiguous(), b.contiguous(), cache.contiguous()
+  y = torch.empty_like(x)
+  new_cache = torch.empty_like(cache) if return_cache else None
+  with torch.cuda.device(x.device):
+    rc = load().cg_conv1d_decode(x.data_ptr(), w.data_ptr(), b.data_ptr(),
+                                 cache.data_ptr(), dtype_code(cache.dtype),
+                                 y.data_ptr(), _ptr(new_cache), bsz, width, tw,
+                                 dtype_code(x.dtype), arith_mode, _stream(x))
+  _check(rc, "cg_conv1d_decode")
+  launch_count += 1
+  return y, new_cache
+
+
+def rglru_fwd(x, gemm_x, gemm_a, bias_x, bias_a, a_param, segment_pos, h0=None,
+              return_cache=True, arith_mode=ARITH_REFERENCE, out=None):
+  """Gate math + scan.  gemm_x / gemm_a may be row-strided views ([..., E] with
+  a common row stride, unit inner stride)."""
+  global launch_count
+  _require_cuda(x, gemm_x, gemm_a, a_param, segment_pos, h0)
+  bsz, steps, width = x.shape
+  x = x.contiguous()
+  assert gemm_x.shape == x.shape and gemm_a.shape == x.shape
+  assert gemm_x.dtype == x.dtype and gemm_a.dtype == x.dtype
+  assert a_param.dtype == x.dtype, "a_param must have the activation dtype"
+  assert h0 is None or h0.dtype == torch.float32, "layers.py:170"
+
+  def rows(t):
+    if t.stride(2) == 1 and t.stride(0) == steps * t.stride(1):
+      return t, t.stride(1)
+    t = t.contiguous()
+    return t, width
+
+  gemm_x, ldx = rows(gemm_x)
+  gemm_a, lda = rows(gemm_a)
+  if ldx != lda:
+    gemm_x, gemm_a, ldx = gemm_x.contiguous(), gemm_a.contiguous(), width
+  seg, is64, stride = _seg_args(segment_pos, bsz, steps)
+  y = torch.empty_like(x) if out is None else out
+  last_h = (torch.empty((bsz, width), dtype=torch.float32, device=x.device)
+            if return_cache else None)
+  ws = scan_workspace(x.device, bsz, steps, width, x.dtype)
+  bx = None if bias_x is None else bias_x.contiguous().view(-1)
+  ba = None if bias_a is None else bias_a.contiguous().view(-1)
+  h0c = None if h0 is None else h0.contiguous()
+  with torch.cuda.device(x.device):
+    rc = load().cg_rglru_fwd(x.data_ptr(), gemm_x.data_ptr(), gemm_a.data_ptr(),
+                             ldx, _ptr(bx), _ptr(ba), a_param.contiguous().data_ptr(),
+                             seg.data_ptr(), is64, stride, _ptr(h0c), y.data_ptr(),
+                             _ptr(last_h), ws.data_ptr(), ws.numel(), bsz, steps,
+                             width, dtype_code(x.dtype), arith_mode, _stream(x))
+  _check(rc, "cg_rglru_fwd")
+  launch_count += 2   # softplus(a_param) prologue + scan kernel
+  return y, last_h
+
+
+def rnn_scan_fwd(x, a, reset, h0=None, arith_mode=ARITH_REFERENCE):
+  global launch_count
+  _require_cuda(x, a, reset, h0)
+  bsz, steps, width = x.shape
+  x, a = x.contiguous(), a.contiguous()
+  rs = reset.to(torch.uint8).contiguous()
+  assert rs.shape == (bsz, steps)
+  y = torch.empty_like(x)
+  h_last = torch.empty((bsz, width), dtype=torch.float32, device=x.device)
+  ws = scan_workspace(x.device, bsz, steps, width, x.dtype)
+  h0c = None if h0 is None else h0.contiguous()
+  with torch.cuda.device(x.device):
+    rc = load().cg_rnn_scan_fwd(x.data_ptr(), a.data_ptr(), rs.data_ptr(),
+                                _ptr(h0c), y.data_ptr(), h_last.data_ptr(),
+                                ws.data_ptr(), ws.numel(), bsz, steps, width,
+                                dtype_code(x.dtype), arith_mode, _stream(x))
+  _check(rc, "cg_rnn_scan_fwd")
+  launch_count += 1
+  return y, h_last

@@ -1,0 +1,282 @@
+// C ABI of the B200 recurrent hot path (see include/cadence_b200.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared
+//        -Xcompiler -fPIC  (cadence_gemma_b200/build.py)
+// No --use_fast_math: the "exact" arithmetic modes rely on IEEE division,
+// sqrt.rn and the accurate expf/log1pf of the CUDA math library.
+#include "../../include/cadence_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cg_common.cuh"
+#include "cg_conv1d.cuh"
+#include "cg_scan.cuh"
+
+namespace {
+
+using cg::ConvParams;
+using cg::ScanParams;
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr int kMinL = 4;  // smallest steps-per-lane of any compiled geometry
+
+struct Geometry { int EC; int TC; };
+
+// scratch layout: [ticket 256 B][flags][agg_p][agg_h][pref][neg8sp]
+struct Workspace {
+  int* counter; int* flags; float* agg_p; float* agg_h; float* pref; float* neg8sp;
+  size_t zero_bytes;  // ticket + flags, cleared before every launch
+  size_t total;
+};
+
+Workspace carve(void* base, int B, int T, int E, int EC, int TC) {
+  Workspace w;
+  const size_t ctiles = (E + EC - 1) / EC;
+  const size_t nitems = (size_t)B * ctiles * ((T + TC - 1) / TC);
+  char* p = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  w.counter = reinterpret_cast<int*>(p + off); off += 256;
+  w.flags = reinterpret_cast<int*>(p + off); off += round_up(nitems * sizeof(int), 256);
+  w.zero_bytes = off;
+  w.agg_p = reinterpret_cast<float*>(p + off); off += nitems * EC * sizeof(float);
+  w.agg_h = reinterpret_cast<float*>(p + off); off += nitems * EC * sizeof(float);
+  w.pref = reinterpret_cast<float*>(p + off); off += nitems * EC * sizeof(float);
+  w.neg8sp = reinterpret_cast<float*>(p + off); off += round_up((size_t)E * sizeof(float), 256);
+  w.total = off;
+  return w;
+}
+
+template <typename IO, int KIND, int ARITH, int L, int WARPS, int MINB>
+int launch_scan(ScanParams p, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  constexpr int EC = cg::kCvl * cg::IoVec<IO>::V;
+  constexpr int TC = cg::kSegs * L;
+  const Workspace ws = carve(workspace, p.B, p.T, p.E, EC, TC);
+  if (ws.total > workspace_bytes) return CG_ERR_WORKSPACE;
+  p.ctiles = (p.E + EC - 1) / EC;
+  p.ncols = p.B * p.ctiles;
+  p.nchunks = (p.T + TC - 1) / TC;
+  p.nitems = p.ncols * p.nchunks;
+  p.counter = ws.counter; p.flags = ws.flags;
+  p.agg_p = ws.agg_p; p.agg_h = ws.agg_h; p.pref = ws.pref;
+  cudaError_t err = cudaMemsetAsync(ws.counter, 0, ws.zero_bytes, stream);
+  if (err != cudaSuccess) return (int)err;
+  const int blocks = (p.nitems + WARPS - 1) / WARPS;
+  cg::scan_kernel<IO, KIND, ARITH, L, WARPS, MINB><<<blocks, WARPS * 32, 0, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+template <typename IO, int KIND, int ARITH>
+int launch_strict(const ScanParams& p, cudaStream_t stream) {
+  dim3 grid((p.E + 127) / 128, p.B);
+  cg::strict_scan_kernel<IO, KIND, ARITH><<<grid, 128, 0, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+// Kernel geometry per variant id: L steps per lane, warps per block and the
+// minimum resident blocks per SM (caps registers: 4 -> 128, 3 -> 168, ...).
+// Variant 0 is the default; the others exist for the tuning scripts.
+template <typename IO, int KIND, int ARITH>
+int dispatch_geometry(int variant, const ScanParams& p, void* ws, size_t ws_bytes,
+                      cudaStream_t stream) {
+  constexpr bool BF = cg::IoVec<IO>::kBf16;
+  constexpr bool PACKED = BF && (KIND == 1 || (ARITH & 1) == 0);
+  if constexpr (PACKED || !BF) {   // 64 state registers at L = 8
+    switch (variant) {
+      case 0: return launch_scan<IO, KIND, ARITH, 8, 4, 4>(p, ws, ws_bytes, stream);
+      case 1: return launch_scan<IO, KIND, ARITH, 8, 4, 3>(p, ws, ws_bytes, stream);
+      case 2: return launch_scan<IO, KIND, ARITH, 8, 4, 2>(p, ws, ws_bytes, stream);
+      case 3: return launch_scan<IO, KIND, ARITH, 4, 4, 4>(p, ws, ws_bytes, stream);
+      case 4: return launch_scan<IO, KIND, ARITH, 4, 4, 5>(p, ws, ws_bytes, stream);
+      case 5: return launch_scan<IO, KIND, ARITH, 4, 4, 6>(p, ws, ws_bytes, stream);
+      case 6: return launch_scan<IO, KIND, ARITH, 8, 4, 5>(p, ws, ws_bytes, stream);
+      default: return CG_ERR_MODE;
+    }
+  } else {                         // bf16 I/O with fp32 state: 64 registers at L = 4
+    switch (variant) {
+      case 0: return launch_scan<IO, KIND, ARITH, 4, 4, 4>(p, ws, ws_bytes, stream);
+      case 1: return launch_scan<IO, KIND, ARITH, 4, 4, 3>(p, ws, ws_bytes, stream);
+      case 2: return launch_scan<IO, KIND, ARITH, 4, 4, 5>(p, ws, ws_bytes, stream);
+      default: return CG_ERR_MODE;
+    }
+  }
+}
+
+int check_common(int B, int T, int E, int dtype) {
+  if (B < 1 || T < 1 || E < 1) return CG_ERR_SHAPE;
+  if (dtype != CG_DTYPE_F32 && dtype != CG_DTYPE_BF16) return CG_ERR_DTYPE;
+  return CG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cg_abi_version(void) { return CG_ABI_VERSION; }
+
+const char* cg_status_string(int status) {
+  switch (status) {
+    case CG_OK: return "ok";
+    case CG_ERR_NULL: return "null pointer argument";
+    case CG_ERR_SHAPE: return "invalid shape (B, T, E, W must be >= 1; decode needs T == 1)";
+    case CG_ERR_DTYPE: return "unsupported dtype (fp32 = 0, bf16 = 1)";
+    case CG_ERR_ALIGN: return "pointers must be 16-byte aligned and E / row strides a multiple of 16 bytes";
+    case CG_ERR_WORKSPACE: return "workspace too small (see cg_scan_workspace_bytes)";
+    case CG_ERR_MODE: return "unsupported arith_mode / mask_mode / variant";
+    default: break;
+  }
+  if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
+  return "unknown status";
+}
+
+size_t cg_scan_workspace_bytes(int B, int T, int E, int dtype) {
+  if (B < 1 || T < 1 || E < 1) return 0;
+  const int V = dtype == CG_DTYPE_BF16 ? 8 : 4;
+  return carve(nullptr, B, T, E, cg::kCvl * V, cg::kSegs * kMinL).total;
+}
+
+int cg_conv1d_fwd(const void* x, const void* w, const void* b, const void* seg, int seg_is_i64,
+                  long long seg_batch_stride, void* y, void* cache_out, int B, int T, int E, int W,
+                  int dtype, int mask_mode, int arith_mode, cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !w || !b || !seg || !y) return CG_ERR_NULL;
+  if (int rc = check_common(B, T, E, dtype)) return rc;
+  if (W < 1 || W > 17) return CG_ERR_SHAPE;
+  if (mask_mode != CG_MASK_FORK && mask_mode != CG_MASK_UPSTREAM) return CG_ERR_MODE;
+  const bool bf = dtype == CG_DTYPE_BF16;
+  const bool emul = (arith_mode & CG_ARITH_FP32) == 0;
+  ConvParams p{};
+  p.x = x; p.w = w; p.bias = b; p.seg = seg; p.seg_bstride = seg_batch_stride;
+  p.seg_is_i64 = seg_is_i64; p.y = y; p.cache_out = cache_out;
+  p.B = B; p.T = T; p.E = E; p.W = W; p.mask_mode = mask_mode;
+  const int V = bf ? 8 : 4;
+  const bool vec_ok = W == 4 && E % V == 0 && aligned16(x) && aligned16(w) && aligned16(b) &&
+                      aligned16(y) && (!cache_out || aligned16(cache_out));
+  if (vec_ok) {
+    constexpr int LC = 16;
+    const int tslots = (T + LC - 1) / LC;
+    dim3 grid((tslots + 15) / 16, (E + 8 * V - 1) / (8 * V), B);
+    if (bf && emul) cg::conv1d_w4_kernel<uint16_t, true, LC><<<grid, 128, 0, stream>>>(p);
+    else if (bf) cg::conv1d_w4_kernel<uint16_t, false, LC><<<grid, 128, 0, stream>>>(p);
+    else cg::conv1d_w4_kernel<float, true, LC><<<grid, 128, 0, stream>>>(p);
+  } else {
+    if (T > 65535 || B > 65535) return CG_ERR_SHAPE;
+    dim3 grid((E + 127) / 128, T, B);
+    if (bf && emul) cg::conv1d_generic_kernel<uint16_t, true><<<grid, 128, 0, stream>>>(p);
+    else if (bf) cg::conv1d_generic_kernel<uint16_t, false><<<grid, 128, 0, stream>>>(p);
+    else cg::conv1d_generic_kernel<float, true><<<grid, 128, 0, stream>>>(p);
+  }
+  return (int)cudaGetLastError();
+}
+
+int cg_conv1d_decode(const void* x, const void* w, const void* b, const void* cache_in,
+                     int cache_dtype, void* y, void* cache_out, int B, int E, int W, int dtype,
+                     int arith_mode, cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !w || !b || !cache_in || !y) return CG_ERR_NULL;
+  if (int rc = check_common(B, 1, E, dtype)) return rc;
+  if (cache_dtype != CG_DTYPE_F32 && cache_dtype != CG_DTYPE_BF16) return CG_ERR_DTYPE;
+  if (W < 2 || W > 17 || B > 65535) return CG_ERR_SHAPE;
+  const bool bf = dtype == CG_DTYPE_BF16;
+  const bool emul = (arith_mode & CG_ARITH_FP32) == 0;
+  ConvParams p{};
+  p.x = x; p.w = w; p.bias = b; p.y = y; p.cache_in = cache_in; p.cache_out = cache_out;
+  p.cache_is_bf16 = cache_dtype == CG_DTYPE_BF16;
+  p.B = B; p.T = 1; p.E = E; p.W = W;
+  dim3 grid((E + 127) / 128, B);
+  if (bf && emul) cg::conv1d_decode_kernel<uint16_t, true><<<grid, 128, 0, stream>>>(p);
+  else if (bf) cg::conv1d_decode_kernel<uint16_t, false><<<grid, 128, 0, stream>>>(p);
+  else cg::conv1d_decode_kernel<float, true><<<grid, 128, 0, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int cg_rglru_fwd(const void* x, const void* gemm_x, const void* gemm_a, long long gate_row_stride,
+                 const void* bias_x, const void* bias_a, const void* a_param, const void* seg,
+                 int seg_is_i64, long long seg_batch_stride, const float* h0, void* y,
+                 float* last_h, void* workspace, size_t workspace_bytes, int B, int T, int E,
+                 int dtype, int arith_mode, cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !gemm_x || !gemm_a || !a_param || !seg || !y || !workspace) return CG_ERR_NULL;
+  if (int rc = check_common(B, T, E, dtype)) return rc;
+  if (B > 65535) return CG_ERR_SHAPE;
+  const bool bf = dtype == CG_DTYPE_BF16;
+  const int V = bf ? 8 : 4;
+  const int variant = (arith_mode >> 8) & 0xff;
+  const int mode = arith_mode & 7;
+  const bool strict = (mode & CG_ARITH_STRICT) != 0;
+  if ((arith_mode & ~0xff07) != 0) return CG_ERR_MODE;
+  if (gate_row_stride < E) return CG_ERR_SHAPE;
+  if (!strict) {
+    if (E % V != 0 || gate_row_stride % V != 0) return CG_ERR_ALIGN;
+    if (!aligned16(x) || !aligned16(gemm_x) || !aligned16(gemm_a) || !aligned16(y) ||
+        (bias_x && !aligned16(bias_x)) || (bias_a && !aligned16(bias_a)) ||
+        (h0 && !aligned16(h0)) || (last_h && !aligned16(last_h)) || !aligned16(workspace))
+      return CG_ERR_ALIGN;
+  }
+  // -8 * softplus(a_param) lives at the tail of the scratch for every geometry
+  const Workspace ws_min = carve(workspace, B, T, E, cg::kCvl * V, cg::kSegs * kMinL);
+  if (ws_min.total > workspace_bytes) return CG_ERR_WORKSPACE;
+  float* neg8sp = ws_min.neg8sp;
+  const int emulate = (mode & CG_ARITH_FP32) == 0;
+  cg::softplus_param_kernel<<<(E + 127) / 128, 128, 0, stream>>>(a_param, neg8sp, E, bf ? 1 : 0,
+                                                                  emulate);
+  if (cudaError_t err = cudaGetLastError()) return (int)err;
+
+  ScanParams p{};
+  p.x = x; p.gemm_x = gemm_x; p.gemm_a = gemm_a; p.bias_x = bias_x; p.bias_a = bias_a;
+  p.neg8sp = neg8sp; p.seg = seg; p.seg_bstride = seg_batch_stride; p.seg_is_i64 = seg_is_i64;
+  p.gate_ld = gate_row_stride; p.h0 = h0; p.y = y; p.last_h = last_h;
+  p.B = B; p.T = T; p.E = E;
+
+  if (strict) {
+    const int m = mode & 3;
+    if (bf) {
+      switch (m) {
+        case 0: return launch_strict<uint16_t, 0, 0>(p, stream);
+        case 1: return launch_strict<uint16_t, 0, 1>(p, stream);
+        case 2: return launch_strict<uint16_t, 0, 2>(p, stream);
+        default: return launch_strict<uint16_t, 0, 3>(p, stream);
+      }
+    }
+    return (m & 2) ? launch_strict<float, 0, 3>(p, stream) : launch_strict<float, 0, 1>(p, stream);
+  }
+  if (bf) {
+    switch (mode & 3) {
+      case 0: return dispatch_geometry<uint16_t, 0, 0>(variant, p, workspace, workspace_bytes, stream);
+      case 1: return dispatch_geometry<uint16_t, 0, 1>(variant, p, workspace, workspace_bytes, stream);
+      case 2: return dispatch_geometry<uint16_t, 0, 2>(variant, p, workspace, workspace_bytes, stream);
+      default: return dispatch_geometry<uint16_t, 0, 3>(variant, p, workspace, workspace_bytes, stream);
+    }
+  }
+  return (mode & 2) ? dispatch_geometry<float, 0, 3>(variant, p, workspace, workspace_bytes, stream)
+                    : dispatch_geometry<float, 0, 1>(variant, p, workspace, workspace_bytes, stream);
+}
+
+int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset, const float* h0,
+                    void* y, float* last_h, void* workspace, size_t workspace_bytes, int B, int T,
+                    int E, int dtype, int arith_mode, cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !a || !reset || !y) return CG_ERR_NULL;
+  if (int rc = check_common(B, T, E, dtype)) return rc;
+  if (B > 65535) return CG_ERR_SHAPE;
+  const bool bf = dtype == CG_DTYPE_BF16;
+  const int V = bf ? 8 : 4;
+  const int variant = (arith_mode >> 8) & 0xff;
+  if ((arith_mode & ~0xff07) != 0) return CG_ERR_MODE;
+  ScanParams p{};
+  p.x = x; p.a = a; p.reset = reset; p.h0 = h0; p.y = y; p.last_h = last_h;
+  p.B = B; p.T = T; p.E = E;
+  if (arith_mode & CG_ARITH_STRICT) {
+    return bf ? launch_strict<uint16_t, 1, 0>(p, stream) : launch_strict<float, 1, 1>(p, stream);
+  }
+  if (!workspace) return CG_ERR_NULL;
+  if (E % V != 0) return CG_ERR_ALIGN;
+  if (!aligned16(x) || !aligned16(a) || !aligned16(y) || (h0 && !aligned16(h0)) ||
+      (last_h && !aligned16(last_h)) || !aligned16(workspace))
+    return CG_ERR_ALIGN;
+  return bf ? dispatch_geometry<uint16_t, 1, 0>(variant, p, workspace, workspace_bytes, stream)
+            : dispatch_geometry<float, 1, 1>(variant, p, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,134 @@
+// Device helpers shared by the sm_100a kernels of the recurrent hot path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cg {
+
+constexpr uint32_t kOne2 = 0x3f803f80u;  // bf16x2 {1.0, 1.0}
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ---------------------------------------------------------------- bf16 <-> f32
+__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+// {lo, hi} fp32 -> packed bf16x2, round-to-nearest-even (what ATen's cast does).
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// fp32 -> nearest bf16 -> fp32 (one eager rounding point of the reference).
+__device__ __forceinline__ float round_bf(float v) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(v), "f"(v));
+  return __uint_as_float(d & 0xffff0000u);
+}
+
+// Packed bf16 arithmetic with ONE rounding per op and no contraction.  The
+// reference evaluates bf16 elementwise ops as fp32 op + round-to-bf16; since
+// fp32 carries >= 2*8+2 significand bits that double rounding is innocuous
+// for +,-,*,sqrt, i.e. it equals the correctly rounded bf16 op computed here.
+__device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf2_sub(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
+// ------------------------------------------------------------- transcendentals
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool FAST>
+__device__ __forceinline__ float exp_f(float x) {
+  if constexpr (FAST) return ex2_approx(x * kLog2e);
+  else return expf(x);
+}
+template <bool FAST>
+__device__ __forceinline__ float sqrt_f(float x) {
+  if constexpr (FAST) return sqrt_approx(x);
+  else return sqrtf(x);
+}
+// sigmoid of two values.  Exact: the ATen formula 1/(1+exp(-v)) with IEEE
+// division.  Fast: one shared reciprocal, r = 1/((1+e0)(1+e1)); arguments are
+// clamped at -43 so the product stays finite.
+template <bool FAST>
+__device__ __forceinline__ void sigmoid2(float v0, float v1, float& s0, float& s1) {
+  if constexpr (FAST) {
+    float d0 = 1.0f + ex2_approx(fmaxf(v0, -43.0f) * -kLog2e);
+    float d1 = 1.0f + ex2_approx(fmaxf(v1, -43.0f) * -kLog2e);
+    float r = rcp_approx(d0 * d1);
+    s0 = r * d1;
+    s1 = r * d0;
+  } else {
+    s0 = 1.0f / (1.0f + expf(-v0));
+    s1 = 1.0f / (1.0f + expf(-v1));
+  }
+}
+// F.softplus (beta 1, threshold 20) -- parameters only, always accurate.
+__device__ __forceinline__ float softplus_f(float v) {
+  return v > 20.0f ? v : log1pf(expf(v));
+}
+
+// ------------------------------------------------------------ global memory I/O
+// Streaming 128-bit accesses: inputs are read once (no L1 allocation), outputs
+// are written once (evict-first).
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(void* p, uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// L2-coherent accesses for the cross-warp carry exchange.
+__device__ __forceinline__ uint4 ldg_cg(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void stg_cg(void* p, uint4 v) {
+  asm volatile("st.global.cg.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ long long load_seg(const void* seg, bool is_i64, long long idx) {
+  return is_i64 ? reinterpret_cast<const long long*>(seg)[idx]
+                : static_cast<long long>(reinterpret_cast<const int*>(seg)[idx]);
+}
+
+}  // namespace cg

@@ -1,0 +1,237 @@
+// Depth-wise causal temporal convolution for sm_100a.
+// Replaces reference recurrentgemma/torch/layers.py:458-546 (Conv1D.forward):
+// prefill with the fork's document mask (:592-633), decode step (:478-483),
+// returned cache (:541-546, :650-662).
+#pragma once
+
+#include "cg_common.cuh"
+#include "cg_scan.cuh"   // IoVec, load_io / store_io
+
+namespace cg {
+
+struct ConvParams {
+  const void* x;      // [B,T,E]
+  const void* w;      // [W,E]
+  const void* bias;   // [E]
+  const void* seg;    // prefill only
+  long long seg_bstride;
+  int seg_is_i64;
+  void* y;            // [B,T,E]
+  void* cache_out;    // [B,W-1,E] or null
+  const void* cache_in;   // decode only
+  int cache_is_bf16;      // decode only
+  int B, T, E, W;
+  int mask_mode;
+};
+
+// ---------------------------------------------------------------------------
+// W == 4 prefill.  Thread = 16-byte channel vector x LC consecutive steps with
+// a 3-row register window; 8 lanes cover one 128 B row, lane groups / warps
+// cover consecutive time tiles.  EMUL: accumulate in the tensor dtype with one
+// rounding per eager op of the reference (:533-536) -- for bf16 these are
+// packed HMUL2/HADD2, for fp32 non-contracted FMUL/FADD, both bit-exact with
+// the reference.  !EMUL (bf16 only): fp32 accumulation, one final rounding.
+// ---------------------------------------------------------------------------
+template <typename IO, bool EMUL, int LC>
+__global__ void __launch_bounds__(128)
+conv1d_w4_kernel(const ConvParams p) {
+  constexpr int V = IoVec<IO>::V;
+  constexpr bool BF = IoVec<IO>::kBf16;
+  constexpr int EC = kCvl * V;
+  const int cv = threadIdx.x & 7;
+  const int tslot = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  const int ch0 = blockIdx.y * EC + cv * V;
+  const int b = blockIdx.z;
+  const int t0 = tslot * LC;
+  if (ch0 >= p.E || t0 >= p.T) return;
+  const IO* xb = reinterpret_cast<const IO*>(p.x) + (size_t)b * p.T * p.E + ch0;
+  IO* yb = reinterpret_cast<IO*>(p.y) + (size_t)b * p.T * p.E + ch0;
+  const long long seg0 = (long long)b * p.seg_bstride;
+
+  // taps: wk[k] multiplies x[t - (3 - k)]  (w[W-1-shift], :530)
+  uint4 wk[4], bv;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    wk[k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const IO*>(p.w) + (size_t)k * p.E + ch0);
+  bv = *reinterpret_cast<const uint4*>(reinterpret_cast<const IO*>(p.bias) + ch0);
+
+  // register window: xm3 = x[t-3], xm2 = x[t-2], xm1 = x[t-1]
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  uint4 xm3 = t0 >= 3 ? ldg_stream(xb + (size_t)(t0 - 3) * p.E) : zero;
+  uint4 xm2 = t0 >= 2 ? ldg_stream(xb + (size_t)(t0 - 2) * p.E) : zero;
+  uint4 xm1 = t0 >= 1 ? ldg_stream(xb + (size_t)(t0 - 1) * p.E) : zero;
+  // nb bit k = (segment_pos[t-k] != 0); positions before 0 are never consulted
+  // for a tap that exists, so their value is irrelevant.
+  unsigned nb = 0;
+  if (t0 >= 1) nb |= (load_seg(p.seg, p.seg_is_i64 != 0, seg0 + t0 - 1) != 0) ? 1u : 0u;
+  if (t0 >= 2) nb |= (load_seg(p.seg, p.seg_is_i64 != 0, seg0 + t0 - 2) != 0) ? 2u : 0u;
+
+#pragma unroll
+  for (int j = 0; j < LC; ++j) {
+    const int t = t0 + j;
+    if (t >= p.T) break;
+    const uint4 x0 = ldg_stream(xb + (size_t)t * p.E);
+    nb = (nb << 1) | ((load_seg(p.seg, p.seg_is_i64 != 0, seg0 + t) != 0) ? 1u : 0u);
+    // document mask per tap (shift s looks at segment_pos[t-s+1 .. ])
+    bool m1 = true, m2 = true, m3;
+    if (p.mask_mode == 0) {
+      m3 = (nb & 4u) != 0;                        // fork: only seg[t-2], :629-632
+    } else {
+      m1 = (nb & 1u) != 0;                        // upstream: seg[t-s+1..t] all != 0
+      m2 = (nb & 3u) == 3u;
+      m3 = (nb & 7u) == 7u;
+    }
+    const uint4 a1 = m1 ? xm1 : zero, a2 = m2 ? xm2 : zero, a3 = m3 ? xm3 : zero;
+    uint4 out;
+    const uint32_t s0[4] = {x0.x, x0.y, x0.z, x0.w}, s1[4] = {a1.x, a1.y, a1.z, a1.w};
+    const uint32_t s2[4] = {a2.x, a2.y, a2.z, a2.w}, s3[4] = {a3.x, a3.y, a3.z, a3.w};
+    const uint32_t k0[4] = {wk[0].x, wk[0].y, wk[0].z, wk[0].w}, k1[4] = {wk[1].x, wk[1].y, wk[1].z, wk[1].w};
+    const uint32_t k2[4] = {wk[2].x, wk[2].y, wk[2].z, wk[2].w}, k3[4] = {wk[3].x, wk[3].y, wk[3].z, wk[3].w};
+    const uint32_t bb[4] = {bv.x, bv.y, bv.z, bv.w};
+    uint32_t o[4];
+    if constexpr (BF && EMUL) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t acc = bf2_mul(s0[i], k3[i]);                 // shift 0
+        acc = bf2_add(acc, bf2_mul(s1[i], k2[i]));            // shift 1
+        acc = bf2_add(acc, bf2_mul(s2[i], k1[i]));            // shift 2
+        acc = bf2_add(acc, bf2_mul(s3[i], k0[i]));            // shift 3
+        o[i] = bf2_add(acc, bb[i]);                           // + b, :536
+      }
+    } else if constexpr (BF) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float lo = bf_lo(s0[i]) * bf_lo(k3[i]), hi = bf_hi(s0[i]) * bf_hi(k3[i]);
+        lo = fmaf(bf_lo(s1[i]), bf_lo(k2[i]), lo); hi = fmaf(bf_hi(s1[i]), bf_hi(k2[i]), hi);
+        lo = fmaf(bf_lo(s2[i]), bf_lo(k1[i]), lo); hi = fmaf(bf_hi(s2[i]), bf_hi(k1[i]), hi);
+        lo = fmaf(bf_lo(s3[i]), bf_lo(k0[i]), lo); hi = fmaf(bf_hi(s3[i]), bf_hi(k0[i]), hi);
+        o[i] = pack_bf2(lo + bf_lo(bb[i]), hi + bf_hi(bb[i]));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float acc = __fmul_rn(__uint_as_float(s0[i]), __uint_as_float(k3[i]));
+        acc = __fadd_rn(acc, __fmul_rn(__uint_as_float(s1[i]), __uint_as_float(k2[i])));
+        acc = __fadd_rn(acc, __fmul_rn(__uint_as_float(s2[i]), __uint_as_float(k1[i])));
+        acc = __fadd_rn(acc, __fmul_rn(__uint_as_float(s3[i]), __uint_as_float(k0[i])));
+        o[i] = __float_as_uint(__fadd_rn(acc, __uint_as_float(bb[i])));
+      }
+    }
+    out = make_uint4(o[0], o[1], o[2], o[3]);
+    stg_stream(yb + (size_t)t * p.E, out);
+    xm3 = xm2; xm2 = xm1; xm1 = x0;
+  }
+
+  // new cache = last 3 input rows, left zero padded (:542-543); written by the
+  // thread whose tile holds the final step.
+  if (p.cache_out != nullptr && t0 + LC >= p.T) {
+    IO* cb = reinterpret_cast<IO*>(p.cache_out) + (size_t)b * 3 * p.E + ch0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ti = p.T - 3 + r;
+      const uint4 v = ti >= 0 ? ldg_stream(xb + (size_t)ti * p.E) : zero;
+      *reinterpret_cast<uint4*>(cb + (size_t)r * p.E) = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Generic temporal width (W != 4): one thread per output element.  Slow path,
+// kept for API completeness (the reference's tests also run W = 8).
+// Reproduces the accumulated in-place masking of the returned cache
+// (quirk D2, see oracle/rglru_oracle.c).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool tap_mask_generic(const ConvParams& p, long long seg0, int ti,
+                                                 int shift, int mask_mode) {
+  const int hi = mask_mode == 0 ? shift - 2 : shift;
+  for (int j = 1; j <= hi; ++j)
+    if (load_seg(p.seg, p.seg_is_i64 != 0, seg0 + ti + j) == 0) return false;
+  return true;
+}
+
+template <typename IO, bool EMUL>
+__global__ void conv1d_generic_kernel(const ConvParams p) {
+  constexpr bool BF = IoVec<IO>::kBf16;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  const int b = blockIdx.z;
+  if (e >= p.E) return;
+  const long long seg0 = (long long)b * p.seg_bstride;
+  const int taps = p.W < p.T ? p.W : p.T;
+  float acc = 0.0f;
+  for (int s = 0; s < taps; ++s) {
+    const int ti = t - s;
+    float term = 0.0f;
+    if (ti >= 0) {
+      float xv = load_io<IO>(p.x, ((size_t)b * p.T + ti) * p.E + e);
+      if (!tap_mask_generic(p, seg0, ti, s, p.mask_mode)) xv = 0.0f;
+      term = __fmul_rn(xv, load_io<IO>(p.w, (size_t)(p.W - 1 - s) * p.E + e));
+      if (BF && EMUL) term = round_bf(term);
+    }
+    acc = s == 0 ? term : __fadd_rn(acc, term);
+    if (BF && EMUL) acc = round_bf(acc);
+  }
+  acc = __fadd_rn(acc, load_io<IO>(p.bias, e));
+  store_io<IO>(p.y, ((size_t)b * p.T + t) * p.E + e, acc);
+
+  if (p.cache_out != nullptr && t == p.T - 1) {
+    for (int r = 0; r < p.W - 1; ++r) {
+      const int ti = p.T - (p.W - 1) + r;
+      float xv = 0.0f;
+      if (ti >= 0) {
+        xv = load_io<IO>(p.x, ((size_t)b * p.T + ti) * p.E + e);
+        if (p.mask_mode == 0) {
+          int smax = taps - 1 < p.T - 1 - ti ? taps - 1 : p.T - 1 - ti;
+          if (smax >= 3 && !tap_mask_generic(p, seg0, ti, smax, 0)) xv = 0.0f;
+        }
+      }
+      store_io<IO>(p.cache_out, ((size_t)b * (p.W - 1) + r) * p.E + e, xv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Decode step (T == 1, cache given, no mask): one thread per (b, channel).
+// cache_out may alias cache_in (each thread reads its column before writing).
+// ---------------------------------------------------------------------------
+template <typename IO, bool EMUL>
+__global__ void conv1d_decode_kernel(const ConvParams p) {
+  constexpr bool BF = IoVec<IO>::kBf16;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (e >= p.E) return;
+  const int W = p.W;
+  auto cache_at = [&](int k) -> float {   // cache.type(x.dtype), :567
+    const size_t i = ((size_t)b * (W - 1) + k) * p.E + e;
+    float v = p.cache_is_bf16
+                  ? __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(p.cache_in)[i] << 16)
+                  : reinterpret_cast<const float*>(p.cache_in)[i];
+    if (BF) v = round_bf(v);
+    return v;
+  };
+  const float xnew = load_io<IO>(p.x, (size_t)b * p.E + e);
+  float acc = 0.0f;
+  for (int s = 0; s < W; ++s) {
+    const int k = W - 1 - s;
+    const float xv = k == W - 1 ? xnew : cache_at(k);
+    float term = __fmul_rn(xv, load_io<IO>(p.w, (size_t)k * p.E + e));
+    if (BF && EMUL) term = round_bf(term);
+    acc = s == 0 ? term : __fadd_rn(acc, term);
+    if (BF && EMUL) acc = round_bf(acc);
+  }
+  acc = __fadd_rn(acc, load_io<IO>(p.bias, e));
+  store_io<IO>(p.y, (size_t)b * p.E + e, acc);
+  if (p.cache_out != nullptr) {
+    // new_cache[k-1] = xcat[k] (:542): read all surviving rows first so that
+    // cache_out may alias cache_in, then write
+    float keep[16];
+    for (int k = 1; k < W; ++k) keep[k - 1] = k == W - 1 ? xnew : cache_at(k);
+    for (int k = 1; k < W; ++k) {
+      const size_t i = ((size_t)b * (W - 1) + (k - 1)) * p.E + e;
+      if (p.cache_is_bf16) reinterpret_cast<uint16_t*>(p.cache_out)[i] = (uint16_t)(pack_bf2(keep[k - 1], keep[k - 1]) & 0xffffu);
+      else reinterpret_cast<float*>(p.cache_out)[i] = keep[k - 1];
+    }
+  }
+}
+
+}  // namespace cg

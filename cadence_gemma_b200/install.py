@@ -1,0 +1,76 @@
+"""Drops the CUDA path into an imported copy of the reference.
+
+``install(ref_layers, ref_modules)`` rebinds, inside the *reference's own*
+modules, exactly the three entry points of the hot path:
+
+  * ``layers.rnn_scan``        (looked up as a module global at call time,
+                                reference layers.py:366)
+  * ``layers.RGLRU.forward``   (reference layers.py:322-375)
+  * ``layers.Conv1D.forward``  (reference layers.py:458-546)
+
+so an unmodified ``RecurrentBlock`` / ``ResidualBlock`` / ``Griffin`` built
+from the reference classes (``examples/cadence_sampler.py`` included) runs the
+sm_100a kernels with its own parameters.  ``uninstall`` restores the originals.
+"""
+from __future__ import annotations
+
+import torch
+
+from cadence_gemma_b200 import _abi, layers as cg_layers
+
+_saved = {}
+
+
+def _gemm_no_bias(bdl, x):
+  heads, bw = bdl.num_blocks, bdl.block_width
+  x2 = x.reshape(-1, heads, bw)
+  out = torch.empty_like(x2)
+  torch.bmm(x2.transpose(0, 1), bdl.w, out=out.transpose(0, 1))
+  return out.view(x.shape)
+
+
+def _rglru_forward(self, x, segment_pos, cache=None, return_cache=True):
+  bs, length, _ = x.shape
+  if segment_pos.shape != (bs, length):
+    segment_pos = segment_pos[None, :]
+  assert segment_pos.shape == (bs, length)
+  cg_layers._forward_only(x, cache)
+  with torch.no_grad():
+    return _abi.rglru_fwd(
+        x, _gemm_no_bias(self.input_gate, x), _gemm_no_bias(self.a_gate, x),
+        self.input_gate.b, self.a_gate.b, self.a_param, segment_pos, h0=cache,
+        return_cache=return_cache, arith_mode=cg_layers.get_arith_mode())
+
+
+def _conv1d_forward(self, x, segment_pos, cache=None, return_cache=True):
+  cg_layers._forward_only(x, cache)
+  mode = cg_layers.get_arith_mode() & _abi.ARITH_FP32
+  with torch.no_grad():
+    if cache is not None:
+      return _abi.conv1d_decode(x, self.w, self.b, cache,
+                                return_cache=return_cache, arith_mode=mode)
+    return _abi.conv1d_fwd(x, self.w, self.b, segment_pos,
+                           return_cache=return_cache, arith_mode=mode)
+
+
+def install(ref_layers, ref_modules=None) -> None:
+  """Patches the given reference modules in place (idempotent)."""
+  if "rnn_scan" in _saved:
+    return
+  _abi.load()   # fail loudly now if the library was not built
+  _saved["rnn_scan"] = ref_layers.rnn_scan
+  _saved["rglru_forward"] = ref_layers.RGLRU.forward
+  _saved["conv1d_forward"] = ref_layers.Conv1D.forward
+  _saved["layers"] = ref_layers
+  ref_layers.rnn_scan = cg_layers.rnn_scan
+  ref_layers.RGLRU.forward = _rglru_forward
+  ref_layers.Conv1D.forward = _conv1d_forward
+
+
+def uninstall() -> None:
+  if "rnn_scan" not in _saved:
+    return
+  ref_layers = _saved.pop("layers")
+  ref_layers.rnn_scan = _saved.pop("rnn_scan")
+  ref_layers.RGLRU.forward = _saved.pop("rglru_forward")
+  ref_layers.Conv1D.forward = _saved.pop("conv1d_forward")

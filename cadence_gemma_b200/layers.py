@@ -1,0 +1,199 @@
+"""Host-side mirror of the reference's recurrent layers, backed by sm_100a CUDA.
+
+Same names, constructor arguments, parameter attributes / state-dict keys,
+call signatures and return conventions as the reference
+(``recurrentgemma/torch/layers.py``), so these classes drop into
+``RecurrentBlock`` / ``ResidualBlock`` / ``Griffin``:
+
+  * ``rnn_scan``             layers.py:146-199
+  * ``BlockDiagonalLinear``  layers.py:81-142   (stays a cuBLAS GEMM)
+  * ``RGLRU``                layers.py:241-386
+  * ``Conv1D``               layers.py:389-676
+
+The arithmetic runs in ``libcadence_b200.so`` through the C ABI
+(``include/cadence_b200.h``).  Forward only; there is no CPU / eager fallback:
+CPU tensors or a missing library raise.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from cadence_gemma_b200 import _abi
+
+# Default arithmetic of the kernels (see include/cadence_b200.h):
+# reproduce every eager rounding point of the reference, fast transcendentals.
+DEFAULT_ARITH = _abi.ARITH_REFERENCE | _abi.ARITH_FAST
+_arith_mode = DEFAULT_ARITH
+
+
+def set_arith_mode(mode: int) -> int:
+  """Sets the process-wide arithmetic mode of the shims; returns the old one."""
+  global _arith_mode
+  old, _arith_mode = _arith_mode, int(mode)
+  return old
+
+
+def get_arith_mode() -> int:
+  return _arith_mode
+
+
+def _forward_only(*tensors):
+  if torch.is_grad_enabled() and any(
+      t is not None and t.requires_grad for t in tensors):
+    raise RuntimeError(
+        "cadence_gemma_b200 kernels are forward-only; call under "
+        "torch.no_grad() (there is no autograd or eager fallback)")
+
+
+def rnn_scan(x, a, reset, h0, acc_dtype=torch.float32):
+  """Linear recurrence h_t = a_t h_{t-1} + x_t (reference layers.py:146-199).
+
+  Returns ``(y in x.dtype, h_last in fp32)``.
+  """
+  assert x.ndim == 3
+  assert a.shape == x.shape[-a.ndim:]
+  assert a.dtype == x.dtype
+  assert acc_dtype == torch.float32, "only fp32 accumulation is implemented"
+  assert h0 is None or h0.dtype == acc_dtype
+  _forward_only(x, a, h0)
+  if a.shape != x.shape:
+    a = a.expand_as(x)
+  mode = _arith_mode & _abi.ARITH_STRICT
+  return _abi.rnn_scan_fwd(x, a, reset, h0, arith_mode=mode)
+
+
+class BlockDiagonalLinear(nn.Module):
+  """Block-diagonal linear layer (reference layers.py:81-142)."""
+
+  def __init__(self, width, num_blocks, w_init_variance_scale=1.0, device=None,
+               dtype=None):
+    super().__init__()
+    self.width = width
+    self.num_blocks = num_blocks
+    self.w_init_variance_scale = w_init_variance_scale
+    self.block_width = width // num_blocks
+    bw = self.block_width
+    self.w = nn.Parameter(torch.empty((num_blocks, bw, bw), device=device, dtype=dtype))
+    self.b = nn.Parameter(torch.empty((num_blocks, bw), device=device, dtype=dtype))
+    self.reset_parameters()
+
+  def reset_parameters(self) -> None:
+    self.w_init_(self.w)
+    nn.init.zeros_(self.b)
+
+  def w_init_(self, w: torch.Tensor) -> None:
+    nn.init.normal_(w, mean=0.0,
+                    std=math.sqrt(self.w_init_variance_scale / self.block_width))
+
+  def gemm(self, x: torch.Tensor) -> torch.Tensor:
+    """``x @ blockdiag(w)`` WITHOUT bias, laid out like ``x`` ([..., H*bw]).
+
+    One strided-batched cuBLAS GEMM writing straight into the flat layout (no
+    permute / reshape copies); the bias is added inside the scan kernel.
+    """
+    heads, bw = self.num_blocks, self.block_width
+    x2 = x.reshape(-1, heads, bw)
+    out = torch.empty_like(x2)
+    torch.bmm(x2.transpose(0, 1), self.w, out=out.transpose(0, 1))
+    return out.view(x.shape)
+
+  def forward(self, x: torch.Tensor) -> torch.Tensor:
+    heads, bw = self.num_blocks, self.block_width
+    y = self.gemm(x).view(*x.shape[:-1], heads, bw) + self.b
+    return y.view(x.shape)
+
+
+class RGLRU(nn.Module):
+  """Real-Gated Linear Recurrent Unit (reference layers.py:241-386)."""
+
+  def __init__(self, width, num_heads, w_init_variance_scale=1.0, device=None,
+               dtype=None):
+    super().__init__()
+    self.width = width
+    self.num_heads = num_heads
+    self.w_init_variance_scale = w_init_variance_scale
+    self.a_param = nn.Parameter(torch.empty((width,), device=device, dtype=dtype))
+    self.input_gate = BlockDiagonalLinear(width, num_heads, w_init_variance_scale,
+                                          device=device, dtype=dtype)
+    self.a_gate = BlockDiagonalLinear(width, num_heads, w_init_variance_scale,
+                                      device=device, dtype=dtype)
+    self.reset_parameters()
+
+  def reset_parameters(self) -> None:
+    self.input_gate.reset_parameters()
+    self.a_gate.reset_parameters()
+    self.a_param_init(self.a_param)
+
+  def a_param_init(self, w: torch.Tensor) -> torch.Tensor:
+    """`a` uniform on the ring [0.9, 0.999], softplus-inverse (layers.py:202-221)."""
+    lo, hi, eps = 0.9, 0.999, 1e-8
+    with torch.no_grad():
+      w.uniform_(lo * lo + eps, hi * hi + eps)
+      w.log_().mul_(0.5)
+      return w.neg_().exp_().sub_(1.0).log_()
+
+  def forward(self, x, segment_pos, cache=None, return_cache=True):
+    """Returns ``(y in x.dtype, last_h fp32 | None)``."""
+    bs, length, _ = x.shape
+    if segment_pos.shape != (bs, length):
+      segment_pos = segment_pos[None, :]
+    assert segment_pos.shape == (bs, length)      # layers.py:344
+    _forward_only(x, cache)
+    with torch.no_grad():
+      gemm_x = self.input_gate.gemm(x)
+      gemm_a = self.a_gate.gemm(x)
+      y, last_h = _abi.rglru_fwd(
+          x, gemm_x, gemm_a, self.input_gate.b, self.a_gate.b, self.a_param,
+          segment_pos, h0=cache, return_cache=return_cache,
+          arith_mode=_arith_mode)
+    return y, last_h
+
+  @classmethod
+  def init_cache(cls, batch_size, width, device=None):
+    return torch.zeros((batch_size, width), dtype=torch.float32, device=device)
+
+
+class Conv1D(nn.Module):
+  """Depth-wise causal temporal convolution (reference layers.py:389-676)."""
+
+  def __init__(self, width, temporal_width, w_init_variance_scale=0.01,
+               device=None, dtype=None):
+    super().__init__()
+    self.width = width
+    self.temporal_width = temporal_width
+    self.w_init_variance_scale = w_init_variance_scale
+    self.w = nn.Parameter(torch.empty((temporal_width, width), device=device, dtype=dtype))
+    self.b = nn.Parameter(torch.empty((width,), device=device, dtype=dtype))
+    # CG_MASK_FORK reproduces the fork's document mask (layers.py:629-632);
+    # set to _abi.MASK_UPSTREAM for the upstream / JAX behaviour.
+    self.mask_mode = _abi.MASK_FORK
+    self.reset_parameters()
+
+  def reset_parameters(self) -> None:
+    self.w_init_(self.w)
+    nn.init.zeros_(self.b)
+
+  def w_init_(self, w: torch.Tensor) -> None:
+    nn.init.normal_(w, mean=0.0,
+                    std=math.sqrt(self.w_init_variance_scale / self.temporal_width))
+
+  def forward(self, x, segment_pos, cache=None, return_cache=True):
+    """Returns ``(y, new_cache | None)``; decode when ``cache`` is given."""
+    _forward_only(x, cache)
+    mode = _arith_mode & (_abi.ARITH_FP32)
+    with torch.no_grad():
+      if cache is not None:
+        return _abi.conv1d_decode(x, self.w, self.b, cache,
+                                  return_cache=return_cache, arith_mode=mode)
+      return _abi.conv1d_fwd(x, self.w, self.b, segment_pos,
+                             return_cache=return_cache, mask_mode=self.mask_mode,
+                             arith_mode=mode)
+
+  @classmethod
+  def init_cache(cls, *, batch_size, width, dtype, conv1d_temporal_width=4,
+                 device=None):
+    return torch.zeros((batch_size, conv1d_temporal_width - 1, width),
+                       dtype=dtype, device=device)

@@ -1,0 +1,141 @@
+/*
+ * cadence_b200.h -- C ABI of the B200 (sm_100a) recurrent hot path.
+ *
+ * Drop-in boundary for the recurrent block of surakku/cadence-gemma
+ * (reference paths relative to the reference checkout):
+ *
+ *   cg_conv1d_fwd / cg_conv1d_decode  replace the body of
+ *       Conv1D.forward           recurrentgemma/torch/layers.py:458-546
+ *   cg_rglru_fwd                 replaces everything in RGLRU.forward after the
+ *       two BlockDiagonalLinear GEMMs (gate math + rnn_scan)
+ *                                recurrentgemma/torch/layers.py:345-375
+ *   cg_rnn_scan_fwd              replaces rnn_scan
+ *                                recurrentgemma/torch/layers.py:146-199
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     stated otherwise; tensors are dense row-major [B,T,E] with E contiguous;
+ *   - the callee allocates nothing, frees nothing and keeps no state between
+ *     calls; outputs and scratch are caller-provided;
+ *   - all work is enqueued on `stream` (a cudaStream_t); no host<->device
+ *     synchronisation, no host reads of device memory: calls are CUDA-graph
+ *     capturable;
+ *   - inputs are read-only (the reference's in-place masking of Conv1D's input,
+ *     layers.py:524, is intentionally not reproduced);
+ *   - return value: 0 = success, < 0 = argument error (cg_status_string),
+ *     > 0 = a cudaError_t raised by a launch.  Nothing is thrown across the ABI.
+ */
+#ifndef CADENCE_B200_H_
+#define CADENCE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CG_ABI_VERSION 1
+
+/* activation dtype of x / y / gate GEMM outputs / parameters */
+#define CG_DTYPE_F32 0
+#define CG_DTYPE_BF16 1
+
+/* arithmetic modes (bit field)
+ *   bit 0  keep fp32 in registers between load and the final store instead of
+ *          reproducing the reference's per-op rounding to the tensor dtype
+ *   bit 1  fast transcendentals (ex2.approx / rcp.approx / sqrt.approx, one
+ *          shared reciprocal for both sigmoids, a^2 = a*a)
+ *   bit 2  strict sequential kernel (one thread per channel, no FMA
+ *          contraction): the device-side oracle, not a performance path
+ *   bits 8..15  kernel geometry variant (0 = default); used by the tuning
+ *          scripts only, results are identical across variants of one mode
+ * For fp32 tensors bit 0 is irrelevant (every op already rounds to fp32).
+ */
+#define CG_ARITH_REFERENCE 0
+#define CG_ARITH_FP32 1
+#define CG_ARITH_FAST 2
+#define CG_ARITH_STRICT 4
+#define CG_ARITH_VARIANT(v) (((v) & 0xff) << 8)
+
+/* Conv1D document-mask variants */
+#define CG_MASK_FORK 0     /* layers.py:629-632 as the fork has it (default) */
+#define CG_MASK_UPSTREAM 1 /* the commented-out upstream loop, layers.py:620-627 */
+
+/* status codes */
+#define CG_OK 0
+#define CG_ERR_NULL (-1)
+#define CG_ERR_SHAPE (-2)
+#define CG_ERR_DTYPE (-3)
+#define CG_ERR_ALIGN (-4)
+#define CG_ERR_WORKSPACE (-5)
+#define CG_ERR_MODE (-6)
+
+typedef struct CUstream_st* cg_stream_t; /* == cudaStream_t */
+
+int cg_abi_version(void);
+const char* cg_status_string(int status);
+
+/* Bytes of scratch cg_rglru_fwd / cg_rnn_scan_fwd need for a [B,T,E] problem
+ * (upper bound over all arithmetic modes).  The scratch needs no
+ * initialisation and may be reused by later calls on the same stream. */
+size_t cg_scan_workspace_bytes(int B, int T, int E, int dtype);
+
+/*
+ * Conv1D prefill (cache is None): layers.py:484-546.
+ *   x [B,T,E], w [W,E], b [E], y [B,T,E] in `dtype`;
+ *   seg: segment positions, int32 or int64 (seg_is_i64), row b at
+ *        seg + b*seg_batch_stride elements (0 broadcasts one row, :512-513);
+ *   cache_out (nullable): [B,W-1,E] in `dtype` -- the last W-1 input rows, left
+ *        zero padded (:542-543).
+ * W == 4 runs the vectorised kernel; any other W >= 1 a generic one.
+ */
+int cg_conv1d_fwd(const void* x, const void* w, const void* b, const void* seg,
+                  int seg_is_i64, long long seg_batch_stride, void* y,
+                  void* cache_out, int B, int T, int E, int W, int dtype,
+                  int mask_mode, int arith_mode, cg_stream_t stream);
+
+/*
+ * Conv1D decode step (cache given, T == 1, no mask): layers.py:478-483, :542.
+ *   x [B,1,E], cache_in / cache_out [B,W-1,E] in cache_dtype (fp32 or bf16;
+ *   cache_out may alias cache_in), y [B,1,E].
+ */
+int cg_conv1d_decode(const void* x, const void* w, const void* b,
+                     const void* cache_in, int cache_dtype, void* y,
+                     void* cache_out, int B, int E, int W, int dtype,
+                     int arith_mode, cg_stream_t stream);
+
+/*
+ * RG-LRU after the gate GEMMs: layers.py:345-375 (gate math + rnn_scan).
+ *   x       [B,T,E]  Conv1D output
+ *   gemm_x  [B,T,E]  input_gate GEMM output WITHOUT bias (row stride
+ *   gemm_a  [B,T,E]  a_gate GEMM output     gate_row_stride elements)
+ *   bias_x, bias_a  [E] or NULL: pre = round(gemm + bias) (layers.py:139)
+ *   a_param [E]
+ *   h0      [B,E] fp32 or NULL;  last_h [B,E] fp32 or NULL
+ *   y       [B,T,E]
+ * T == 1 follows rnn_scan's sampling branch (:175-182).
+ */
+int cg_rglru_fwd(const void* x, const void* gemm_x, const void* gemm_a,
+                 long long gate_row_stride, const void* bias_x,
+                 const void* bias_a, const void* a_param, const void* seg,
+                 int seg_is_i64, long long seg_batch_stride, const float* h0,
+                 void* y, float* last_h, void* workspace,
+                 size_t workspace_bytes, int B, int T, int E, int dtype,
+                 int arith_mode, cg_stream_t stream);
+
+/*
+ * rnn_scan: layers.py:146-199.  x, a, y [B,T,E] in `dtype`; reset [B,T] uint8
+ * (non-zero = reset); h0 / last_h as above.  arith_mode: 0 = chunked two-level
+ * scan, CG_ARITH_STRICT = sequential non-FMA kernel (bit-exact with the
+ * reference loop).
+ */
+int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset,
+                    const float* h0, void* y, float* last_h, void* workspace,
+                    size_t workspace_bytes, int B, int T, int E, int dtype,
+                    int arith_mode, cg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CADENCE_B200_H_ */

@@ -1,0 +1,111 @@
+"""Times every compiled kernel geometry / arithmetic mode on BASELINE config 2.
+
+    python scripts/tune_scan.py [--out gpurun_out/tune.json] [--B 8 --T 2048]
+
+CUDA-event timing, 3 warm-ups, L2 flushed (256 MB write) between iterations,
+median of N.  Reports algorithmic GB/s: K2 (RG-LRU) 4*s bytes per element,
+K1 (Conv1D) 2*s bytes per element.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cadence_gemma_b200 import _abi  # noqa: E402
+
+
+def time_fn(fn, iters, flush):
+  times = []
+  for i in range(iters + 3):
+    flush.fill_(float(i))
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    fn()
+    e.record()
+    e.synchronize()
+    if i >= 3:
+      times.append(s.elapsed_time(e) * 1e3)
+  times.sort()
+  return times[len(times) // 2], times[0]
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--out", default="gpurun_out/tune.json")
+  ap.add_argument("--B", type=int, default=8)
+  ap.add_argument("--T", type=int, default=2048)
+  ap.add_argument("--E", type=int, default=2560)
+  ap.add_argument("--iters", type=int, default=15)
+  ap.add_argument("--variants", default="0,1,2,3,4,5,6")
+  args = ap.parse_args()
+  dev = "cuda:0"
+  B, T, E = args.B, args.T, args.E
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+  results = []
+  for dtype, s in ((torch.bfloat16, 2), (torch.float32, 4)):
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn((B, T, E), device=dev, generator=g).to(dtype)
+    gx = (torch.randn((B, T, E), device=dev, generator=g) * 1.5).to(dtype)
+    ga = (torch.randn((B, T, E), device=dev, generator=g) * 1.5).to(dtype)
+    ap_ = (torch.rand((E,), device=dev, generator=g) * -7 + 1).to(dtype)
+    bx = torch.randn((E,), device=dev, generator=g).to(dtype)
+    ba = torch.randn((E,), device=dev, generator=g).to(dtype)
+    seg = torch.arange(T, dtype=torch.int32, device=dev)[None].repeat(B, 1)
+    w = (torch.randn((4, E), device=dev, generator=g) * 0.5).to(dtype)
+    nelem = B * T * E
+    y = torch.empty_like(x)
+    modes = [0, 2, 1, 3] if dtype == torch.bfloat16 else [1, 3]
+    for mode in modes:
+      for variant in [int(v) for v in args.variants.split(",")]:
+        am = mode | (variant << 8)
+        try:
+          fn = lambda: _abi.rglru_fwd(x, gx, ga, bx, ba, ap_, seg, arith_mode=am, out=y)
+          fn()
+          torch.cuda.synchronize()
+        except AssertionError:
+          continue
+        med, best = time_fn(fn, args.iters, flush)
+        rec = dict(kernel="rglru", dtype=str(dtype), mode=mode, variant=variant,
+                   us_median=med, us_best=best,
+                   gbps_median=4 * s * nelem / med / 1e3,
+                   gbps_best=4 * s * nelem / best / 1e3)
+        print(json.dumps(rec), flush=True)
+        results.append(rec)
+    for mode in (0, 1):
+      fn = lambda: _abi.conv1d_fwd(x, w, bx, seg, arith_mode=mode)
+      fn()
+      med, best = time_fn(fn, args.iters, flush)
+      rec = dict(kernel="conv1d", dtype=str(dtype), mode=mode, us_median=med,
+                 us_best=best, gbps_median=2 * s * nelem / med / 1e3,
+                 gbps_best=2 * s * nelem / best / 1e3)
+      print(json.dumps(rec), flush=True)
+      results.append(rec)
+    rs = torch.zeros((B, T), dtype=torch.bool, device=dev)
+    a = torch.rand_like(x)
+    for mode in (0, 4):
+      fn = lambda: _abi.rnn_scan_fwd(x, a, rs, None, arith_mode=mode)
+      fn()
+      med, best = time_fn(fn, max(3, args.iters // 3), flush)
+      rec = dict(kernel="rnn_scan", dtype=str(dtype), mode=mode, us_median=med,
+                 us_best=best, gbps_median=3 * s * nelem / med / 1e3)
+      print(json.dumps(rec), flush=True)
+      results.append(rec)
+    # reference point: a plain device copy of the same bytes as K2
+    src = torch.empty(4 * s * nelem // 2, dtype=torch.uint8, device=dev)
+    dst = torch.empty_like(src)
+    med, best = time_fn(lambda: dst.copy_(src), args.iters, flush)
+    rec = dict(kernel="copy_same_bytes", dtype=str(dtype), us_median=med, us_best=best,
+               gbps_median=4 * s * nelem / med / 1e3)
+    print(json.dumps(rec), flush=True)
+    results.append(rec)
+    del x, gx, ga, y, src, dst, a
+  os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+  with open(args.out, "w") as f:
+    json.dump(results, f, indent=1)
+
+
+if __name__ == "__main__":
+  main()

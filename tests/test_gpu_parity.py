@@ -1,0 +1,341 @@
+"""GPU parity tests: the sm_100a kernels (through the C ABI) against
+
+  * the golden vectors produced by the unmodified reference (tests/golden/),
+  * the CPU oracles on fresh seeded inputs (ragged sizes, resets, h0, padding),
+  * the strict sequential device kernel at BASELINE.json's full sizes, plus
+    size-independent properties (chunked continuation, reset isolation,
+    run-to-run determinism).
+
+Tolerances (north star): fp32 <= 1e-5 normwise; bf16 within the reference's
+own test tolerance rtol 1e-2 / atol 3e-2 (recurrentgemma/torch/layers_test.py
+:131) *and* a minimum fraction of bit-identical elements; Conv1D and the
+strict scan are bit-exact.
+"""
+import pytest
+import torch
+
+from tests.golden import fixture_io
+from tests.helpers import (assert_bitexact, assert_close_bf16, assert_close_f32,
+                           identical_fraction, normwise)
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+REF, FP32, FAST, STRICT = 0, 1, 2, 4
+
+
+def _abi():
+  from cadence_gemma_b200 import _abi as abi
+  abi.load()
+  return abi
+
+
+def cu(t):
+  return None if t is None else t.to(DEV)
+
+
+def _close(a, b, what, min_identical=0.98):
+  a, b = a.cpu(), b.cpu()
+  if a.dtype == torch.bfloat16:
+    assert_close_bf16(a, b, what, min_identical=min_identical)
+  else:
+    assert_close_f32(a, b, what)
+
+
+# ------------------------------------------------------------------ rnn_scan
+@pytest.mark.parametrize("case", fixture_io.cases("rnn_scan_"))
+def test_rnn_scan_golden(case):
+  abi = _abi()
+  g = fixture_io.load(case)
+  x, a, rs, h0 = cu(g["x"]), cu(g["a"]), cu(g["reset"]), cu(g.get("h0"))
+  y, h = abi.rnn_scan_fwd(x, a, rs, h0, arith_mode=STRICT)
+  assert_bitexact(y.cpu(), g["y"], case + " strict y")
+  assert_bitexact(h.cpu(), g["h_last"], case + " strict h")
+  y, h = abi.rnn_scan_fwd(x, a, rs, h0, arith_mode=REF)
+  _close(y, g["y"], case + " y", min_identical=0.995)
+  assert_close_f32(h.cpu(), g["h_last"], case + " h")
+
+
+def test_rnn_scan_api_matches_reference_contract():
+  import cadence_gemma_b200 as cg
+  x = torch.randn(2, 5, 64, device=DEV, dtype=torch.bfloat16)
+  a = torch.rand_like(x)
+  rs = torch.zeros(2, 5, dtype=torch.bool, device=DEV)
+  with pytest.raises(AssertionError):      # layers.py:170: h0 must be fp32
+    cg.rnn_scan(x, a, rs, torch.zeros(2, 64, device=DEV, dtype=torch.bfloat16))
+  y, h = cg.rnn_scan(x, a, rs, None)
+  assert y.dtype == torch.bfloat16 and h.dtype == torch.float32
+  assert y.shape == x.shape and h.shape == (2, 64)
+  with pytest.raises(RuntimeError):        # no CPU fallback
+    cg.rnn_scan(x.cpu(), a.cpu(), rs.cpu(), None)
+
+
+# -------------------------------------------------------------------- conv1d
+@pytest.mark.parametrize("case", fixture_io.cases("conv1d_"))
+def test_conv1d_golden(case):
+  abi = _abi()
+  g = fixture_io.load(case)
+  w, b = cu(g["w"]), cu(g["b"])
+  if "x" in g:
+    x = cu(g["x"])
+    x_before = x.clone()
+    y, cache = abi.conv1d_fwd(x, w, b, cu(g["seg"]))
+    assert torch.equal(x, x_before), "input must stay untouched"
+    assert_bitexact(y.cpu(), g["y"], case + " y")
+    assert_bitexact(cache.cpu(), g["cache"], case + " cache")
+  else:
+    cache = cu(g["cache_in"])
+  for i in range(2):
+    if f"step{i}_x" not in g:
+      break
+    ys, cache = abi.conv1d_decode(cu(g[f"step{i}_x"]), w, b, cache)
+    assert_bitexact(ys.cpu(), g[f"step{i}_y"], f"{case} step{i} y")
+    assert_bitexact(cache.cpu(), g[f"step{i}_cache"], f"{case} step{i} cache")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mask_mode", [0, 1])
+def test_conv1d_random_vs_oracle(dtype, mask_mode):
+  from oracle import c_oracle
+  abi = _abi()
+  g = torch.Generator().manual_seed(11 + mask_mode)
+  bsz, steps, width = 3, 157, 192
+  x = torch.randn((bsz, steps, width), generator=g).to(dtype)
+  w = (torch.randn((4, width), generator=g) * 0.5).to(dtype)
+  b = (torch.randn((width,), generator=g) * 0.1).to(dtype)
+  seg = (torch.rand((bsz, steps), generator=g) > 0.2).long() * torch.arange(steps)[None]
+  seg[:, :4] = -1
+  y_ref, c_ref = c_oracle.conv1d_forward(w, b, x, seg, mask_mode=mask_mode)
+  y, c = abi.conv1d_fwd(cu(x), cu(w), cu(b), cu(seg.to(torch.int32)),
+                        mask_mode=mask_mode)
+  assert_bitexact(y.cpu(), y_ref, "conv y")
+  assert_bitexact(c.cpu(), c_ref, "conv cache")
+  if dtype == torch.bfloat16:   # fp32-accumulate mode: within 2 bf16 ulp
+    y32, _ = abi.conv1d_fwd(cu(x), cu(w), cu(b), cu(seg), mask_mode=mask_mode,
+                            arith_mode=FP32)
+    y_o, _ = c_oracle.conv1d_forward(w, b, x, seg, mask_mode=mask_mode,
+                                     arith_mode=1)
+    assert identical_fraction(y32.cpu(), y_o) >= 0.999
+
+
+# --------------------------------------------------------------------- rglru
+@pytest.mark.parametrize("case", fixture_io.cases("rglru_"))
+@pytest.mark.parametrize("mode", [REF, REF | FAST, REF | STRICT, FP32, FP32 | FAST])
+def test_rglru_golden_from_preacts(case, mode):
+  """Kernel boundary: same pre-activations as the reference computed."""
+  abi = _abi()
+  g = fixture_io.load(case)
+  bf = g["x"].dtype == torch.bfloat16
+  x, px, pa = cu(g["x"]), cu(g["pre_x"]), cu(g["pre_a"])
+  y, h = abi.rglru_fwd(x, px, pa, None, None, cu(g["a_param"]), cu(g["seg"]),
+                       arith_mode=mode)
+  if bf and (mode & FP32):
+    # fp32-in-register mode is judged against the fp32-arithmetic oracle on
+    # the same bf16 inputs (it does not reproduce the eager rounding points)
+    from oracle import c_oracle
+    y_ref, h_ref = c_oracle.rglru_from_preacts(g["x"], g["pre_x"], g["pre_a"],
+                                               g["a_param"], g["seg"], arith_mode=1)
+    _close(y, y_ref, f"{case} mode {mode} y", min_identical=0.99)
+    assert normwise(h.cpu(), h_ref) <= 1e-4
+    return
+  _close(y, g["y"], f"{case} mode {mode} y")
+  if bf:
+    assert normwise(h.cpu(), g["last_h"]) <= 2e-2
+  else:
+    assert_close_f32(h.cpu(), g["last_h"], f"{case} mode {mode} h")
+  cache = h
+  for i in range(2):
+    ys, cache = abi.rglru_fwd(cu(g[f"step{i}_x"]), cu(g[f"step{i}_pre_x"]),
+                              cu(g[f"step{i}_pre_a"]), None, None, cu(g["a_param"]),
+                              cu(g["seg"][:, -1:] + 1 + i), h0=cache,
+                              arith_mode=mode)
+    _close(ys, g[f"step{i}_y"], f"{case} mode {mode} step{i}", min_identical=0.9)
+
+
+@pytest.mark.parametrize("case", fixture_io.cases("rglru_"))
+def test_rglru_module_golden(case):
+  """Module API incl. the cuBLAS gate GEMMs (state-dict keys as the reference)."""
+  import cadence_gemma_b200 as cg
+  g = fixture_io.load(case)
+  width, heads = g["x"].shape[-1], g["input_gate_w"].shape[0]
+  lru = cg.RGLRU(width, heads, device=DEV, dtype=g["x"].dtype)
+  lru.load_state_dict({
+      "a_param": g["a_param"], "input_gate.w": g["input_gate_w"],
+      "input_gate.b": g["input_gate_b"], "a_gate.w": g["a_gate_w"],
+      "a_gate.b": g["a_gate_b"]})
+  with torch.no_grad():
+    y, h = lru(cu(g["x"]), cu(g["seg"]))
+    assert y.dtype == g["x"].dtype and h.dtype == torch.float32
+    if y.dtype == torch.bfloat16:
+      assert_close_bf16(y.cpu(), g["y"], case, min_identical=0.9)
+    else:
+      assert_close_f32(y.cpu(), g["y"], case, tol=2e-5)
+    cache = h
+    for i in range(2):
+      ys, cache = lru(cu(g[f"step{i}_x"]), cu(g["seg"][:, -1:] + 1 + i), cache)
+      if ys.dtype == torch.bfloat16:
+        assert_close_bf16(ys.cpu(), g[f"step{i}_y"], f"{case} step{i}",
+                          min_identical=0.8)
+      else:
+        assert_close_f32(ys.cpu(), g[f"step{i}_y"], f"{case} step{i}", tol=2e-5)
+    y2, none = lru(cu(g["x"]), cu(g["seg"]), return_cache=False)
+    assert none is None and torch.equal(y2, y)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 301, 256), (1, 1000, 64), (5, 33, 2560),
+                                   (3, 1, 128)])
+def test_rglru_random_vs_oracle(dtype, shape):
+  """Ragged T / narrow E / bias split / h0 / int32 positions vs the C oracle."""
+  from oracle import c_oracle, torch_port
+  abi = _abi()
+  bsz, steps, width = shape
+  g = torch.Generator().manual_seed(steps * 7 + width)
+  p = torch_port.init_rglru_params(width, max(1, width // 64), g, dtype)
+  x = torch.randn(shape, generator=g).to(dtype)
+  gx = torch.randn(shape, generator=g).to(dtype) * 2
+  ga = torch.randn(shape, generator=g).to(dtype) * 2
+  bx = p.input_gate_b.reshape(-1)
+  ba = p.a_gate_b.reshape(-1)
+  seg = torch.arange(steps)[None].repeat(bsz, 1)
+  for b in range(bsz):
+    cut = int(torch.randint(1, max(2, steps), (1,), generator=g))
+    seg[b, cut:] -= cut
+  h0 = torch.randn((bsz, width), generator=g)
+  for mode in (REF, REF | FAST):
+    y_ref, h_ref = c_oracle.rglru_from_preacts(x, gx, ga, p.a_param, seg, h0,
+                                               bias_x=bx, bias_a=ba)
+    y, h = abi.rglru_fwd(cu(x), cu(gx), cu(ga), cu(bx), cu(ba), cu(p.a_param),
+                         cu(seg.to(torch.int32)), h0=cu(h0), arith_mode=mode)
+    _close(y, y_ref, f"{shape} {dtype} mode {mode}", min_identical=0.97)
+    assert normwise(h.cpu(), h_ref) <= (2e-2 if dtype == torch.bfloat16 else 1e-5)
+
+
+# ------------------------------------------------------------ recurrent block
+@pytest.mark.parametrize("case", fixture_io.cases("recurrent_block_"))
+def test_recurrent_block_golden(case):
+  from cadence_gemma_b200.modules import RecurrentBlock
+  g = fixture_io.load(case)
+  dtype = g["x"].dtype
+  blk = RecurrentBlock(width=96, num_heads=4, lru_width=128, device=DEV, dtype=dtype)
+  blk.load_state_dict({k[len("param."):]: v for k, v in g.items()
+                       if k.startswith("param.")})
+  bf = dtype == torch.bfloat16
+
+  def check(a, b, what):
+    if bf:
+      assert_close_bf16(a.cpu(), b, what, min_identical=0.6)
+    else:
+      assert_close_f32(a.cpu(), b, what, tol=5e-5)
+
+  with torch.no_grad():
+    y, cache = blk(cu(g["x"]), cu(g["seg"]))
+    check(y, g["y"], case + " y")
+    assert cache.rg_lru_state.dtype == torch.float32
+    assert normwise(cache.rg_lru_state.cpu(), g["rg_lru_state"]) <= (3e-2 if bf else 5e-5)
+    check(cache.conv1d_state, g["conv1d_state"], case + " conv state")
+    for i in range(2):
+      ys, cache = blk(cu(g[f"step{i}_x"]), cu(g["seg"][:, -1:] + 1 + i), cache)
+      check(ys, g[f"step{i}_y"], f"{case} step{i}")
+    # hot path alone on the tensors captured inside the reference block
+    xc, conv_state = blk.conv_1d(cu(g["conv_in"]), cu(g["seg"]))
+    out, _ = blk.rg_lru(xc, cu(g["seg"]))
+    check(out, g["rglru_out"], case + " captured hot path")
+    assert_bitexact(conv_state.cpu(), g["conv1d_state"], case + " conv cache")
+
+
+def test_griffin_tiny_hot_path():
+  """BASELINE config 1: the hot path inside the real tiny Griffin (fp32)."""
+  import cadence_gemma_b200 as cg
+  g = fixture_io.load("griffin_tiny_f32_t128")
+  for blk in (0, 1):
+    P = lambda k: g[f"blk{blk}_param.{k}"]
+    conv = cg.Conv1D(256, 4, device=DEV, dtype=torch.float32)
+    conv.load_state_dict({"w": P("conv_1d.w"), "b": P("conv_1d.b")})
+    lru = cg.RGLRU(256, 8, device=DEV, dtype=torch.float32)
+    lru.load_state_dict({k[len("rg_lru."):]: g[f"blk{blk}_param.{k}"]
+                         for k in ("rg_lru.a_param", "rg_lru.input_gate.w",
+                                   "rg_lru.input_gate.b", "rg_lru.a_gate.w",
+                                   "rg_lru.a_gate.b")})
+    with torch.no_grad():
+      xc, conv_state = conv(cu(g[f"blk{blk}_conv_in"]), cu(g["seg"]))
+      y, h = lru(xc, cu(g["seg"]))
+    assert_bitexact(conv_state.cpu(), g[f"blk{blk}_conv1d_state"], "conv state")
+    assert_close_f32(y.cpu(), g[f"blk{blk}_rglru_out"], f"blk{blk} out", tol=2e-5)
+    assert_close_f32(h.cpu(), g[f"blk{blk}_rg_lru_state"], f"blk{blk} h", tol=2e-5)
+
+
+# -------------------------------------------- full-size properties (config 2/4)
+def _full_inputs(bsz, steps, width, dtype, seed, resets):
+  from oracle import torch_port
+  g = torch.Generator().manual_seed(seed)
+  p = torch_port.init_rglru_params(width, 10, g, dtype)
+  x = torch.randn((bsz, steps, width), generator=g).to(dtype).to(DEV)
+  gx = (torch.randn((bsz, steps, width), generator=g) * 1.5).to(dtype).to(DEV)
+  ga = (torch.randn((bsz, steps, width), generator=g) * 1.5).to(dtype).to(DEV)
+  seg = torch.arange(steps, dtype=torch.int32)[None].repeat(bsz, 1)
+  for b in range(bsz):
+    for cut in sorted(torch.randint(1, steps, (resets,), generator=g).tolist()):
+      seg[b, cut:] = torch.arange(steps - cut, dtype=torch.int32)
+  return p, x, gx, ga, seg.to(DEV)
+
+
+@pytest.mark.parametrize("dtype,steps,bsz", [(torch.bfloat16, 2048, 8),
+                                             (torch.float32, 2048, 4),
+                                             (torch.bfloat16, 8192, 2)])
+def test_full_size_fast_vs_strict(dtype, steps, bsz):
+  """RecurrentGemma-2B shapes: chunked kernel vs the sequential device oracle."""
+  abi = _abi()
+  width = 2560
+  p, x, gx, ga, seg = _full_inputs(bsz, steps, width, dtype, 1, resets=7)
+  args = (x, gx, ga, cu(p.input_gate_b.reshape(-1)), cu(p.a_gate_b.reshape(-1)),
+          cu(p.a_param), seg)
+  y_s, h_s = abi.rglru_fwd(*args, arith_mode=REF | STRICT)
+  for mode in (REF, REF | FAST):
+    y, h = abi.rglru_fwd(*args, arith_mode=mode)
+    y2, h2 = abi.rglru_fwd(*args, arith_mode=mode)
+    assert torch.equal(y, y2) and torch.equal(h, h2), "run-to-run determinism"
+    if dtype == torch.bfloat16:
+      frac = identical_fraction(y, y_s)
+      assert frac >= (0.999 if mode == REF else 0.97), (mode, frac)
+      torch.testing.assert_close(y.float(), y_s.float(), rtol=1e-2, atol=3e-2)
+    else:
+      assert normwise(y, y_s) <= 1e-5, (mode, normwise(y, y_s))
+    assert normwise(h, h_s) <= (1e-2 if dtype == torch.bfloat16 else 1e-5)
+
+
+def test_full_size_continuation_and_reset_isolation():
+  """Config 4 properties: prefill(T) == prefill(T1) ; prefill(T2, h0), and a
+  reset makes the output independent of everything before it."""
+  abi = _abi()
+  bsz, steps, width, dtype = 2, 8192, 2560, torch.float32
+  p, x, gx, ga, seg = _full_inputs(bsz, steps, width, dtype, 3, resets=7)
+  consts = (None, None, cu(p.a_param))
+  y, h = abi.rglru_fwd(x, gx, ga, *consts, seg, arith_mode=REF)
+  cut = 3000
+  y1, h1 = abi.rglru_fwd(x[:, :cut], gx[:, :cut], ga[:, :cut], *consts,
+                         seg[:, :cut], arith_mode=REF)
+  y2, h2 = abi.rglru_fwd(x[:, cut:], gx[:, cut:], ga[:, cut:], *consts,
+                         seg[:, cut:], h0=h1, arith_mode=REF)
+  assert normwise(torch.cat([y1, y2], 1), y) <= 1e-5
+  assert normwise(h2, h) <= 1e-5
+  # reset isolation: force a reset at `cut`, scramble the prefix
+  seg2 = seg.clone()
+  seg2[:, cut] = 0
+  ya, _ = abi.rglru_fwd(x, gx, ga, *consts, seg2, arith_mode=REF)
+  xb = x.clone()
+  xb[:, :cut] = torch.randn_like(xb[:, :cut]) * 3
+  yb, _ = abi.rglru_fwd(xb, gx, ga, *consts, seg2, arith_mode=REF)
+  assert torch.equal(ya[:, cut:], yb[:, cut:])
+
+
+def test_abi_argument_errors():
+  abi = _abi()
+  x = torch.zeros(1, 4, 12, device=DEV, dtype=torch.bfloat16)   # E % 8 != 0
+  seg = torch.zeros(1, 4, dtype=torch.int32, device=DEV)
+  ap = torch.zeros(12, device=DEV, dtype=torch.bfloat16)
+  with pytest.raises(AssertionError):
+    abi.rglru_fwd(x, x, x, None, None, ap, seg)
+  with pytest.raises(AssertionError):   # decode wants exactly one token
+    abi.conv1d_decode(torch.zeros(1, 2, 16, device=DEV), torch.zeros(4, 16, device=DEV),
+                      torch.zeros(16, device=DEV), torch.zeros(1, 3, 16, device=DEV))
