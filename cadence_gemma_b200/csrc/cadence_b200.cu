@@ -20,9 +20,7 @@ using cg::ScanParams;
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-constexpr int kMinL = 4;  // smallest steps-per-lane of any compiled geometry
-
-struct Geometry { int EC; int TC; };
+constexpr int kMinSuperChunk = 64;  // smallest NW * 4 * L of any compiled geometry
 
 // scratch layout: [ticket 256 B][flags][agg_p][agg_h][pref][neg8sp]
 struct Workspace {
@@ -31,10 +29,11 @@ struct Workspace {
   size_t total;
 };
 
-Workspace carve(void* base, int B, int T, int E, int EC, int TC) {
+// EC: channels per column tile, SC: time steps per work item (super-chunk).
+Workspace carve(void* base, int B, int T, int E, int EC, int SC) {
   Workspace w;
   const size_t ctiles = (E + EC - 1) / EC;
-  const size_t nitems = (size_t)B * ctiles * ((T + TC - 1) / TC);
+  const size_t nitems = (size_t)B * ctiles * ((T + SC - 1) / SC);
   char* p = reinterpret_cast<char*>(base);
   size_t off = 0;
   w.counter = reinterpret_cast<int*>(p + off); off += 256;
@@ -48,22 +47,32 @@ Workspace carve(void* base, int B, int T, int E, int EC, int TC) {
   return w;
 }
 
-template <typename IO, int KIND, int ARITH, int L, int WARPS, int MINB>
+template <typename IO, int KIND, int ARITH, int L, int NW, int MINB>
 int launch_scan(ScanParams p, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   constexpr int EC = cg::kCvl * cg::IoVec<IO>::V;
-  constexpr int TC = cg::kSegs * L;
-  const Workspace ws = carve(workspace, p.B, p.T, p.E, EC, TC);
+  constexpr int SC = cg::kSegs * L * NW;
+  static_assert(SC >= kMinSuperChunk, "update kMinSuperChunk");
+  const Workspace ws = carve(workspace, p.B, p.T, p.E, EC, SC);
   if (ws.total > workspace_bytes) return CG_ERR_WORKSPACE;
   p.ctiles = (p.E + EC - 1) / EC;
   p.ncols = p.B * p.ctiles;
-  p.nchunks = (p.T + TC - 1) / TC;
+  p.nchunks = (p.T + SC - 1) / SC;
   p.nitems = p.ncols * p.nchunks;
   p.counter = ws.counter; p.flags = ws.flags;
   p.agg_p = ws.agg_p; p.agg_h = ws.agg_h; p.pref = ws.pref;
+  auto kernel = cg::scan_kernel<IO, KIND, ARITH, L, NW, MINB>;
+  constexpr size_t smem = cg::scan_smem_bytes<IO, KIND, ARITH, L, NW>();
+  static bool configured = false;   // idempotent attribute, set once per process
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
   cudaError_t err = cudaMemsetAsync(ws.counter, 0, ws.zero_bytes, stream);
   if (err != cudaSuccess) return (int)err;
-  const int blocks = (p.nitems + WARPS - 1) / WARPS;
-  cg::scan_kernel<IO, KIND, ARITH, L, WARPS, MINB><<<blocks, WARPS * 32, 0, stream>>>(p);
+  kernel<<<p.nitems, NW * 32, smem, stream>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -74,32 +83,22 @@ int launch_strict(const ScanParams& p, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
-// Kernel geometry per variant id: L steps per lane, warps per block and the
-// minimum resident blocks per SM (caps registers: 4 -> 128, 3 -> 168, ...).
-// Variant 0 is the default; the others exist for the tuning scripts.
+// Kernel geometry per variant id: L steps per lane, NW warps (= chunks) per CTA
+// and the minimum resident CTAs per SM (caps registers).  Staging is 512 B per
+// (warp, step, slot).  Variant 0 is the default; the others exist for tuning.
 template <typename IO, int KIND, int ARITH>
 int dispatch_geometry(int variant, const ScanParams& p, void* ws, size_t ws_bytes,
                       cudaStream_t stream) {
-  constexpr bool BF = cg::IoVec<IO>::kBf16;
-  constexpr bool PACKED = BF && (KIND == 1 || (ARITH & 1) == 0);
-  if constexpr (PACKED || !BF) {   // 64 state registers at L = 8
-    switch (variant) {
-      case 0: return launch_scan<IO, KIND, ARITH, 8, 4, 4>(p, ws, ws_bytes, stream);
-      case 1: return launch_scan<IO, KIND, ARITH, 8, 4, 3>(p, ws, ws_bytes, stream);
-      case 2: return launch_scan<IO, KIND, ARITH, 8, 4, 2>(p, ws, ws_bytes, stream);
-      case 3: return launch_scan<IO, KIND, ARITH, 4, 4, 4>(p, ws, ws_bytes, stream);
-      case 4: return launch_scan<IO, KIND, ARITH, 4, 4, 5>(p, ws, ws_bytes, stream);
-      case 5: return launch_scan<IO, KIND, ARITH, 4, 4, 6>(p, ws, ws_bytes, stream);
-      case 6: return launch_scan<IO, KIND, ARITH, 8, 4, 5>(p, ws, ws_bytes, stream);
-      default: return CG_ERR_MODE;
-    }
-  } else {                         // bf16 I/O with fp32 state: 64 registers at L = 4
-    switch (variant) {
-      case 0: return launch_scan<IO, KIND, ARITH, 4, 4, 4>(p, ws, ws_bytes, stream);
-      case 1: return launch_scan<IO, KIND, ARITH, 4, 4, 3>(p, ws, ws_bytes, stream);
-      case 2: return launch_scan<IO, KIND, ARITH, 4, 4, 5>(p, ws, ws_bytes, stream);
-      default: return CG_ERR_MODE;
-    }
+  switch (variant) {
+    case 0: return launch_scan<IO, KIND, ARITH, 8, 8, 2>(p, ws, ws_bytes, stream);
+    case 1: return launch_scan<IO, KIND, ARITH, 8, 4, 4>(p, ws, ws_bytes, stream);
+    case 2: return launch_scan<IO, KIND, ARITH, 4, 8, 4>(p, ws, ws_bytes, stream);
+    case 3: return launch_scan<IO, KIND, ARITH, 4, 8, 3>(p, ws, ws_bytes, stream);
+    case 4: return launch_scan<IO, KIND, ARITH, 4, 4, 6>(p, ws, ws_bytes, stream);
+    case 5: return launch_scan<IO, KIND, ARITH, 8, 6, 3>(p, ws, ws_bytes, stream);
+    case 6: return launch_scan<IO, KIND, ARITH, 4, 16, 2>(p, ws, ws_bytes, stream);
+    case 7: return launch_scan<IO, KIND, ARITH, 8, 8, 1>(p, ws, ws_bytes, stream);
+    default: return CG_ERR_MODE;
   }
 }
 
@@ -133,7 +132,7 @@ const char* cg_status_string(int status) {
 size_t cg_scan_workspace_bytes(int B, int T, int E, int dtype) {
   if (B < 1 || T < 1 || E < 1) return 0;
   const int V = dtype == CG_DTYPE_BF16 ? 8 : 4;
-  return carve(nullptr, B, T, E, cg::kCvl * V, cg::kSegs * kMinL).total;
+  return carve(nullptr, B, T, E, cg::kCvl * V, kMinSuperChunk).total;
 }
 
 int cg_conv1d_fwd(const void* x, const void* w, const void* b, const void* seg, int seg_is_i64,
@@ -154,12 +153,18 @@ int cg_conv1d_fwd(const void* x, const void* w, const void* b, const void* seg, 
   const bool vec_ok = W == 4 && E % V == 0 && aligned16(x) && aligned16(w) && aligned16(b) &&
                       aligned16(y) && (!cache_out || aligned16(cache_out));
   if (vec_ok) {
-    constexpr int LC = 16;
-    const int tslots = (T + LC - 1) / LC;
-    dim3 grid((tslots + 15) / 16, (E + 8 * V - 1) / (8 * V), B);
-    if (bf && emul) cg::conv1d_w4_kernel<uint16_t, true, LC><<<grid, 128, 0, stream>>>(p);
-    else if (bf) cg::conv1d_w4_kernel<uint16_t, false, LC><<<grid, 128, 0, stream>>>(p);
-    else cg::conv1d_w4_kernel<float, true, LC><<<grid, 128, 0, stream>>>(p);
+    const int variant = (arith_mode >> 8) & 0xff;
+    // LC rows per thread (+3 halo rows re-read through L2): 8 by default
+#define CG_CONV(LCV)                                                                       \
+    {                                                                                      \
+      const int tslots = (T + LCV - 1) / LCV;                                              \
+      dim3 grid((tslots + 15) / 16, (E + 8 * V - 1) / (8 * V), B);                         \
+      if (bf && emul) cg::conv1d_w4_kernel<uint16_t, true, LCV><<<grid, 128, 0, stream>>>(p);   \
+      else if (bf) cg::conv1d_w4_kernel<uint16_t, false, LCV><<<grid, 128, 0, stream>>>(p);     \
+      else cg::conv1d_w4_kernel<float, true, LCV><<<grid, 128, 0, stream>>>(p);            \
+    }
+    if (variant == 1) CG_CONV(16) else if (variant == 2) CG_CONV(4) else CG_CONV(8)
+#undef CG_CONV
   } else {
     if (T > 65535 || B > 65535) return CG_ERR_SHAPE;
     dim3 grid((E + 127) / 128, T, B);
@@ -215,7 +220,7 @@ int cg_rglru_fwd(const void* x, const void* gemm_x, const void* gemm_a, long lon
       return CG_ERR_ALIGN;
   }
   // -8 * softplus(a_param) lives at the tail of the scratch for every geometry
-  const Workspace ws_min = carve(workspace, B, T, E, cg::kCvl * V, cg::kSegs * kMinL);
+  const Workspace ws_min = carve(workspace, B, T, E, cg::kCvl * V, kMinSuperChunk);
   if (ws_min.total > workspace_bytes) return CG_ERR_WORKSPACE;
   float* neg8sp = ws_min.neg8sp;
   const int emulate = (mode & CG_ARITH_FP32) == 0;

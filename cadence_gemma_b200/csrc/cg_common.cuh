@@ -126,6 +126,31 @@ __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+// cp.async (LDGSTS): 16-byte global -> shared copy that bypasses L1 and holds
+// no registers while in flight.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+// wait until at most `pending` of this thread's groups are outstanding
+// (`pending` is a compile-time value after unrolling; MAXN bounds the switch).
+template <int MAXN>
+__device__ __forceinline__ void cp_async_wait_dyn(int pending) {
+  if constexpr (MAXN > 0) {
+    if (pending >= MAXN - 1) { cp_async_wait<MAXN - 1>(); return; }
+    cp_async_wait_dyn<MAXN - 1>(pending);
+  } else {
+    cp_async_wait<0>();
+  }
+}
+
 __device__ __forceinline__ long long load_seg(const void* seg, bool is_i64, long long idx) {
   return is_i64 ? reinterpret_cast<const long long*>(seg)[idx]
                 : static_cast<long long>(reinterpret_cast<const int*>(seg)[idx]);

@@ -55,39 +55,46 @@ conv1d_w4_kernel(const ConvParams p) {
     wk[k] = *reinterpret_cast<const uint4*>(reinterpret_cast<const IO*>(p.w) + (size_t)k * p.E + ch0);
   bv = *reinterpret_cast<const uint4*>(reinterpret_cast<const IO*>(p.bias) + ch0);
 
-  // register window: xm3 = x[t-3], xm2 = x[t-2], xm1 = x[t-1]
+  // All LC + 3 input rows of this thread's tile are requested before any
+  // arithmetic (memory-level parallelism: the kernel is pure streaming).
   const uint4 zero = make_uint4(0, 0, 0, 0);
-  uint4 xm3 = t0 >= 3 ? ldg_stream(xb + (size_t)(t0 - 3) * p.E) : zero;
-  uint4 xm2 = t0 >= 2 ? ldg_stream(xb + (size_t)(t0 - 2) * p.E) : zero;
-  uint4 xm1 = t0 >= 1 ? ldg_stream(xb + (size_t)(t0 - 1) * p.E) : zero;
-  // nb bit k = (segment_pos[t-k] != 0); positions before 0 are never consulted
-  // for a tap that exists, so their value is irrelevant.
+  uint4 xr[LC + 3];            // xr[r] = x[t0 - 3 + r]
+#pragma unroll
+  for (int r = 0; r < LC + 3; ++r) {
+    const int t = t0 - 3 + r;
+    xr[r] = (t >= 0 && t < p.T) ? ldg_stream(xb + (size_t)t * p.E) : zero;
+  }
+  // nb bit r = (segment_pos[t0 - 2 + r] != 0); positions before 0 are never
+  // consulted for a tap that exists, so their value is irrelevant.
   unsigned nb = 0;
-  if (t0 >= 1) nb |= (load_seg(p.seg, p.seg_is_i64 != 0, seg0 + t0 - 1) != 0) ? 1u : 0u;
-  if (t0 >= 2) nb |= (load_seg(p.seg, p.seg_is_i64 != 0, seg0 + t0 - 2) != 0) ? 2u : 0u;
+#pragma unroll
+  for (int r = 0; r < LC + 2; ++r) {
+    const int t = t0 - 2 + r;
+    if (t >= 0 && t < p.T)
+      nb |= (load_seg(p.seg, p.seg_is_i64 != 0, seg0 + t) != 0 ? 1u : 0u) << r;
+  }
+  const uint32_t k0[4] = {wk[0].x, wk[0].y, wk[0].z, wk[0].w}, k1[4] = {wk[1].x, wk[1].y, wk[1].z, wk[1].w};
+  const uint32_t k2[4] = {wk[2].x, wk[2].y, wk[2].z, wk[2].w}, k3[4] = {wk[3].x, wk[3].y, wk[3].z, wk[3].w};
+  const uint32_t bb[4] = {bv.x, bv.y, bv.z, bv.w};
 
 #pragma unroll
   for (int j = 0; j < LC; ++j) {
     const int t = t0 + j;
     if (t >= p.T) break;
-    const uint4 x0 = ldg_stream(xb + (size_t)t * p.E);
-    nb = (nb << 1) | ((load_seg(p.seg, p.seg_is_i64 != 0, seg0 + t) != 0) ? 1u : 0u);
     // document mask per tap (shift s looks at segment_pos[t-s+1 .. ])
+    const unsigned w3 = nb >> j;       // bit 0: seg[t-2], bit 1: seg[t-1], bit 2: seg[t]
     bool m1 = true, m2 = true, m3;
     if (p.mask_mode == 0) {
-      m3 = (nb & 4u) != 0;                        // fork: only seg[t-2], :629-632
+      m3 = (w3 & 1u) != 0;                        // fork: only seg[t-2], :629-632
     } else {
-      m1 = (nb & 1u) != 0;                        // upstream: seg[t-s+1..t] all != 0
-      m2 = (nb & 3u) == 3u;
-      m3 = (nb & 7u) == 7u;
+      m1 = (w3 & 4u) != 0;                        // upstream: seg[t-s+1..t] all != 0
+      m2 = (w3 & 6u) == 6u;
+      m3 = (w3 & 7u) == 7u;
     }
-    const uint4 a1 = m1 ? xm1 : zero, a2 = m2 ? xm2 : zero, a3 = m3 ? xm3 : zero;
-    uint4 out;
+    const uint4 x0 = xr[j + 3];
+    const uint4 a1 = m1 ? xr[j + 2] : zero, a2 = m2 ? xr[j + 1] : zero, a3 = m3 ? xr[j] : zero;
     const uint32_t s0[4] = {x0.x, x0.y, x0.z, x0.w}, s1[4] = {a1.x, a1.y, a1.z, a1.w};
     const uint32_t s2[4] = {a2.x, a2.y, a2.z, a2.w}, s3[4] = {a3.x, a3.y, a3.z, a3.w};
-    const uint32_t k0[4] = {wk[0].x, wk[0].y, wk[0].z, wk[0].w}, k1[4] = {wk[1].x, wk[1].y, wk[1].z, wk[1].w};
-    const uint32_t k2[4] = {wk[2].x, wk[2].y, wk[2].z, wk[2].w}, k3[4] = {wk[3].x, wk[3].y, wk[3].z, wk[3].w};
-    const uint32_t bb[4] = {bv.x, bv.y, bv.z, bv.w};
     uint32_t o[4];
     if constexpr (BF && EMUL) {
 #pragma unroll
@@ -117,9 +124,7 @@ conv1d_w4_kernel(const ConvParams p) {
         o[i] = __float_as_uint(__fadd_rn(acc, __uint_as_float(bb[i])));
       }
     }
-    out = make_uint4(o[0], o[1], o[2], o[3]);
-    stg_stream(yb + (size_t)t * p.E, out);
-    xm3 = xm2; xm2 = xm1; xm1 = x0;
+    stg_stream(yb + (size_t)t * p.E, make_uint4(o[0], o[1], o[2], o[3]));
   }
 
   // new cache = last 3 input rows, left zero padded (:542-543); written by the

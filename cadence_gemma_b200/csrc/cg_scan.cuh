@@ -2,22 +2,28 @@
 // gate math.  Replaces reference recurrentgemma/torch/layers.py:345-375
 // (RGLRU.forward after the gate GEMMs) and :146-199 (rnn_scan).
 //
-// Decomposition (one WARP per work item, no shared memory, no block barrier):
-//   item   = (batch row b, channel tile of EC = 8*V channels, chunk of TC steps)
-//   lane   = (seg = lane / 8, cv = lane % 8):  8 lanes x V channels cover one
-//            contiguous 128-byte row (V = 8 bf16 / 4 fp32 -> 16-byte vectors),
-//            the 4 lane groups take 4 consecutive time segments of L steps
-//            => every warp load/store instruction moves 4 full 128 B lines.
-//   pass 1 : each lane streams its L steps, evaluates the gates in registers
-//            and keeps (a_t, x~_t) (packed bf16x2 when they are bf16-exact),
-//            accumulating the segment transform h -> P*h + H.
-//   carry  : warp-shuffle scan of (P,H) over the 4 segments; chunks of one
-//            column are chained through global memory with a decoupled
-//            look-back (flag 1 = aggregate published, 2 = inclusive state
-//            published).  The carry is always folded left-to-right over the
-//            chunk aggregates, so results do not depend on timing.
-//   pass 2 : replay h = a_t*h + x~_t from the true carry-in, store y.
-// Items are handed out by an atomic ticket in time-major order, so every
+// Decomposition:
+//   CTA    = NW warps = NW consecutive time chunks ("super-chunk") of one channel
+//            tile (batch row b, EC = 8*V channels = one 128-byte row).
+//   warp   = one chunk of TC = 4*L steps.  lane = (seg = lane / 8, cv = lane % 8):
+//            8 lanes x V channels (16-byte vectors) cover one contiguous 128-byte
+//            row, the 4 lane groups take 4 consecutive time segments of L steps
+//            => every warp-wide access moves 4 full 128 B lines.
+//   stage  : each lane copies its own L steps of x / gate pre-activations
+//            global -> shared with cp.async (LDGSTS, 16 B, L1 bypass): the
+//            bytes in flight live in shared memory, not registers.
+//   pass 1 : lanes evaluate the gates in registers (sigmoid, softplus-exp,
+//            sqrt(1-a^2), every bf16 rounding point of the reference), write
+//            (x~_t, a_t) back over the staged inputs and accumulate the
+//            segment transform h -> P*h + H in fp32.
+//   carry  : warp-shuffle scan of (P,H) over the 4 segments; the CTA's chunks
+//            are combined through shared memory; super-chunks of one column
+//            are chained through global memory with a decoupled look-back
+//            (flag 1 = aggregate published, 2 = state published).  The carry is
+//            always folded left-to-right over aggregates, so results do not
+//            depend on timing (bit-reproducible run to run).
+//   pass 2 : replay h = a_t*h + x~_t from the true carry-in, store y (bf16/fp32).
+// CTAs take their work item from an atomic ticket in time-major order, so every
 // item's predecessors are already running: the look-back cannot deadlock.
 #pragma once
 
@@ -121,35 +127,100 @@ __device__ __forceinline__ void gate_f32(float xc, float gxr, float gar, float b
 
 // KIND: 0 = RG-LRU (gates fused), 1 = plain rnn_scan(x, a, reset, h0).
 // ARITH: CG_ARITH_* bits 0 (fp32 in registers) and 1 (fast math).
-template <typename IO, int KIND, int ARITH, int L, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-scan_kernel(const ScanParams p) {
-  constexpr int V = IoVec<IO>::V;
-  constexpr bool BF = IoVec<IO>::kBf16;
-  constexpr bool FAST = (ARITH & 2) != 0;
-  // (a, x~) are exactly bf16 -> keep them packed between the two passes
-  constexpr bool PACKED = BF && (KIND == 1 || (ARITH & 1) == 0);
-  constexpr int EC = kCvl * V;
-  constexpr int TC = kSegs * L;
-  constexpr int NV = PACKED ? V / 2 : V;   // registers per stored vector
+template <typename IO, int KIND, int ARITH>
+struct ScanTraits {
+  static constexpr int V = IoVec<IO>::V;
+  static constexpr bool BF = IoVec<IO>::kBf16;
+  static constexpr bool FAST = (ARITH & 2) != 0;
+  // (a, x~) are exactly bf16 -> kept packed between the two passes
+  static constexpr bool PACKED = BF && (KIND == 1 || (ARITH & 1) == 0);
+  static constexpr int EC = kCvl * V;          // channels per tile (128 B rows)
+  static constexpr int CPL = EC / 32;          // channels per lane in the carry warp
+  // 16-byte staging slots per (step, lane): inputs x, g1, g2 (or x, a); the
+  // (x~, a) state overwrites them in place (fp32 state of 8 channels needs 4)
+  static constexpr int NT = KIND == 1 ? 2 : ((BF && !PACKED) ? 4 : 3);
+};
 
+template <typename IO, int KIND, int ARITH, int L, int NW>
+constexpr size_t scan_smem_bytes() {
+  using Tr = ScanTraits<IO, KIND, ARITH>;
+  return (size_t)NW * L * Tr::NT * 512 + (size_t)(2 * NW + 1) * Tr::EC * sizeof(float) + 16;
+}
+
+// One CTA = NW warps = NW consecutive chunks (a "super-chunk" of NW*4*L steps)
+// of one 128-byte-wide channel column.
+template <typename IO, int KIND, int ARITH, int L, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+scan_kernel(const ScanParams p) {
+  using Tr = ScanTraits<IO, KIND, ARITH>;
+  constexpr int V = Tr::V;
+  constexpr bool BF = Tr::BF;
+  constexpr bool FAST = Tr::FAST;
+  constexpr bool PACKED = Tr::PACKED;
+  constexpr int EC = Tr::EC;
+  constexpr int CPL = Tr::CPL;
+  constexpr int NT = Tr::NT;
+  constexpr int TC = kSegs * L;
+  constexpr int NV = PACKED ? V / 2 : V;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* stage = reinterpret_cast<uint4*>(smem_raw);
+  float* s_agg_p = reinterpret_cast<float*>(smem_raw + (size_t)NW * L * NT * 512);
+  float* s_agg_h = s_agg_p + NW * EC;
+  float* s_c0 = s_agg_h + NW * EC;
+  int* s_item = reinterpret_cast<int*>(s_c0 + EC);
+
+  const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int seg_id = lane >> 3;
   const int cv = lane & 7;
 
-  int item = 0;
-  if (lane == 0) item = atomicAdd(p.counter, 1);
-  item = __shfl_sync(0xffffffffu, item, 0);
-  if (item >= p.nitems) return;
-  const int chunk = item / p.ncols;          // time-major ticket order
-  const int col = item - chunk * p.ncols;
+  if (threadIdx.x == 0) *s_item = atomicAdd(p.counter, 1);
+  __syncthreads();
+  const int item = *s_item;                  // grid == nitems
+  const int sc = item / p.ncols;             // time-major ticket order
+  const int col = item - sc * p.ncols;
   const int b = col / p.ctiles;
-  const int ch0 = (col - b * p.ctiles) * EC + cv * V;
+  const int e0 = (col - b * p.ctiles) * EC;
+  const int ch0 = e0 + cv * V;
   const bool ch_ok = ch0 < p.E;
-  const int t_first = chunk * TC + seg_id * L;
+  const int t_first = (sc * NW + warp) * TC + seg_id * L;
   const size_t row0 = (size_t)b * p.T;
+  uint4* my = stage + (size_t)warp * L * NT * 32 + lane;   // slot (j,k): my[(j*NT+k)*32]
 
-  // per-lane constants
+  // ---- stage this lane's L steps: global -> shared, asynchronously (LDGSTS).
+  // Every lane later consumes exactly the bytes it copied itself, so no
+  // barrier is needed, only cp.async.wait_group.
+  unsigned rs_mask = 0;
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    const int t = t_first + j;
+    if (ch_ok && t < p.T) {
+      const size_t row = row0 + t;
+      cp_async16(my + (j * NT + 0) * 32, reinterpret_cast<const IO*>(p.x) + row * p.E + ch0);
+      if constexpr (KIND == 0) {
+        cp_async16(my + (j * NT + 1) * 32, reinterpret_cast<const IO*>(p.gemm_x) + row * p.gate_ld + ch0);
+        cp_async16(my + (j * NT + 2) * 32, reinterpret_cast<const IO*>(p.gemm_a) + row * p.gate_ld + ch0);
+      } else {
+        cp_async16(my + (j * NT + 1) * 32, reinterpret_cast<const IO*>(p.a) + row * p.E + ch0);
+      }
+    }
+    cp_async_commit();
+  }
+#pragma unroll
+  for (int j = 0; j < L; ++j) {
+    const int t = t_first + j;
+    if (ch_ok && t < p.T) {
+      bool rs;
+      if constexpr (KIND == 0)
+        rs = load_seg(p.seg, p.seg_is_i64 != 0, (long long)b * p.seg_bstride + t) == 0;
+      else
+        rs = p.reset[row0 + t] != 0;
+      rs_mask |= (rs ? 1u : 0u) << j;
+    }
+  }
+
+  // per-lane constants (overlaps the copies)
   uint32_t cbx[NV], cba[NV], csp[NV];
   if constexpr (KIND == 0) {
     float fbx[V], fba[V], fsp[V];
@@ -194,79 +265,79 @@ scan_kernel(const ScanParams p) {
   }
 
   // ------------------------------------------------------------ pass 1
-  uint32_t st_a[L][NV], st_x[L][NV];   // (a_t, x~_t): packed bf16x2 or fp32 bits
   float P[V], H[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { P[i] = 1.0f; H[i] = 0.0f; }
 
 #pragma unroll
   for (int j = 0; j < L; ++j) {
+    cp_async_wait_dyn<L>(L - 1 - j);           // copies of step j have landed
     const int t = t_first + j;
-    const bool ok = ch_ok && t < p.T;
-    uint4 vx = make_uint4(0, 0, 0, 0), v1 = vx, v2 = vx;
-    bool rs = false;
-    if (ok) {
-      const size_t row = row0 + t;
-      vx = ldg_stream(reinterpret_cast<const IO*>(p.x) + row * p.E + ch0);
-      if constexpr (KIND == 0) {
-        v1 = ldg_stream(reinterpret_cast<const IO*>(p.gemm_x) + row * p.gate_ld + ch0);
-        v2 = ldg_stream(reinterpret_cast<const IO*>(p.gemm_a) + row * p.gate_ld + ch0);
-        rs = load_seg(p.seg, p.seg_is_i64 != 0, (long long)b * p.seg_bstride + t) == 0;
+    if (ch_ok && t < p.T) {                    // steps beyond T / E are identities
+      const bool rs = (rs_mask >> j) & 1u;
+      const uint4 vx = my[(j * NT + 0) * 32];
+      const uint4 v1 = my[(j * NT + 1) * 32];
+      uint4 v2 = make_uint4(0, 0, 0, 0);
+      if constexpr (KIND == 0) v2 = my[(j * NT + 2) * 32];
+      const uint32_t wx[4] = {vx.x, vx.y, vx.z, vx.w};
+      const uint32_t w1[4] = {v1.x, v1.y, v1.z, v1.w};
+      const uint32_t w2[4] = {v2.x, v2.y, v2.z, v2.w};
+      if constexpr (PACKED) {
+        uint32_t sa[4], sx[4];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          uint32_t av, nx;
+          if constexpr (KIND == 0) {
+            gate_pair_emul<FAST>(wx[i], w1[i], w2[i], cbx[i], cba[i], csp[i], rs, av, nx);
+          } else {
+            av = rs ? 0u : w1[i];   // a * ~reset (:173)
+            nx = wx[i];
+          }
+          sa[i] = av; sx[i] = nx;
+          const float a0 = bf_lo(av), a1 = bf_hi(av);
+          H[2 * i] = fmaf(a0, H[2 * i], bf_lo(nx));
+          H[2 * i + 1] = fmaf(a1, H[2 * i + 1], bf_hi(nx));
+          P[2 * i] *= a0; P[2 * i + 1] *= a1;
+        }
+        my[(j * NT + 0) * 32] = make_uint4(sx[0], sx[1], sx[2], sx[3]);
+        my[(j * NT + 1) * 32] = make_uint4(sa[0], sa[1], sa[2], sa[3]);
       } else {
-        v1 = ldg_stream(reinterpret_cast<const IO*>(p.a) + row * p.E + ch0);
-        rs = p.reset[row] != 0;
-      }
-    }
-    const uint32_t wx[4] = {vx.x, vx.y, vx.z, vx.w};
-    const uint32_t w1[4] = {v1.x, v1.y, v1.z, v1.w};
-    const uint32_t w2[4] = {v2.x, v2.y, v2.z, v2.w};
-    if constexpr (PACKED) {
+        float fx[V], f1[V], f2[V], fa[V], fn[V];
+        if constexpr (BF) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        uint32_t av, nx;
-        if constexpr (KIND == 0) {
-          gate_pair_emul<FAST>(wx[i], w1[i], w2[i], cbx[i], cba[i], csp[i], rs, av, nx);
+          for (int i = 0; i < 4; ++i) {
+            fx[2 * i] = bf_lo(wx[i]); fx[2 * i + 1] = bf_hi(wx[i]);
+            f1[2 * i] = bf_lo(w1[i]); f1[2 * i + 1] = bf_hi(w1[i]);
+            f2[2 * i] = bf_lo(w2[i]); f2[2 * i + 1] = bf_hi(w2[i]);
+          }
         } else {
-          av = rs ? 0u : w1[i];   // a * ~reset (:173)
-          nx = wx[i];
-        }
-        if (!ok) { av = kOne2; nx = 0u; }   // identity step beyond T / E
-        st_a[j][i] = av; st_x[j][i] = nx;
-        const float a0 = bf_lo(av), a1 = bf_hi(av);
-        H[2 * i] = fmaf(a0, H[2 * i], bf_lo(nx));
-        H[2 * i + 1] = fmaf(a1, H[2 * i + 1], bf_hi(nx));
-        P[2 * i] *= a0; P[2 * i + 1] *= a1;
-      }
-    } else {
-      float fx[V], f1[V], f2[V];
-      if constexpr (BF) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          fx[2 * i] = bf_lo(wx[i]); fx[2 * i + 1] = bf_hi(wx[i]);
-          f1[2 * i] = bf_lo(w1[i]); f1[2 * i + 1] = bf_hi(w1[i]);
-          f2[2 * i] = bf_lo(w2[i]); f2[2 * i + 1] = bf_hi(w2[i]);
+          for (int i = 0; i < 4; ++i) {
+            fx[i] = __uint_as_float(wx[i]); f1[i] = __uint_as_float(w1[i]);
+            f2[i] = __uint_as_float(w2[i]);
+          }
         }
-      } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          fx[i] = __uint_as_float(wx[i]); f1[i] = __uint_as_float(w1[i]);
-          f2[i] = __uint_as_float(w2[i]);
+        for (int i = 0; i < V; ++i) {
+          float av, nx;
+          if constexpr (KIND == 0) {
+            gate_f32<FAST>(fx[i], f1[i], f2[i], __uint_as_float(cbx[i]), __uint_as_float(cba[i]),
+                           __uint_as_float(csp[i]), rs, av, nx);
+          } else {
+            av = rs ? 0.0f : f1[i];
+            nx = fx[i];
+          }
+          fa[i] = av; fn[i] = nx;
+          H[i] = fmaf(av, H[i], nx);
+          P[i] *= av;
         }
-      }
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        float av, nx;
-        if constexpr (KIND == 0) {
-          gate_f32<FAST>(fx[i], f1[i], f2[i], __uint_as_float(cbx[i]), __uint_as_float(cba[i]),
-                         __uint_as_float(csp[i]), rs, av, nx);
-        } else {
-          av = rs ? 0.0f : f1[i];
-          nx = fx[i];
+        for (int i = 0; i < V; i += 4) {       // x~ in slots 0.., a after them
+          my[(j * NT + i / 4) * 32] = make_uint4(__float_as_uint(fn[i]), __float_as_uint(fn[i + 1]),
+                                                 __float_as_uint(fn[i + 2]), __float_as_uint(fn[i + 3]));
+          my[(j * NT + V / 4 + i / 4) * 32] = make_uint4(__float_as_uint(fa[i]), __float_as_uint(fa[i + 1]),
+                                                         __float_as_uint(fa[i + 2]), __float_as_uint(fa[i + 3]));
         }
-        if (!ok) { av = 1.0f; nx = 0.0f; }
-        st_a[j][i] = __float_as_uint(av); st_x[j][i] = __float_as_uint(nx);
-        H[i] = fmaf(av, H[i], nx);
-        P[i] *= av;
       }
     }
   }
@@ -281,138 +352,160 @@ scan_kernel(const ScanParams p) {
       if (lane >= d) { H[i] = fmaf(P[i], hp, H[i]); P[i] *= pp; }
     }
   }
-  float Pex[V], Hex[V];   // transform of the segments before mine
+  float Pex[V], Hex[V];   // transform of this warp's segments before mine
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     Pex[i] = __shfl_up_sync(0xffffffffu, P[i], 8);
     Hex[i] = __shfl_up_sync(0xffffffffu, H[i], 8);
     if (seg_id == 0) { Pex[i] = 1.0f; Hex[i] = 0.0f; }
   }
-  // lanes 24..31 now hold the whole chunk's (P,H).
+  if (seg_id == kSegs - 1) {   // lanes 24..31 hold the chunk's (P,H)
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+      *reinterpret_cast<float4*>(s_agg_p + warp * EC + cv * V + i) = make_float4(P[i], P[i + 1], P[i + 2], P[i + 3]);
+      *reinterpret_cast<float4*>(s_agg_h + warp * EC + cv * V + i) = make_float4(H[i], H[i + 1], H[i + 2], H[i + 3]);
+    }
+  }
+  __syncthreads();
 
-  // ------------------------------------------------ carry across chunks
-  float c[V];
-  const size_t ws_off = (size_t)item * EC + cv * V;
-  if (chunk == 0) {
+  // ------------------------------------------------ carry across super-chunks
+  // The last warp folds the CTA's chunks, obtains the state entering this
+  // super-chunk (decoupled look-back over the column's earlier CTAs) and
+  // publishes the state leaving it.  Lane l owns channels [l*CPL, l*CPL+CPL).
+  if (warp == NW - 1) {
+    float pt[CPL], ht[CPL], c0[CPL];
 #pragma unroll
-    for (int i = 0; i < V; ++i) c[i] = 0.0f;
-    if (p.h0 != nullptr && ch_ok) {
+    for (int i = 0; i < CPL; ++i) { pt[i] = 1.0f; ht[i] = 0.0f; }
 #pragma unroll
-      for (int i = 0; i < V; i += 4) {
-        float4 v = *reinterpret_cast<const float4*>(p.h0 + (size_t)b * p.E + ch0 + i);
-        c[i] = v.x; c[i + 1] = v.y; c[i + 2] = v.z; c[i + 3] = v.w;
+    for (int w = 0; w < NW; ++w) {
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const float pw = s_agg_p[w * EC + lane * CPL + i], hw = s_agg_h[w * EC + lane * CPL + i];
+        ht[i] = fmaf(pw, ht[i], hw);
+        pt[i] *= pw;
       }
     }
-  } else {
-    int j = chunk - 1;
-    int f = ld_acquire(p.flags + (size_t)j * p.ncols + col);
-    if (f != 2) {
-      // predecessor state not final yet: publish my aggregate so successors
-      // can fold over it, then look back.
-      if (seg_id == kSegs - 1) {
+    const size_t ws_off = (size_t)item * EC + lane * CPL;
+    if (sc == 0) {
 #pragma unroll
-        for (int i = 0; i < V; i += 4) {
-          stg_cg(p.agg_p + ws_off + i, make_uint4(__float_as_uint(P[i]), __float_as_uint(P[i + 1]),
-                                                  __float_as_uint(P[i + 2]), __float_as_uint(P[i + 3])));
-          stg_cg(p.agg_h + ws_off + i, make_uint4(__float_as_uint(H[i]), __float_as_uint(H[i + 1]),
-                                                  __float_as_uint(H[i + 2]), __float_as_uint(H[i + 3])));
+      for (int i = 0; i < CPL; ++i) {
+        const int ch = e0 + lane * CPL + i;
+        c0[i] = (p.h0 != nullptr && ch < p.E) ? p.h0[(size_t)b * p.E + ch] : 0.0f;
+      }
+    } else {
+      int j = sc - 1;
+      int f = ld_acquire(p.flags + (size_t)j * p.ncols + col);
+      if (f != 2) {
+        // predecessor not final yet: publish my aggregate so successors can
+        // fold over it, then look back.
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+          __stcg(p.agg_p + ws_off + i, pt[i]);
+          __stcg(p.agg_h + ws_off + i, ht[i]);
         }
         __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release(p.flags + item, 1);
+        for (;;) {
+          f = ld_acquire(p.flags + (size_t)j * p.ncols + col);
+          if (f == 2) break;
+          if (f == 1) { --j; continue; }   // super-chunk 0 always ends at 2
+          __nanosleep(32);
+        }
       }
-      __syncwarp();
-      if (lane == 0) st_release(p.flags + item, 1);
-      for (;;) {
-        f = ld_acquire(p.flags + (size_t)j * p.ncols + col);
-        if (f == 2) break;
-        if (f == 1) { --j; continue; }   // chunk 0 always ends at 2, so j >= 0
-        __nanosleep(64);
+      const size_t src = ((size_t)j * p.ncols + col) * EC + lane * CPL;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) c0[i] = __ldcg(p.pref + src + i);
+      for (int k = j + 1; k < sc; ++k) {   // fold aggregates left to right
+        const size_t off = ((size_t)k * p.ncols + col) * EC + lane * CPL;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i)
+          c0[i] = fmaf(__ldcg(p.agg_p + off + i), c0[i], __ldcg(p.agg_h + off + i));
       }
     }
-    // c = state after chunk j, then fold aggregates j+1 .. chunk-1 in order
-    {
-      const float* src = p.pref + ((size_t)j * p.ncols + col) * EC + cv * V;
+    if (sc + 1 < p.nchunks) {   // state leaving this super-chunk
 #pragma unroll
-      for (int i = 0; i < V; i += 4) {
-        uint4 v = ldg_cg(src + i);
-        c[i] = __uint_as_float(v.x); c[i + 1] = __uint_as_float(v.y);
-        c[i + 2] = __uint_as_float(v.z); c[i + 3] = __uint_as_float(v.w);
-      }
-    }
-    for (int k = j + 1; k < chunk; ++k) {
-      const size_t off = ((size_t)k * p.ncols + col) * EC + cv * V;
-#pragma unroll
-      for (int i = 0; i < V; i += 4) {
-        uint4 vp = ldg_cg(p.agg_p + off + i);
-        uint4 vh = ldg_cg(p.agg_h + off + i);
-        c[i] = fmaf(__uint_as_float(vp.x), c[i], __uint_as_float(vh.x));
-        c[i + 1] = fmaf(__uint_as_float(vp.y), c[i + 1], __uint_as_float(vh.y));
-        c[i + 2] = fmaf(__uint_as_float(vp.z), c[i + 2], __uint_as_float(vh.z));
-        c[i + 3] = fmaf(__uint_as_float(vp.w), c[i + 3], __uint_as_float(vh.w));
-      }
-    }
-  }
-  // publish the state after this chunk (not needed after the last one)
-  if (chunk + 1 < p.nchunks) {
-    if (seg_id == kSegs - 1) {
-#pragma unroll
-      for (int i = 0; i < V; i += 4) {
-        stg_cg(p.pref + ws_off + i,
-               make_uint4(__float_as_uint(fmaf(P[i], c[i], H[i])),
-                          __float_as_uint(fmaf(P[i + 1], c[i + 1], H[i + 1])),
-                          __float_as_uint(fmaf(P[i + 2], c[i + 2], H[i + 2])),
-                          __float_as_uint(fmaf(P[i + 3], c[i + 3], H[i + 3]))));
-      }
+      for (int i = 0; i < CPL; ++i) __stcg(p.pref + ws_off + i, fmaf(pt[i], c0[i], ht[i]));
       __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release(p.flags + item, 2);
     }
-    __syncwarp();
-    if (lane == 0) st_release(p.flags + item, 2);
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) s_c0[lane * CPL + i] = c0[i];
   }
+  __syncthreads();
 
-  // ------------------------------------------------------------ pass 2 (replay)
+  // carry into this warp's chunk: fold the CTA's earlier chunks, in order
   float h[V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) h[i] = fmaf(Pex[i], c[i], Hex[i]);
+  for (int i = 0; i < V; i += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(s_c0 + cv * V + i);
+    h[i] = v.x; h[i + 1] = v.y; h[i + 2] = v.z; h[i + 3] = v.w;
+  }
+  for (int w = 0; w < warp; ++w) {
+#pragma unroll
+    for (int i = 0; i < V; i += 4) {
+      const float4 vp = *reinterpret_cast<const float4*>(s_agg_p + w * EC + cv * V + i);
+      const float4 vh = *reinterpret_cast<const float4*>(s_agg_h + w * EC + cv * V + i);
+      h[i] = fmaf(vp.x, h[i], vh.x); h[i + 1] = fmaf(vp.y, h[i + 1], vh.y);
+      h[i + 2] = fmaf(vp.z, h[i + 2], vh.z); h[i + 3] = fmaf(vp.w, h[i + 3], vh.w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) h[i] = fmaf(Pex[i], h[i], Hex[i]);   // ... and my warp's earlier segments
 
+  // ------------------------------------------------------------ pass 2 (replay)
 #pragma unroll
   for (int j = 0; j < L; ++j) {
     const int t = t_first + j;
-    const bool ok = ch_ok && t < p.T;
-    uint4 out;
-    if constexpr (PACKED) {
-      uint32_t o[4];
+    if (ch_ok && t < p.T) {
+      uint4 out;
+      if constexpr (PACKED) {
+        const uint4 vn = my[(j * NT + 0) * 32];
+        const uint4 va = my[(j * NT + 1) * 32];
+        const uint32_t sx[4] = {vn.x, vn.y, vn.z, vn.w}, sa[4] = {va.x, va.y, va.z, va.w};
+        uint32_t o[4];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const uint32_t av = st_a[j][i], nx = st_x[j][i];
-        if constexpr (FAST) {
-          h[2 * i] = fmaf(bf_lo(av), h[2 * i], bf_lo(nx));
-          h[2 * i + 1] = fmaf(bf_hi(av), h[2 * i + 1], bf_hi(nx));
-        } else {   // mul then add, as the reference loop (:196)
-          h[2 * i] = __fadd_rn(__fmul_rn(bf_lo(av), h[2 * i]), bf_lo(nx));
-          h[2 * i + 1] = __fadd_rn(__fmul_rn(bf_hi(av), h[2 * i + 1]), bf_hi(nx));
+        for (int i = 0; i < NV; ++i) {
+          if constexpr (FAST) {
+            h[2 * i] = fmaf(bf_lo(sa[i]), h[2 * i], bf_lo(sx[i]));
+            h[2 * i + 1] = fmaf(bf_hi(sa[i]), h[2 * i + 1], bf_hi(sx[i]));
+          } else {   // mul then add, as the reference loop (:196)
+            h[2 * i] = __fadd_rn(__fmul_rn(bf_lo(sa[i]), h[2 * i]), bf_lo(sx[i]));
+            h[2 * i + 1] = __fadd_rn(__fmul_rn(bf_hi(sa[i]), h[2 * i + 1]), bf_hi(sx[i]));
+          }
+          o[i] = pack_bf2(h[2 * i], h[2 * i + 1]);
         }
-        o[i] = pack_bf2(h[2 * i], h[2 * i + 1]);
-      }
-      out = make_uint4(o[0], o[1], o[2], o[3]);
-      if (ok) stg_stream(reinterpret_cast<IO*>(p.y) + (row0 + t) * p.E + ch0, out);
-    } else {
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float av = __uint_as_float(st_a[j][i]), nx = __uint_as_float(st_x[j][i]);
-        if constexpr (FAST) h[i] = fmaf(av, h[i], nx);
-        else h[i] = __fadd_rn(__fmul_rn(av, h[i]), nx);
-      }
-      if constexpr (BF) {
-        out = make_uint4(pack_bf2(h[0], h[1]), pack_bf2(h[2], h[3]),
-                         pack_bf2(h[4 % V], h[5 % V]), pack_bf2(h[6 % V], h[7 % V]));
+        out = make_uint4(o[0], o[1], o[2], o[3]);
       } else {
-        out = make_uint4(__float_as_uint(h[0]), __float_as_uint(h[1]),
-                         __float_as_uint(h[2]), __float_as_uint(h[3]));
+        float fn[V], fa[V];
+#pragma unroll
+        for (int i = 0; i < V; i += 4) {
+          const uint4 vn = my[(j * NT + i / 4) * 32];
+          const uint4 va = my[(j * NT + V / 4 + i / 4) * 32];
+          fn[i] = __uint_as_float(vn.x); fn[i + 1] = __uint_as_float(vn.y);
+          fn[i + 2] = __uint_as_float(vn.z); fn[i + 3] = __uint_as_float(vn.w);
+          fa[i] = __uint_as_float(va.x); fa[i + 1] = __uint_as_float(va.y);
+          fa[i + 2] = __uint_as_float(va.z); fa[i + 3] = __uint_as_float(va.w);
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          if constexpr (FAST) h[i] = fmaf(fa[i], h[i], fn[i]);
+          else h[i] = __fadd_rn(__fmul_rn(fa[i], h[i]), fn[i]);
+        }
+        if constexpr (BF) {
+          out = make_uint4(pack_bf2(h[0], h[1]), pack_bf2(h[2], h[3]),
+                           pack_bf2(h[4 % V], h[5 % V]), pack_bf2(h[6 % V], h[7 % V]));
+        } else {
+          out = make_uint4(__float_as_uint(h[0]), __float_as_uint(h[1]),
+                           __float_as_uint(h[2]), __float_as_uint(h[3]));
+        }
       }
-      if (ok) stg_stream(reinterpret_cast<IO*>(p.y) + (row0 + t) * p.E + ch0, out);
+      stg_stream(reinterpret_cast<IO*>(p.y) + (row0 + t) * p.E + ch0, out);
     }
   }
   // hidden state after the last valid step (padding steps are identities)
-  if (p.last_h != nullptr && chunk == p.nchunks - 1 && seg_id == kSegs - 1 && ch_ok) {
+  if (p.last_h != nullptr && sc == p.nchunks - 1 && warp == NW - 1 && seg_id == kSegs - 1 && ch_ok) {
 #pragma unroll
     for (int i = 0; i < V; i += 4)
       *reinterpret_cast<float4*>(p.last_h + (size_t)b * p.E + ch0 + i) =

@@ -193,8 +193,8 @@ def test_rglru_random_vs_oracle(dtype, shape):
   g = torch.Generator().manual_seed(steps * 7 + width)
   p = torch_port.init_rglru_params(width, max(1, width // 64), g, dtype)
   x = torch.randn(shape, generator=g).to(dtype)
-  gx = torch.randn(shape, generator=g).to(dtype) * 2
-  ga = torch.randn(shape, generator=g).to(dtype) * 2
+  gx = torch.randn(shape, generator=g).to(dtype)
+  ga = torch.randn(shape, generator=g).to(dtype)
   bx = p.input_gate_b.reshape(-1)
   ba = p.a_gate_b.reshape(-1)
   seg = torch.arange(steps)[None].repeat(bsz, 1)
