@@ -26,6 +26,7 @@ import os
 import statistics
 import subprocess
 import sys
+import threading
 import time
 
 import torch
@@ -83,47 +84,61 @@ def make_host_inputs(dtype, seed=1):
 # clocks / throttle sampling during the timed region
 # ----------------------------------------------------------------------------
 class ClockSampler:
-  QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-           "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-           "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+  """Samples SM clock and throttle reasons through NVML from a background
+  thread while the timed region runs (nvidia-smi -lms is too slow to start for
+  regions of a few milliseconds)."""
+
+  REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40,
+             "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
   def __init__(self, gpu_index):
-    self.gpu_index, self.proc = gpu_index, None
+    self.gpu_index = gpu_index
+    self.samples, self.reasons = [], set()
+    self.sm_max = None
+    self._stop = threading.Event()
+    self._thread = None
+    self._err = None
+
+  def _run(self):
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      # CUDA_VISIBLE_DEVICES remapping: match by PCI bus id of the torch device
+      bus = torch.cuda.get_device_properties(self.gpu_index).pci_bus_id
+      handle = None
+      for i in range(pynvml.nvmlDeviceGetCount()):
+        h = pynvml.nvmlDeviceGetHandleByIndex(i)
+        if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+          handle = h
+          break
+      if handle is None:
+        handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+      self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+      while not self._stop.is_set():
+        self.samples.append(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
+        for name, bit in self.REASONS.items():
+          if mask & bit:
+            self.reasons.add(name)
+        time.sleep(0.002)
+    except Exception as exc:  # pylint: disable=broad-except
+      self._err = repr(exc)
 
   def start(self):
-    try:
-      self.proc = subprocess.Popen(
-          ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-           "-lms", "100", "-i", str(self.gpu_index)],
-          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-    except OSError:
-      self.proc = None
+    self._thread = threading.Thread(target=self._run, daemon=True)
+    self._thread.start()
+    time.sleep(0.05)   # let NVML initialise before the timed region starts
 
   def stop(self):
-    if self.proc is None:
-      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    self.proc.terminate()
-    try:
-      out, _ = self.proc.communicate(timeout=5)
-    except subprocess.TimeoutExpired:
-      self.proc.kill()
-      out, _ = self.proc.communicate()
-    sm, smax, reasons = [], [], set()
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    for line in out.strip().splitlines():
-      f = [c.strip() for c in line.split(",")]
-      if len(f) < 9:
-        continue
-      try:
-        sm.append(float(f[1])); smax.append(float(f[2]))
-      except ValueError:
-        continue
-      for name, val in zip(names, f[5:9]):
-        if val.lower().startswith("active"):
-          reasons.add(name)
-    return {"sm_mhz": statistics.median(sm) if sm else None,
-            "sm_max_mhz": max(smax) if smax else None,
-            "reasons": sorted(reasons), "samples": len(sm)}
+    self._stop.set()
+    if self._thread is not None:
+      self._thread.join(timeout=5)
+    out = {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+           "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+           "samples": len(self.samples)}
+    if self._err:
+      out["error"] = self._err
+    return out
 
 
 # ----------------------------------------------------------------------------

@@ -117,13 +117,13 @@ _workspaces: dict = {}
 
 
 def scan_workspace(device, batch: int, steps: int, width: int, dtype) -> torch.Tensor:
-  """Cached scratch buffer per (device, stream, shape); never initialised."""
+  """Cached scratch buffer per (device, stream, shape), zero-filled once."""
   key = (device, torch.cuda.current_stream(device).cuda_stream, batch, steps,
          width, dtype)
   ws = _workspaces.get(key)
   if ws is None:
     nbytes = load().cg_scan_workspace_bytes(batch, steps, width, dtype_code(dtype))
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
     if len(_workspaces) > 64:
       _workspaces.clear()
     _workspaces[key] = ws
@@ -210,7 +210,7 @@ def rglru_fwd(x, gemm_x, gemm_a, bias_x, bias_a, a_param, segment_pos, h0=None,
                              _ptr(last_h), ws.data_ptr(), ws.numel(), bsz, steps,
                              width, dtype_code(x.dtype), arith_mode, _stream(x))
   _check(rc, "cg_rglru_fwd")
-  launch_count += 2   # softplus(a_param) prologue + scan kernel
+  launch_count += 2   # prologue (ticket/epoch/softplus) + scan kernel
   return y, last_h
 
 
@@ -231,5 +231,5 @@ def rnn_scan_fwd(x, a, reset, h0=None, arith_mode=ARITH_REFERENCE):
                                 ws.data_ptr(), ws.numel(), bsz, steps, width,
                                 dtype_code(x.dtype), arith_mode, _stream(x))
   _check(rc, "cg_rnn_scan_fwd")
-  launch_count += 1
+  launch_count += 1 if (arith_mode & ARITH_STRICT) else 2
   return y, h_last

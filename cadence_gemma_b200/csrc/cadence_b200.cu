@@ -20,12 +20,15 @@ using cg::ScanParams;
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-constexpr int kMinSuperChunk = 64;  // smallest NW * 4 * L of any compiled geometry
+constexpr int kMinSuperChunk = 32;  // smallest NW * 4 * L of any compiled geometry
 
-// scratch layout: [ticket 256 B][flags][agg_p][agg_h][pref][neg8sp]
+// scratch layout: [ticket, epoch | 256 B][agg_p][agg_h][pref][neg8sp]
+// The exchange arrays hold 64-bit {value, epoch} words; the scratch must be
+// zero-filled once before its first use and is self-cleaning afterwards.
 struct Workspace {
-  int* counter; int* flags; float* agg_p; float* agg_h; float* pref; float* neg8sp;
-  size_t zero_bytes;  // ticket + flags, cleared before every launch
+  int* counter; unsigned* epoch;
+  unsigned long long *agg_p, *agg_h, *pref;
+  float* neg8sp;
   size_t total;
 };
 
@@ -36,43 +39,49 @@ Workspace carve(void* base, int B, int T, int E, int EC, int SC) {
   const size_t nitems = (size_t)B * ctiles * ((T + SC - 1) / SC);
   char* p = reinterpret_cast<char*>(base);
   size_t off = 0;
-  w.counter = reinterpret_cast<int*>(p + off); off += 256;
-  w.flags = reinterpret_cast<int*>(p + off); off += round_up(nitems * sizeof(int), 256);
-  w.zero_bytes = off;
-  w.agg_p = reinterpret_cast<float*>(p + off); off += nitems * EC * sizeof(float);
-  w.agg_h = reinterpret_cast<float*>(p + off); off += nitems * EC * sizeof(float);
-  w.pref = reinterpret_cast<float*>(p + off); off += nitems * EC * sizeof(float);
+  w.counter = reinterpret_cast<int*>(p + off);
+  w.epoch = reinterpret_cast<unsigned*>(p + off + 4);
+  off += 256;
+  w.agg_p = reinterpret_cast<unsigned long long*>(p + off); off += nitems * EC * 8;
+  w.agg_h = reinterpret_cast<unsigned long long*>(p + off); off += nitems * EC * 8;
+  w.pref = reinterpret_cast<unsigned long long*>(p + off); off += nitems * EC * 8;
   w.neg8sp = reinterpret_cast<float*>(p + off); off += round_up((size_t)E * sizeof(float), 256);
   w.total = off;
   return w;
 }
 
-template <typename IO, int KIND, int ARITH, int L, int NW, int MINB>
+template <typename IO, int KIND, int ARITH, int L, int NW, int STAGES, int MINB>
 int launch_scan(ScanParams p, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   constexpr int EC = cg::kCvl * cg::IoVec<IO>::V;
   constexpr int SC = cg::kSegs * L * NW;
   static_assert(SC >= kMinSuperChunk, "update kMinSuperChunk");
+  constexpr size_t smem = cg::scan_smem_bytes<IO, KIND, ARITH, L, NW, STAGES>();
+  if (smem > 227 * 1024) return CG_ERR_MODE;   // geometry does not fit this dtype / mode
   const Workspace ws = carve(workspace, p.B, p.T, p.E, EC, SC);
   if (ws.total > workspace_bytes) return CG_ERR_WORKSPACE;
   p.ctiles = (p.E + EC - 1) / EC;
   p.ncols = p.B * p.ctiles;
   p.nchunks = (p.T + SC - 1) / SC;
   p.nitems = p.ncols * p.nchunks;
-  p.counter = ws.counter; p.flags = ws.flags;
+  p.counter = ws.counter; p.epoch = ws.epoch;
   p.agg_p = ws.agg_p; p.agg_h = ws.agg_h; p.pref = ws.pref;
-  auto kernel = cg::scan_kernel<IO, KIND, ARITH, L, NW, MINB>;
-  constexpr size_t smem = cg::scan_smem_bytes<IO, KIND, ARITH, L, NW>();
-  static bool configured = false;   // idempotent attribute, set once per process
-  if (!configured) {
+  auto kernel = cg::scan_kernel<IO, KIND, ARITH, L, NW, STAGES, MINB>;
+  static int resident = 0;   // CTAs that fit on the device; queried once per process
+  if (resident == 0) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
-    configured = true;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NW * 32, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1 || sms < 1) return (int)cudaErrorLaunchOutOfResources;
+    resident = per_sm * sms;
   }
-  cudaError_t err = cudaMemsetAsync(ws.counter, 0, ws.zero_bytes, stream);
-  if (err != cudaSuccess) return (int)err;
-  kernel<<<p.nitems, NW * 32, smem, stream>>>(p);
+  const int grid = p.nitems < resident ? p.nitems : resident;
+  kernel<<<grid, NW * 32, smem, stream>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -83,21 +92,22 @@ int launch_strict(const ScanParams& p, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
-// Kernel geometry per variant id: L steps per lane, NW warps (= chunks) per CTA
-// and the minimum resident CTAs per SM (caps registers).  Staging is 512 B per
-// (warp, step, slot).  Variant 0 is the default; the others exist for tuning.
+// Kernel geometry per variant id: L steps per lane, NW warps (= chunks) per
+// CTA, staging buffers, minimum resident CTAs per SM (caps registers).
+// Variant 0 is the default; the others exist for the tuning scripts.
 template <typename IO, int KIND, int ARITH>
 int dispatch_geometry(int variant, const ScanParams& p, void* ws, size_t ws_bytes,
                       cudaStream_t stream) {
   switch (variant) {
-    case 0: return launch_scan<IO, KIND, ARITH, 8, 8, 2>(p, ws, ws_bytes, stream);
-    case 1: return launch_scan<IO, KIND, ARITH, 8, 4, 4>(p, ws, ws_bytes, stream);
-    case 2: return launch_scan<IO, KIND, ARITH, 4, 8, 4>(p, ws, ws_bytes, stream);
-    case 3: return launch_scan<IO, KIND, ARITH, 4, 8, 3>(p, ws, ws_bytes, stream);
-    case 4: return launch_scan<IO, KIND, ARITH, 4, 4, 6>(p, ws, ws_bytes, stream);
-    case 5: return launch_scan<IO, KIND, ARITH, 8, 6, 3>(p, ws, ws_bytes, stream);
-    case 6: return launch_scan<IO, KIND, ARITH, 4, 16, 2>(p, ws, ws_bytes, stream);
-    case 7: return launch_scan<IO, KIND, ARITH, 8, 8, 1>(p, ws, ws_bytes, stream);
+    case 0: return launch_scan<IO, KIND, ARITH, 4, 8, 2, 2>(p, ws, ws_bytes, stream);
+    case 1: return launch_scan<IO, KIND, ARITH, 4, 8, 1, 3>(p, ws, ws_bytes, stream);
+    case 2: return launch_scan<IO, KIND, ARITH, 4, 4, 1, 6>(p, ws, ws_bytes, stream);
+    case 3: return launch_scan<IO, KIND, ARITH, 4, 4, 2, 4>(p, ws, ws_bytes, stream);
+    case 4: return launch_scan<IO, KIND, ARITH, 2, 8, 2, 3>(p, ws, ws_bytes, stream);
+    case 5: return launch_scan<IO, KIND, ARITH, 8, 4, 1, 4>(p, ws, ws_bytes, stream);
+    case 6: return launch_scan<IO, KIND, ARITH, 8, 8, 1, 2>(p, ws, ws_bytes, stream);
+    case 7: return launch_scan<IO, KIND, ARITH, 4, 16, 2, 1>(p, ws, ws_bytes, stream);
+    case 8: return launch_scan<IO, KIND, ARITH, 2, 4, 1, 8>(p, ws, ws_bytes, stream);
     default: return CG_ERR_MODE;
   }
 }
@@ -158,7 +168,7 @@ int cg_conv1d_fwd(const void* x, const void* w, const void* b, const void* seg, 
 #define CG_CONV(LCV)                                                                       \
     {                                                                                      \
       const int tslots = (T + LCV - 1) / LCV;                                              \
-      dim3 grid((tslots + 15) / 16, (E + 8 * V - 1) / (8 * V), B);                         \
+      dim3 grid((E + 8 * V - 1) / (8 * V), (tslots + 15) / 16, B);                         \
       if (bf && emul) cg::conv1d_w4_kernel<uint16_t, true, LCV><<<grid, 128, 0, stream>>>(p);   \
       else if (bf) cg::conv1d_w4_kernel<uint16_t, false, LCV><<<grid, 128, 0, stream>>>(p);     \
       else cg::conv1d_w4_kernel<float, true, LCV><<<grid, 128, 0, stream>>>(p);            \
@@ -219,13 +229,14 @@ int cg_rglru_fwd(const void* x, const void* gemm_x, const void* gemm_a, long lon
         (h0 && !aligned16(h0)) || (last_h && !aligned16(last_h)) || !aligned16(workspace))
       return CG_ERR_ALIGN;
   }
-  // -8 * softplus(a_param) lives at the tail of the scratch for every geometry
+  // ticket / epoch live at the head and -8 * softplus(a_param) at the tail of
+  // the (largest-geometry) scratch layout, i.e. outside every geometry's arrays
   const Workspace ws_min = carve(workspace, B, T, E, cg::kCvl * V, kMinSuperChunk);
   if (ws_min.total > workspace_bytes) return CG_ERR_WORKSPACE;
   float* neg8sp = ws_min.neg8sp;
   const int emulate = (mode & CG_ARITH_FP32) == 0;
-  cg::softplus_param_kernel<<<(E + 127) / 128, 128, 0, stream>>>(a_param, neg8sp, E, bf ? 1 : 0,
-                                                                  emulate);
+  cg::scan_prologue_kernel<<<(E + 127) / 128, 128, 0, stream>>>(
+      a_param, neg8sp, E, bf ? 1 : 0, emulate, strict ? nullptr : ws_min.counter, ws_min.epoch);
   if (cudaError_t err = cudaGetLastError()) return (int)err;
 
   ScanParams p{};
@@ -280,6 +291,11 @@ int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset, co
   if (!aligned16(x) || !aligned16(a) || !aligned16(y) || (h0 && !aligned16(h0)) ||
       (last_h && !aligned16(last_h)) || !aligned16(workspace))
     return CG_ERR_ALIGN;
+  const Workspace ws_min = carve(workspace, B, T, E, cg::kCvl * V, kMinSuperChunk);
+  if (ws_min.total > workspace_bytes) return CG_ERR_WORKSPACE;
+  cg::scan_prologue_kernel<<<1, 32, 0, stream>>>(nullptr, nullptr, 0, 0, 0, ws_min.counter,
+                                                 ws_min.epoch);
+  if (cudaError_t err = cudaGetLastError()) return (int)err;
   return bf ? dispatch_geometry<uint16_t, 1, 0>(variant, p, workspace, workspace_bytes, stream)
             : dispatch_geometry<float, 1, 1>(variant, p, workspace, workspace_bytes, stream);
 }

@@ -73,16 +73,13 @@ __device__ __forceinline__ float sqrt_f(float x) {
   else return sqrtf(x);
 }
 // sigmoid of two values.  Exact: the ATen formula 1/(1+exp(-v)) with IEEE
-// division.  Fast: one shared reciprocal, r = 1/((1+e0)(1+e1)); arguments are
-// clamped at -43 so the product stays finite.
+// division.  Fast: ex2.approx + rcp.approx (exp overflow gives rcp(inf) = 0,
+// the correct limit, so no clamping is needed).
 template <bool FAST>
 __device__ __forceinline__ void sigmoid2(float v0, float v1, float& s0, float& s1) {
   if constexpr (FAST) {
-    float d0 = 1.0f + ex2_approx(fmaxf(v0, -43.0f) * -kLog2e);
-    float d1 = 1.0f + ex2_approx(fmaxf(v1, -43.0f) * -kLog2e);
-    float r = rcp_approx(d0 * d1);
-    s0 = r * d1;
-    s1 = r * d0;
+    s0 = rcp_approx(1.0f + ex2_approx(v0 * -kLog2e));
+    s1 = rcp_approx(1.0f + ex2_approx(v1 * -kLog2e));
   } else {
     s0 = 1.0f / (1.0f + expf(-v0));
     s1 = 1.0f / (1.0f + expf(-v1));
@@ -126,6 +123,23 @@ __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+// 64-bit exchange words {fp32 value : high 32, tag : low 32}.  An aligned
+// 8-byte access is single-copy atomic, so value and tag always travel together.
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long pack_tagged(float v, unsigned tag) {
+  return ((unsigned long long)__float_as_uint(v) << 32) | tag;
+}
+__device__ __forceinline__ float tagged_value(unsigned long long w) {
+  return __uint_as_float((unsigned)(w >> 32));
+}
+
 // cp.async (LDGSTS): 16-byte global -> shared copy that bypasses L1 and holds
 // no registers while in flight.
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -151,6 +165,14 @@ __device__ __forceinline__ void cp_async_wait_dyn(int pending) {
   }
 }
 
+// segment_pos[idx] == 0 (a document start), int32 or int64 positions
+__device__ __forceinline__ bool seg_is_zero(const void* seg, bool is_i64, long long idx) {
+  if (is_i64) {
+    const uint2 v = reinterpret_cast<const uint2*>(seg)[idx];
+    return (v.x | v.y) == 0u;
+  }
+  return reinterpret_cast<const int*>(seg)[idx] == 0;
+}
 __device__ __forceinline__ long long load_seg(const void* seg, bool is_i64, long long idx) {
   return is_i64 ? reinterpret_cast<const long long*>(seg)[idx]
                 : static_cast<long long>(reinterpret_cast<const int*>(seg)[idx]);

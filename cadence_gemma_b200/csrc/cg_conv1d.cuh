@@ -39,8 +39,10 @@ conv1d_w4_kernel(const ConvParams p) {
   constexpr bool BF = IoVec<IO>::kBf16;
   constexpr int EC = kCvl * V;
   const int cv = threadIdx.x & 7;
-  const int tslot = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
-  const int ch0 = blockIdx.y * EC + cv * V;
+  // blockIdx.x walks the channel tiles of a row first, so concurrently
+  // running blocks sweep whole rows (DRAM page locality)
+  const int tslot = blockIdx.y * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  const int ch0 = blockIdx.x * EC + cv * V;
   const int b = blockIdx.z;
   const int t0 = tslot * LC;
   if (ch0 >= p.E || t0 >= p.T) return;

@@ -3,28 +3,32 @@
 // (RGLRU.forward after the gate GEMMs) and :146-199 (rnn_scan).
 //
 // Decomposition:
-//   CTA    = NW warps = NW consecutive time chunks ("super-chunk") of one channel
-//            tile (batch row b, EC = 8*V channels = one 128-byte row).
+//   CTA    = persistent, NW warps.  Work item = NW consecutive time chunks (a
+//            "super-chunk") of one channel tile (batch row b, EC = 8*V channels
+//            = one 128-byte row), taken from an atomic ticket in time-major
+//            order (adjacent tickets = adjacent column tiles of the same rows).
 //   warp   = one chunk of TC = 4*L steps.  lane = (seg = lane / 8, cv = lane % 8):
 //            8 lanes x V channels (16-byte vectors) cover one contiguous 128-byte
 //            row, the 4 lane groups take 4 consecutive time segments of L steps
 //            => every warp-wide access moves 4 full 128 B lines.
 //   stage  : each lane copies its own L steps of x / gate pre-activations
-//            global -> shared with cp.async (LDGSTS, 16 B, L1 bypass): the
-//            bytes in flight live in shared memory, not registers.
+//            global -> shared with cp.async (LDGSTS, 16 B, L1 bypass) into one
+//            of two buffers: the next item streams in while the current one is
+//            computed, and the bytes in flight live in shared memory, not
+//            registers.
 //   pass 1 : lanes evaluate the gates in registers (sigmoid, softplus-exp,
 //            sqrt(1-a^2), every bf16 rounding point of the reference), write
-//            (x~_t, a_t) back over the staged inputs and accumulate the
-//            segment transform h -> P*h + H in fp32.
-//   carry  : warp-shuffle scan of (P,H) over the 4 segments; the CTA's chunks
-//            are combined through shared memory; super-chunks of one column
-//            are chained through global memory with a decoupled look-back
-//            (flag 1 = aggregate published, 2 = state published).  The carry is
-//            always folded left-to-right over aggregates, so results do not
-//            depend on timing (bit-reproducible run to run).
+//            (x~_t, a_t) back over the staged inputs and accumulate their
+//            segment's transform h -> P*h + H in fp32.
+//   carry  : the last warp scans the item's 4*NW segment transforms in shared
+//            memory; items of one column are chained through global memory with
+//            a decoupled look-back (flag 1 = aggregate published, 2 = state
+//            published).  Carries are always folded left-to-right over
+//            aggregates, so results do not depend on timing (bit-reproducible).
 //   pass 2 : replay h = a_t*h + x~_t from the true carry-in, store y (bf16/fp32).
-// CTAs take their work item from an atomic ticket in time-major order, so every
-// item's predecessors are already running: the look-back cannot deadlock.
+// A claimed ticket belongs to a resident CTA that works its tickets in
+// increasing order and dependencies only point to lower tickets, so the
+// look-back cannot deadlock.
 #pragma once
 
 #include "cg_common.cuh"
@@ -53,12 +57,15 @@ struct ScanParams {
   const float* h0;   // [B,E] or null
   void* y;           // [B,T,E]
   float* last_h;     // [B,E] or null
-  // scratch
-  int* counter;      // ticket
-  int* flags;        // [nitems]
-  float* agg_p;      // [nitems][EC]
-  float* agg_h;
-  float* pref;       // [nitems][EC]
+  // scratch (see cadence_b200.cu: carve()).  The three exchange arrays hold
+  // 64-bit words {fp32 value : high, launch epoch : low}; a word is valid for
+  // this launch iff its low half equals *epoch, so one relaxed 8-byte access
+  // carries data and "ready" flag together (no fence, no separate flag load).
+  int* counter;                 // ticket, reset by the prologue kernel
+  const unsigned* epoch;        // bumped by the prologue kernel
+  unsigned long long* agg_p;    // [nitems][EC] item aggregate  h -> P*h + H
+  unsigned long long* agg_h;
+  unsigned long long* pref;     // [nitems][EC] state leaving the item
   int B, T, E;
   int ncols;         // B * ceil(E / EC)
   int ctiles;        // ceil(E / EC)
@@ -141,15 +148,21 @@ struct ScanTraits {
   static constexpr int NT = KIND == 1 ? 2 : ((BF && !PACKED) ? 4 : 3);
 };
 
-template <typename IO, int KIND, int ARITH, int L, int NW>
+// STAGES staging buffers per CTA: with 2, item i+1 streams in while item i is
+// computed; with 1 the latency is covered by the other resident CTAs instead.
+template <typename IO, int KIND, int ARITH, int L, int NW, int STAGES>
 constexpr size_t scan_smem_bytes() {
   using Tr = ScanTraits<IO, KIND, ARITH>;
-  return (size_t)NW * L * Tr::NT * 512 + (size_t)(2 * NW + 1) * Tr::EC * sizeof(float) + 16;
+  return (size_t)STAGES * NW * L * Tr::NT * 512                // staged inputs / (x~, a) state
+         + (size_t)(2 * NW * kSegs + 1) * Tr::EC * sizeof(float)  // segment transforms + carry
+         + 128;                                                 // 4 claimed work items
 }
 
-// One CTA = NW warps = NW consecutive chunks (a "super-chunk" of NW*4*L steps)
-// of one 128-byte-wide channel column.
-template <typename IO, int KIND, int ARITH, int L, int NW, int MINB>
+// Persistent CTA of NW warps.  Work item = NW consecutive chunks (a super-chunk
+// of NW*4*L steps) of one 128-byte-wide channel column; items come from an
+// atomic ticket in time-major order.  Two staging buffers: the inputs of the
+// next item stream in (cp.async) while the current one is computed.
+template <typename IO, int KIND, int ARITH, int L, int NW, int STAGES, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 scan_kernel(const ScanParams p) {
   using Tr = ScanTraits<IO, KIND, ARITH>;
@@ -162,118 +175,175 @@ scan_kernel(const ScanParams p) {
   constexpr int NT = Tr::NT;
   constexpr int TC = kSegs * L;
   constexpr int NV = PACKED ? V / 2 : V;
+  constexpr int NSEG = NW * kSegs;           // time segments per item
+  constexpr int STAGE_U4 = NW * L * NT * 32; // uint4 per staging buffer
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint4* stage = reinterpret_cast<uint4*>(smem_raw);
-  float* s_agg_p = reinterpret_cast<float*>(smem_raw + (size_t)NW * L * NT * 512);
-  float* s_agg_h = s_agg_p + NW * EC;
-  float* s_c0 = s_agg_h + NW * EC;
-  int* s_item = reinterpret_cast<int*>(s_c0 + EC);
+  float* s_p = reinterpret_cast<float*>(smem_raw + (size_t)STAGES * STAGE_U4 * 16);
+  float* s_h = s_p + NSEG * EC;
+  float* s_c0 = s_h + NSEG * EC;
+  int* s_tk = reinterpret_cast<int*>(s_c0 + EC);   // 4 slots x 8 ints of claimed work items
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int seg_id = lane >> 3;
   const int cv = lane & 7;
+  const int my_seg = warp * kSegs + seg_id;  // segment index inside the item
 
-  if (threadIdx.x == 0) *s_item = atomicAdd(p.counter, 1);
-  __syncthreads();
-  const int item = *s_item;                  // grid == nitems
-  const int sc = item / p.ncols;             // time-major ticket order
-  const int col = item - sc * p.ncols;
-  const int b = col / p.ctiles;
-  const int e0 = (col - b * p.ctiles) * EC;
-  const int ch0 = e0 + cv * V;
-  const bool ch_ok = ch0 < p.E;
-  const int t_first = (sc * NW + warp) * TC + seg_id * L;
-  const size_t row0 = (size_t)b * p.T;
-  uint4* my = stage + (size_t)warp * L * NT * 32 + lane;   // slot (j,k): my[(j*NT+k)*32]
-
-  // ---- stage this lane's L steps: global -> shared, asynchronously (LDGSTS).
-  // Every lane later consumes exactly the bytes it copied itself, so no
-  // barrier is needed, only cp.async.wait_group.
-  unsigned rs_mask = 0;
+  // Work-item coordinates, decoded once per ticket by thread 0.
+  struct Coord { int item, sc, col, b, e0; };
+  auto claim = [&](int slot) {               // thread 0 only
+    const int item = atomicAdd(p.counter, 1);
+    int sc = 0, col = 0, b = 0, e0 = 0;
+    if (item < p.nitems) {
+      sc = item / p.ncols;                   // time-major ticket order
+      col = item - sc * p.ncols;
+      b = col / p.ctiles;
+      e0 = (col - b * p.ctiles) * EC;
+    }
+    int* d = s_tk + slot * 8;
+    d[0] = item; d[1] = sc; d[2] = col; d[3] = b; d[4] = e0;
+  };
+  auto fetch = [&](int slot) {
+    const int* d = s_tk + slot * 8;
+    Coord c; c.item = d[0]; c.sc = d[1]; c.col = d[2]; c.b = d[3]; c.e0 = d[4];
+    return c;
+  };
+  // number of this lane's L steps that exist (0 beyond T or E)
+  auto valid_steps = [&](const Coord& c) {
+    if (c.item >= p.nitems || c.e0 + cv * V >= p.E) return 0;
+    const int left = p.T - ((c.sc * NW + warp) * TC + seg_id * L);
+    return left < 0 ? 0 : (left > L ? L : left);
+  };
+  // global -> shared copies of this lane's own steps (LDGSTS, 16 B each).
+  // Every lane later consumes exactly the bytes it copied itself: no barrier,
+  // only cp.async.wait_group.  One commit group per item.
+  auto issue_loads = [&](const Coord& c, int buf) {
+    const int nv = valid_steps(c);
+    if (nv > 0) {
+      const int ch0 = c.e0 + cv * V;
+      const size_t row = (size_t)c.b * p.T + (c.sc * NW + warp) * TC + seg_id * L;
+      uint4* dst = stage + (size_t)buf * STAGE_U4 + (size_t)warp * L * NT * 32 + lane;
+      const IO* px = reinterpret_cast<const IO*>(p.x) + row * p.E + ch0;
+      const IO* p1 = KIND == 0 ? reinterpret_cast<const IO*>(p.gemm_x) + row * p.gate_ld + ch0
+                               : reinterpret_cast<const IO*>(p.a) + row * p.E + ch0;
+      const IO* p2 = reinterpret_cast<const IO*>(p.gemm_a) + row * p.gate_ld + ch0;
+      const size_t ld1 = KIND == 0 ? (size_t)p.gate_ld : (size_t)p.E;
+      auto one = [&](int j) {
+        cp_async16(dst + (j * NT + 0) * 32, px + (size_t)j * p.E);
+        cp_async16(dst + (j * NT + 1) * 32, p1 + (size_t)j * ld1);
+        if constexpr (KIND == 0) cp_async16(dst + (j * NT + 2) * 32, p2 + (size_t)j * ld1);
+      };
+      if (nv == L) {
 #pragma unroll
-  for (int j = 0; j < L; ++j) {
-    const int t = t_first + j;
-    if (ch_ok && t < p.T) {
-      const size_t row = row0 + t;
-      cp_async16(my + (j * NT + 0) * 32, reinterpret_cast<const IO*>(p.x) + row * p.E + ch0);
-      if constexpr (KIND == 0) {
-        cp_async16(my + (j * NT + 1) * 32, reinterpret_cast<const IO*>(p.gemm_x) + row * p.gate_ld + ch0);
-        cp_async16(my + (j * NT + 2) * 32, reinterpret_cast<const IO*>(p.gemm_a) + row * p.gate_ld + ch0);
+        for (int j = 0; j < L; ++j) one(j);
       } else {
-        cp_async16(my + (j * NT + 1) * 32, reinterpret_cast<const IO*>(p.a) + row * p.E + ch0);
+        for (int j = 0; j < nv; ++j) one(j);
       }
     }
     cp_async_commit();
-  }
-#pragma unroll
-  for (int j = 0; j < L; ++j) {
-    const int t = t_first + j;
-    if (ch_ok && t < p.T) {
-      bool rs;
-      if constexpr (KIND == 0)
-        rs = load_seg(p.seg, p.seg_is_i64 != 0, (long long)b * p.seg_bstride + t) == 0;
-      else
-        rs = p.reset[row0 + t] != 0;
-      rs_mask |= (rs ? 1u : 0u) << j;
-    }
-  }
+  };
 
-  // per-lane constants (overlaps the copies)
-  uint32_t cbx[NV], cba[NV], csp[NV];
-  if constexpr (KIND == 0) {
-    float fbx[V], fba[V], fsp[V];
+  if (threadIdx.x == 0) {
+    claim(0);
+    if constexpr (STAGES == 2) claim(1);
+  }
+  __syncthreads();
+  Coord cur = fetch(0), nxt = fetch(STAGES == 2 ? 1 : 0);
+  const unsigned epoch = *p.epoch;
+  issue_loads(cur, 0);
+  if constexpr (STAGES == 2) issue_loads(nxt, 1);
+
+  for (int it = 0; cur.item < p.nitems; ++it) {
+    const int buf = STAGES == 2 ? (it & 1) : 0;
+    // ticket of the item that will refill this buffer; slots 2,3 alternate so a
+    // slow thread still reading the previous claim is never overwritten
+    const int slot = 2 + (it & 1);
+    if (threadIdx.x == 0) claim(slot);
+
+    const int sc = cur.sc, col = cur.col, b = cur.b, e0 = cur.e0;
+    const int ch0 = e0 + cv * V;
+    const int nvalid = valid_steps(cur);
+    const int t_first = (sc * NW + warp) * TC + seg_id * L;
+    const size_t row0 = (size_t)b * p.T;
+    uint4* my = stage + (size_t)buf * STAGE_U4 + (size_t)warp * L * NT * 32 + lane;
+
+    // carry warp: request the state that enters this item (left by the
+    // column's previous item) now, so its L2 round trip overlaps pass 1
+    unsigned long long pw[CPL];
 #pragma unroll
-    for (int i = 0; i < V; ++i) { fbx[i] = 0.f; fba[i] = 0.f; fsp[i] = 0.f; }
-    if (ch_ok) {
-      if constexpr (BF) {
-        if (p.bias_x) { uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias_x) + ch0);
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    for (int i = 0; i < CPL; ++i) pw[i] = 0ull;
+    if (warp == NW - 1 && sc > 0) {
+      const size_t src = ((size_t)(sc - 1) * p.ncols + col) * EC + lane * CPL;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { fbx[2 * i] = bf_lo(w[i]); fbx[2 * i + 1] = bf_hi(w[i]); } }
-        if (p.bias_a) { uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias_a) + ch0);
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      for (int i = 0; i < CPL; ++i) pw[i] = ld_relaxed_u64(p.pref + src + i);
+    }
+
+    // reset flags of my steps
+    unsigned rs_mask = 0;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { fba[2 * i] = bf_lo(w[i]); fba[2 * i + 1] = bf_hi(w[i]); } }
+    for (int j = 0; j < L; ++j) {
+      if (j < nvalid) {
+        bool rs;
+        if constexpr (KIND == 0)
+          rs = seg_is_zero(p.seg, p.seg_is_i64 != 0, (long long)b * p.seg_bstride + t_first + j);
+        else
+          rs = p.reset[row0 + t_first + j] != 0;
+        rs_mask |= (rs ? 1u : 0u) << j;
+      }
+    }
+    // per-lane constants of this column
+    uint32_t cbx[NV], cba[NV], csp[NV];
+    if constexpr (KIND == 0) {
+      float fbx[V], fba[V], fsp[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) { fbx[i] = 0.f; fba[i] = 0.f; fsp[i] = 0.f; }
+      if (nvalid > 0) {
+        if constexpr (BF) {
+          if (p.bias_x) { uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias_x) + ch0);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { fbx[2 * i] = bf_lo(w[i]); fbx[2 * i + 1] = bf_hi(w[i]); } }
+          if (p.bias_a) { uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias_a) + ch0);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { fba[2 * i] = bf_lo(w[i]); fba[2 * i + 1] = bf_hi(w[i]); } }
+        } else {
+          if (p.bias_x) { float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias_x) + ch0);
+            fbx[0] = v.x; fbx[1] = v.y; fbx[2] = v.z; fbx[3] = v.w; }
+          if (p.bias_a) { float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias_a) + ch0);
+            fba[0] = v.x; fba[1] = v.y; fba[2] = v.z; fba[3] = v.w; }
+        }
+#pragma unroll
+        for (int i = 0; i < V; i += 4) {
+          float4 v = *reinterpret_cast<const float4*>(p.neg8sp + ch0 + i);
+          fsp[i] = v.x; fsp[i + 1] = v.y; fsp[i + 2] = v.z; fsp[i + 3] = v.w;
+        }
+      }
+      if constexpr (PACKED) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          cbx[i] = pack_bf2(fbx[2 * i], fbx[2 * i + 1]);   // exact: values are bf16
+          cba[i] = pack_bf2(fba[2 * i], fba[2 * i + 1]);
+          csp[i] = pack_bf2(fsp[2 * i], fsp[2 * i + 1]);
+        }
       } else {
-        if (p.bias_x) { float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias_x) + ch0);
-          fbx[0] = v.x; fbx[1] = v.y; fbx[2] = v.z; fbx[3] = v.w; }
-        if (p.bias_a) { float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias_a) + ch0);
-          fba[0] = v.x; fba[1] = v.y; fba[2] = v.z; fba[3] = v.w; }
-      }
 #pragma unroll
-      for (int i = 0; i < V; i += 4) {
-        float4 v = *reinterpret_cast<const float4*>(p.neg8sp + ch0 + i);
-        fsp[i] = v.x; fsp[i + 1] = v.y; fsp[i + 2] = v.z; fsp[i + 3] = v.w;
+        for (int i = 0; i < V; ++i) {
+          cbx[i] = __float_as_uint(fbx[i]); cba[i] = __float_as_uint(fba[i]);
+          csp[i] = __float_as_uint(fsp[i]);
+        }
       }
     }
-    if constexpr (PACKED) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        cbx[i] = pack_bf2(fbx[2 * i], fbx[2 * i + 1]);   // exact: values are bf16
-        cba[i] = pack_bf2(fba[2 * i], fba[2 * i + 1]);
-        csp[i] = pack_bf2(fsp[2 * i], fsp[2 * i + 1]);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        cbx[i] = __float_as_uint(fbx[i]); cba[i] = __float_as_uint(fba[i]);
-        csp[i] = __float_as_uint(fsp[i]);
-      }
-    }
-  }
 
-  // ------------------------------------------------------------ pass 1
-  float P[V], H[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) { P[i] = 1.0f; H[i] = 0.0f; }
+    cp_async_wait<STAGES - 1>();   // this item's copies have landed (the next item's may still fly)
 
+    // ---------------------------------------------------------- pass 1
+    float P[V], H[V];
 #pragma unroll
-  for (int j = 0; j < L; ++j) {
-    cp_async_wait_dyn<L>(L - 1 - j);           // copies of step j have landed
-    const int t = t_first + j;
-    if (ch_ok && t < p.T) {                    // steps beyond T / E are identities
+    for (int i = 0; i < V; ++i) { P[i] = 1.0f; H[i] = 0.0f; }
+    auto step1 = [&](int j) {
       const bool rs = (rs_mask >> j) & 1u;
       const uint4 vx = my[(j * NT + 0) * 32];
       const uint4 v1 = my[(j * NT + 1) * 32];
@@ -339,126 +409,125 @@ scan_kernel(const ScanParams p) {
                                                          __float_as_uint(fa[i + 2]), __float_as_uint(fa[i + 3]));
         }
       }
+    };
+    if (nvalid == L) {                         // interior of the sequence: no predicates
+#pragma unroll
+      for (int j = 0; j < L; ++j) step1(j);
+    } else {                                   // ragged tail: missing steps are identities
+      for (int j = 0; j < nvalid; ++j) step1(j);
     }
-  }
-
-  // ------------------------------------------------ warp scan over the 4 segments
-#pragma unroll
-  for (int d = 8; d <= 16; d <<= 1) {
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float pp = __shfl_up_sync(0xffffffffu, P[i], d);
-      const float hp = __shfl_up_sync(0xffffffffu, H[i], d);
-      if (lane >= d) { H[i] = fmaf(P[i], hp, H[i]); P[i] *= pp; }
-    }
-  }
-  float Pex[V], Hex[V];   // transform of this warp's segments before mine
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    Pex[i] = __shfl_up_sync(0xffffffffu, P[i], 8);
-    Hex[i] = __shfl_up_sync(0xffffffffu, H[i], 8);
-    if (seg_id == 0) { Pex[i] = 1.0f; Hex[i] = 0.0f; }
-  }
-  if (seg_id == kSegs - 1) {   // lanes 24..31 hold the chunk's (P,H)
+    // my segment's transform h -> P*h + H
 #pragma unroll
     for (int i = 0; i < V; i += 4) {
-      *reinterpret_cast<float4*>(s_agg_p + warp * EC + cv * V + i) = make_float4(P[i], P[i + 1], P[i + 2], P[i + 3]);
-      *reinterpret_cast<float4*>(s_agg_h + warp * EC + cv * V + i) = make_float4(H[i], H[i + 1], H[i + 2], H[i + 3]);
+      *reinterpret_cast<float4*>(s_p + my_seg * EC + cv * V + i) = make_float4(P[i], P[i + 1], P[i + 2], P[i + 3]);
+      *reinterpret_cast<float4*>(s_h + my_seg * EC + cv * V + i) = make_float4(H[i], H[i + 1], H[i + 2], H[i + 3]);
     }
-  }
-  __syncthreads();
+    __syncthreads();
 
-  // ------------------------------------------------ carry across super-chunks
-  // The last warp folds the CTA's chunks, obtains the state entering this
-  // super-chunk (decoupled look-back over the column's earlier CTAs) and
-  // publishes the state leaving it.  Lane l owns channels [l*CPL, l*CPL+CPL).
-  if (warp == NW - 1) {
-    float pt[CPL], ht[CPL], c0[CPL];
+    // ------------------------------------------------ carries (last warp)
+    // Lane l owns channels [l*CPL, l*CPL+CPL).  (1) exclusive scan of the NSEG
+    // segment transforms in shared memory; (2) state entering this item from
+    // the column's earlier items (decoupled look-back through global memory);
+    // (3) publish the state leaving it.
+    if (warp == NW - 1) {
+      float pt[CPL], ht[CPL], c0[CPL];
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) { pt[i] = 1.0f; ht[i] = 0.0f; }
+      for (int i = 0; i < CPL; ++i) { pt[i] = 1.0f; ht[i] = 0.0f; }
+      constexpr int SB = NSEG < 8 ? NSEG : 8;   // segments per batch of shared loads
+#pragma unroll 1
+      for (int s0 = 0; s0 < NSEG; s0 += SB) {
+        float ps[SB][CPL], hs[SB][CPL];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
+        for (int k = 0; k < SB; ++k)
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) {
-        const float pw = s_agg_p[w * EC + lane * CPL + i], hw = s_agg_h[w * EC + lane * CPL + i];
-        ht[i] = fmaf(pw, ht[i], hw);
-        pt[i] *= pw;
+          for (int i = 0; i < CPL; ++i) {
+            ps[k][i] = s_p[(s0 + k) * EC + lane * CPL + i];
+            hs[k][i] = s_h[(s0 + k) * EC + lane * CPL + i];
+          }
+#pragma unroll
+        for (int k = 0; k < SB; ++k)
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) {
+            const int idx = (s0 + k) * EC + lane * CPL + i;
+            s_p[idx] = pt[i]; s_h[idx] = ht[i];    // transform of everything before this segment
+            ht[i] = fmaf(ps[k][i], ht[i], hs[k][i]);
+            pt[i] *= ps[k][i];
+          }
       }
-    }
-    const size_t ws_off = (size_t)item * EC + lane * CPL;
-    if (sc == 0) {
-#pragma unroll
-      for (int i = 0; i < CPL; ++i) {
-        const int ch = e0 + lane * CPL + i;
-        c0[i] = (p.h0 != nullptr && ch < p.E) ? p.h0[(size_t)b * p.E + ch] : 0.0f;
-      }
-    } else {
-      int j = sc - 1;
-      int f = ld_acquire(p.flags + (size_t)j * p.ncols + col);
-      if (f != 2) {
-        // predecessor not final yet: publish my aggregate so successors can
-        // fold over it, then look back.
+      const size_t ws_off = (size_t)cur.item * EC + lane * CPL;
+      if (sc == 0) {
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
-          __stcg(p.agg_p + ws_off + i, pt[i]);
-          __stcg(p.agg_h + ws_off + i, ht[i]);
+          const int ch = e0 + lane * CPL + i;
+          c0[i] = (p.h0 != nullptr && ch < p.E) ? p.h0[(size_t)b * p.E + ch] : 0.0f;
         }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) st_release(p.flags + item, 1);
-        for (;;) {
-          f = ld_acquire(p.flags + (size_t)j * p.ncols + col);
-          if (f == 2) break;
-          if (f == 1) { --j; continue; }   // super-chunk 0 always ends at 2
-          __nanosleep(32);
+      } else {
+        bool ready = true;
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) ready = ready && (unsigned)pw[i] == epoch;
+        int j = sc - 1;
+        if (!__all_sync(0xffffffffu, ready)) {
+          // predecessor not final yet: publish my aggregate so successors can
+          // fold over it, then look back along the column.
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) {
+            st_relaxed_u64(p.agg_p + ws_off + i, pack_tagged(pt[i], epoch));
+            st_relaxed_u64(p.agg_h + ws_off + i, pack_tagged(ht[i], epoch));
+          }
+          for (;;) {
+            const size_t src = ((size_t)j * p.ncols + col) * EC + lane * CPL;
+            ready = true;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+              pw[i] = ld_relaxed_u64(p.pref + src + i);
+              ready = ready && (unsigned)pw[i] == epoch;
+            }
+            if (__all_sync(0xffffffffu, ready)) break;
+            bool agg = true;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+              agg = agg && (unsigned)ld_relaxed_u64(p.agg_p + src + i) == epoch &&
+                    (unsigned)ld_relaxed_u64(p.agg_h + src + i) == epoch;
+            }
+            if (__all_sync(0xffffffffu, agg)) { --j; continue; }   // item 0 of a column always publishes its state
+            __nanosleep(20);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) c0[i] = tagged_value(pw[i]);
+        for (int k = j + 1; k < sc; ++k) {   // fold the aggregates seen on the way, left to right
+          const size_t off = ((size_t)k * p.ncols + col) * EC + lane * CPL;
+#pragma unroll
+          for (int i = 0; i < CPL; ++i)
+            c0[i] = fmaf(tagged_value(ld_relaxed_u64(p.agg_p + off + i)), c0[i],
+                         tagged_value(ld_relaxed_u64(p.agg_h + off + i)));
         }
       }
-      const size_t src = ((size_t)j * p.ncols + col) * EC + lane * CPL;
-#pragma unroll
-      for (int i = 0; i < CPL; ++i) c0[i] = __ldcg(p.pref + src + i);
-      for (int k = j + 1; k < sc; ++k) {   // fold aggregates left to right
-        const size_t off = ((size_t)k * p.ncols + col) * EC + lane * CPL;
+      if (sc + 1 < p.nchunks) {   // state leaving this item: one 8-byte store per channel
 #pragma unroll
         for (int i = 0; i < CPL; ++i)
-          c0[i] = fmaf(__ldcg(p.agg_p + off + i), c0[i], __ldcg(p.agg_h + off + i));
+          st_relaxed_u64(p.pref + ws_off + i, pack_tagged(fmaf(pt[i], c0[i], ht[i]), epoch));
       }
-    }
-    if (sc + 1 < p.nchunks) {   // state leaving this super-chunk
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) __stcg(p.pref + ws_off + i, fmaf(pt[i], c0[i], ht[i]));
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) st_release(p.flags + item, 2);
+      for (int i = 0; i < CPL; ++i) s_c0[lane * CPL + i] = c0[i];
     }
-#pragma unroll
-    for (int i = 0; i < CPL; ++i) s_c0[lane * CPL + i] = c0[i];
-  }
-  __syncthreads();
+    __syncthreads();
+    const Coord nn = fetch(slot);
 
-  // carry into this warp's chunk: fold the CTA's earlier chunks, in order
-  float h[V];
-#pragma unroll
-  for (int i = 0; i < V; i += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(s_c0 + cv * V + i);
-    h[i] = v.x; h[i + 1] = v.y; h[i + 2] = v.z; h[i + 3] = v.w;
-  }
-  for (int w = 0; w < warp; ++w) {
+    // carry into my segment
+    float h[V];
 #pragma unroll
     for (int i = 0; i < V; i += 4) {
-      const float4 vp = *reinterpret_cast<const float4*>(s_agg_p + w * EC + cv * V + i);
-      const float4 vh = *reinterpret_cast<const float4*>(s_agg_h + w * EC + cv * V + i);
-      h[i] = fmaf(vp.x, h[i], vh.x); h[i + 1] = fmaf(vp.y, h[i + 1], vh.y);
-      h[i + 2] = fmaf(vp.z, h[i + 2], vh.z); h[i + 3] = fmaf(vp.w, h[i + 3], vh.w);
+      const float4 vc = *reinterpret_cast<const float4*>(s_c0 + cv * V + i);
+      const float4 vp = *reinterpret_cast<const float4*>(s_p + my_seg * EC + cv * V + i);
+      const float4 vh = *reinterpret_cast<const float4*>(s_h + my_seg * EC + cv * V + i);
+      h[i] = fmaf(vp.x, vc.x, vh.x); h[i + 1] = fmaf(vp.y, vc.y, vh.y);
+      h[i + 2] = fmaf(vp.z, vc.z, vh.z); h[i + 3] = fmaf(vp.w, vc.w, vh.w);
     }
-  }
-#pragma unroll
-  for (int i = 0; i < V; ++i) h[i] = fmaf(Pex[i], h[i], Hex[i]);   // ... and my warp's earlier segments
 
-  // ------------------------------------------------------------ pass 2 (replay)
-#pragma unroll
-  for (int j = 0; j < L; ++j) {
-    const int t = t_first + j;
-    if (ch_ok && t < p.T) {
+    // ---------------------------------------------------------- pass 2 (replay)
+    IO* yrow = reinterpret_cast<IO*>(p.y) + (row0 + t_first) * p.E + ch0;
+    auto step2 = [&](int j) {
       uint4 out;
       if constexpr (PACKED) {
         const uint4 vn = my[(j * NT + 0) * 32];
@@ -501,26 +570,40 @@ scan_kernel(const ScanParams p) {
                            __float_as_uint(h[2]), __float_as_uint(h[3]));
         }
       }
-      stg_stream(reinterpret_cast<IO*>(p.y) + (row0 + t) * p.E + ch0, out);
-    }
-  }
-  // hidden state after the last valid step (padding steps are identities)
-  if (p.last_h != nullptr && sc == p.nchunks - 1 && warp == NW - 1 && seg_id == kSegs - 1 && ch_ok) {
+      stg_stream(yrow + (size_t)j * p.E, out);
+    };
+    if (nvalid == L) {
 #pragma unroll
-    for (int i = 0; i < V; i += 4)
-      *reinterpret_cast<float4*>(p.last_h + (size_t)b * p.E + ch0 + i) =
-          make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
+      for (int j = 0; j < L; ++j) step2(j);
+    } else {
+      for (int j = 0; j < nvalid; ++j) step2(j);
+    }
+    // hidden state after the last valid step (padding steps are identities)
+    if (p.last_h != nullptr && sc == p.nchunks - 1 && my_seg == NSEG - 1 && ch0 < p.E) {
+#pragma unroll
+      for (int i = 0; i < V; i += 4)
+        *reinterpret_cast<float4*>(p.last_h + (size_t)b * p.E + ch0 + i) =
+            make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
+    }
+
+    // refill this buffer with the newly claimed item (own slots only)
+    issue_loads(nn, buf);
+    if constexpr (STAGES == 2) { cur = nxt; nxt = nn; } else { cur = nn; }
   }
+  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------
-// -8 * softplus(a_param): once per call, E threads.  Accurate libdevice math.
-// emulate != 0 (bf16 reference mode): round softplus to bf16 first (:352).
+// Per-call prologue (one small launch): resets the ticket, opens a new epoch
+// for the exchange words, and evaluates -8 * softplus(a_param) once per channel
+// with accurate libdevice math.  emulate != 0 (bf16 reference mode): softplus
+// is rounded to bf16 first (layers.py:352).  a_param == nullptr: plain scan.
 // ---------------------------------------------------------------------------
-__global__ void softplus_param_kernel(const void* a_param, float* out, int E, int is_bf16,
-                                      int emulate) {
+__global__ void scan_prologue_kernel(const void* a_param, float* out, int E, int is_bf16,
+                                     int emulate, int* counter, unsigned* epoch) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
+  if (e == 0 && counter != nullptr) { *counter = 0; *epoch = *epoch + 1u; }
+  if (a_param == nullptr || e >= E) return;
   float ap = is_bf16 ? __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(a_param)[e] << 16)
                      : reinterpret_cast<const float*>(a_param)[e];
   float sp = softplus_f(ap);

@@ -77,8 +77,10 @@ int cg_abi_version(void);
 const char* cg_status_string(int status);
 
 /* Bytes of scratch cg_rglru_fwd / cg_rnn_scan_fwd need for a [B,T,E] problem
- * (upper bound over all arithmetic modes).  The scratch needs no
- * initialisation and may be reused by later calls on the same stream. */
+ * (upper bound over all arithmetic modes and kernel geometries).  The scratch
+ * must be ZERO-FILLED ONCE before its first use (cudaMemset / torch.zeros); it
+ * is self-cleaning afterwards and may be reused by any later call, of any
+ * shape that fits, issued on the same stream. */
 size_t cg_scan_workspace_bytes(int B, int T, int E, int dtype);
 
 /*
