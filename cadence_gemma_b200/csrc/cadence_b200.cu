@@ -28,7 +28,7 @@ constexpr int kMinSuperChunk = 32;  // smallest NW * 4 * L of any compiled geome
 struct Workspace {
   int* counter; unsigned* epoch;
   unsigned long long *agg_p, *agg_h, *pref;
-  float* neg8sp;
+  float* neg8sp; uint16_t* neg8sp_bf; unsigned* reset_bits;
   size_t total;
 };
 
@@ -46,6 +46,9 @@ Workspace carve(void* base, int B, int T, int E, int EC, int SC) {
   w.agg_h = reinterpret_cast<unsigned long long*>(p + off); off += nitems * EC * 8;
   w.pref = reinterpret_cast<unsigned long long*>(p + off); off += nitems * EC * 8;
   w.neg8sp = reinterpret_cast<float*>(p + off); off += round_up((size_t)E * sizeof(float), 256);
+  w.neg8sp_bf = reinterpret_cast<uint16_t*>(p + off); off += round_up((size_t)E * sizeof(uint16_t), 256);
+  w.reset_bits = reinterpret_cast<unsigned*>(p + off);
+  off += round_up((size_t)B * ((T + 31) / 32) * sizeof(unsigned), 256);
   w.total = off;
   return w;
 }
@@ -99,15 +102,14 @@ template <typename IO, int KIND, int ARITH>
 int dispatch_geometry(int variant, const ScanParams& p, void* ws, size_t ws_bytes,
                       cudaStream_t stream) {
   switch (variant) {
-    case 0: return launch_scan<IO, KIND, ARITH, 4, 8, 2, 2>(p, ws, ws_bytes, stream);
+    case 0: return launch_scan<IO, KIND, ARITH, 8, 4, 1, 4>(p, ws, ws_bytes, stream);
     case 1: return launch_scan<IO, KIND, ARITH, 4, 8, 1, 3>(p, ws, ws_bytes, stream);
     case 2: return launch_scan<IO, KIND, ARITH, 4, 4, 1, 6>(p, ws, ws_bytes, stream);
-    case 3: return launch_scan<IO, KIND, ARITH, 4, 4, 2, 4>(p, ws, ws_bytes, stream);
-    case 4: return launch_scan<IO, KIND, ARITH, 2, 8, 2, 3>(p, ws, ws_bytes, stream);
-    case 5: return launch_scan<IO, KIND, ARITH, 8, 4, 1, 4>(p, ws, ws_bytes, stream);
-    case 6: return launch_scan<IO, KIND, ARITH, 8, 8, 1, 2>(p, ws, ws_bytes, stream);
-    case 7: return launch_scan<IO, KIND, ARITH, 4, 16, 2, 1>(p, ws, ws_bytes, stream);
-    case 8: return launch_scan<IO, KIND, ARITH, 2, 4, 1, 8>(p, ws, ws_bytes, stream);
+    case 3: return launch_scan<IO, KIND, ARITH, 8, 2, 1, 8>(p, ws, ws_bytes, stream);
+    case 4: return launch_scan<IO, KIND, ARITH, 4, 8, 2, 2>(p, ws, ws_bytes, stream);
+    case 5: return launch_scan<IO, KIND, ARITH, 8, 8, 1, 2>(p, ws, ws_bytes, stream);
+    case 6: return launch_scan<IO, KIND, ARITH, 8, 1, 1, 16>(p, ws, ws_bytes, stream);
+    case 7: return launch_scan<IO, KIND, ARITH, 4, 2, 1, 12>(p, ws, ws_bytes, stream);
     default: return CG_ERR_MODE;
   }
 }
@@ -233,15 +235,26 @@ int cg_rglru_fwd(const void* x, const void* gemm_x, const void* gemm_a, long lon
   // the (largest-geometry) scratch layout, i.e. outside every geometry's arrays
   const Workspace ws_min = carve(workspace, B, T, E, cg::kCvl * V, kMinSuperChunk);
   if (ws_min.total > workspace_bytes) return CG_ERR_WORKSPACE;
-  float* neg8sp = ws_min.neg8sp;
   const int emulate = (mode & CG_ARITH_FP32) == 0;
-  cg::scan_prologue_kernel<<<(E + 127) / 128, 128, 0, stream>>>(
-      a_param, neg8sp, E, bf ? 1 : 0, emulate, strict ? nullptr : ws_min.counter, ws_min.epoch);
-  if (cudaError_t err = cudaGetLastError()) return (int)err;
+  const int words = (T + 31) / 32;
+  {
+    cg::PrologueParams q{};
+    q.a_param = a_param; q.neg8sp = ws_min.neg8sp; q.neg8sp_bf = ws_min.neg8sp_bf;
+    q.E = E; q.is_bf16 = bf ? 1 : 0; q.emulate = emulate;
+    q.counter = strict ? nullptr : ws_min.counter; q.epoch = ws_min.epoch;
+    q.seg = seg; q.seg_is_i64 = seg_is_i64; q.seg_bstride = seg_batch_stride;
+    q.reset_bits = strict ? nullptr : ws_min.reset_bits;
+    q.rows = seg_batch_stride == 0 ? 1 : B; q.T = T; q.words_per_row = words;
+    const int n = E > q.rows * words ? E : q.rows * words;
+    cg::scan_prologue_kernel<<<(n + 127) / 128, 128, 0, stream>>>(q);
+    if (cudaError_t err = cudaGetLastError()) return (int)err;
+  }
 
   ScanParams p{};
   p.x = x; p.gemm_x = gemm_x; p.gemm_a = gemm_a; p.bias_x = bias_x; p.bias_a = bias_a;
-  p.neg8sp = neg8sp; p.seg = seg; p.seg_bstride = seg_batch_stride; p.seg_is_i64 = seg_is_i64;
+  p.neg8sp = ws_min.neg8sp; p.neg8sp_bf = ws_min.neg8sp_bf; p.seg = seg;
+  p.reset_bits = ws_min.reset_bits; p.bits_bstride = seg_batch_stride == 0 ? 0 : words;
+  p.seg_bstride = seg_batch_stride; p.seg_is_i64 = seg_is_i64;
   p.gate_ld = gate_row_stride; p.h0 = h0; p.y = y; p.last_h = last_h;
   p.B = B; p.T = T; p.E = E;
 
@@ -293,9 +306,15 @@ int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset, co
     return CG_ERR_ALIGN;
   const Workspace ws_min = carve(workspace, B, T, E, cg::kCvl * V, kMinSuperChunk);
   if (ws_min.total > workspace_bytes) return CG_ERR_WORKSPACE;
-  cg::scan_prologue_kernel<<<1, 32, 0, stream>>>(nullptr, nullptr, 0, 0, 0, ws_min.counter,
-                                                 ws_min.epoch);
-  if (cudaError_t err = cudaGetLastError()) return (int)err;
+  {
+    const int words = (T + 31) / 32;
+    cg::PrologueParams q{};
+    q.counter = ws_min.counter; q.epoch = ws_min.epoch;
+    q.reset = reset; q.reset_bits = ws_min.reset_bits; q.rows = B; q.T = T; q.words_per_row = words;
+    cg::scan_prologue_kernel<<<(B * words + 127) / 128, 128, 0, stream>>>(q);
+    if (cudaError_t err = cudaGetLastError()) return (int)err;
+    p.reset_bits = ws_min.reset_bits; p.bits_bstride = words;
+  }
   return bf ? dispatch_geometry<uint16_t, 1, 0>(variant, p, workspace, workspace_bytes, stream)
             : dispatch_geometry<float, 1, 1>(variant, p, workspace, workspace_bytes, stream);
 }

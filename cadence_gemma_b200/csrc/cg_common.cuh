@@ -73,17 +73,29 @@ __device__ __forceinline__ float sqrt_f(float x) {
   else return sqrtf(x);
 }
 // sigmoid of two values.  Exact: the ATen formula 1/(1+exp(-v)) with IEEE
-// division.  Fast: ex2.approx + rcp.approx (exp overflow gives rcp(inf) = 0,
-// the correct limit, so no clamping is needed).
+// division.  Fast: ex2.approx and ONE shared reciprocal,
+// r = 1/((1+e0)(1+e1)), s0 = r(1+e1), s1 = r(1+e0): the MUFU unit (16 lanes /
+// clk / SM) is the busiest pipe of the fused kernel, so trading a MUFU.RCP for
+// three FMULs pays.  Callers clamp the arguments at -43 (packed, one HMNMX2
+// per pair) so that (1+e0)(1+e1) <= 2^124 stays finite.
 template <bool FAST>
 __device__ __forceinline__ void sigmoid2(float v0, float v1, float& s0, float& s1) {
   if constexpr (FAST) {
-    s0 = rcp_approx(1.0f + ex2_approx(v0 * -kLog2e));
-    s1 = rcp_approx(1.0f + ex2_approx(v1 * -kLog2e));
+    const float d0 = 1.0f + ex2_approx(v0 * -kLog2e);
+    const float d1 = 1.0f + ex2_approx(v1 * -kLog2e);
+    const float r = rcp_approx(d0 * d1);
+    s0 = r * d1;
+    s1 = r * d0;
   } else {
     s0 = 1.0f / (1.0f + expf(-v0));
     s1 = 1.0f / (1.0f + expf(-v1));
   }
+}
+// max(v, -43) on a bf16x2 pair (one instruction for two values).
+__device__ __forceinline__ uint32_t bf2_clamp_lo(uint32_t v) {
+  uint32_t d;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(0xc22cc22cu));   // -43.0 | -43.0
+  return d;
 }
 // F.softplus (beta 1, threshold 20) -- parameters only, always accurate.
 __device__ __forceinline__ float softplus_f(float v) {

@@ -46,6 +46,9 @@ struct ScanParams {
   const void* bias_x;   // [E] or null
   const void* bias_a;
   const float* neg8sp;  // [E] fp32: -8*softplus(a_param) (rounded per mode)
+  const uint16_t* neg8sp_bf;   // [E] the same as bf16 (exact in reference mode)
+  const unsigned* reset_bits;  // [rows][ceil(T/32)] bit t%32 of word t/32 = reset at t
+  long long bits_bstride;      // words per batch row (0 = one row broadcast)
   const void* seg;      // segment positions
   long long seg_bstride;
   int seg_is_i64;
@@ -87,8 +90,9 @@ __device__ __forceinline__ void gate_pair_emul(uint32_t xc, uint32_t gxr, uint32
   const uint32_t pa = bf2_add(gar, ba);
   float sx0, sx1, sa0, sa1;
   if constexpr (FAST) {                          // pair each x gate with an a gate
-    sigmoid2<true>(bf_lo(px), bf_lo(pa), sx0, sa0);
-    sigmoid2<true>(bf_hi(px), bf_hi(pa), sx1, sa1);
+    const uint32_t cx = bf2_clamp_lo(px), ca = bf2_clamp_lo(pa);
+    sigmoid2<true>(bf_lo(cx), bf_lo(ca), sx0, sa0);
+    sigmoid2<true>(bf_hi(cx), bf_hi(ca), sx1, sa1);
   } else {
     sigmoid2<false>(bf_lo(px), bf_hi(px), sx0, sx1);
     sigmoid2<false>(bf_lo(pa), bf_hi(pa), sa0, sa1);
@@ -118,7 +122,8 @@ __device__ __forceinline__ void gate_pair_emul(uint32_t xc, uint32_t gxr, uint32
 template <bool FAST>
 __device__ __forceinline__ void gate_f32(float xc, float gxr, float gar, float bx, float ba,
                                          float sp8, bool reset, float& a_out, float& nx_out) {
-  const float px = gxr + bx, pa = gar + ba;
+  float px = gxr + bx, pa = gar + ba;
+  if constexpr (FAST) { px = fmaxf(px, -43.0f); pa = fmaxf(pa, -43.0f); }
   float gx, ga;
   sigmoid2<FAST>(px, pa, gx, ga);
   const float la = ga * sp8;
@@ -146,6 +151,9 @@ struct ScanTraits {
   // 16-byte staging slots per (step, lane): inputs x, g1, g2 (or x, a); the
   // (x~, a) state overwrites them in place (fp32 state of 8 channels needs 4)
   static constexpr int NT = KIND == 1 ? 2 : ((BF && !PACKED) ? 4 : 3);
+  // With 3 slots the third one (gemm_a) is dead after pass 1: the segment
+  // transforms live there instead of in a separate shared array.
+  static constexpr bool ALIAS = NT == 3;
 };
 
 // STAGES staging buffers per CTA: with 2, item i+1 streams in while item i is
@@ -154,7 +162,7 @@ template <typename IO, int KIND, int ARITH, int L, int NW, int STAGES>
 constexpr size_t scan_smem_bytes() {
   using Tr = ScanTraits<IO, KIND, ARITH>;
   return (size_t)STAGES * NW * L * Tr::NT * 512                // staged inputs / (x~, a) state
-         + (size_t)(2 * NW * kSegs + 1) * Tr::EC * sizeof(float)  // segment transforms + carry
+         + (size_t)((Tr::ALIAS ? 0 : 2 * NW * kSegs) + 1) * Tr::EC * sizeof(float)  // segment transforms + carry
          + 128;                                                 // 4 claimed work items
 }
 
@@ -180,9 +188,11 @@ scan_kernel(const ScanParams p) {
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint4* stage = reinterpret_cast<uint4*>(smem_raw);
+  constexpr bool ALIAS = Tr::ALIAS;
+  static_assert(!ALIAS || L >= V / 2, "aliased segment transforms need V/2 steps");
   float* s_p = reinterpret_cast<float*>(smem_raw + (size_t)STAGES * STAGE_U4 * 16);
-  float* s_h = s_p + NSEG * EC;
-  float* s_c0 = s_h + NSEG * EC;
+  float* s_h = s_p + (ALIAS ? 0 : NSEG * EC);
+  float* s_c0 = s_h + (ALIAS ? 0 : NSEG * EC);
   int* s_tk = reinterpret_cast<int*>(s_c0 + EC);   // 4 slots x 8 ints of claimed work items
 
   const int warp = threadIdx.x >> 5;
@@ -235,14 +245,59 @@ scan_kernel(const ScanParams p) {
         cp_async16(dst + (j * NT + 1) * 32, p1 + (size_t)j * ld1);
         if constexpr (KIND == 0) cp_async16(dst + (j * NT + 2) * 32, p2 + (size_t)j * ld1);
       };
-      if (nv == L) {
-#pragma unroll
-        for (int j = 0; j < L; ++j) one(j);
-      } else {
-        for (int j = 0; j < nv; ++j) one(j);
-      }
+#pragma unroll 2
+      for (int j = 0; j < nv; ++j) one(j);
     }
     cp_async_commit();
+  };
+
+  // Per-item metadata of this lane: the L reset flags of its steps (consecutive
+  // bits of the prologue's bitmask; bits at and beyond T are zero and L divides
+  // 32, so they never straddle a word) and the per-channel constants.  Loaded
+  // as soon as an item is known, one iteration before it is computed, so the
+  // L2 latency is off the critical path.
+  unsigned meta_rs = 0;
+  uint32_t meta_bx[NV], meta_ba[NV], meta_sp[NV];
+  auto load_meta = [&](const Coord& c) {
+    meta_rs = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { meta_bx[i] = 0u; meta_ba[i] = 0u; meta_sp[i] = 0u; }
+    if (valid_steps(c) == 0) return;
+    const int ch0 = c.e0 + cv * V;
+    const int t_first = (c.sc * NW + warp) * TC + seg_id * L;
+    meta_rs = (p.reset_bits[(long long)c.b * p.bits_bstride + (t_first >> 5)] >> (t_first & 31)) &
+              ((1u << L) - 1u);
+    if constexpr (KIND == 0) {
+      if constexpr (PACKED) {   // bf16 parameters are already packed pairs
+        if (p.bias_x) { const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias_x) + ch0);
+          meta_bx[0] = v.x; meta_bx[1] = v.y; meta_bx[2] = v.z; meta_bx[3] = v.w; }
+        if (p.bias_a) { const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias_a) + ch0);
+          meta_ba[0] = v.x; meta_ba[1] = v.y; meta_ba[2] = v.z; meta_ba[3] = v.w; }
+        const uint4 v = *reinterpret_cast<const uint4*>(p.neg8sp_bf + ch0);
+        meta_sp[0] = v.x; meta_sp[1] = v.y; meta_sp[2] = v.z; meta_sp[3] = v.w;
+      } else {
+        if constexpr (BF) {
+          if (p.bias_x) { const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias_x) + ch0);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { meta_bx[2 * i] = w[i] << 16; meta_bx[2 * i + 1] = w[i] & 0xffff0000u; } }
+          if (p.bias_a) { const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias_a) + ch0);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { meta_ba[2 * i] = w[i] << 16; meta_ba[2 * i + 1] = w[i] & 0xffff0000u; } }
+        } else {
+          if (p.bias_x) { const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.bias_x) + ch0);
+            meta_bx[0] = v.x; meta_bx[1] = v.y; meta_bx[2] = v.z; meta_bx[3] = v.w; }
+          if (p.bias_a) { const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.bias_a) + ch0);
+            meta_ba[0] = v.x; meta_ba[1] = v.y; meta_ba[2] = v.z; meta_ba[3] = v.w; }
+        }
+#pragma unroll
+        for (int i = 0; i < V; i += 4) {
+          const uint4 v = *reinterpret_cast<const uint4*>(p.neg8sp + ch0 + i);
+          meta_sp[i] = v.x; meta_sp[i + 1] = v.y; meta_sp[i + 2] = v.z; meta_sp[i + 3] = v.w;
+        }
+      }
+    }
   };
 
   if (threadIdx.x == 0) {
@@ -254,6 +309,7 @@ scan_kernel(const ScanParams p) {
   const unsigned epoch = *p.epoch;
   issue_loads(cur, 0);
   if constexpr (STAGES == 2) issue_loads(nxt, 1);
+  load_meta(cur);
 
   for (int it = 0; cur.item < p.nitems; ++it) {
     const int buf = STAGES == 2 ? (it & 1) : 0;
@@ -268,6 +324,19 @@ scan_kernel(const ScanParams p) {
     const int t_first = (sc * NW + warp) * TC + seg_id * L;
     const size_t row0 = (size_t)b * p.T;
     uint4* my = stage + (size_t)buf * STAGE_U4 + (size_t)warp * L * NT * 32 + lane;
+    // where the transform (kind 0: P, 1: H) of segment `sgm`, channel `ch` of the
+    // tile lives: in the dead third staging slot of the lane that owns it, or
+    // in the separate array.  Four consecutive channels are contiguous.
+    uint4* const stage_buf = stage + (size_t)buf * STAGE_U4;
+    auto xf = [&](int kind, int sgm, int ch) -> float* {
+      if constexpr (ALIAS) {
+        const int w = sgm / kSegs, sg = sgm % kSegs;
+        const int j = kind * (V / 4) + (ch % V) / 4;
+        return reinterpret_cast<float*>(stage_buf + ((w * L + j) * NT + 2) * 32 + sg * 8 + ch / V) + (ch & 3);
+      } else {
+        return (kind ? s_h : s_p) + sgm * EC + ch;
+      }
+    };
 
     // carry warp: request the state that enters this item (left by the
     // column's previous item) now, so its L2 round trip overlaps pass 1
@@ -280,62 +349,12 @@ scan_kernel(const ScanParams p) {
       for (int i = 0; i < CPL; ++i) pw[i] = ld_relaxed_u64(p.pref + src + i);
     }
 
-    // reset flags of my steps
-    unsigned rs_mask = 0;
-#pragma unroll
-    for (int j = 0; j < L; ++j) {
-      if (j < nvalid) {
-        bool rs;
-        if constexpr (KIND == 0)
-          rs = seg_is_zero(p.seg, p.seg_is_i64 != 0, (long long)b * p.seg_bstride + t_first + j);
-        else
-          rs = p.reset[row0 + t_first + j] != 0;
-        rs_mask |= (rs ? 1u : 0u) << j;
-      }
-    }
-    // per-lane constants of this column
+    // per-item metadata (reset bits, per-channel constants) was requested one
+    // iteration ahead, see load_meta() below
+    const unsigned rs_mask = meta_rs;
     uint32_t cbx[NV], cba[NV], csp[NV];
-    if constexpr (KIND == 0) {
-      float fbx[V], fba[V], fsp[V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) { fbx[i] = 0.f; fba[i] = 0.f; fsp[i] = 0.f; }
-      if (nvalid > 0) {
-        if constexpr (BF) {
-          if (p.bias_x) { uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias_x) + ch0);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { fbx[2 * i] = bf_lo(w[i]); fbx[2 * i + 1] = bf_hi(w[i]); } }
-          if (p.bias_a) { uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.bias_a) + ch0);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { fba[2 * i] = bf_lo(w[i]); fba[2 * i + 1] = bf_hi(w[i]); } }
-        } else {
-          if (p.bias_x) { float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias_x) + ch0);
-            fbx[0] = v.x; fbx[1] = v.y; fbx[2] = v.z; fbx[3] = v.w; }
-          if (p.bias_a) { float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias_a) + ch0);
-            fba[0] = v.x; fba[1] = v.y; fba[2] = v.z; fba[3] = v.w; }
-        }
-#pragma unroll
-        for (int i = 0; i < V; i += 4) {
-          float4 v = *reinterpret_cast<const float4*>(p.neg8sp + ch0 + i);
-          fsp[i] = v.x; fsp[i + 1] = v.y; fsp[i + 2] = v.z; fsp[i + 3] = v.w;
-        }
-      }
-      if constexpr (PACKED) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-          cbx[i] = pack_bf2(fbx[2 * i], fbx[2 * i + 1]);   // exact: values are bf16
-          cba[i] = pack_bf2(fba[2 * i], fba[2 * i + 1]);
-          csp[i] = pack_bf2(fsp[2 * i], fsp[2 * i + 1]);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          cbx[i] = __float_as_uint(fbx[i]); cba[i] = __float_as_uint(fba[i]);
-          csp[i] = __float_as_uint(fsp[i]);
-        }
-      }
-    }
+    for (int i = 0; i < NV; ++i) { cbx[i] = meta_bx[i]; cba[i] = meta_ba[i]; csp[i] = meta_sp[i]; }
 
     cp_async_wait<STAGES - 1>();   // this item's copies have landed (the next item's may still fly)
 
@@ -410,17 +429,16 @@ scan_kernel(const ScanParams p) {
         }
       }
     };
-    if (nvalid == L) {                         // interior of the sequence: no predicates
-#pragma unroll
-      for (int j = 0; j < L; ++j) step1(j);
-    } else {                                   // ragged tail: missing steps are identities
-      for (int j = 0; j < nvalid; ++j) step1(j);
-    }
+    // steps beyond T / E are identities: simply not executed.  Not unrolled:
+    // one step already carries 4 independent bf16x2 chains per lane, and a
+    // fully unrolled body overflows the instruction cache.
+#pragma unroll 1
+    for (int j = 0; j < nvalid; ++j) step1(j);
     // my segment's transform h -> P*h + H
 #pragma unroll
     for (int i = 0; i < V; i += 4) {
-      *reinterpret_cast<float4*>(s_p + my_seg * EC + cv * V + i) = make_float4(P[i], P[i + 1], P[i + 2], P[i + 3]);
-      *reinterpret_cast<float4*>(s_h + my_seg * EC + cv * V + i) = make_float4(H[i], H[i + 1], H[i + 2], H[i + 3]);
+      *reinterpret_cast<float4*>(xf(0, my_seg, cv * V + i)) = make_float4(P[i], P[i + 1], P[i + 2], P[i + 3]);
+      *reinterpret_cast<float4*>(xf(1, my_seg, cv * V + i)) = make_float4(H[i], H[i + 1], H[i + 2], H[i + 3]);
     }
     __syncthreads();
 
@@ -441,15 +459,15 @@ scan_kernel(const ScanParams p) {
         for (int k = 0; k < SB; ++k)
 #pragma unroll
           for (int i = 0; i < CPL; ++i) {
-            ps[k][i] = s_p[(s0 + k) * EC + lane * CPL + i];
-            hs[k][i] = s_h[(s0 + k) * EC + lane * CPL + i];
+            ps[k][i] = *xf(0, s0 + k, lane * CPL + i);
+            hs[k][i] = *xf(1, s0 + k, lane * CPL + i);
           }
 #pragma unroll
         for (int k = 0; k < SB; ++k)
 #pragma unroll
           for (int i = 0; i < CPL; ++i) {
-            const int idx = (s0 + k) * EC + lane * CPL + i;
-            s_p[idx] = pt[i]; s_h[idx] = ht[i];    // transform of everything before this segment
+            *xf(0, s0 + k, lane * CPL + i) = pt[i];   // transform of everything before this segment
+            *xf(1, s0 + k, lane * CPL + i) = ht[i];
             ht[i] = fmaf(ps[k][i], ht[i], hs[k][i]);
             pt[i] *= ps[k][i];
           }
@@ -513,14 +531,15 @@ scan_kernel(const ScanParams p) {
     }
     __syncthreads();
     const Coord nn = fetch(slot);
+    load_meta(STAGES == 2 ? nxt : nn);   // metadata of the item computed next
 
     // carry into my segment
     float h[V];
 #pragma unroll
     for (int i = 0; i < V; i += 4) {
       const float4 vc = *reinterpret_cast<const float4*>(s_c0 + cv * V + i);
-      const float4 vp = *reinterpret_cast<const float4*>(s_p + my_seg * EC + cv * V + i);
-      const float4 vh = *reinterpret_cast<const float4*>(s_h + my_seg * EC + cv * V + i);
+      const float4 vp = *reinterpret_cast<const float4*>(xf(0, my_seg, cv * V + i));
+      const float4 vh = *reinterpret_cast<const float4*>(xf(1, my_seg, cv * V + i));
       h[i] = fmaf(vp.x, vc.x, vh.x); h[i + 1] = fmaf(vp.y, vc.y, vh.y);
       h[i + 2] = fmaf(vp.z, vc.z, vh.z); h[i + 3] = fmaf(vp.w, vc.w, vh.w);
     }
@@ -572,12 +591,8 @@ scan_kernel(const ScanParams p) {
       }
       stg_stream(yrow + (size_t)j * p.E, out);
     };
-    if (nvalid == L) {
-#pragma unroll
-      for (int j = 0; j < L; ++j) step2(j);
-    } else {
-      for (int j = 0; j < nvalid; ++j) step2(j);
-    }
+#pragma unroll 2
+    for (int j = 0; j < nvalid; ++j) step2(j);
     // hidden state after the last valid step (padding steps are identities)
     if (p.last_h != nullptr && sc == p.nchunks - 1 && my_seg == NSEG - 1 && ch0 < p.E) {
 #pragma unroll
@@ -594,21 +609,49 @@ scan_kernel(const ScanParams p) {
 }
 
 // ---------------------------------------------------------------------------
-// Per-call prologue (one small launch): resets the ticket, opens a new epoch
-// for the exchange words, and evaluates -8 * softplus(a_param) once per channel
-// with accurate libdevice math.  emulate != 0 (bf16 reference mode): softplus
-// is rounded to bf16 first (layers.py:352).  a_param == nullptr: plain scan.
+// Per-call prologue (one small launch):
+//   * resets the ticket and opens a new epoch for the exchange words;
+//   * evaluates -8 * softplus(a_param) once per channel with accurate libdevice
+//     math, as fp32 and as bf16.  emulate != 0 (bf16 reference mode): softplus
+//     is rounded to bf16 first (layers.py:352), so the bf16 copy is exact;
+//   * turns `segment_pos == 0` (layers.py:345) or the rnn_scan reset mask into
+//     a bitmask, one 32-bit word per 32 time steps.
 // ---------------------------------------------------------------------------
-__global__ void scan_prologue_kernel(const void* a_param, float* out, int E, int is_bf16,
-                                     int emulate, int* counter, unsigned* epoch) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e == 0 && counter != nullptr) { *counter = 0; *epoch = *epoch + 1u; }
-  if (a_param == nullptr || e >= E) return;
-  float ap = is_bf16 ? __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(a_param)[e] << 16)
-                     : reinterpret_cast<const float*>(a_param)[e];
-  float sp = softplus_f(ap);
-  if (is_bf16 && emulate) sp = round_bf(sp);
-  out[e] = -8.0f * sp;
+struct PrologueParams {
+  const void* a_param;        // [E] or null (plain scan)
+  float* neg8sp; uint16_t* neg8sp_bf;
+  int E, is_bf16, emulate;
+  int* counter; unsigned* epoch;   // null for the strict kernels
+  const void* seg; int seg_is_i64; long long seg_bstride;   // RG-LRU
+  const unsigned char* reset;                               // plain scan
+  unsigned* reset_bits; int rows, T, words_per_row;
+};
+
+__global__ void scan_prologue_kernel(const PrologueParams q) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && q.counter != nullptr) { *q.counter = 0; *q.epoch = *q.epoch + 1u; }
+  if (q.a_param != nullptr && i < q.E) {
+    float ap = q.is_bf16 ? __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(q.a_param)[i] << 16)
+                         : reinterpret_cast<const float*>(q.a_param)[i];
+    float sp = softplus_f(ap);
+    if (q.is_bf16 && q.emulate) sp = round_bf(sp);
+    const float v = -8.0f * sp;
+    q.neg8sp[i] = v;
+    q.neg8sp_bf[i] = (uint16_t)(pack_bf2(v, v) & 0xffffu);
+  }
+  if (q.reset_bits != nullptr && i < q.rows * q.words_per_row) {
+    const int r = i / q.words_per_row, w = i - r * q.words_per_row;
+    unsigned bits = 0;
+    for (int k = 0; k < 32; ++k) {
+      const int t = w * 32 + k;
+      if (t >= q.T) break;
+      bool rs;
+      if (q.seg != nullptr) rs = seg_is_zero(q.seg, q.seg_is_i64 != 0, (long long)r * q.seg_bstride + t);
+      else rs = q.reset[(size_t)r * q.T + t] != 0;
+      bits |= (rs ? 1u : 0u) << k;
+    }
+    q.reset_bits[i] = bits;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -655,7 +698,8 @@ __global__ void strict_scan_kernel(const ScanParams p) {
       const float g2 = load_io<IO>(p.gemm_a, row * p.gate_ld + e);
       if constexpr (EMUL) {
         // scalar spelling of gate_pair_emul: round after every eager op
-        const float px = round_bf(g1 + bx), pa = round_bf(g2 + ba);
+        float px = round_bf(g1 + bx), pa = round_bf(g2 + ba);
+        if constexpr (FAST) { px = fmaxf(px, -43.0f); pa = fmaxf(pa, -43.0f); }
         float gx, ga;
         sigmoid2<FAST>(px, pa, gx, ga);
         gx = round_bf(gx); ga = round_bf(ga);
