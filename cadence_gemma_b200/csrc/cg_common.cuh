@@ -158,6 +158,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(gmem_src) : "memory");
 }
+// Prefetch the 128-byte line containing `gmem_src` into L2 (per-thread address;
+// the bulk form needs warp-uniform operands and would serialise over lanes).
+__device__ __forceinline__ void prefetch_l2_line(const void* gmem_src) {
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() {
   asm volatile("cp.async.commit_group;" ::: "memory");
 }

@@ -161,9 +161,10 @@ struct ScanTraits {
 template <typename IO, int KIND, int ARITH, int L, int NW, int STAGES>
 constexpr size_t scan_smem_bytes() {
   using Tr = ScanTraits<IO, KIND, ARITH>;
-  return (size_t)STAGES * NW * L * Tr::NT * 512                // staged inputs / (x~, a) state
-         + (size_t)((Tr::ALIAS ? 0 : 2 * NW * kSegs) + 1) * Tr::EC * sizeof(float)  // segment transforms + carry
-         + 128;                                                 // 4 claimed work items
+  return (size_t)STAGES * NW * L * Tr::NT * 512                 // staged inputs / (x~, a) state
+         + (Tr::ALIAS ? 0 : (size_t)2 * NW * kSegs * Tr::EC * sizeof(float))   // segment transforms
+         + (size_t)2 * (2 * NW + 1) * Tr::EC * sizeof(float)    // warp transforms + carry, 2 parities
+         + 128 + 16;                                            // 4 claimed work items, flags
 }
 
 // Persistent CTA of NW warps.  Work item = NW consecutive chunks (a super-chunk
@@ -192,8 +193,11 @@ scan_kernel(const ScanParams p) {
   static_assert(!ALIAS || L >= V / 2, "aliased segment transforms need V/2 steps");
   float* s_p = reinterpret_cast<float*>(smem_raw + (size_t)STAGES * STAGE_U4 * 16);
   float* s_h = s_p + (ALIAS ? 0 : NSEG * EC);
-  float* s_c0 = s_h + (ALIAS ? 0 : NSEG * EC);
-  int* s_tk = reinterpret_cast<int*>(s_c0 + EC);   // 4 slots x 8 ints of claimed work items
+  float* s_wp = s_h + (ALIAS ? 0 : NSEG * EC);    // [2][NW][EC] warp transforms (P)
+  float* s_wh = s_wp + 2 * NW * EC;               // [2][NW][EC] warp transforms (H)
+  float* s_c0 = s_wh + 2 * NW * EC;               // [2][EC] state entering the item
+  int* s_tk = reinterpret_cast<int*>(s_c0 + 2 * EC);   // 4 slots x 8 ints of claimed work items
+  int* s_flag = s_tk + 32;                        // [2] carry-in known before the barrier?
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -249,6 +253,22 @@ scan_kernel(const ScanParams p) {
       for (int j = 0; j < nv; ++j) one(j);
     }
     cp_async_commit();
+  };
+
+  // L2 prefetch of an item's input rows (one 128-byte row per lane and tensor),
+  // issued as soon as the item is known: the later cp.async then hit L2.
+  auto prefetch_l2 = [&](const Coord& c) {
+    if (c.item >= p.nitems || lane >= TC) return;
+    const int t = (c.sc * NW + warp) * TC + lane;
+    if (t >= p.T) return;
+    const size_t row = (size_t)c.b * p.T + t;
+    prefetch_l2_line(reinterpret_cast<const IO*>(p.x) + row * p.E + c.e0);
+    if constexpr (KIND == 0) {
+      prefetch_l2_line(reinterpret_cast<const IO*>(p.gemm_x) + row * p.gate_ld + c.e0);
+      prefetch_l2_line(reinterpret_cast<const IO*>(p.gemm_a) + row * p.gate_ld + c.e0);
+    } else {
+      prefetch_l2_line(reinterpret_cast<const IO*>(p.a) + row * p.E + c.e0);
+    }
   };
 
   // Per-item metadata of this lane: the L reset flags of its steps (consecutive
@@ -338,12 +358,13 @@ scan_kernel(const ScanParams p) {
       }
     };
 
-    // carry warp: request the state that enters this item (left by the
-    // column's previous item) now, so its L2 round trip overlaps pass 1
+    // warp 0 requests the state that enters this item (left by the column's
+    // previous item) now, so its L2 round trip overlaps pass 1
+    const int par = it & 1;
     unsigned long long pw[CPL];
 #pragma unroll
     for (int i = 0; i < CPL; ++i) pw[i] = 0ull;
-    if (warp == NW - 1 && sc > 0) {
+    if (warp == 0 && sc > 0) {
       const size_t src = ((size_t)(sc - 1) * p.ncols + col) * EC + lane * CPL;
 #pragma unroll
       for (int i = 0; i < CPL; ++i) pw[i] = ld_relaxed_u64(p.pref + src + i);
@@ -434,45 +455,47 @@ scan_kernel(const ScanParams p) {
     // fully unrolled body overflows the instruction cache.
 #pragma unroll 1
     for (int j = 0; j < nvalid; ++j) step1(j);
-    // my segment's transform h -> P*h + H
+    // ---- carries inside the warp: my segment's transform h -> P*h + H goes to
+    // shared memory; each lane composes the transforms of its warp's earlier
+    // segments (<= 3), the last lane group also the warp's total.
 #pragma unroll
     for (int i = 0; i < V; i += 4) {
       *reinterpret_cast<float4*>(xf(0, my_seg, cv * V + i)) = make_float4(P[i], P[i + 1], P[i + 2], P[i + 3]);
       *reinterpret_cast<float4*>(xf(1, my_seg, cv * V + i)) = make_float4(H[i], H[i + 1], H[i + 2], H[i + 3]);
     }
-    __syncthreads();
-
-    // ------------------------------------------------ carries (last warp)
-    // Lane l owns channels [l*CPL, l*CPL+CPL).  (1) exclusive scan of the NSEG
-    // segment transforms in shared memory; (2) state entering this item from
-    // the column's earlier items (decoupled look-back through global memory);
-    // (3) publish the state leaving it.
-    if (warp == NW - 1) {
-      float pt[CPL], ht[CPL], c0[CPL];
+    __syncwarp();
+    float Pex[V], Hex[V];
 #pragma unroll
-      for (int i = 0; i < CPL; ++i) { pt[i] = 1.0f; ht[i] = 0.0f; }
-      constexpr int SB = NSEG < 8 ? NSEG : 8;   // segments per batch of shared loads
-#pragma unroll 1
-      for (int s0 = 0; s0 < NSEG; s0 += SB) {
-        float ps[SB][CPL], hs[SB][CPL];
+    for (int i = 0; i < V; ++i) { Pex[i] = 1.0f; Hex[i] = 0.0f; }
+    for (int sg = 0; sg < seg_id; ++sg) {
 #pragma unroll
-        for (int k = 0; k < SB; ++k)
-#pragma unroll
-          for (int i = 0; i < CPL; ++i) {
-            ps[k][i] = *xf(0, s0 + k, lane * CPL + i);
-            hs[k][i] = *xf(1, s0 + k, lane * CPL + i);
-          }
-#pragma unroll
-        for (int k = 0; k < SB; ++k)
-#pragma unroll
-          for (int i = 0; i < CPL; ++i) {
-            *xf(0, s0 + k, lane * CPL + i) = pt[i];   // transform of everything before this segment
-            *xf(1, s0 + k, lane * CPL + i) = ht[i];
-            ht[i] = fmaf(ps[k][i], ht[i], hs[k][i]);
-            pt[i] *= ps[k][i];
-          }
+      for (int i = 0; i < V; i += 4) {
+        const float4 vp = *reinterpret_cast<const float4*>(xf(0, warp * kSegs + sg, cv * V + i));
+        const float4 vh = *reinterpret_cast<const float4*>(xf(1, warp * kSegs + sg, cv * V + i));
+        Hex[i] = fmaf(vp.x, Hex[i], vh.x); Hex[i + 1] = fmaf(vp.y, Hex[i + 1], vh.y);
+        Hex[i + 2] = fmaf(vp.z, Hex[i + 2], vh.z); Hex[i + 3] = fmaf(vp.w, Hex[i + 3], vh.w);
+        Pex[i] *= vp.x; Pex[i + 1] *= vp.y; Pex[i + 2] *= vp.z; Pex[i + 3] *= vp.w;
       }
-      const size_t ws_off = (size_t)cur.item * EC + lane * CPL;
+    }
+    float* wp = s_wp + (par * NW) * EC;
+    float* wh = s_wh + (par * NW) * EC;
+    float* c0s = s_c0 + par * EC;
+    if (seg_id == kSegs - 1) {   // transform of the whole warp (chunk)
+#pragma unroll
+      for (int i = 0; i < V; i += 4) {
+        *reinterpret_cast<float4*>(wp + warp * EC + cv * V + i) =
+            make_float4(P[i] * Pex[i], P[i + 1] * Pex[i + 1], P[i + 2] * Pex[i + 2], P[i + 3] * Pex[i + 3]);
+        *reinterpret_cast<float4*>(wh + warp * EC + cv * V + i) =
+            make_float4(fmaf(P[i], Hex[i], H[i]), fmaf(P[i + 1], Hex[i + 1], H[i + 1]),
+                        fmaf(P[i + 2], Hex[i + 2], H[i + 2]), fmaf(P[i + 3], Hex[i + 3], H[i + 3]));
+      }
+    }
+    // ---- state entering the item.  Lane l of warp 0 owns channels
+    // [l*CPL, l*CPL+CPL).  Usually the predecessor published long ago and the
+    // prefetched words are valid: no second barrier is needed then.
+    if (warp == 0) {
+      bool ready = true;
+      float c0[CPL];
       if (sc == 0) {
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
@@ -480,36 +503,60 @@ scan_kernel(const ScanParams p) {
           c0[i] = (p.h0 != nullptr && ch < p.E) ? p.h0[(size_t)b * p.E + ch] : 0.0f;
         }
       } else {
-        bool ready = true;
 #pragma unroll
-        for (int i = 0; i < CPL; ++i) ready = ready && (unsigned)pw[i] == epoch;
-        int j = sc - 1;
-        if (!__all_sync(0xffffffffu, ready)) {
-          // predecessor not final yet: publish my aggregate so successors can
-          // fold over it, then look back along the column.
+        for (int i = 0; i < CPL; ++i) {
+          ready = ready && (unsigned)pw[i] == epoch;
+          c0[i] = tagged_value(pw[i]);
+        }
+        ready = __all_sync(0xffffffffu, ready);
+      }
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) c0s[lane * CPL + i] = c0[i];
+      if (lane == 0) s_flag[par] = ready ? 1 : 0;
+    }
+    __syncthreads();
+    const Coord nn = fetch(slot);
+    prefetch_l2(nn);
+    load_meta(STAGES == 2 ? nxt : nn);   // metadata of the item computed next
+
+    if (s_flag[par] == 0) {   // CTA-uniform slow path: decoupled look-back
+      if (warp == 0) {
+        float pt[CPL], ht[CPL], c0[CPL];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) { pt[i] = 1.0f; ht[i] = 0.0f; }
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
 #pragma unroll
           for (int i = 0; i < CPL; ++i) {
-            st_relaxed_u64(p.agg_p + ws_off + i, pack_tagged(pt[i], epoch));
-            st_relaxed_u64(p.agg_h + ws_off + i, pack_tagged(ht[i], epoch));
+            const float pv = wp[w * EC + lane * CPL + i], hv = wh[w * EC + lane * CPL + i];
+            ht[i] = fmaf(pv, ht[i], hv);
+            pt[i] *= pv;
           }
-          for (;;) {
-            const size_t src = ((size_t)j * p.ncols + col) * EC + lane * CPL;
-            ready = true;
+        // publish my aggregate so successors can fold over it, then look back
+        const size_t ws_off = (size_t)cur.item * EC + lane * CPL;
 #pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-              pw[i] = ld_relaxed_u64(p.pref + src + i);
-              ready = ready && (unsigned)pw[i] == epoch;
-            }
-            if (__all_sync(0xffffffffu, ready)) break;
-            bool agg = true;
+        for (int i = 0; i < CPL; ++i) {
+          st_relaxed_u64(p.agg_p + ws_off + i, pack_tagged(pt[i], epoch));
+          st_relaxed_u64(p.agg_h + ws_off + i, pack_tagged(ht[i], epoch));
+        }
+        int j = sc - 1;
+        for (;;) {
+          const size_t src = ((size_t)j * p.ncols + col) * EC + lane * CPL;
+          bool ready = true;
 #pragma unroll
-            for (int i = 0; i < CPL; ++i) {
-              agg = agg && (unsigned)ld_relaxed_u64(p.agg_p + src + i) == epoch &&
-                    (unsigned)ld_relaxed_u64(p.agg_h + src + i) == epoch;
-            }
-            if (__all_sync(0xffffffffu, agg)) { --j; continue; }   // item 0 of a column always publishes its state
-            __nanosleep(20);
+          for (int i = 0; i < CPL; ++i) {
+            pw[i] = ld_relaxed_u64(p.pref + src + i);
+            ready = ready && (unsigned)pw[i] == epoch;
           }
+          if (__all_sync(0xffffffffu, ready)) break;
+          bool agg = true;
+#pragma unroll
+          for (int i = 0; i < CPL; ++i) {
+            agg = agg && (unsigned)ld_relaxed_u64(p.agg_p + src + i) == epoch &&
+                  (unsigned)ld_relaxed_u64(p.agg_h + src + i) == epoch;
+          }
+          if (__all_sync(0xffffffffu, agg)) { --j; continue; }   // item 0 of a column always publishes its state
+          __nanosleep(20);
         }
 #pragma unroll
         for (int i = 0; i < CPL; ++i) c0[i] = tagged_value(pw[i]);
@@ -520,29 +567,49 @@ scan_kernel(const ScanParams p) {
             c0[i] = fmaf(tagged_value(ld_relaxed_u64(p.agg_p + off + i)), c0[i],
                          tagged_value(ld_relaxed_u64(p.agg_h + off + i)));
         }
-      }
-      if (sc + 1 < p.nchunks) {   // state leaving this item: one 8-byte store per channel
 #pragma unroll
-        for (int i = 0; i < CPL; ++i)
-          st_relaxed_u64(p.pref + ws_off + i, pack_tagged(fmaf(pt[i], c0[i], ht[i]), epoch));
+        for (int i = 0; i < CPL; ++i) c0s[lane * CPL + i] = c0[i];
       }
-#pragma unroll
-      for (int i = 0; i < CPL; ++i) s_c0[lane * CPL + i] = c0[i];
+      __syncthreads();
     }
-    __syncthreads();
-    const Coord nn = fetch(slot);
-    load_meta(STAGES == 2 ? nxt : nn);   // metadata of the item computed next
 
-    // carry into my segment
+    // ---- the last warp publishes the state leaving the item: the item's
+    // aggregate (warp transforms composed in order) applied to the carry-in --
+    // the same expression the look-back uses, so values never depend on timing.
+    if (warp == NW - 1 && sc + 1 < p.nchunks) {
+      const size_t ws_off = (size_t)cur.item * EC + lane * CPL;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        float pt = 1.0f, ht = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const float pv = wp[w * EC + lane * CPL + i], hv = wh[w * EC + lane * CPL + i];
+          ht = fmaf(pv, ht, hv);
+          pt *= pv;
+        }
+        st_relaxed_u64(p.pref + ws_off + i, pack_tagged(fmaf(pt, c0s[lane * CPL + i], ht), epoch));
+      }
+    }
+
+    // ---- carry into my segment: fold the item's earlier chunks, then my
+    // warp's earlier segments
     float h[V];
 #pragma unroll
     for (int i = 0; i < V; i += 4) {
-      const float4 vc = *reinterpret_cast<const float4*>(s_c0 + cv * V + i);
-      const float4 vp = *reinterpret_cast<const float4*>(xf(0, my_seg, cv * V + i));
-      const float4 vh = *reinterpret_cast<const float4*>(xf(1, my_seg, cv * V + i));
-      h[i] = fmaf(vp.x, vc.x, vh.x); h[i + 1] = fmaf(vp.y, vc.y, vh.y);
-      h[i + 2] = fmaf(vp.z, vc.z, vh.z); h[i + 3] = fmaf(vp.w, vc.w, vh.w);
+      const float4 vc = *reinterpret_cast<const float4*>(c0s + cv * V + i);
+      h[i] = vc.x; h[i + 1] = vc.y; h[i + 2] = vc.z; h[i + 3] = vc.w;
     }
+    for (int w = 0; w < warp; ++w) {
+#pragma unroll
+      for (int i = 0; i < V; i += 4) {
+        const float4 vp = *reinterpret_cast<const float4*>(wp + w * EC + cv * V + i);
+        const float4 vh = *reinterpret_cast<const float4*>(wh + w * EC + cv * V + i);
+        h[i] = fmaf(vp.x, h[i], vh.x); h[i + 1] = fmaf(vp.y, h[i + 1], vh.y);
+        h[i + 2] = fmaf(vp.z, h[i + 2], vh.z); h[i + 3] = fmaf(vp.w, h[i + 3], vh.w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) h[i] = fmaf(Pex[i], h[i], Hex[i]);
 
     // ---------------------------------------------------------- pass 2 (replay)
     IO* yrow = reinterpret_cast<IO*>(p.y) + (row0 + t_first) * p.E + ch0;
