@@ -20,7 +20,7 @@ using cg::ScanParams;
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-constexpr int kMinSuperChunk = 32;  // smallest NW * 4 * L of any compiled geometry
+constexpr int kMinSuperChunk = 64;  // smallest NW * 4 * L of any compiled geometry
 
 // scratch layout: [ticket, epoch | 256 B][agg_p][agg_h][pref][neg8sp]
 // The exchange arrays hold 64-bit {value, epoch} words; the scratch must be
@@ -102,14 +102,12 @@ template <typename IO, int KIND, int ARITH>
 int dispatch_geometry(int variant, const ScanParams& p, void* ws, size_t ws_bytes,
                       cudaStream_t stream) {
   switch (variant) {
-    case 0: return launch_scan<IO, KIND, ARITH, 8, 4, 1, 4>(p, ws, ws_bytes, stream);
+    case 0: return launch_scan<IO, KIND, ARITH, 8, 4, 1, 4>(p, ws, ws_bytes, stream);   // default
     case 1: return launch_scan<IO, KIND, ARITH, 4, 8, 1, 3>(p, ws, ws_bytes, stream);
     case 2: return launch_scan<IO, KIND, ARITH, 4, 4, 1, 6>(p, ws, ws_bytes, stream);
     case 3: return launch_scan<IO, KIND, ARITH, 8, 2, 1, 8>(p, ws, ws_bytes, stream);
     case 4: return launch_scan<IO, KIND, ARITH, 4, 8, 2, 2>(p, ws, ws_bytes, stream);
     case 5: return launch_scan<IO, KIND, ARITH, 8, 8, 1, 2>(p, ws, ws_bytes, stream);
-    case 6: return launch_scan<IO, KIND, ARITH, 8, 1, 1, 16>(p, ws, ws_bytes, stream);
-    case 7: return launch_scan<IO, KIND, ARITH, 4, 2, 1, 12>(p, ws, ws_bytes, stream);
     default: return CG_ERR_MODE;
   }
 }

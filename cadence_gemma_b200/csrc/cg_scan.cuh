@@ -35,6 +35,8 @@
 
 namespace cg {
 
+constexpr int kP1Unroll = 2;   // pass-1 steps interleaved per lane (ILP vs instruction-cache footprint)
+
 constexpr int kSegs = 4;   // time segments per warp (lane / 8)
 constexpr int kCvl = 8;    // lanes across channels (lane % 8)
 
@@ -76,16 +78,19 @@ struct ScanParams {
   int nitems;
 };
 
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
+
 template <typename IO> struct IoVec;
 template <> struct IoVec<uint16_t> { static constexpr int V = 8; static constexpr bool kBf16 = true; };
 template <> struct IoVec<float> { static constexpr int V = 4; static constexpr bool kBf16 = false; };
 
 // ---- RG-LRU gates on one bf16x2 pair, every eager rounding point reproduced.
 // layers.py:348-365 + :173; see SURVEY.md section 7 "bf16 rounding points".
-template <bool FAST>
+template <bool FAST, bool RESET>
 __device__ __forceinline__ void gate_pair_emul(uint32_t xc, uint32_t gxr, uint32_t gar,
                                                uint32_t bx, uint32_t ba, uint32_t sp8,
-                                               bool reset, uint32_t& a_out, uint32_t& nx_out) {
+                                               uint32_t& a_out, uint32_t& nx_out) {
   const uint32_t px = bf2_add(gxr, bx);          // r(gemm + b)            :139
   const uint32_t pa = bf2_add(gar, ba);
   float sx0, sx1, sa0, sa1;
@@ -98,6 +103,12 @@ __device__ __forceinline__ void gate_pair_emul(uint32_t xc, uint32_t gxr, uint32
     sigmoid2<false>(bf_lo(pa), bf_hi(pa), sa0, sa1);
   }
   const uint32_t gx = pack_bf2(sx0, sx1);        // r(sigmoid)             :348
+  if constexpr (RESET) {
+    // a document start: a = 0 (:173), multiplier = 1 (:364): x~ = r(x*gx)
+    nx_out = bf2_mul(xc, gx);
+    a_out = 0u;
+    return;
+  }
   const uint32_t ga = pack_bf2(sa0, sa1);        //                        :349
   const uint32_t la = bf2_mul(ga, sp8);          // r(r(-8 ga) * sp)       :352
   const float l0 = bf_lo(la), l1 = bf_hi(la);
@@ -109,32 +120,34 @@ __device__ __forceinline__ void gate_pair_emul(uint32_t xc, uint32_t gxr, uint32
     e0 = expf(l0); e1 = expf(l1);                //                        :353
     q0 = expf(2.0f * l0); q1 = expf(2.0f * l1);  // 2*log_a is exact       :354
   }
-  uint32_t av = pack_bf2(e0, e1);
+  const uint32_t av = pack_bf2(e0, e1);
   const uint32_t om = bf2_sub(kOne2, pack_bf2(q0, q1));   // r(1 - a^2)    :361
-  uint32_t mu = pack_bf2(sqrt_f<FAST>(bf_lo(om)), sqrt_f<FAST>(bf_hi(om)));
-  if (reset) { mu = kOne2; av = 0u; }            //                  :364, :173
+  const uint32_t mu = pack_bf2(sqrt_f<FAST>(bf_lo(om)), sqrt_f<FAST>(bf_hi(om)));
   nx_out = bf2_mul(bf2_mul(xc, gx), mu);         // r(r(x*gx)*mu)    :357, :365
   a_out = av;
 }
 
 // ---- same, fp32 kept in registers (bf16 or fp32 inputs already widened).
 // For fp32 tensors this IS the reference op order (each op rounds to fp32).
-template <bool FAST>
+template <bool FAST, bool RESET>
 __device__ __forceinline__ void gate_f32(float xc, float gxr, float gar, float bx, float ba,
-                                         float sp8, bool reset, float& a_out, float& nx_out) {
+                                         float sp8, float& a_out, float& nx_out) {
   float px = gxr + bx, pa = gar + ba;
   if constexpr (FAST) { px = fmaxf(px, -43.0f); pa = fmaxf(pa, -43.0f); }
   float gx, ga;
   sigmoid2<FAST>(px, pa, gx, ga);
+  if constexpr (RESET) {   // a document start: a = 0 (:173), multiplier = 1 (:364)
+    nx_out = __fmul_rn(xc, gx);
+    a_out = 0.0f;
+    return;
+  }
   const float la = ga * sp8;
   const float e = exp_f<FAST>(la);
   float q;
   if constexpr (FAST) q = e * e; else q = expf(2.0f * la);
-  float mu = sqrt_f<FAST>(1.0f - q);
-  float av = e;
-  if (reset) { mu = 1.0f; av = 0.0f; }
+  const float mu = sqrt_f<FAST>(1.0f - q);
   nx_out = __fmul_rn(__fmul_rn(xc, gx), mu);
-  a_out = av;
+  a_out = e;
 }
 
 // KIND: 0 = RG-LRU (gates fused), 1 = plain rnn_scan(x, a, reset, h0).
@@ -244,13 +257,13 @@ scan_kernel(const ScanParams p) {
                                : reinterpret_cast<const IO*>(p.a) + row * p.E + ch0;
       const IO* p2 = reinterpret_cast<const IO*>(p.gemm_a) + row * p.gate_ld + ch0;
       const size_t ld1 = KIND == 0 ? (size_t)p.gate_ld : (size_t)p.E;
-      auto one = [&](int j) {
-        cp_async16(dst + (j * NT + 0) * 32, px + (size_t)j * p.E);
-        cp_async16(dst + (j * NT + 1) * 32, p1 + (size_t)j * ld1);
-        if constexpr (KIND == 0) cp_async16(dst + (j * NT + 2) * 32, p2 + (size_t)j * ld1);
-      };
 #pragma unroll 2
-      for (int j = 0; j < nv; ++j) one(j);
+      for (int j = 0; j < nv; ++j) {
+        cp_async16(dst, px);
+        cp_async16(dst + 32, p1);
+        if constexpr (KIND == 0) cp_async16(dst + 64, p2);
+        dst += NT * 32; px += p.E; p1 += ld1; p2 += ld1;
+      }
     }
     cp_async_commit();
   };
@@ -383,8 +396,8 @@ scan_kernel(const ScanParams p) {
     float P[V], H[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) { P[i] = 1.0f; H[i] = 0.0f; }
-    auto step1 = [&](int j) {
-      const bool rs = (rs_mask >> j) & 1u;
+    auto step1 = [&](int j, auto reset_tag) {
+      constexpr bool RS = decltype(reset_tag)::value;
       const uint4 vx = my[(j * NT + 0) * 32];
       const uint4 v1 = my[(j * NT + 1) * 32];
       uint4 v2 = make_uint4(0, 0, 0, 0);
@@ -398,9 +411,9 @@ scan_kernel(const ScanParams p) {
         for (int i = 0; i < NV; ++i) {
           uint32_t av, nx;
           if constexpr (KIND == 0) {
-            gate_pair_emul<FAST>(wx[i], w1[i], w2[i], cbx[i], cba[i], csp[i], rs, av, nx);
+            gate_pair_emul<FAST, RS>(wx[i], w1[i], w2[i], cbx[i], cba[i], csp[i], av, nx);
           } else {
-            av = rs ? 0u : w1[i];   // a * ~reset (:173)
+            av = RS ? 0u : w1[i];   // a * ~reset (:173)
             nx = wx[i];
           }
           sa[i] = av; sx[i] = nx;
@@ -431,10 +444,10 @@ scan_kernel(const ScanParams p) {
         for (int i = 0; i < V; ++i) {
           float av, nx;
           if constexpr (KIND == 0) {
-            gate_f32<FAST>(fx[i], f1[i], f2[i], __uint_as_float(cbx[i]), __uint_as_float(cba[i]),
-                           __uint_as_float(csp[i]), rs, av, nx);
+            gate_f32<FAST, RS>(fx[i], f1[i], f2[i], __uint_as_float(cbx[i]), __uint_as_float(cba[i]),
+                               __uint_as_float(csp[i]), av, nx);
           } else {
-            av = rs ? 0.0f : f1[i];
+            av = RS ? 0.0f : f1[i];
             nx = fx[i];
           }
           fa[i] = av; fn[i] = nx;
@@ -453,8 +466,16 @@ scan_kernel(const ScanParams p) {
     // steps beyond T / E are identities: simply not executed.  Not unrolled:
     // one step already carries 4 independent bf16x2 chains per lane, and a
     // fully unrolled body overflows the instruction cache.
+    if (rs_mask == 0u && nvalid == L) {          // common case: no document start, full segment
+#pragma unroll (kP1Unroll)
+      for (int j = 0; j < L; ++j) step1(j, FalseTag{});
+    } else {
 #pragma unroll 1
-    for (int j = 0; j < nvalid; ++j) step1(j);
+      for (int j = 0; j < nvalid; ++j) {
+        if ((rs_mask >> j) & 1u) step1(j, TrueTag{});   // document start (rare): own code path
+        else step1(j, FalseTag{});
+      }
+    }
     // ---- carries inside the warp: my segment's transform h -> P*h + H goes to
     // shared memory; each lane composes the transforms of its warp's earlier
     // segments (<= 3), the last lane group also the warp's total.
@@ -779,7 +800,8 @@ __global__ void strict_scan_kernel(const ScanParams p) {
         if (rs) { mu = 1.0f; av = 0.0f; }
         nx = round_bf(round_bf(xv * gx) * mu);
       } else {
-        gate_f32<FAST>(xv, g1, g2, bx, ba, sp8, rs, av, nx);
+        if (rs) gate_f32<FAST, true>(xv, g1, g2, bx, ba, sp8, av, nx);
+        else gate_f32<FAST, false>(xv, g1, g2, bx, ba, sp8, av, nx);
       }
     } else {
       av = p.reset[row] ? 0.0f : load_io<IO>(p.a, row * p.E + e);

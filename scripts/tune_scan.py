@@ -49,7 +49,7 @@ def main():
   ap.add_argument("--T", type=int, default=2048)
   ap.add_argument("--E", type=int, default=2560)
   ap.add_argument("--iters", type=int, default=20)
-  ap.add_argument("--variants", default="0,1,2,3,4,5,6,7")
+  ap.add_argument("--variants", default="0,1,2,3,4,5")
   args = ap.parse_args()
   dev = "cuda:0"
   B, T, E = args.B, args.T, args.E
