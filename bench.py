@@ -244,20 +244,29 @@ def own_arm(args, dtype):
   gather_out = (torch.empty(state_numel * world, dtype=torch.float32, device=dev)
                 if world > 1 else None)
 
-  k2_events = []
+  k_events = {"conv1d": [], "gate_gemm": [], "rglru": []}
+
+  def ev():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
 
   def step(x, seg, record=False):
-    xc, conv_state = conv(x, seg)
-    if record:
-      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      gx = lru.input_gate.gemm(xc)
-      ga = lru.a_gate.gemm(xc)
-      e0.record()
-      y, last_h = _abi.rglru_fwd(xc, gx, ga, lru.input_gate.b, lru.a_gate.b, lru.a_param,
-                                 seg, arith_mode=cg.get_arith_mode())
-      e1.record()
-      k2_events.append((e0, e1))
+    if record:   # same calls as the module API makes, with events between the kernels
+      e0 = ev()
+      xc, conv_state = conv(x, seg)
+      e1 = ev()
+      gates = lru.gate_gemm(xc)
+      e2 = ev()
+      y, last_h = _abi.rglru_fwd(xc, None, None, lru.input_gate.b, lru.a_gate.b, lru.a_param,
+                                 seg, arith_mode=cg.get_arith_mode(), gemm_fused=gates,
+                                 block_width=w["width"] // w["heads"])
+      e3 = ev()
+      k_events["conv1d"].append((e0, e1))
+      k_events["gate_gemm"].append((e1, e2))
+      k_events["rglru"].append((e2, e3))
     else:
+      xc, conv_state = conv(x, seg)
       y, last_h = lru(xc, seg)
     if world > 1:
       gather_in[: last_h.numel()].copy_(last_h.view(-1))
@@ -294,7 +303,7 @@ def own_arm(args, dtype):
     launches = _abi.launch_count - launches0
     clocks = sampler.stop()
     ms_total = t_start.elapsed_time(t_end)
-    k2_us = [a.elapsed_time(b) * 1e3 for a, b in k2_events]
+    k_us = {k: statistics.mean(a.elapsed_time(b) * 1e3 for a, b in v) for k, v in k_events.items()}
 
     # ---------------- end to end: pinned host buffers in, results out ------------
     x_pin = host["x_lin"].pin_memory()
@@ -330,10 +339,11 @@ def own_arm(args, dtype):
     e2e_ms = e_start.elapsed_time(e_end)
 
   # max over ranks (device time)
-  t = torch.tensor([ms_total, e2e_ms, statistics.mean(k2_us)], dtype=torch.float64, device=dev)
+  t = torch.tensor([ms_total, e2e_ms, k_us["rglru"], k_us["conv1d"], k_us["gate_gemm"]],
+                   dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  ms_total, e2e_ms, k2_mean_us = t.tolist()
+  ms_total, e2e_ms, k2_mean_us, conv_us, gemm_us = t.tolist()
 
   if rank == 0:
     peak, peak_src = measured_peak_gbs()
@@ -352,12 +362,20 @@ def own_arm(args, dtype):
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "cg::scan_kernel (RG-LRU gates + scan; "
-                     "events bracket the C-ABI call incl. its 1-block softplus prologue)",
+        "roofline": {"bound": "hbm", "kernel": "cg::scan_kernel (RG-LRU gates + scan; events bracket the "
+                     "cg_rglru_fwd call incl. its small prologue launch)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": k2_bytes,
                      "us_per_launch": k2_mean_us, "traffic": None},
+        "kernels_us": {"conv1d": conv_us, "gate_gemm_cublas_fused": gemm_us, "rglru": k2_mean_us},
+        "roofline_conv1d": {"bound": "hbm", "achieved": 2 * esize * nelem / (conv_us * 1e-6) / 1e9,
+                            "peak": peak, "unit": "GB/s",
+                            "frac": 2 * esize * nelem / (conv_us * 1e-6) / 1e9 / peak},
+        "roofline_conv1d_plus_rglru": {
+            "bound": "hbm", "achieved": 6 * esize * nelem / ((conv_us + k2_mean_us) * 1e-6) / 1e9,
+            "peak": peak, "unit": "GB/s",
+            "frac": 6 * esize * nelem / ((conv_us + k2_mean_us) * 1e-6) / 1e9 / peak},
         "arith_mode": cg.get_arith_mode(),
     }
     if world == 1 and not args.no_cpu_baseline:

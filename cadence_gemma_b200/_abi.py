@@ -29,7 +29,7 @@ SYMBOLS = {
                            _i, _i, _i, _vp]),
     "cg_conv1d_decode": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i,
                               _i, _vp]),
-    "cg_rglru_fwd": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _ll, _vp,
+    "cg_rglru_fwd": (_i, [_vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _vp, _i, _ll, _vp,
                           _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "cg_rnn_scan_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i,
                              _i, _i, _vp]),
@@ -173,28 +173,44 @@ def conv1d_decode(x, w, b, cache, return_cache=True, arith_mode=ARITH_REFERENCE)
 
 
 def rglru_fwd(x, gemm_x, gemm_a, bias_x, bias_a, a_param, segment_pos, h0=None,
-              return_cache=True, arith_mode=ARITH_REFERENCE, out=None):
-  """Gate math + scan.  gemm_x / gemm_a may be row-strided views ([..., E] with
-  a common row stride, unit inner stride)."""
+              return_cache=True, arith_mode=ARITH_REFERENCE, out=None,
+              gemm_fused=None, block_width=0):
+  """Gate math + scan.
+
+  Either ``gemm_x`` / ``gemm_a`` ([B,T,E], possibly row-strided views with unit
+  inner stride), or ``gemm_fused``: the [B*T, H, 2*bw] output of ONE fused
+  block-diagonal GEMM (per head: input-gate columns, then a-gate columns) with
+  ``block_width = bw``.
+  """
   global launch_count
-  _require_cuda(x, gemm_x, gemm_a, a_param, segment_pos, h0)
+  _require_cuda(x, gemm_x, gemm_a, gemm_fused, a_param, segment_pos, h0)
   bsz, steps, width = x.shape
   x = x.contiguous()
-  assert gemm_x.shape == x.shape and gemm_a.shape == x.shape
-  assert gemm_x.dtype == x.dtype and gemm_a.dtype == x.dtype
   assert a_param.dtype == x.dtype, "a_param must have the activation dtype"
   assert h0 is None or h0.dtype == torch.float32, "layers.py:170"
+  if gemm_fused is not None:
+    assert block_width > 0 and width % block_width == 0
+    assert gemm_fused.is_contiguous() and gemm_fused.dtype == x.dtype
+    assert gemm_fused.numel() == 2 * x.numel()
+    px, pa = gemm_fused.data_ptr(), gemm_fused.data_ptr() + block_width * x.element_size()
+    ldx, gbw = 2 * width, block_width
+    keep = (gemm_fused,)
+  else:
+    assert gemm_x.shape == x.shape and gemm_a.shape == x.shape
+    assert gemm_x.dtype == x.dtype and gemm_a.dtype == x.dtype
 
-  def rows(t):
-    if t.stride(2) == 1 and t.stride(0) == steps * t.stride(1):
-      return t, t.stride(1)
-    t = t.contiguous()
-    return t, width
+    def rows(t):
+      if t.stride(2) == 1 and t.stride(0) == steps * t.stride(1):
+        return t, t.stride(1)
+      t = t.contiguous()
+      return t, width
 
-  gemm_x, ldx = rows(gemm_x)
-  gemm_a, lda = rows(gemm_a)
-  if ldx != lda:
-    gemm_x, gemm_a, ldx = gemm_x.contiguous(), gemm_a.contiguous(), width
+    gemm_x, ldx = rows(gemm_x)
+    gemm_a, lda = rows(gemm_a)
+    if ldx != lda:
+      gemm_x, gemm_a, ldx = gemm_x.contiguous(), gemm_a.contiguous(), width
+    px, pa, gbw = gemm_x.data_ptr(), gemm_a.data_ptr(), 0
+    keep = (gemm_x, gemm_a)
   seg, is64, stride = _seg_args(segment_pos, bsz, steps)
   y = torch.empty_like(x) if out is None else out
   last_h = (torch.empty((bsz, width), dtype=torch.float32, device=x.device)
@@ -204,11 +220,12 @@ def rglru_fwd(x, gemm_x, gemm_a, bias_x, bias_a, a_param, segment_pos, h0=None,
   ba = None if bias_a is None else bias_a.contiguous().view(-1)
   h0c = None if h0 is None else h0.contiguous()
   with torch.cuda.device(x.device):
-    rc = load().cg_rglru_fwd(x.data_ptr(), gemm_x.data_ptr(), gemm_a.data_ptr(),
-                             ldx, _ptr(bx), _ptr(ba), a_param.contiguous().data_ptr(),
-                             seg.data_ptr(), is64, stride, _ptr(h0c), y.data_ptr(),
-                             _ptr(last_h), ws.data_ptr(), ws.numel(), bsz, steps,
-                             width, dtype_code(x.dtype), arith_mode, _stream(x))
+    rc = load().cg_rglru_fwd(x.data_ptr(), px, pa, ldx, gbw, _ptr(bx), _ptr(ba),
+                             a_param.contiguous().data_ptr(), seg.data_ptr(), is64,
+                             stride, _ptr(h0c), y.data_ptr(), _ptr(last_h),
+                             ws.data_ptr(), ws.numel(), bsz, steps, width,
+                             dtype_code(x.dtype), arith_mode, _stream(x))
+  del keep
   _check(rc, "cg_rglru_fwd")
   launch_count += 2   # prologue (ticket/epoch/softplus) + scan kernel
   return y, last_h

@@ -207,7 +207,7 @@ int cg_conv1d_decode(const void* x, const void* w, const void* b, const void* ca
 }
 
 int cg_rglru_fwd(const void* x, const void* gemm_x, const void* gemm_a, long long gate_row_stride,
-                 const void* bias_x, const void* bias_a, const void* a_param, const void* seg,
+                 int gate_block_width, const void* bias_x, const void* bias_a, const void* a_param, const void* seg,
                  int seg_is_i64, long long seg_batch_stride, const float* h0, void* y,
                  float* last_h, void* workspace, size_t workspace_bytes, int B, int T, int E,
                  int dtype, int arith_mode, cg_stream_t stream_) {
@@ -221,9 +221,10 @@ int cg_rglru_fwd(const void* x, const void* gemm_x, const void* gemm_a, long lon
   const int mode = arith_mode & 7;
   const bool strict = (mode & CG_ARITH_STRICT) != 0;
   if ((arith_mode & ~0xff07) != 0) return CG_ERR_MODE;
-  if (gate_row_stride < E) return CG_ERR_SHAPE;
+  if (gate_row_stride < E || gate_block_width < 0) return CG_ERR_SHAPE;
+  if (gate_block_width > 0 && (E % gate_block_width != 0 || gate_row_stride < 2LL * E)) return CG_ERR_SHAPE;
   if (!strict) {
-    if (E % V != 0 || gate_row_stride % V != 0) return CG_ERR_ALIGN;
+    if (E % V != 0 || gate_row_stride % V != 0 || gate_block_width % V != 0) return CG_ERR_ALIGN;
     if (!aligned16(x) || !aligned16(gemm_x) || !aligned16(gemm_a) || !aligned16(y) ||
         (bias_x && !aligned16(bias_x)) || (bias_a && !aligned16(bias_a)) ||
         (h0 && !aligned16(h0)) || (last_h && !aligned16(last_h)) || !aligned16(workspace))
@@ -253,7 +254,7 @@ int cg_rglru_fwd(const void* x, const void* gemm_x, const void* gemm_a, long lon
   p.neg8sp = ws_min.neg8sp; p.neg8sp_bf = ws_min.neg8sp_bf; p.seg = seg;
   p.reset_bits = ws_min.reset_bits; p.bits_bstride = seg_batch_stride == 0 ? 0 : words;
   p.seg_bstride = seg_batch_stride; p.seg_is_i64 = seg_is_i64;
-  p.gate_ld = gate_row_stride; p.h0 = h0; p.y = y; p.last_h = last_h;
+  p.gate_ld = gate_row_stride; p.gate_bw = gate_block_width; p.h0 = h0; p.y = y; p.last_h = last_h;
   p.B = B; p.T = T; p.E = E;
 
   if (strict) {

@@ -55,6 +55,7 @@ struct ScanParams {
   long long seg_bstride;
   int seg_is_i64;
   long long gate_ld;
+  int gate_bw;          // > 0: gate GEMM outputs are interleaved per head, see gate_off()
   // plain scan inputs (KIND 1): x above, plus
   const void* a;                 // [B,T,E]
   const unsigned char* reset;    // [B,T]
@@ -80,6 +81,13 @@ struct ScanParams {
 
 struct TrueTag { static constexpr bool value = true; };
 struct FalseTag { static constexpr bool value = false; };
+
+// Column of channel `ch` inside a gate-GEMM output row.  gate_bw == 0: plain
+// [.., E] rows.  gate_bw == bw > 0: one fused GEMM wrote [.., H, 2*bw] rows
+// (input-gate block then a-gate block per head); gemm_a points bw further.
+__device__ __forceinline__ int gate_off(int ch, int gate_bw) {
+  return gate_bw > 0 ? ch + (ch / gate_bw) * gate_bw : ch;
+}
 
 template <typename IO> struct IoVec;
 template <> struct IoVec<uint16_t> { static constexpr int V = 8; static constexpr bool kBf16 = true; };
@@ -253,9 +261,10 @@ scan_kernel(const ScanParams p) {
       const size_t row = (size_t)c.b * p.T + (c.sc * NW + warp) * TC + seg_id * L;
       uint4* dst = stage + (size_t)buf * STAGE_U4 + (size_t)warp * L * NT * 32 + lane;
       const IO* px = reinterpret_cast<const IO*>(p.x) + row * p.E + ch0;
-      const IO* p1 = KIND == 0 ? reinterpret_cast<const IO*>(p.gemm_x) + row * p.gate_ld + ch0
+      const int g0 = KIND == 0 ? gate_off(ch0, p.gate_bw) : ch0;
+      const IO* p1 = KIND == 0 ? reinterpret_cast<const IO*>(p.gemm_x) + row * p.gate_ld + g0
                                : reinterpret_cast<const IO*>(p.a) + row * p.E + ch0;
-      const IO* p2 = reinterpret_cast<const IO*>(p.gemm_a) + row * p.gate_ld + ch0;
+      const IO* p2 = reinterpret_cast<const IO*>(p.gemm_a) + row * p.gate_ld + g0;
       const size_t ld1 = KIND == 0 ? (size_t)p.gate_ld : (size_t)p.E;
 #pragma unroll 2
       for (int j = 0; j < nv; ++j) {
@@ -277,8 +286,9 @@ scan_kernel(const ScanParams p) {
     const size_t row = (size_t)c.b * p.T + t;
     prefetch_l2_line(reinterpret_cast<const IO*>(p.x) + row * p.E + c.e0);
     if constexpr (KIND == 0) {
-      prefetch_l2_line(reinterpret_cast<const IO*>(p.gemm_x) + row * p.gate_ld + c.e0);
-      prefetch_l2_line(reinterpret_cast<const IO*>(p.gemm_a) + row * p.gate_ld + c.e0);
+      const int g0 = gate_off(c.e0, p.gate_bw);
+      prefetch_l2_line(reinterpret_cast<const IO*>(p.gemm_x) + row * p.gate_ld + g0);
+      prefetch_l2_line(reinterpret_cast<const IO*>(p.gemm_a) + row * p.gate_ld + g0);
     } else {
       prefetch_l2_line(reinterpret_cast<const IO*>(p.a) + row * p.E + c.e0);
     }
@@ -782,8 +792,8 @@ __global__ void strict_scan_kernel(const ScanParams p) {
     float av, nx;
     if constexpr (KIND == 0) {
       const bool rs = load_seg(p.seg, p.seg_is_i64 != 0, (long long)b * p.seg_bstride + t) == 0;
-      const float g1 = load_io<IO>(p.gemm_x, row * p.gate_ld + e);
-      const float g2 = load_io<IO>(p.gemm_a, row * p.gate_ld + e);
+      const float g1 = load_io<IO>(p.gemm_x, row * p.gate_ld + gate_off(e, p.gate_bw));
+      const float g2 = load_io<IO>(p.gemm_a, row * p.gate_ld + gate_off(e, p.gate_bw));
       if constexpr (EMUL) {
         // scalar spelling of gate_pair_emul: round after every eager op
         float px = round_bf(g1 + bx), pa = round_bf(g2 + ba);

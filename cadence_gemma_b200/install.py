@@ -14,6 +14,8 @@ sm_100a kernels with its own parameters.  ``uninstall`` restores the originals.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from cadence_gemma_b200 import _abi, layers as cg_layers
@@ -21,12 +23,22 @@ from cadence_gemma_b200 import _abi, layers as cg_layers
 _saved = {}
 
 
-def _gemm_no_bias(bdl, x):
-  heads, bw = bdl.num_blocks, bdl.block_width
+_wcat_cache = weakref.WeakKeyDictionary()
+
+
+def _fused_gate_gemm(lru, x):
+  """One cuBLAS GEMM for both gates of a *reference* RGLRU module -> [N, H, 2*bw]."""
+  wx, wa = lru.input_gate.w, lru.a_gate.w
+  key = (wx.data_ptr(), wa.data_ptr(), wx._version, wa._version, wx.dtype, wx.device)
+  hit = _wcat_cache.get(lru)
+  if hit is None or hit[0] != key:
+    hit = (key, torch.cat([wx.detach(), wa.detach()], dim=2).contiguous())
+    _wcat_cache[lru] = hit
+  heads, bw = lru.input_gate.num_blocks, lru.input_gate.block_width
   x2 = x.reshape(-1, heads, bw)
-  out = torch.empty_like(x2)
-  torch.bmm(x2.transpose(0, 1), bdl.w, out=out.transpose(0, 1))
-  return out.view(x.shape)
+  out = torch.empty((x2.shape[0], heads, 2 * bw), dtype=x.dtype, device=x.device)
+  torch.bmm(x2.transpose(0, 1), hit[1], out=out.transpose(0, 1))
+  return out, bw
 
 
 def _rglru_forward(self, x, segment_pos, cache=None, return_cache=True):
@@ -36,10 +48,11 @@ def _rglru_forward(self, x, segment_pos, cache=None, return_cache=True):
   assert segment_pos.shape == (bs, length)
   cg_layers._forward_only(x, cache)
   with torch.no_grad():
+    gates, bw = _fused_gate_gemm(self, x)
     return _abi.rglru_fwd(
-        x, _gemm_no_bias(self.input_gate, x), _gemm_no_bias(self.a_gate, x),
-        self.input_gate.b, self.a_gate.b, self.a_param, segment_pos, h0=cache,
-        return_cache=return_cache, arith_mode=cg_layers.get_arith_mode())
+        x, None, None, self.input_gate.b, self.a_gate.b, self.a_param, segment_pos,
+        h0=cache, return_cache=return_cache, arith_mode=cg_layers.get_arith_mode(),
+        gemm_fused=gates, block_width=bw)
 
 
 def _conv1d_forward(self, x, segment_pos, cache=None, return_cache=True):

@@ -135,6 +135,25 @@ class RGLRU(nn.Module):
       w.log_().mul_(0.5)
       return w.neg_().exp_().sub_(1.0).log_()
 
+  def _fused_gate_weight(self) -> torch.Tensor:
+    """[H, bw, 2*bw]: input-gate and a-gate weights side by side, so ONE
+    strided-batched cuBLAS GEMM reads the activations once for both gates.
+    Rebuilt only when a gate weight changes (in-place update or re-assignment)."""
+    wx, wa = self.input_gate.w, self.a_gate.w
+    key = (wx.data_ptr(), wa.data_ptr(), wx._version, wa._version, wx.dtype, wx.device)
+    if getattr(self, "_wcat_key", None) != key:
+      self._wcat = torch.cat([wx.detach(), wa.detach()], dim=2).contiguous()
+      self._wcat_key = key
+    return self._wcat
+
+  def gate_gemm(self, x: torch.Tensor) -> torch.Tensor:
+    """Both gate GEMMs (no bias) in one call -> [B*T, H, 2*bw]."""
+    heads, bw = self.num_heads, self.width // self.num_heads
+    x2 = x.reshape(-1, heads, bw)
+    out = torch.empty((x2.shape[0], heads, 2 * bw), dtype=x.dtype, device=x.device)
+    torch.bmm(x2.transpose(0, 1), self._fused_gate_weight(), out=out.transpose(0, 1))
+    return out
+
   def forward(self, x, segment_pos, cache=None, return_cache=True):
     """Returns ``(y in x.dtype, last_h fp32 | None)``."""
     bs, length, _ = x.shape
@@ -143,12 +162,11 @@ class RGLRU(nn.Module):
     assert segment_pos.shape == (bs, length)      # layers.py:344
     _forward_only(x, cache)
     with torch.no_grad():
-      gemm_x = self.input_gate.gemm(x)
-      gemm_a = self.a_gate.gemm(x)
       y, last_h = _abi.rglru_fwd(
-          x, gemm_x, gemm_a, self.input_gate.b, self.a_gate.b, self.a_param,
+          x, None, None, self.input_gate.b, self.a_gate.b, self.a_param,
           segment_pos, h0=cache, return_cache=return_cache,
-          arith_mode=_arith_mode)
+          arith_mode=_arith_mode, gemm_fused=self.gate_gemm(x),
+          block_width=self.width // self.num_heads)
     return y, last_h
 
   @classmethod

@@ -110,8 +110,13 @@ int cg_conv1d_decode(const void* x, const void* w, const void* b,
 /*
  * RG-LRU after the gate GEMMs: layers.py:345-375 (gate math + rnn_scan).
  *   x       [B,T,E]  Conv1D output
- *   gemm_x  [B,T,E]  input_gate GEMM output WITHOUT bias (row stride
- *   gemm_a  [B,T,E]  a_gate GEMM output     gate_row_stride elements)
+ *   gemm_x  [B,T,E]  input_gate GEMM output WITHOUT bias  } rows gate_row_stride
+ *   gemm_a  [B,T,E]  a_gate GEMM output WITHOUT bias      } elements apart
+ *   gate_block_width  0: both are plain rows, channel c at column c.
+ *        bw > 0 (= E / num_heads): ONE fused block-diagonal GEMM wrote rows of
+ *        [num_heads][2*bw] (per head: bw input-gate then bw a-gate columns);
+ *        channel c then sits at column c + (c / bw) * bw of gemm_x, and gemm_a
+ *        must point bw elements past gemm_x (gate_row_stride >= 2E).
  *   bias_x, bias_a  [E] or NULL: pre = round(gemm + bias) (layers.py:139)
  *   a_param [E]
  *   h0      [B,E] fp32 or NULL;  last_h [B,E] fp32 or NULL
@@ -119,8 +124,9 @@ int cg_conv1d_decode(const void* x, const void* w, const void* b,
  * T == 1 follows rnn_scan's sampling branch (:175-182).
  */
 int cg_rglru_fwd(const void* x, const void* gemm_x, const void* gemm_a,
-                 long long gate_row_stride, const void* bias_x,
-                 const void* bias_a, const void* a_param, const void* seg,
+                 long long gate_row_stride, int gate_block_width,
+                 const void* bias_x, const void* bias_a, const void* a_param,
+                 const void* seg,
                  int seg_is_i64, long long seg_batch_stride, const float* h0,
                  void* y, float* last_h, void* workspace,
                  size_t workspace_bytes, int B, int T, int E, int dtype,

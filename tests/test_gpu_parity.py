@@ -329,6 +329,33 @@ def test_full_size_continuation_and_reset_isolation():
   assert torch.equal(ya[:, cut:], yb[:, cut:])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("width,heads", [(256, 8), (128, 16), (2560, 10)])
+def test_fused_gate_layout_equals_separate(dtype, width, heads):
+  """One fused [N,H,2bw] gate GEMM and two separate GEMM outputs give the same bits."""
+  import cadence_gemma_b200 as cg
+  abi = _abi()
+  torch.manual_seed(5)
+  lru = cg.RGLRU(width, heads, device=DEV, dtype=dtype)
+  with torch.no_grad():
+    lru.input_gate.b.normal_()
+    lru.a_gate.b.normal_()
+    x = torch.randn(2, 75, width, device=DEV).to(dtype)
+    seg = torch.arange(75, device=DEV)[None].repeat(2, 1)
+    seg[1, 40:] -= 40
+    y_f, h_f = lru(x, seg)
+    y_s, h_s = abi.rglru_fwd(x, lru.input_gate.gemm(x), lru.a_gate.gemm(x), lru.input_gate.b,
+                             lru.a_gate.b, lru.a_param, seg, arith_mode=cg.get_arith_mode())
+    y_t, _ = abi.rglru_fwd(x, None, None, lru.input_gate.b, lru.a_gate.b, lru.a_param, seg,
+                           arith_mode=STRICT, gemm_fused=lru.gate_gemm(x),
+                           block_width=width // heads)
+  assert torch.equal(y_f, y_s) and torch.equal(h_f, h_s)
+  if dtype == torch.bfloat16:
+    assert identical_fraction(y_f, y_t) >= 0.97
+  else:
+    assert normwise(y_f, y_t) <= 1e-5
+
+
 def test_abi_argument_errors():
   abi = _abi()
   x = torch.zeros(1, 4, 12, device=DEV, dtype=torch.bfloat16)   # E % 8 != 0
