@@ -244,7 +244,7 @@ int cg_rglru_fwd(const void* x, const void* gemm_x, const void* gemm_a, long lon
     q.seg = seg; q.seg_is_i64 = seg_is_i64; q.seg_bstride = seg_batch_stride;
     q.reset_bits = strict ? nullptr : ws_min.reset_bits;
     q.rows = seg_batch_stride == 0 ? 1 : B; q.T = T; q.words_per_row = words;
-    const int n = E > q.rows * words ? E : q.rows * words;
+    const int n = E > q.rows * words * 32 ? E : q.rows * words * 32;
     cg::scan_prologue_kernel<<<(n + 127) / 128, 128, 0, stream>>>(q);
     if (cudaError_t err = cudaGetLastError()) return (int)err;
   }
@@ -310,7 +310,7 @@ int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset, co
     cg::PrologueParams q{};
     q.counter = ws_min.counter; q.epoch = ws_min.epoch;
     q.reset = reset; q.reset_bits = ws_min.reset_bits; q.rows = B; q.T = T; q.words_per_row = words;
-    cg::scan_prologue_kernel<<<(B * words + 127) / 128, 128, 0, stream>>>(q);
+    cg::scan_prologue_kernel<<<(B * words * 32 + 127) / 128, 128, 0, stream>>>(q);
     if (cudaError_t err = cudaGetLastError()) return (int)err;
     p.reset_bits = ws_min.reset_bits; p.bits_bstride = words;
   }

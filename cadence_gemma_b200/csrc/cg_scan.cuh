@@ -737,18 +737,17 @@ __global__ void scan_prologue_kernel(const PrologueParams q) {
     q.neg8sp[i] = v;
     q.neg8sp_bf[i] = (uint16_t)(pack_bf2(v, v) & 0xffffu);
   }
-  if (q.reset_bits != nullptr && i < q.rows * q.words_per_row) {
-    const int r = i / q.words_per_row, w = i - r * q.words_per_row;
-    unsigned bits = 0;
-    for (int k = 0; k < 32; ++k) {
-      const int t = w * 32 + k;
-      if (t >= q.T) break;
-      bool rs;
+  // one thread per (row, step); a warp covers the 32 steps of one bitmask word
+  const int tpad = q.words_per_row * 32;
+  if (q.reset_bits != nullptr && i < q.rows * tpad) {
+    const int r = i / tpad, t = i - r * tpad;
+    bool rs = false;
+    if (t < q.T) {
       if (q.seg != nullptr) rs = seg_is_zero(q.seg, q.seg_is_i64 != 0, (long long)r * q.seg_bstride + t);
       else rs = q.reset[(size_t)r * q.T + t] != 0;
-      bits |= (rs ? 1u : 0u) << k;
     }
-    q.reset_bits[i] = bits;
+    const unsigned bits = __ballot_sync(0xffffffffu, rs);
+    if ((threadIdx.x & 31) == 0) q.reset_bits[r * q.words_per_row + (t >> 5)] = bits;
   }
 }
 

@@ -1,0 +1,87 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads without a GPU and
+exports every symbol include/cadence_b200.h declares; the Python shims mirror
+the reference API and refuse to run on CPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+  text = open(os.path.join(ROOT, "include", "cadence_b200.h")).read()
+  text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+  return sorted(set(re.findall(r"\b(cg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+  from cadence_gemma_b200 import _abi, build
+  lib_path = build.build()           # cross-compiles for sm_100a if stale
+  lib = ctypes.CDLL(lib_path)
+  declared = _declared_symbols()
+  assert len(declared) >= 7, declared
+  for name in declared:
+    assert hasattr(lib, name), f"{name} declared in the header but not exported"
+  assert sorted(_abi.SYMBOLS) == declared, "ctypes table out of sync with the header"
+  loaded = _abi.load()
+  assert loaded.cg_abi_version() == 1
+  assert b"workspace" in loaded.cg_status_string(-5)
+  assert loaded.cg_scan_workspace_bytes(8, 2048, 2560, 1) > 0
+  assert loaded.cg_scan_workspace_bytes(0, 1, 1, 1) == 0
+
+
+def test_shims_mirror_reference_api_and_have_no_cpu_fallback():
+  import cadence_gemma_b200 as cg
+  lru = cg.RGLRU(64, 2)
+  conv = cg.Conv1D(64, 4)
+  assert sorted(lru.state_dict()) == ["a_gate.b", "a_gate.w", "a_param",
+                                      "input_gate.b", "input_gate.w"]
+  assert sorted(conv.state_dict()) == ["b", "w"]
+  assert lru.input_gate.w.shape == (2, 32, 32) and conv.w.shape == (4, 64)
+  assert cg.RGLRU.init_cache(3, 64).dtype == torch.float32
+  assert cg.Conv1D.init_cache(batch_size=3, width=64, dtype=torch.bfloat16).shape == (3, 3, 64)
+  x = torch.randn(1, 8, 64)
+  seg = torch.arange(8)[None]
+  with torch.no_grad():
+    for call in (lambda: lru(x, seg), lambda: conv(x, seg),
+                 lambda: cg.rnn_scan(x, x, seg == 0, None)):
+      with pytest.raises(RuntimeError, match="no CPU"):
+        call()
+  xg = torch.randn(1, 8, 64, requires_grad=True)
+  with pytest.raises(RuntimeError, match="forward-only"):
+    conv(xg, seg)
+
+
+def test_recurrent_block_mirror_state_dict_keys():
+  from cadence_gemma_b200.modules import RecurrentBlock
+  blk = RecurrentBlock(width=32, num_heads=2, lru_width=64)
+  keys = set(blk.state_dict())
+  for k in ("linear_x.weight", "linear_y.bias", "linear_out.weight", "conv_1d.w",
+            "conv_1d.b", "rg_lru.a_param", "rg_lru.input_gate.w", "rg_lru.a_gate.b"):
+    assert k in keys
+  cache = RecurrentBlock.init_cache(2, 64, torch.bfloat16)
+  assert cache.rg_lru_state.dtype == torch.float32 and cache.conv1d_state.shape == (2, 3, 64)
+
+
+def test_install_patches_reference_entry_points():
+  from oracle import ref_loader
+  if not ref_loader.reference_available():
+    pytest.skip("reference checkout not mounted")
+  from cadence_gemma_b200 import install
+  ref = ref_loader.load_reference()
+  orig = (ref.layers.rnn_scan, ref.layers.RGLRU.forward, ref.layers.Conv1D.forward)
+  install.install(ref.layers, ref.modules)
+  try:
+    assert ref.layers.rnn_scan is not orig[0]
+    assert ref.layers.RGLRU.forward is not orig[1]
+    assert ref.layers.Conv1D.forward is not orig[2]
+    # state dicts of the reference classes are what the kernels consume
+    blk = ref.modules.RecurrentBlock(width=32, num_heads=2, lru_width=64)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU"):
+      blk(torch.randn(1, 4, 32), torch.arange(4)[None])
+  finally:
+    install.uninstall()
+  assert (ref.layers.rnn_scan, ref.layers.RGLRU.forward, ref.layers.Conv1D.forward) == orig
