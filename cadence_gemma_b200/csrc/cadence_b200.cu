@@ -230,6 +230,28 @@ int cg_rglru_fwd(const void* x, const void* gemm_x, const void* gemm_a, long lon
         (h0 && !aligned16(h0)) || (last_h && !aligned16(last_h)) || !aligned16(workspace))
       return CG_ERR_ALIGN;
   }
+  if (T == 1 && !strict) {   // decode step: one fused launch, no scratch traffic
+    ScanParams p{};
+    p.x = x; p.gemm_x = gemm_x; p.gemm_a = gemm_a; p.bias_x = bias_x; p.bias_a = bias_a;
+    p.seg = seg; p.seg_bstride = seg_batch_stride; p.seg_is_i64 = seg_is_i64;
+    p.gate_ld = gate_row_stride; p.gate_bw = gate_block_width; p.h0 = h0; p.y = y;
+    p.last_h = last_h; p.B = B; p.T = 1; p.E = E;
+    const int threads = B * (E / V);
+    const int grid = (threads + 127) / 128;
+    if (bf) {
+      switch (mode & 3) {
+        case 0: cg::rglru_step_kernel<uint16_t, 0><<<grid, 128, 0, stream>>>(p, a_param); break;
+        case 1: cg::rglru_step_kernel<uint16_t, 1><<<grid, 128, 0, stream>>>(p, a_param); break;
+        case 2: cg::rglru_step_kernel<uint16_t, 2><<<grid, 128, 0, stream>>>(p, a_param); break;
+        default: cg::rglru_step_kernel<uint16_t, 3><<<grid, 128, 0, stream>>>(p, a_param); break;
+      }
+    } else if (mode & 2) {
+      cg::rglru_step_kernel<float, 3><<<grid, 128, 0, stream>>>(p, a_param);
+    } else {
+      cg::rglru_step_kernel<float, 1><<<grid, 128, 0, stream>>>(p, a_param);
+    }
+    return (int)cudaGetLastError();
+  }
   // ticket / epoch live at the head and -8 * softplus(a_param) at the tail of
   // the (largest-geometry) scratch layout, i.e. outside every geometry's arrays
   const Workspace ws_min = carve(workspace, B, T, E, cg::kCvl * V, kMinSuperChunk);

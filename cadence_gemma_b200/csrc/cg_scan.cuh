@@ -823,4 +823,92 @@ __global__ void strict_scan_kernel(const ScanParams p) {
   if (p.last_h) p.last_h[(size_t)b * p.E + e] = h;
 }
 
+// ---------------------------------------------------------------------------
+// Decode step (T == 1): rnn_scan's sampling branch (layers.py:175-182) fused with
+// the gate math.  One thread per 16-byte channel vector, ONE launch (softplus is
+// evaluated inline: B*E elements only).  y = r(a*h0 + x~) with separate fp32
+// mul and add; last_h is the unrounded fp32 value; h0 == nullptr returns x~.
+// ---------------------------------------------------------------------------
+template <typename IO, int ARITH>
+__global__ void __launch_bounds__(128)
+rglru_step_kernel(const ScanParams p, const void* a_param) {
+  using Tr = ScanTraits<IO, 0, ARITH>;
+  constexpr int V = Tr::V;
+  constexpr bool BF = Tr::BF;
+  constexpr bool FAST = Tr::FAST;
+  constexpr bool PACKED = Tr::PACKED;
+  const int vecs = p.E / V;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.B * vecs) return;
+  const int b = idx / vecs, ch0 = (idx - b * vecs) * V;
+  const bool rs = seg_is_zero(p.seg, p.seg_is_i64 != 0, (long long)b * p.seg_bstride);
+  const size_t row = b;   // T == 1
+  const uint4 vx = ldg_stream(reinterpret_cast<const IO*>(p.x) + row * p.E + ch0);
+  const int g0 = gate_off(ch0, p.gate_bw);
+  const uint4 v1 = ldg_stream(reinterpret_cast<const IO*>(p.gemm_x) + row * p.gate_ld + g0);
+  const uint4 v2 = ldg_stream(reinterpret_cast<const IO*>(p.gemm_a) + row * p.gate_ld + g0);
+  float av[V], nx[V], bx[V], ba[V], sp8[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float ap = load_io<IO>(a_param, ch0 + i);
+    float sp = softplus_f(ap);
+    if (PACKED) sp = round_bf(sp);
+    sp8[i] = -8.0f * sp;
+    bx[i] = p.bias_x ? load_io<IO>(p.bias_x, ch0 + i) : 0.0f;
+    ba[i] = p.bias_a ? load_io<IO>(p.bias_a, ch0 + i) : 0.0f;
+  }
+  const uint32_t wx[4] = {vx.x, vx.y, vx.z, vx.w};
+  const uint32_t w1[4] = {v1.x, v1.y, v1.z, v1.w};
+  const uint32_t w2[4] = {v2.x, v2.y, v2.z, v2.w};
+  if constexpr (PACKED) {
+#pragma unroll
+    for (int i = 0; i < V / 2; ++i) {
+      uint32_t a2, n2;
+      const uint32_t cbx = pack_bf2(bx[2 * i], bx[2 * i + 1]), cba = pack_bf2(ba[2 * i], ba[2 * i + 1]);
+      const uint32_t csp = pack_bf2(sp8[2 * i], sp8[2 * i + 1]);
+      if (rs) gate_pair_emul<FAST, true>(wx[i], w1[i], w2[i], cbx, cba, csp, a2, n2);
+      else gate_pair_emul<FAST, false>(wx[i], w1[i], w2[i], cbx, cba, csp, a2, n2);
+      av[2 * i] = bf_lo(a2); av[2 * i + 1] = bf_hi(a2);
+      nx[2 * i] = bf_lo(n2); nx[2 * i + 1] = bf_hi(n2);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float fx, f1, f2;
+      if constexpr (BF) {
+        fx = (i & 1) ? bf_hi(wx[i / 2]) : bf_lo(wx[i / 2]);
+        f1 = (i & 1) ? bf_hi(w1[i / 2]) : bf_lo(w1[i / 2]);
+        f2 = (i & 1) ? bf_hi(w2[i / 2]) : bf_lo(w2[i / 2]);
+      } else {
+        fx = __uint_as_float(wx[i % 4]); f1 = __uint_as_float(w1[i % 4]); f2 = __uint_as_float(w2[i % 4]);
+      }
+      if (rs) gate_f32<FAST, true>(fx, f1, f2, bx[i], ba[i], sp8[i], av[i], nx[i]);
+      else gate_f32<FAST, false>(fx, f1, f2, bx[i], ba[i], sp8[i], av[i], nx[i]);
+    }
+  }
+  float h[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    if (p.h0 == nullptr) h[i] = nx[i];                                           // :177-178
+    else h[i] = __fadd_rn(__fmul_rn(av[i], p.h0[(size_t)b * p.E + ch0 + i]), nx[i]);   // :181
+  }
+  uint4 out;
+  if constexpr (BF) {
+    out = make_uint4(pack_bf2(h[0], h[1]), pack_bf2(h[2], h[3]), pack_bf2(h[4 % V], h[5 % V]),
+                     pack_bf2(h[6 % V], h[7 % V]));
+  } else {
+    out = make_uint4(__float_as_uint(h[0]), __float_as_uint(h[1]), __float_as_uint(h[2]),
+                     __float_as_uint(h[3]));
+  }
+  stg_stream(reinterpret_cast<IO*>(p.y) + row * p.E + ch0, out);
+  if (p.last_h != nullptr) {
+    // (without h0 the reference returns x[:, 0] widened; in reference mode x~ is
+    // already bf16-exact, so the fp32 value below is that very number)
+#pragma unroll
+    for (int i = 0; i < V; i += 4)
+      *reinterpret_cast<float4*>(p.last_h + (size_t)b * p.E + ch0 + i) =
+          make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
+  }
+}
+
 }  // namespace cg
