@@ -33,6 +33,12 @@ SYMBOLS = {
                           _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "cg_rnn_scan_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i,
                              _i, _i, _vp]),
+    "cg_rglru_fused_supported": (_i, [_i, _i, _i]),
+    "cg_rglru_gate_pack_bytes": (_sz, [_i, _i]),
+    "cg_rglru_pack_gate_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "cg_rglru_fused_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cg_rglru_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp,
+                                _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }
 
 _lib = None
@@ -250,3 +256,85 @@ def rnn_scan_fwd(x, a, reset, h0=None, arith_mode=ARITH_REFERENCE):
   _check(rc, "cg_rnn_scan_fwd")
   launch_count += 1 if (arith_mode & ARITH_STRICT) else 2
   return y, h_last
+
+
+# ---------------------------------------------------------------------------
+# Fused tensor-core path: gate GEMMs + gate math + scan in one kernel
+# ---------------------------------------------------------------------------
+def fused_supported(width: int, heads: int, dtype) -> bool:
+  """True if cg_rglru_fused_fwd takes this (E, H, dtype)."""
+  if dtype != torch.bfloat16:
+    return False
+  return bool(load().cg_rglru_fused_supported(width, heads, DTYPE_BF16))
+
+
+def pack_gate_weights(wx: torch.Tensor, wa: torch.Tensor) -> torch.Tensor:
+  """[H, bw, bw] x 2 -> the packed shared-memory image the fused kernel reads."""
+  global launch_count
+  _require_cuda(wx, wa)
+  heads, bw, bw2 = wx.shape
+  assert bw == bw2 and wa.shape == wx.shape and wa.dtype == wx.dtype
+  width = heads * bw
+  nbytes = load().cg_rglru_gate_pack_bytes(width, heads)
+  assert nbytes > 0, "shape not supported by the fused path"
+  out = torch.empty(nbytes, dtype=torch.uint8, device=wx.device)
+  wx, wa = wx.detach().contiguous(), wa.detach().contiguous()
+  with torch.cuda.device(wx.device):
+    rc = load().cg_rglru_pack_gate_weights(wx.data_ptr(), wa.data_ptr(), out.data_ptr(),
+                                           width, heads, dtype_code(wx.dtype), _stream(wx))
+  _check(rc, "cg_rglru_pack_gate_weights")
+  launch_count += 1
+  return out
+
+
+_fused_workspaces: dict = {}
+
+
+def fused_workspace(device, batch: int, steps: int, width: int) -> torch.Tensor:
+  key = (device, torch.cuda.current_stream(device).cuda_stream, batch, steps, width)
+  ws = _fused_workspaces.get(key)
+  if ws is None:
+    nbytes = load().cg_rglru_fused_workspace_bytes(batch, steps, width)
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    if len(_fused_workspaces) > 64:
+      _fused_workspaces.clear()
+    _fused_workspaces[key] = ws
+  return ws
+
+
+def fused_watchdog_code(ws: torch.Tensor) -> int:
+  """Non-zero after a launch whose kernel-side watchdog fired (synchronises)."""
+  return int(ws[8:12].view(torch.int32).item())
+
+
+def rglru_fused_fwd(x, wpack, bias_x, bias_a, a_param, segment_pos, heads, h0=None,
+                    return_cache=True, arith_mode=ARITH_FAST, out=None, debug=False,
+                    workspace=None):
+  """RGLRU.forward (gate GEMMs included) on the fused tcgen05 kernel."""
+  global launch_count
+  _require_cuda(x, wpack, bias_x, bias_a, a_param, segment_pos, h0)
+  bsz, steps, width = x.shape
+  assert x.dtype == torch.bfloat16 and a_param.dtype == x.dtype
+  assert h0 is None or h0.dtype == torch.float32, "layers.py:170"
+  x = x.contiguous()
+  seg, is64, stride = _seg_args(segment_pos, bsz, steps)
+  y = torch.empty_like(x) if out is None else out
+  last_h = (torch.empty((bsz, width), dtype=torch.float32, device=x.device)
+            if return_cache else None)
+  ws = fused_workspace(x.device, bsz, steps, width) if workspace is None else workspace
+  bx = None if bias_x is None else bias_x.contiguous().view(-1)
+  ba = None if bias_a is None else bias_a.contiguous().view(-1)
+  h0c = None if h0 is None else h0.contiguous()
+  dbg = (torch.zeros((3, bsz, steps, width), dtype=x.dtype, device=x.device)
+         if debug else None)
+  with torch.cuda.device(x.device):
+    rc = load().cg_rglru_fused_fwd(x.data_ptr(), wpack.data_ptr(), _ptr(bx), _ptr(ba),
+                                   a_param.contiguous().data_ptr(), seg.data_ptr(), is64,
+                                   stride, _ptr(h0c), y.data_ptr(), _ptr(last_h),
+                                   ws.data_ptr(), ws.numel(), bsz, steps, width, heads,
+                                   dtype_code(x.dtype), arith_mode, _ptr(dbg), _stream(x))
+  _check(rc, "cg_rglru_fused_fwd")
+  launch_count += 2   # prologue + fused kernel
+  if debug:
+    return y, last_h, dbg
+  return y, last_h

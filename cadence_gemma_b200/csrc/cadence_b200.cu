@@ -11,6 +11,7 @@
 #include "cg_common.cuh"
 #include "cg_conv1d.cuh"
 #include "cg_scan.cuh"
+#include "cg_fused.cuh"
 
 namespace {
 
@@ -133,6 +134,7 @@ const char* cg_status_string(int status) {
     case CG_ERR_ALIGN: return "pointers must be 16-byte aligned and E / row strides a multiple of 16 bytes";
     case CG_ERR_WORKSPACE: return "workspace too small (see cg_scan_workspace_bytes)";
     case CG_ERR_MODE: return "unsupported arith_mode / mask_mode / variant";
+    case CG_ERR_UNSUPPORTED: return "shape / dtype not supported by the fused tensor-core path (use cg_rglru_fwd)";
     default: break;
   }
   if (status > 0) return cudaGetErrorString(static_cast<cudaError_t>(status));
@@ -338,6 +340,170 @@ int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset, co
   }
   return bf ? dispatch_geometry<uint16_t, 1, 0>(variant, p, workspace, workspace_bytes, stream)
             : dispatch_geometry<float, 1, 1>(variant, p, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Fused tensor-core path (cg_fused.cuh)
+// ---------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup, so
+// the library needs no link-time dependency on libcuda.
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+bool fused_shape_ok(int E, int H, int dtype) {
+  if (dtype != CG_DTYPE_BF16 || H < 1 || E < 1 || E % H != 0) return false;
+  const int bw = E / H;
+  return bw == 128 || bw == 256;
+}
+
+template <int KB, int GPT, bool FAST, bool DBG>
+int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, cudaStream_t stream) {
+  using Cfg = cg::fused::FusedCfg<KB, GPT>;
+  auto kernel = cg::fused::rglru_fused_kernel<KB, GPT, FAST, DBG>;
+  static int sms = 0;
+  if (sms == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 1) return (int)cudaErrorLaunchOutOfResources;
+  }
+  kernel<<<sms, cg::fused::kThreads, Cfg::kSmemBytes, stream>>>(tmap, p);
+  return (int)cudaGetLastError();
+}
+
+template <int KB, int GPT>
+int dispatch_fused(bool fast, bool dbg, const CUtensorMap& tmap, const cg::fused::FusedParams& p,
+                   cudaStream_t stream) {
+  if (dbg) return fast ? launch_fused<KB, GPT, true, true>(tmap, p, stream)
+                       : launch_fused<KB, GPT, false, true>(tmap, p, stream);
+  return fast ? launch_fused<KB, GPT, true, false>(tmap, p, stream)
+              : launch_fused<KB, GPT, false, false>(tmap, p, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cg_rglru_fused_supported(int E, int H, int dtype) { return fused_shape_ok(E, H, dtype) ? 1 : 0; }
+
+size_t cg_rglru_gate_pack_bytes(int E, int H) {
+  if (!fused_shape_ok(E, H, CG_DTYPE_BF16)) return 0;
+  const size_t bw = (size_t)E / H;
+  // [E/128 families][2 gates][bw/64 K blocks][128 rows][128 B] + identity [2][128][128 B]
+  return (size_t)(E / 128) * 2 * (bw / 64) * cg::fused::kKBlockBytes + 2 * cg::fused::kKBlockBytes;
+}
+
+int cg_rglru_pack_gate_weights(const void* wx, const void* wa, void* wpack, int E, int H, int dtype,
+                               cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!wx || !wa || !wpack) return CG_ERR_NULL;
+  if (!fused_shape_ok(E, H, dtype)) return CG_ERR_UNSUPPORTED;
+  if (!aligned16(wpack)) return CG_ERR_ALIGN;
+  const int bw = E / H;
+  const size_t wbytes = cg_rglru_gate_pack_bytes(E, H) - 2 * cg::fused::kKBlockBytes;
+  const long long chunks = (long long)(wbytes / 16) + 2 * 128 * 8;
+  cg::fused::pack_gate_weights_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint16_t*>(wx), reinterpret_cast<const uint16_t*>(wa),
+      reinterpret_cast<unsigned char*>(wpack), reinterpret_cast<unsigned char*>(wpack) + wbytes, H, bw);
+  return (int)cudaGetLastError();
+}
+
+size_t cg_rglru_fused_workspace_bytes(int B, int T, int E) {
+  if (B < 1 || T < 1 || E < 1) return 0;
+  return carve(nullptr, B, T, E, cg::fused::kMch, cg::fused::kGran).total;   // smallest tile = 1 granule
+}
+
+int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, const void* bias_a,
+                       const void* a_param, const void* seg, int seg_is_i64, long long seg_batch_stride,
+                       const float* h0, void* y, float* last_h, void* workspace, size_t workspace_bytes,
+                       int B, int T, int E, int H, int dtype, int arith_mode, void* debug_out,
+                       cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !wpack || !a_param || !seg || !y || !workspace) return CG_ERR_NULL;
+  if (int rc = check_common(B, T, E, dtype)) return rc;
+  if (!fused_shape_ok(E, H, dtype)) return CG_ERR_UNSUPPORTED;
+  const int mode = arith_mode & 7;
+  const int variant = (arith_mode >> 8) & 0xff;
+  if ((arith_mode & ~0xff07) != 0 || (mode & (CG_ARITH_FP32 | CG_ARITH_STRICT)) != 0) return CG_ERR_MODE;
+  if (variant > 1) return CG_ERR_MODE;
+  if (!aligned16(x) || !aligned16(wpack) || !aligned16(y) || !aligned16(workspace)) return CG_ERR_ALIGN;
+  if (B > 65535) return CG_ERR_SHAPE;
+  const int bw = E / H;
+  const int gpt = variant == 1 ? 1 : 2;
+  const int tile_t = cg::fused::kGran * gpt;
+  const Workspace ws_min = carve(workspace, B, T, E, cg::fused::kMch, cg::fused::kGran);
+  if (ws_min.total > workspace_bytes) return CG_ERR_WORKSPACE;
+  const Workspace ws = carve(workspace, B, T, E, cg::fused::kMch, tile_t);
+  const int words = (T + 31) / 32;
+  {   // epoch bump, -8*softplus(a_param), reset bitmask (shared with the unfused path)
+    cg::PrologueParams q{};
+    q.a_param = a_param; q.neg8sp = ws_min.neg8sp; q.neg8sp_bf = ws_min.neg8sp_bf;
+    q.E = E; q.is_bf16 = 1; q.emulate = 1;
+    q.counter = ws_min.counter; q.epoch = ws_min.epoch;
+    q.seg = seg; q.seg_is_i64 = seg_is_i64; q.seg_bstride = seg_batch_stride;
+    q.reset_bits = ws_min.reset_bits;
+    q.rows = seg_batch_stride == 0 ? 1 : B; q.T = T; q.words_per_row = words;
+    const int n = E > q.rows * words * 32 ? E : q.rows * words * 32;
+    cg::scan_prologue_kernel<<<(n + 127) / 128, 128, 0, stream>>>(q);
+    if (cudaError_t err = cudaGetLastError()) return (int)err;
+  }
+  EncodeTiledFn encode = encode_tiled_fn();
+  if (encode == nullptr) return (int)cudaErrorNotSupported;
+  CUtensorMap tmap;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)E, (cuuint64_t)T, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)E * 2, (cuuint64_t)T * E * 2};
+    const cuuint32_t box[3] = {64, (cuuint32_t)tile_t, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(x), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+  }
+  cg::fused::FusedParams p{};
+  const size_t wbytes = cg_rglru_gate_pack_bytes(E, H) - 2 * cg::fused::kKBlockBytes;
+  p.wpack = reinterpret_cast<const unsigned char*>(wpack);
+  p.ident = p.wpack + wbytes;
+  p.bias_x = reinterpret_cast<const uint16_t*>(bias_x);
+  p.bias_a = reinterpret_cast<const uint16_t*>(bias_a);
+  p.neg8sp_bf = ws_min.neg8sp_bf;
+  p.reset_bits = ws_min.reset_bits;
+  p.bits_bstride = seg_batch_stride == 0 ? 0 : words;
+  p.words = words;
+  p.h0 = h0; p.y = reinterpret_cast<uint16_t*>(y); p.last_h = last_h;
+  p.epoch = ws.epoch; p.agg_p = ws.agg_p; p.agg_h = ws.agg_h; p.pref = ws.pref;
+  p.dbg = reinterpret_cast<uint16_t*>(debug_out);
+  p.err = ws.counter + 2;   // third word of the scratch header
+  p.B = B; p.T = T; p.E = E;
+  p.ntt = (T + tile_t - 1) / tile_t;
+  p.families = E / cg::fused::kMch;
+  const bool fast = (mode & CG_ARITH_FAST) != 0;
+  const bool dbg = debug_out != nullptr;
+  if (bw == 256) return gpt == 2 ? dispatch_fused<4, 2>(fast, dbg, tmap, p, stream)
+                                 : dispatch_fused<4, 1>(fast, dbg, tmap, p, stream);
+  return gpt == 2 ? dispatch_fused<2, 2>(fast, dbg, tmap, p, stream)
+                  : dispatch_fused<2, 1>(fast, dbg, tmap, p, stream);
 }
 
 }  // extern "C"

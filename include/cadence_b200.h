@@ -70,6 +70,7 @@ extern "C" {
 #define CG_ERR_ALIGN (-4)
 #define CG_ERR_WORKSPACE (-5)
 #define CG_ERR_MODE (-6)
+#define CG_ERR_UNSUPPORTED (-7)
 
 typedef struct CUstream_st* cg_stream_t; /* == cudaStream_t */
 
@@ -142,6 +143,46 @@ int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset,
                     const float* h0, void* y, float* last_h, void* workspace,
                     size_t workspace_bytes, int B, int T, int E, int dtype,
                     int arith_mode, cg_stream_t stream);
+
+/*
+ * Fused tensor-core RG-LRU (bf16): the two BlockDiagonalLinear gate GEMMs
+ * (layers.py:133-142, :348-349), the gate math (:350-365) and rnn_scan
+ * (:146-199, :366-371) in ONE kernel -- tcgen05 MMAs with TMEM accumulators,
+ * TMA operand loads, gate math + scan in the epilogue; the pre-activations
+ * never reach HBM.  SURVEY.md section 8(f) row F1.
+ *
+ *   cg_rglru_fused_supported   1 if (E, H, dtype) can take this path: bf16 and a
+ *                              head width E/H of 128 or 256; else use cg_rglru_fwd.
+ *   cg_rglru_gate_pack_bytes   size of the packed gate-weight buffer.
+ *   cg_rglru_pack_gate_weights wx, wa [H, bw, bw] (reference layout, layers.py:103:
+ *                              y = x @ w[h]) -> wpack: the shared-memory image
+ *                              (K-major, 128 B swizzle) the MMAs read.  Call once
+ *                              per weight update.
+ *   cg_rglru_fused_workspace_bytes  scratch size; zero-fill ONCE before first use
+ *                              (same rules as cg_scan_workspace_bytes).  A non-zero
+ *                              int32 at byte offset 8 of the scratch after a launch
+ *                              means the kernel's watchdog fired (protocol error).
+ *   cg_rglru_fused_fwd         x [B,T,E] Conv1D output; biases [E] or NULL;
+ *                              h0 / last_h / y / seg as in cg_rglru_fwd.
+ *                              arith_mode: CG_ARITH_REFERENCE or CG_ARITH_FAST
+ *                              (every eager bf16 rounding point reproduced in both;
+ *                              the GEMM accumulates in fp32 and rounds once to bf16
+ *                              like the reference's einsum); variant 1 = 32-step tiles.
+ *                              debug_out (nullable): [3][B][T][E] bf16 -- the rounded
+ *                              pre_x, pre_a and the transposed x the epilogue saw.
+ */
+int cg_rglru_fused_supported(int E, int H, int dtype);
+size_t cg_rglru_gate_pack_bytes(int E, int H);
+int cg_rglru_pack_gate_weights(const void* wx, const void* wa, void* wpack,
+                               int E, int H, int dtype, cg_stream_t stream);
+size_t cg_rglru_fused_workspace_bytes(int B, int T, int E);
+int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x,
+                       const void* bias_a, const void* a_param, const void* seg,
+                       int seg_is_i64, long long seg_batch_stride,
+                       const float* h0, void* y, float* last_h, void* workspace,
+                       size_t workspace_bytes, int B, int T, int E, int H,
+                       int dtype, int arith_mode, void* debug_out,
+                       cg_stream_t stream);
 
 #ifdef __cplusplus
 }
