@@ -374,10 +374,10 @@ bool fused_shape_ok(int E, int H, int dtype) {
   return bw == 128 || bw == 256;
 }
 
-template <int KB, int GPT, bool FAST, bool DBG>
+template <int KB, bool FAST, bool DBG>
 int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, cudaStream_t stream) {
-  using Cfg = cg::fused::FusedCfg<KB, GPT>;
-  auto kernel = cg::fused::rglru_fused_kernel<KB, GPT, FAST, DBG>;
+  using Cfg = cg::fused::FusedCfg<KB>;
+  auto kernel = cg::fused::rglru_fused_kernel<KB, FAST, DBG>;
   static int sms = 0;
   if (sms == 0) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -392,13 +392,13 @@ int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, cudaS
   return (int)cudaGetLastError();
 }
 
-template <int KB, int GPT>
+template <int KB>
 int dispatch_fused(bool fast, bool dbg, const CUtensorMap& tmap, const cg::fused::FusedParams& p,
                    cudaStream_t stream) {
-  if (dbg) return fast ? launch_fused<KB, GPT, true, true>(tmap, p, stream)
-                       : launch_fused<KB, GPT, false, true>(tmap, p, stream);
-  return fast ? launch_fused<KB, GPT, true, false>(tmap, p, stream)
-              : launch_fused<KB, GPT, false, false>(tmap, p, stream);
+  if (dbg) return fast ? launch_fused<KB, true, true>(tmap, p, stream)
+                       : launch_fused<KB, false, true>(tmap, p, stream);
+  return fast ? launch_fused<KB, true, false>(tmap, p, stream)
+              : launch_fused<KB, false, false>(tmap, p, stream);
 }
 
 }  // namespace
@@ -431,7 +431,7 @@ int cg_rglru_pack_gate_weights(const void* wx, const void* wa, void* wpack, int 
 
 size_t cg_rglru_fused_workspace_bytes(int B, int T, int E) {
   if (B < 1 || T < 1 || E < 1) return 0;
-  return carve(nullptr, B, T, E, cg::fused::kMch, cg::fused::kGran).total;   // smallest tile = 1 granule
+  return carve(nullptr, B, T, E, cg::fused::kMch, cg::fused::kTile).total;
 }
 
 int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, const void* bias_a,
@@ -446,15 +446,14 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
   const int mode = arith_mode & 7;
   const int variant = (arith_mode >> 8) & 0xff;
   if ((arith_mode & ~0xff07) != 0 || (mode & (CG_ARITH_FP32 | CG_ARITH_STRICT)) != 0) return CG_ERR_MODE;
-  if (variant > 1) return CG_ERR_MODE;
+  if (variant != 0) return CG_ERR_MODE;
   if (!aligned16(x) || !aligned16(wpack) || !aligned16(y) || !aligned16(workspace)) return CG_ERR_ALIGN;
   if (B > 65535) return CG_ERR_SHAPE;
   const int bw = E / H;
-  const int gpt = variant == 1 ? 1 : 2;
-  const int tile_t = cg::fused::kGran * gpt;
-  const Workspace ws_min = carve(workspace, B, T, E, cg::fused::kMch, cg::fused::kGran);
+  const int tile_t = cg::fused::kTile;
+  const Workspace ws_min = carve(workspace, B, T, E, cg::fused::kMch, tile_t);
   if (ws_min.total > workspace_bytes) return CG_ERR_WORKSPACE;
-  const Workspace ws = carve(workspace, B, T, E, cg::fused::kMch, tile_t);
+  const Workspace& ws = ws_min;
   const int words = (T + 31) / 32;
   {   // epoch bump, -8*softplus(a_param), reset bitmask (shared with the unfused path)
     cg::PrologueParams q{};
@@ -500,10 +499,8 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
   p.families = E / cg::fused::kMch;
   const bool fast = (mode & CG_ARITH_FAST) != 0;
   const bool dbg = debug_out != nullptr;
-  if (bw == 256) return gpt == 2 ? dispatch_fused<4, 2>(fast, dbg, tmap, p, stream)
-                                 : dispatch_fused<4, 1>(fast, dbg, tmap, p, stream);
-  return gpt == 2 ? dispatch_fused<2, 2>(fast, dbg, tmap, p, stream)
-                  : dispatch_fused<2, 1>(fast, dbg, tmap, p, stream);
+  return bw == 256 ? dispatch_fused<4>(fast, dbg, tmap, p, stream)
+                   : dispatch_fused<2>(fast, dbg, tmap, p, stream);
 }
 
 }  // extern "C"

@@ -7,32 +7,35 @@
 // and rnn_scan (:146-199).  SURVEY.md section 8(f) row F1.
 //
 // Formulation (transposed GEMM, channels on TMEM lanes, time on TMEM columns):
-//   work column = (batch row b, 128 channels of one head);  tile = 64 time steps
-//   of one column, issued as two "granules" of 32 steps.  Per granule the MMA
-//   warp issues  D_x = Wx^T . X^T,  D_a = Wa^T . X^T  (M = 128 channels, N = 32
-//   steps, K = head width) and  D_t = I . X^T  (identity: the tensor core
-//   transposes the activations, exactly) into a 96-column TMEM slot.
-//   An epilogue thread owns ONE channel: tcgen05.ld hands it the pre-activations
-//   and x of consecutive time steps in registers, so the gate math works on
-//   bf16x2 pairs of (t, t+1), the recurrence is a register-resident sequential
-//   scan, and there is no shared-memory staging of activations at all.
-//   Tiles of one column are chained through global memory with the decoupled
-//   look-back of cg_scan.cuh (tagged 64-bit words, left-to-right folds only =>
-//   bit-reproducible).
+//   work column = (batch row b, 128 channels of one head = a "family");  scan
+//   tile = 32 time steps of one column.  One MMA tile covers TWO scan tiles of
+//   different columns (N = 64: rows 0-31 and 32-63 of the X stage come from two
+//   TMA boxes), so the 128 x K weight operand is fetched from shared memory
+//   once per 64 steps.  Per MMA tile the MMA warp issues
+//       D_x = Wx^T . X^T,   D_a = Wa^T . X^T   (M = 128 channels, K = head width)
+//       D_t = I . X^T       (identity: the tensor core transposes x, exactly)
+//   into 192 TMEM columns.  An epilogue thread owns ONE channel: tcgen05.ld
+//   hands it the pre-activations and x of consecutive time steps in registers,
+//   the gate math works on bf16x2 pairs (t, t+1), the per-step (a, x~) state is
+//   parked in TMEM (tcgen05.st) between the two scan passes, and the recurrence
+//   is a sequential fp32 scan in registers: no shared-memory staging of
+//   activations at all.  Tiles of one column are chained through global memory
+//   with the decoupled look-back of cg_scan.cuh (tagged 64-bit words, folds are
+//   always left-to-right => bit-reproducible).
 //
-// Roles (320 threads, 1 CTA / SM, persistent):
-//   warps 0-3, 4-7  two epilogue warpgroups (tiles alternate between them; each
-//                   owns two TMEM slots, so the MMAs of its next tile run while
-//                   it is still working)
-//   warp 8          TMA producer: gate weights (packed, pre-swizzled) once per
-//                   column family, then one X tile [64 steps x head width] per
-//                   tile through a 3-D tensor map (SWIZZLE_128B, zero fill
-//                   beyond T)
-//   warp 9          MMA issuer (one thread), tcgen05.commit -> mbarriers
-// CTA i works on column family (head, channel half) = i % families; the CTAs
-// of one family take its tiles round-robin in time-major order, so look-back
-// dependencies always point to tiles that are already running (all CTAs are
-// co-resident: grid <= #SMs, 1 CTA / SM).
+// Roles (576 threads, 1 CTA / SM, persistent):
+//   warps 0-15   four epilogue warpgroups in two pairs; pair p owns TMEM columns
+//                [256p, 256p+256): 192 accumulator + 2 x 32 state.  Warpgroup
+//                (p, h) works on half h (columns 32h..32h+31) of every MMA tile
+//                issued for pair p; MMA tiles alternate between the pairs.
+//   warp 16      TMA producer: packed, pre-swizzled gate weights once per
+//                family, then two X boxes [32 steps x head width] per MMA tile
+//                through a 3-D tensor map (SWIZZLE_128B, zero fill beyond T)
+//   warp 17      MMA issuer (one thread), tcgen05.commit -> mbarriers
+// CTA i works on family i % families; the CTAs of one family take its tiles
+// two at a time, round-robin in time-major order, so look-back dependencies
+// always point to tiles that are already running (all CTAs are co-resident:
+// grid <= #SMs, 1 CTA / SM).
 #pragma once
 
 #include <cuda.h>
@@ -43,12 +46,12 @@
 namespace cg {
 namespace fused {
 
-constexpr int kGran = 32;        // time steps per MMA granule (UMMA N)
-constexpr int kMch = 128;        // channels per work column (UMMA M)
-constexpr int kSlotCols = 96;    // TMEM columns per granule: pre_x | pre_a | x^T
-constexpr int kSlots = 4;        // TMEM slots: 2 per epilogue warpgroup
+constexpr int kTile = 32;         // time steps per scan tile (one epilogue warpgroup)
+constexpr int kMmaN = 2 * kTile;  // UMMA N: two scan tiles of different columns
+constexpr int kMch = 128;         // channels per work column (UMMA M)
+constexpr int kPairCols = 256;    // TMEM columns per warpgroup pair: 3 x 64 accumulator + 2 x 32 state
 constexpr int kTmemCols = 512;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;     // four warpgroups
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr uint32_t kKBlockBytes = 128u * 128u;   // 128 rows x 64 bf16 (one swizzle-128B K block)
 
@@ -60,7 +63,7 @@ struct FusedParams {
   const uint16_t* neg8sp_bf;       // [E] -8*softplus(a_param) as bf16 (prologue)
   const unsigned* reset_bits;      // [rows][words] bit t%32 of word t/32
   long long bits_bstride;          // words per batch row (0 = broadcast)
-  int words;                       // words per row
+  int words;                       // words per row (= ntt: one word per 32-step tile)
   const float* h0;                 // [B,E] or null
   uint16_t* y;                     // [B,T,E]
   float* last_h;                   // [B,E] or null
@@ -160,15 +163,36 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                :: "r"(smem_u32(bar)) : "memory");
 }
-// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets lane
+// 32 lanes x 8 consecutive 32-bit columns: thread i of the warp owns lane
 // (quadrant base + i), registers = columns.
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
-      " {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
       : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// fp32 + bf16 half of a packed register in one instruction (FHADD.BF16 with a
+// half selector on sm_100a): no unpack, one rounding -- == fadd_rn(widen(x), c).
+__device__ __forceinline__ float add_bf_lo(uint32_t packed, float c) {
+  float d;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, lo, %2;\n\t}"
+      : "=f"(d) : "r"(packed), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float add_bf_hi(uint32_t packed, float c) {
+  float d;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.bf16 %0, hi, %2;\n\t}"
+      : "=f"(d) : "r"(packed), "f"(c));
+  return d;
 }
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -191,17 +215,16 @@ __host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-template <int KB, int GPT>
+template <int KB>
 struct FusedCfg {
-  static constexpr int kTileT = kGran * GPT;
   static constexpr uint32_t kWBytes = 2u * KB * kKBlockBytes;
   static constexpr uint32_t kIBytes = 2u * kKBlockBytes;
-  static constexpr uint32_t kXStageBytes = static_cast<uint32_t>(KB) * kTileT * 128u;
-  static constexpr int kXStages = 65536 / kXStageBytes;
-  static constexpr int kBars = 2 + 2 * kXStages + 2 * kSlots;
+  static constexpr uint32_t kXKBlock = kMmaN * 128u;               // one K block of an X stage: 64 rows x 128 B
+  static constexpr uint32_t kXStageBytes = static_cast<uint32_t>(KB) * kXKBlock;
+  static constexpr int kXStages = 2;                               // one per warpgroup pair
+  static constexpr int kBars = 2 + 2 * kXStages + 4;
   static constexpr size_t kSmemBytes = 1024 + kWBytes + kIBytes + kXStages * kXStageBytes + kBars * 8 + 16;
   static_assert(KB % 2 == 0, "head width must be a multiple of 128");
-  static_assert(kXStages >= 2, "need at least two X stages");
 };
 
 // ---------------------------------------------------------------------------
@@ -252,18 +275,17 @@ __global__ void pack_gate_weights_kernel(const uint16_t* __restrict__ wx, const 
   }
 }
 
+
 // ---------------------------------------------------------------------------
-// The fused kernel.  KB = head width / 64 (K blocks), GPT = granules per tile.
+// The fused kernel.  KB = head width / 64 (K blocks of the gate GEMMs).
 // ---------------------------------------------------------------------------
-template <int KB, int GPT, bool FAST, bool DBG>
+template <int KB, bool FAST, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1)
 rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams p) {
-  using Cfg = FusedCfg<KB, GPT>;
-  constexpr int TILE_T = Cfg::kTileT;
-  constexpr int NP = TILE_T / 2;            // bf16x2 pairs of consecutive steps per tile
+  using Cfg = FusedCfg<KB>;
   constexpr int CBS = KB / 2;               // 128-channel halves per head
   constexpr int XS = Cfg::kXStages;
-  constexpr uint32_t IDESC = umma_idesc(kMch, kGran);
+  constexpr uint32_t IDESC = umma_idesc(kMch, kMmaN);
 
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -275,9 +297,9 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   uint64_t* w_empty = bars + 1;
   uint64_t* x_full = bars + 2;
   uint64_t* x_empty = x_full + XS;
-  uint64_t* t_full = x_empty + XS;
-  uint64_t* t_empty = t_full + kSlots;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(t_empty + kSlots);
+  uint64_t* t_full = x_empty + XS;          // [2] accumulators of pair p are complete
+  uint64_t* t_empty = t_full + 2;           // [2] both warpgroups of pair p have read them
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -286,7 +308,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     mbar_init(w_full, 1);
     mbar_init(w_empty, 1);
     for (int i = 0; i < XS; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
-    for (int i = 0; i < kSlots; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }
     fence_mbar_init();
   }
   if (warp == kEpiWarps) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
@@ -295,26 +317,26 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  // column-family schedule of this CTA (identical in every role)
+  // family schedule of this CTA (identical in every role).  Tiles of a family
+  // are ticketed time-major (ticket = tt * B + b) and handed out two at a time:
+  // ticket pair j -> CTA (j % nc) of the family, as its MMA tile number j / nc.
   const int G = gridDim.x, nfam = p.families;
   const bool spread = G >= nfam;                  // several CTAs share one family
   const int fam_step = spread ? nfam : G;
   const int rank = spread ? blockIdx.x / nfam : 0;
-  const int ntiles = p.ntt * p.B;                 // tiles of one family, time-major: ticket = tt*B + b
+  const int ntiles = p.ntt * p.B;
+  const int npairs = (ntiles + 1) >> 1;
   auto family_ctas = [&](int fam) { return spread ? (G - 1 - fam) / nfam + 1 : 1; };
-  auto my_tiles = [&](int fam) {
-    const int nc = family_ctas(fam);
-    return rank < ntiles ? (ntiles - rank + nc - 1) / nc : 0;
-  };
+  auto my_mma_tiles = [&](int nc) { return rank < npairs ? (npairs - rank + nc - 1) / nc : 0; };
 
   if (warp == kEpiWarps) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      uint32_t xq = 0, witer = 0;
+      uint32_t mq = 0, witer = 0;
       for (int fam = blockIdx.x % nfam; fam < nfam; fam += fam_step) {
-        const int nmine = my_tiles(fam);
-        if (nmine == 0) continue;
         const int nc = family_ctas(fam);
+        const int nm = my_mma_tiles(nc);
+        if (nm == 0) continue;
         if (witer > 0) mbar_wait(w_empty, (witer - 1) & 1, p.err, 1);
         mbar_expect_tx(w_full, Cfg::kWBytes + Cfg::kIBytes);
         const unsigned char* wsrc = p.wpack + (size_t)fam * Cfg::kWBytes;
@@ -327,17 +349,20 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         ++witer;
         const int c_head = (fam / CBS) * (KB * 64);
 #pragma unroll 1
-        for (int n = 0; n < nmine; ++n) {
-          const int ticket = rank + n * nc;
-          const int tt = ticket / p.B, b = ticket - tt * p.B;
-          const uint32_t stage = xq % XS, use = xq / XS;
+        for (int m = 0; m < nm; ++m, ++mq) {
+          const int t1st = 2 * (rank + m * nc);
+          const int nhalf = t1st + 1 < ntiles ? 2 : 1;
+          const uint32_t stage = mq & 1u, use = mq >> 1;
           mbar_wait(x_empty + stage, (use & 1) ^ 1, p.err, 2);
-          mbar_expect_tx(x_full + stage, Cfg::kXStageBytes);
+          mbar_expect_tx(x_full + stage, nhalf * (Cfg::kXStageBytes / 2));
+          for (int hf = 0; hf < nhalf; ++hf) {
+            const int ticket = t1st + hf;
+            const int tt = ticket / p.B, b = ticket - tt * p.B;
 #pragma unroll
-          for (int kb = 0; kb < KB; ++kb)
-            tma_load_3d(sX + stage * Cfg::kXStageBytes + kb * (TILE_T * 128), &tmap_x, x_full + stage,
-                        c_head + kb * 64, tt * TILE_T, b);
-          ++xq;
+            for (int kb = 0; kb < KB; ++kb)
+              tma_load_3d(sX + stage * Cfg::kXStageBytes + kb * Cfg::kXKBlock + hf * (kTile * 128), &tmap_x,
+                          x_full + stage, c_head + kb * 64, tt * kTile, b);
+          }
         }
       }
     }
@@ -345,53 +370,42 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   } else if (warp == kEpiWarps + 1) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      uint32_t xq = 0, witer = 0, q = 0, gq0 = 0, gq1 = 0;
+      uint32_t mq = 0, witer = 0;
       for (int fam = blockIdx.x % nfam; fam < nfam; fam += fam_step) {
-        const int nmine = my_tiles(fam);
-        if (nmine == 0) continue;
+        const int nm = my_mma_tiles(family_ctas(fam));
+        if (nm == 0) continue;
         const int cb = fam % CBS;
         mbar_wait(w_full, witer & 1, p.err, 3);
         tc_fence_after();
 #pragma unroll 1
-        for (int n = 0; n < nmine; ++n) {
-          const uint32_t wg = q & 1;
-          const uint32_t stage = xq % XS;
-          mbar_wait(x_full + stage, (xq / XS) & 1, p.err, 4);
+        for (int m = 0; m < nm; ++m, ++mq) {
+          const uint32_t pr = mq & 1u, use = mq >> 1;      // warpgroup pair == X stage
+          mbar_wait(x_full + pr, use & 1, p.err, 4);
+          mbar_wait(t_empty + pr, (use & 1) ^ 1, p.err, 5);
           tc_fence_after();
-          const uint32_t xs_addr = sX + stage * Cfg::kXStageBytes;
-#pragma unroll 1
-          for (int g = 0; g < GPT; ++g) {
-            const uint32_t gq = wg ? gq1 : gq0;
-            const uint32_t slot = wg * 2 + (gq & 1);
-            mbar_wait(t_empty + slot, ((gq >> 1) & 1) ^ 1, p.err, 5);
-            tc_fence_after();
-            const uint32_t dcol = tmem_base + slot * kSlotCols;
-            const uint32_t xrow = xs_addr + g * (kGran * 128);   // rows of this granule inside each K block
+          const uint32_t xs = sX + pr * Cfg::kXStageBytes;
+          const uint32_t dcol = tmem_base + pr * kPairCols;
 #pragma unroll
-            for (int gate = 0; gate < 2; ++gate) {
+          for (int gate = 0; gate < 2; ++gate) {
 #pragma unroll
-              for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  umma_bf16(dcol + gate * kGran,
-                            umma_desc(sW + (gate * KB + kb) * kKBlockBytes + k * 32),
-                            umma_desc(xrow + kb * (TILE_T * 128) + k * 32), IDESC, (kb | k) != 0);
-                }
-              }
-            }
-#pragma unroll
-            for (int kb = 0; kb < 2; ++kb) {
+            for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                umma_bf16(dcol + 2 * kGran, umma_desc(sI + kb * kKBlockBytes + k * 32),
-                          umma_desc(xrow + (2 * cb + kb) * (TILE_T * 128) + k * 32), IDESC, (kb | k) != 0);
+                umma_bf16(dcol + gate * kMmaN, umma_desc(sW + (gate * KB + kb) * kKBlockBytes + k * 32),
+                          umma_desc(xs + kb * Cfg::kXKBlock + k * 32), IDESC, (kb | k) != 0);
               }
             }
-            umma_commit(t_full + slot);
-            if (wg) ++gq1; else ++gq0;
           }
-          umma_commit(x_empty + stage);
-          ++xq; ++q;
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(dcol + 2 * kMmaN, umma_desc(sI + kb * kKBlockBytes + k * 32),
+                        umma_desc(xs + (2 * cb + kb) * Cfg::kXKBlock + k * 32), IDESC, (kb | k) != 0);
+            }
+          }
+          umma_commit(t_full + pr);
+          umma_commit(x_empty + pr);
         }
         umma_commit(w_empty);
         ++witer;
@@ -401,94 +415,109 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   } else {
     // ===================================================== epilogue warpgroups
     const int wg = warp >> 2;
+    const uint32_t pr = wg >> 1, hf = wg & 1;
     const int chl = (warp & 3) * 32 + lane;           // TMEM lane = channel inside the column
-    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    // TMEM addresses of this thread: accumulators of my half, my state columns
+    const uint32_t tm_acc = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + pr * kPairCols + hf * kTile;
+    const uint32_t tm_state = tm_acc - hf * kTile + 3 * kMmaN + hf * kTile;
     const unsigned epoch = *p.epoch;
-    uint32_t q = 0, gq = 0;
+    uint32_t mq = 0;
     for (int fam = blockIdx.x % nfam; fam < nfam; fam += fam_step) {
-      const int nmine = my_tiles(fam);
-      if (nmine == 0) continue;
       const int nc = family_ctas(fam);
+      const int nm = my_mma_tiles(nc);
+      if (nm == 0) continue;
       const int ch = fam * kMch + chl;
       uint32_t bx2 = 0, ba2 = 0;
       if (p.bias_x != nullptr) { const uint32_t v = p.bias_x[ch]; bx2 = v | (v << 16); }
       if (p.bias_a != nullptr) { const uint32_t v = p.bias_a[ch]; ba2 = v | (v << 16); }
       uint32_t sp2 = p.neg8sp_bf[ch]; sp2 |= sp2 << 16;
 #pragma unroll 1
-      for (int n = 0; n < nmine; ++n, ++q) {
-        if ((q & 1u) != static_cast<uint32_t>(wg)) continue;
-        const int ticket = rank + n * nc;
+      for (int m = 0; m < nm; ++m, ++mq) {
+        if ((mq & 1u) != pr) continue;
+        const uint32_t use = mq >> 1;
+        const int ticket = 2 * (rank + m * nc) + (int)hf;
+        mbar_wait(t_full + pr, use & 1, p.err, 6);
+        tc_fence_after();
+        if (ticket >= ntiles) {                            // odd tile count: nothing in my half
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_empty + pr);
+          continue;
+        }
         const int tt = ticket / p.B, b = ticket - tt * p.B;
-        const int t0 = tt * TILE_T;
-        uint32_t A2[NP], X2[NP];
+        const int t0 = tt * kTile;
+        const unsigned rbits = p.reset_bits[(long long)b * p.bits_bstride + tt];   // kTile == 32: one word
+        const int nvalid = p.T - t0;                       // >= 1; >= kTile for a full tile
         float P = 1.0f, Hh = 0.0f;
         // ------------------------------------------------------ pass 1
+        // gates for 4 bf16x2 pairs (8 steps) at a time; (a, x~) go to my TMEM
+        // state columns, the tile's transform h -> P*h + H is accumulated
+        auto chunk1 = [&](int c, auto slow_tag) {
+          constexpr bool SLOW = decltype(slow_tag)::value;
+          uint32_t dx[8], da[8], dt[8], st[8];
+          tmem_ld8(tm_acc + c * 8, dx);
+          tmem_ld8(tm_acc + kMmaN + c * 8, da);
+          tmem_ld8(tm_acc + 2 * kMmaN + c * 8, dt);
+          tmem_wait_ld();
 #pragma unroll
-        for (int g = 0; g < GPT; ++g) {
-          const uint32_t slot = wg * 2 + (gq & 1);
-          mbar_wait(t_full + slot, (gq >> 1) & 1, p.err, 6);
-          tc_fence_after();
-          const int word = (t0 >> 5) + g;
-          const unsigned rbits = word < p.words ? p.reset_bits[(long long)b * p.bits_bstride + word] : 0u;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t dx[16], da[16], dt[16];
-            const uint32_t col = tmem_base + lane_base + slot * kSlotCols + c * 16;
-            tmem_ld16(col, dx);
-            tmem_ld16(col + kGran, da);
-            tmem_ld16(col + 2 * kGran, dt);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int pi = g * 16 + c * 8 + i;           // pair index inside the tile
-              const int tl = t0 + 2 * pi;                  // time of the low half
-              // the GEMM output the reference materialises in bf16 (:136-142)
-              const uint32_t gxr = pack_bf2(__uint_as_float(dx[2 * i]), __uint_as_float(dx[2 * i + 1]));
-              const uint32_t gar = pack_bf2(__uint_as_float(da[2 * i]), __uint_as_float(da[2 * i + 1]));
-              const uint32_t xc = pack_bf2(__uint_as_float(dt[2 * i]), __uint_as_float(dt[2 * i + 1]));
-              uint32_t a2, n2;
-              gate_pair_emul<FAST, false>(xc, gxr, gar, bx2, ba2, sp2, a2, n2);
-              const unsigned r2 = (rbits >> (c * 16 + 2 * i)) & 3u;
-              if (r2 != 0u) {                              // document start inside the pair (rare, warp-uniform)
+          for (int i = 0; i < 4; ++i) {
+            // the GEMM output the reference materialises in bf16 (:136-142)
+            const uint32_t gxr = pack_bf2(__uint_as_float(dx[2 * i]), __uint_as_float(dx[2 * i + 1]));
+            const uint32_t gar = pack_bf2(__uint_as_float(da[2 * i]), __uint_as_float(da[2 * i + 1]));
+            const uint32_t xc = pack_bf2(__uint_as_float(dt[2 * i]), __uint_as_float(dt[2 * i + 1]));
+            uint32_t a2, n2;
+            gate_pair_emul<FAST, false>(xc, gxr, gar, bx2, ba2, sp2, a2, n2);
+            if constexpr (SLOW) {
+              const int tl = c * 8 + 2 * i;                // step of the low half inside the tile
+              const unsigned r2 = (rbits >> tl) & 3u;
+              if (r2 != 0u) {                              // document start inside the pair
                 uint32_t az, nr;
                 gate_pair_emul<FAST, true>(xc, gxr, gar, bx2, ba2, sp2, az, nr);
                 if (r2 & 1u) { a2 &= 0xffff0000u; n2 = (n2 & 0xffff0000u) | (nr & 0x0000ffffu); }
                 if (r2 & 2u) { a2 &= 0x0000ffffu; n2 = (n2 & 0x0000ffffu) | (nr & 0xffff0000u); }
               }
-              if (tl + 1 >= p.T) {                         // steps beyond T are identities
-                if (tl >= p.T) { a2 = kOne2; n2 = 0u; }
+              if (tl + 1 >= nvalid) {                      // steps beyond T are identities
+                if (tl >= nvalid) { a2 = kOne2; n2 = 0u; }
                 else { a2 = (a2 & 0x0000ffffu) | 0x3f800000u; n2 &= 0x0000ffffu; }
               }
-              if constexpr (DBG) {
-                const size_t plane = (size_t)p.B * p.T * p.E;
-                const size_t o0 = ((size_t)b * p.T + tl) * p.E + ch;
-                if (tl < p.T) {
-                  p.dbg[o0] = (uint16_t)(gxr & 0xffffu); p.dbg[plane + o0] = (uint16_t)(gar & 0xffffu);
-                  p.dbg[2 * plane + o0] = (uint16_t)(xc & 0xffffu);
-                }
-                if (tl + 1 < p.T) {
-                  p.dbg[o0 + p.E] = (uint16_t)(gxr >> 16); p.dbg[plane + o0 + p.E] = (uint16_t)(gar >> 16);
-                  p.dbg[2 * plane + o0 + p.E] = (uint16_t)(xc >> 16);
-                }
-              }
-              A2[pi] = a2; X2[pi] = n2;
-              const float al = bf_lo(a2), ah = bf_hi(a2);
-              Hh = fmaf(al, Hh, bf_lo(n2));
-              Hh = fmaf(ah, Hh, bf_hi(n2));
-              P *= al; P *= ah;
             }
+            if constexpr (DBG) {
+              const int tl = t0 + c * 8 + 2 * i;
+              const size_t plane = (size_t)p.B * p.T * p.E;
+              const size_t o0 = ((size_t)b * p.T + tl) * p.E + ch;
+              if (tl < p.T) {
+                p.dbg[o0] = (uint16_t)(gxr & 0xffffu); p.dbg[plane + o0] = (uint16_t)(gar & 0xffffu);
+                p.dbg[2 * plane + o0] = (uint16_t)(xc & 0xffffu);
+              }
+              if (tl + 1 < p.T) {
+                p.dbg[o0 + p.E] = (uint16_t)(gxr >> 16); p.dbg[plane + o0 + p.E] = (uint16_t)(gar >> 16);
+                p.dbg[2 * plane + o0 + p.E] = (uint16_t)(xc >> 16);
+              }
+            }
+            st[i] = a2; st[4 + i] = n2;
+            const float al = bf_lo(a2), ah = bf_hi(a2);
+            Hh = add_bf_lo(n2, al * Hh);                   // mul then add, as the reference loop (:196)
+            Hh = add_bf_hi(n2, ah * Hh);
+            P *= al; P *= ah;
           }
-          // this granule's TMEM slot may be overwritten by the next MMA
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty + slot);
-          ++gq;
+          tmem_st8(tm_state + c * 8, st);
+        };
+#pragma unroll 1
+        for (int c = 0; c < kTile / 8; ++c) {
+          const bool slow = ((rbits >> (c * 8)) & 0xffu) != 0u || c * 8 + 8 > nvalid;
+          if (slow) chunk1(c, TrueTag{});                  // rare (warp-uniform): own code path
+          else chunk1(c, FalseTag{});
         }
+        // my half of the accumulators may be overwritten by the next MMA tile
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(t_empty + pr);
         // ------------------------------------------------------ carry chain
         const size_t widx = (((size_t)fam * p.ntt + tt) * p.B + b) * kMch + chl;
         const size_t wstep = (size_t)p.B * kMch;           // one time tile back
         float c0;
-        if (tt > 0 && tt + 1 < p.ntt) {   // tile 0 publishes its state right away instead
+        if (tt > 0 && tt + 1 < p.ntt) {                    // tile 0 publishes its state right away instead
           st_relaxed_u64(p.agg_p + widx, pack_tagged(P, epoch));
           st_relaxed_u64(p.agg_h + widx, pack_tagged(Hh, epoch));
         }
@@ -522,22 +551,35 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         // ------------------------------------------------------ pass 2 (replay)
         float h = c0;
         uint16_t* yp = p.y + ((size_t)b * p.T + t0) * p.E + ch;
-        const bool full = t0 + TILE_T <= p.T;
+        const size_t E = (size_t)p.E;
+#pragma unroll 1
+        for (int c = 0; c < kTile / 8; ++c) {
+          uint32_t st[8];
+          tmem_ld8(tm_state + c * 8, st);
+          tmem_wait_ld();
+          uint32_t o[4];
 #pragma unroll
-        for (int pi = 0; pi < NP; ++pi) {
-          const uint32_t a2 = A2[pi], n2 = X2[pi];
-          float y0, y1;
-          if constexpr (FAST) {
-            y0 = fmaf(bf_lo(a2), h, bf_lo(n2));
-            y1 = fmaf(bf_hi(a2), y0, bf_hi(n2));
-          } else {                                         // mul then add, as the reference loop (:196)
-            y0 = __fadd_rn(__fmul_rn(bf_lo(a2), h), bf_lo(n2));
-            y1 = __fadd_rn(__fmul_rn(bf_hi(a2), y0), bf_hi(n2));
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t a2 = st[i], n2 = st[4 + i];
+            const float y0 = add_bf_lo(n2, bf_lo(a2) * h);
+            const float y1 = add_bf_hi(n2, bf_hi(a2) * y0);
+            h = y1;
+            o[i] = pack_bf2(y0, y1);
           }
-          h = y1;
-          const uint32_t o = pack_bf2(y0, y1);
-          if (full || t0 + 2 * pi < p.T) st_u16(yp + (size_t)(2 * pi) * p.E, o);
-          if (full || t0 + 2 * pi + 1 < p.T) st_u16(yp + (size_t)(2 * pi + 1) * p.E, o >> 16);
+          uint16_t* yc = yp + (size_t)(c * 8) * E;
+          if (c * 8 + 8 <= nvalid) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              st_u16(yc + (size_t)(2 * i) * E, o[i]);
+              st_u16(yc + (size_t)(2 * i + 1) * E, o[i] >> 16);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (c * 8 + 2 * i < nvalid) st_u16(yc + (size_t)(2 * i) * E, o[i]);
+              if (c * 8 + 2 * i + 1 < nvalid) st_u16(yc + (size_t)(2 * i + 1) * E, o[i] >> 16);
+            }
+          }
         }
         if (p.last_h != nullptr && tt == p.ntt - 1) p.last_h[(size_t)b * p.E + ch] = h;
       }
