@@ -13,7 +13,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libcadence_b200.so")
+LIB_PATH = os.environ.get("CG_B200_LIB") or os.path.join(_HERE, "csrc", "libcadence_b200.so")
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ARITH_REFERENCE, ARITH_FP32, ARITH_FAST, ARITH_STRICT = 0, 1, 2, 4

@@ -43,6 +43,36 @@
 #include "cg_common.cuh"
 #include "cg_scan.cuh"
 
+// tuning switches (scripts/build_variants.py); the defaults are the shipped configuration
+#ifndef CGF_SLEEP_NS
+#define CGF_SLEEP_NS 64
+#endif
+#ifndef CGF_PRELOAD
+#define CGF_PRELOAD 1
+#endif
+#ifndef CGF_LOOK
+#define CGF_LOOK 1
+#endif
+#ifndef CGF_HINT_NS
+#define CGF_HINT_NS 20000
+#endif
+// CGF_TRACE: debug_out becomes a timeline buffer [6 roles][1024] of
+// (clock64 << 4 | event) words written by CTA 0 (scripts/fused_trace.py)
+#ifndef CGF_TRACE
+#define CGF_TRACE 0
+#endif
+
+#if CGF_TRACE
+#define CGF_EVENT(role, code)                                                               \
+  do {                                                                                      \
+    if (blockIdx.x == 0 && lane == 0 && tn < 1024)                                          \
+      reinterpret_cast<unsigned long long*>(p.dbg)[(role) * 1024 + tn++] =                  \
+          (static_cast<unsigned long long>(clock64()) << 4) | (unsigned)(code);             \
+  } while (0)
+#else
+#define CGF_EVENT(role, code) do { } while (0)
+#endif
+
 namespace cg {
 namespace fused {
 
@@ -99,9 +129,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"((unsigned)CGF_HINT_NS) : "memory");   // suspend-time hint (ns)
   return ok != 0;
 }
 // Bounded wait: a protocol bug must end the launch, never hang the device.  On
@@ -110,7 +140,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // garbage results) and the host finds the flag.
 constexpr long long kWatchdogCycles = 1000000000LL;   // ~0.5 s
 __device__ __forceinline__ bool watchdog_expired(long long t0, int* err, int code, unsigned& polls) {
-  if ((++polls & 1023u) != 0u) return false;
+  if ((++polls & 63u) != 0u) return false;
   if (*reinterpret_cast<volatile int*>(err) != 0) return true;
   if (clock64() - t0 > kWatchdogCycles) { atomicCAS(err, 0, code); return true; }
   return false;
@@ -120,6 +150,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
   const long long t0 = clock64();
   unsigned polls = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (CGF_SLEEP_NS > 0) __nanosleep(CGF_SLEEP_NS);   // waiting warps must not eat the issue slots of the working ones
     if (watchdog_expired(t0, err, code, polls)) return;
   }
 }
@@ -135,6 +166,17 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       :: "r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// One lane of a CONVERGED warp.  The roles that issue TMA / tcgen05.mma run with
+// all 32 lanes so that descriptors and coordinates stay warp-uniform (uniform
+// registers); only the issuing instruction itself is predicated on the elected
+// lane.  (Inside an `if (lane == 0)` region the compiler cannot prove uniformity
+// and wraps every UTCHMMA in a R2UR broadcast loop -- ~100 cycles per MMA.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+               : "=r"(pred) :: "memory");
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -279,6 +321,8 @@ __global__ void pack_gate_weights_kernel(const uint16_t* __restrict__ wx, const 
 // ---------------------------------------------------------------------------
 // The fused kernel.  KB = head width / 64 (K blocks of the gate GEMMs).
 // ---------------------------------------------------------------------------
+// (registers are allocated in units of four warps: 18 warps count as 20, which
+// caps the kernel at 96 registers per thread)
 template <int KB, bool FAST, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1)
 rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams p) {
@@ -331,21 +375,25 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
 
   if (warp == kEpiWarps) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    {
       uint32_t mq = 0, witer = 0;
+      int tn = 0; (void)tn;
       for (int fam = blockIdx.x % nfam; fam < nfam; fam += fam_step) {
         const int nc = family_ctas(fam);
         const int nm = my_mma_tiles(nc);
         if (nm == 0) continue;
         if (witer > 0) mbar_wait(w_empty, (witer - 1) & 1, p.err, 1);
-        mbar_expect_tx(w_full, Cfg::kWBytes + Cfg::kIBytes);
         const unsigned char* wsrc = p.wpack + (size_t)fam * Cfg::kWBytes;
+        if (elect_one()) {
+          mbar_expect_tx(w_full, Cfg::kWBytes + Cfg::kIBytes);
 #pragma unroll 1
-        for (uint32_t off = 0; off < Cfg::kWBytes; off += kKBlockBytes)
-          bulk_load(sW + off, wsrc + off, kKBlockBytes, w_full);
+          for (uint32_t off = 0; off < Cfg::kWBytes; off += kKBlockBytes)
+            bulk_load(sW + off, wsrc + off, kKBlockBytes, w_full);
 #pragma unroll 1
-        for (uint32_t off = 0; off < Cfg::kIBytes; off += kKBlockBytes)
-          bulk_load(sI + off, p.ident + off, kKBlockBytes, w_full);
+          for (uint32_t off = 0; off < Cfg::kIBytes; off += kKBlockBytes)
+            bulk_load(sI + off, p.ident + off, kKBlockBytes, w_full);
+        }
+        __syncwarp();
         ++witer;
         const int c_head = (fam / CBS) * (KB * 64);
 #pragma unroll 1
@@ -353,24 +401,30 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           const int t1st = 2 * (rank + m * nc);
           const int nhalf = t1st + 1 < ntiles ? 2 : 1;
           const uint32_t stage = mq & 1u, use = mq >> 1;
+          CGF_EVENT(0, 1);
           mbar_wait(x_empty + stage, (use & 1) ^ 1, p.err, 2);
-          mbar_expect_tx(x_full + stage, nhalf * (Cfg::kXStageBytes / 2));
+          CGF_EVENT(0, 2);
+          if (elect_one()) mbar_expect_tx(x_full + stage, nhalf * (Cfg::kXStageBytes / 2));
           for (int hf = 0; hf < nhalf; ++hf) {
             const int ticket = t1st + hf;
             const int tt = ticket / p.B, b = ticket - tt * p.B;
+            if (elect_one()) {
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb)
-              tma_load_3d(sX + stage * Cfg::kXStageBytes + kb * Cfg::kXKBlock + hf * (kTile * 128), &tmap_x,
-                          x_full + stage, c_head + kb * 64, tt * kTile, b);
+              for (int kb = 0; kb < KB; ++kb)
+                tma_load_3d(sX + stage * Cfg::kXStageBytes + kb * Cfg::kXKBlock + hf * (kTile * 128), &tmap_x,
+                            x_full + stage, c_head + kb * 64, tt * kTile, b);
+            }
           }
+          __syncwarp();
         }
       }
     }
     __syncwarp();
   } else if (warp == kEpiWarps + 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    {
       uint32_t mq = 0, witer = 0;
+      int tn = 0; (void)tn;
       for (int fam = blockIdx.x % nfam; fam < nfam; fam += fam_step) {
         const int nm = my_mma_tiles(family_ctas(fam));
         if (nm == 0) continue;
@@ -380,11 +434,15 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
 #pragma unroll 1
         for (int m = 0; m < nm; ++m, ++mq) {
           const uint32_t pr = mq & 1u, use = mq >> 1;      // warpgroup pair == X stage
+          CGF_EVENT(1, 1);
           mbar_wait(x_full + pr, use & 1, p.err, 4);
+          CGF_EVENT(1, 2);
           mbar_wait(t_empty + pr, (use & 1) ^ 1, p.err, 5);
+          CGF_EVENT(1, 3);
           tc_fence_after();
           const uint32_t xs = sX + pr * Cfg::kXStageBytes;
           const uint32_t dcol = tmem_base + pr * kPairCols;
+          if (elect_one()) {
 #pragma unroll
           for (int gate = 0; gate < 2; ++gate) {
 #pragma unroll
@@ -406,14 +464,27 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           }
           umma_commit(t_full + pr);
           umma_commit(x_empty + pr);
+          }
+          __syncwarp();
+          CGF_EVENT(1, 4);
         }
-        umma_commit(w_empty);
+        if (elect_one()) umma_commit(w_empty);
+        __syncwarp();
         ++witer;
       }
     }
     __syncwarp();
   } else {
     // ===================================================== epilogue warpgroups
+    // One warpgroup, tile after tile:
+    //   request the state word of tile k-1's predecessor, wait for tile k's
+    //   accumulators (the look-back round trip hides behind that wait);
+    //   F(k-1) finish the previous tile: carry-in by decoupled look-back and the
+    //          replay pass that writes y;
+    //   G(k)   gates: accumulators -> registers (rounded to bf16) -> (a, x~) into
+    //          my TMEM state columns; the slot goes back to the MMA warp half way
+    //          through, so the MMAs of the pair's next tile run under G and F;
+    //          publish the tile's aggregate.
     const int wg = warp >> 2;
     const uint32_t pr = wg >> 1, hf = wg & 1;
     const int chl = (warp & 3) * 32 + lane;           // TMEM lane = channel inside the column
@@ -422,6 +493,120 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     const uint32_t tm_state = tm_acc - hf * kTile + 3 * kMmaN + hf * kTile;
     const unsigned epoch = *p.epoch;
     uint32_t mq = 0;
+    int tn = 0; (void)tn;
+    const int trole = 2 + wg; (void)trole;
+    const bool twarp = (warp & 3) == 0; (void)twarp;
+
+    // the tile whose pass 2 is still owed
+    struct Pending { bool on; int tt, b, nvalid, ch; size_t widx; uint16_t* yp; float P, H; };
+    Pending pd{}; pd.on = false;
+    const size_t wstep = (size_t)p.B * kMch;             // exchange words: one time tile back
+
+    auto release_slot = [&]() {                          // my half of the accumulators is consumed
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty + pr);
+    };
+
+    // F: carry chain + pass 2 of the pending tile
+    auto finish = [&](unsigned long long early) {
+      // `early`: the predecessor's state word, requested before stage A
+      const int tt = pd.tt;
+      float c0;
+      if (tt == 0) {
+        c0 = p.h0 != nullptr ? p.h0[(size_t)pd.b * p.E + pd.ch] : 0.0f;
+      } else if (__all_sync(0xffffffffu, (unsigned)early == epoch)) {
+        c0 = tagged_value(early);
+      } else {
+        // Decoupled look-back, kLook tiles per round trip.  Tiles [end, tt) are
+        // folded into (fp, fh): h(tt start) = fp * h(end start) + fh; folds run
+        // left to right only, so the result does not depend on timing.
+        constexpr int kLook = CGF_LOOK;
+        int end = tt;
+        float fp = 1.0f, fh = 0.0f;
+        const long long t_start = clock64();
+        unsigned polls = 0;
+        c0 = 0.0f;
+        for (;;) {
+          const int depth = end < kLook ? end : kLook;
+          unsigned long long wpf[kLook], wap[kLook], wah[kLook];
+#pragma unroll
+          for (int k = 0; k < kLook; ++k) {
+            if (k < depth) {
+              const size_t src = pd.widx - (size_t)(tt - end + k + 1) * wstep;
+              wpf[k] = ld_relaxed_u64(p.pref + src);
+              wap[k] = ld_relaxed_u64(p.agg_p + src);
+              wah[k] = ld_relaxed_u64(p.agg_h + src);
+            } else {
+              wpf[k] = wap[k] = wah[k] = 0ull;
+            }
+          }
+          bool done = false;
+          int used = 0;                                  // aggregates consumed this round
+#pragma unroll
+          for (int k = 0; k < kLook; ++k) {
+            if (!done && k == used && k < depth) {
+              if (__all_sync(0xffffffffu, (unsigned)wpf[k] == epoch)) {
+                c0 = fmaf(fp, tagged_value(wpf[k]), fh);
+                done = true;
+              } else if (__all_sync(0xffffffffu, (unsigned)wap[k] == epoch && (unsigned)wah[k] == epoch)) {
+                fh = fmaf(fp, tagged_value(wah[k]), fh);   // compose with the tile before
+                fp = fp * tagged_value(wap[k]);
+                used = k + 1;
+              }
+            }
+          }
+          if (done) break;
+          end -= used;                                   // (tile 0 never publishes an aggregate: end stays > 0)
+          if (used == 0) __nanosleep(40);
+          polls += 3;
+          if (__any_sync(0xffffffffu, watchdog_expired(t_start, p.err, 7, polls))) break;
+        }
+      }
+      if (tt + 1 < p.ntt) st_relaxed_u64(p.pref + pd.widx, pack_tagged(fmaf(pd.P, c0, pd.H), epoch));
+      if (twarp) CGF_EVENT(trole, 5);
+      // ---- pass 2 (replay): h = a*h + x~ from the true carry-in, mul then add as
+      // the reference loop (:196); y leaves as bf16
+      float h = c0;
+      const int E = p.E;
+      const int nvalid = pd.nvalid;
+#pragma unroll 1
+      for (int c = 0; c < kTile / 8; ++c) {
+        uint32_t st[8];
+        tmem_ld8(tm_state + c * 8, st);
+        tmem_wait_ld();
+        uint32_t o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t a2 = st[i], n2 = st[4 + i];
+          const float y0 = add_bf_lo(n2, bf_lo(a2) * h);
+          const float y1 = add_bf_hi(n2, bf_hi(a2) * y0);
+          h = y1;
+          o[i] = pack_bf2(y0, y1);
+        }
+        uint16_t* yc = pd.yp + (size_t)(c * 8) * E;
+        if (c * 8 + 8 <= nvalid) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            st_u16(yc + (2 * i) * E, o[i]);
+            st_u16(yc + (2 * i + 1) * E, o[i] >> 16);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (c * 8 + 2 * i < nvalid) st_u16(yc + (2 * i) * E, o[i]);
+            if (c * 8 + 2 * i + 1 < nvalid) st_u16(yc + (2 * i + 1) * E, o[i] >> 16);
+          }
+        }
+      }
+      if (p.last_h != nullptr && tt == p.ntt - 1) p.last_h[(size_t)pd.b * E + pd.ch] = h;
+      pd.on = false;
+      if (twarp) CGF_EVENT(trole, 6);
+    };
+    auto request_pred = [&]() -> unsigned long long {    // state word of the pending tile's predecessor
+      return (pd.on && pd.tt > 0) ? ld_relaxed_u64(p.pref + pd.widx - wstep) : 0ull;
+    };
+
     for (int fam = blockIdx.x % nfam; fam < nfam; fam += fam_step) {
       const int nc = family_ctas(fam);
       const int nm = my_mma_tiles(nc);
@@ -436,12 +621,15 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         if ((mq & 1u) != pr) continue;
         const uint32_t use = mq >> 1;
         const int ticket = 2 * (rank + m * nc) + (int)hf;
+        if (twarp) CGF_EVENT(trole, 8);
+        const unsigned long long early = request_pred();
+        if (twarp) CGF_EVENT(trole, 1);
         mbar_wait(t_full + pr, use & 1, p.err, 6);
+        if (twarp) CGF_EVENT(trole, 2);
         tc_fence_after();
+        if (pd.on) finish(early);                          // F(k-1)
         if (ticket >= ntiles) {                            // odd tile count: nothing in my half
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty + pr);
+          release_slot();
           continue;
         }
         const int tt = ticket / p.B, b = ticket - tt * p.B;
@@ -449,141 +637,118 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         const unsigned rbits = p.reset_bits[(long long)b * p.bits_bstride + tt];   // kTile == 32: one word
         const int nvalid = p.T - t0;                       // >= 1; >= kTile for a full tile
         float P = 1.0f, Hh = 0.0f;
-        // ------------------------------------------------------ pass 1
-        // gates for 4 bf16x2 pairs (8 steps) at a time; (a, x~) go to my TMEM
-        // state columns, the tile's transform h -> P*h + H is accumulated
-        auto chunk1 = [&](int c, auto slow_tag) {
+        // gates for one bf16x2 pair of steps (t, t+1) -> (a, x~); the tile's
+        // transform h -> P*h + H is accumulated on the way
+        auto gate_step = [&](uint32_t xc, uint32_t gxr, uint32_t gar, int tl, auto slow_tag,
+                             uint32_t& a2, uint32_t& n2) {
           constexpr bool SLOW = decltype(slow_tag)::value;
-          uint32_t dx[8], da[8], dt[8], st[8];
-          tmem_ld8(tm_acc + c * 8, dx);
-          tmem_ld8(tm_acc + kMmaN + c * 8, da);
-          tmem_ld8(tm_acc + 2 * kMmaN + c * 8, dt);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            // the GEMM output the reference materialises in bf16 (:136-142)
-            const uint32_t gxr = pack_bf2(__uint_as_float(dx[2 * i]), __uint_as_float(dx[2 * i + 1]));
-            const uint32_t gar = pack_bf2(__uint_as_float(da[2 * i]), __uint_as_float(da[2 * i + 1]));
-            const uint32_t xc = pack_bf2(__uint_as_float(dt[2 * i]), __uint_as_float(dt[2 * i + 1]));
-            uint32_t a2, n2;
-            gate_pair_emul<FAST, false>(xc, gxr, gar, bx2, ba2, sp2, a2, n2);
-            if constexpr (SLOW) {
-              const int tl = c * 8 + 2 * i;                // step of the low half inside the tile
-              const unsigned r2 = (rbits >> tl) & 3u;
-              if (r2 != 0u) {                              // document start inside the pair
-                uint32_t az, nr;
-                gate_pair_emul<FAST, true>(xc, gxr, gar, bx2, ba2, sp2, az, nr);
-                if (r2 & 1u) { a2 &= 0xffff0000u; n2 = (n2 & 0xffff0000u) | (nr & 0x0000ffffu); }
-                if (r2 & 2u) { a2 &= 0x0000ffffu; n2 = (n2 & 0x0000ffffu) | (nr & 0xffff0000u); }
-              }
-              if (tl + 1 >= nvalid) {                      // steps beyond T are identities
-                if (tl >= nvalid) { a2 = kOne2; n2 = 0u; }
-                else { a2 = (a2 & 0x0000ffffu) | 0x3f800000u; n2 &= 0x0000ffffu; }
-              }
+          gate_pair_emul<FAST, false>(xc, gxr, gar, bx2, ba2, sp2, a2, n2);
+          if constexpr (SLOW) {                            // tl = step of the low half inside the tile
+            const unsigned r2 = (rbits >> tl) & 3u;
+            if (r2 != 0u) {                                // document start inside the pair
+              uint32_t az, nr;
+              gate_pair_emul<FAST, true>(xc, gxr, gar, bx2, ba2, sp2, az, nr);
+              if (r2 & 1u) { a2 &= 0xffff0000u; n2 = (n2 & 0xffff0000u) | (nr & 0x0000ffffu); }
+              if (r2 & 2u) { a2 &= 0x0000ffffu; n2 = (n2 & 0x0000ffffu) | (nr & 0xffff0000u); }
             }
-            if constexpr (DBG) {
-              const int tl = t0 + c * 8 + 2 * i;
-              const size_t plane = (size_t)p.B * p.T * p.E;
-              const size_t o0 = ((size_t)b * p.T + tl) * p.E + ch;
-              if (tl < p.T) {
-                p.dbg[o0] = (uint16_t)(gxr & 0xffffu); p.dbg[plane + o0] = (uint16_t)(gar & 0xffffu);
-                p.dbg[2 * plane + o0] = (uint16_t)(xc & 0xffffu);
-              }
-              if (tl + 1 < p.T) {
-                p.dbg[o0 + p.E] = (uint16_t)(gxr >> 16); p.dbg[plane + o0 + p.E] = (uint16_t)(gar >> 16);
-                p.dbg[2 * plane + o0 + p.E] = (uint16_t)(xc >> 16);
-              }
+            if (tl + 1 >= nvalid) {                        // steps beyond T are identities
+              if (tl >= nvalid) { a2 = kOne2; n2 = 0u; }
+              else { a2 = (a2 & 0x0000ffffu) | 0x3f800000u; n2 &= 0x0000ffffu; }
             }
-            st[i] = a2; st[4 + i] = n2;
-            const float al = bf_lo(a2), ah = bf_hi(a2);
-            Hh = add_bf_lo(n2, al * Hh);                   // mul then add, as the reference loop (:196)
-            Hh = add_bf_hi(n2, ah * Hh);
-            P *= al; P *= ah;
           }
-          tmem_st8(tm_state + c * 8, st);
+          if constexpr (DBG && !CGF_TRACE) {
+            const int tg = t0 + tl;
+            const size_t plane = (size_t)p.B * p.T * p.E;
+            const size_t o0 = ((size_t)b * p.T + tg) * p.E + ch;
+            if (tg < p.T) {
+              p.dbg[o0] = (uint16_t)(gxr & 0xffffu); p.dbg[plane + o0] = (uint16_t)(gar & 0xffffu);
+              p.dbg[2 * plane + o0] = (uint16_t)(xc & 0xffffu);
+            }
+            if (tg + 1 < p.T) {
+              p.dbg[o0 + p.E] = (uint16_t)(gxr >> 16); p.dbg[plane + o0 + p.E] = (uint16_t)(gar >> 16);
+              p.dbg[2 * plane + o0 + p.E] = (uint16_t)(xc >> 16);
+            }
+          }
+          const float al = bf_lo(a2), ah = bf_hi(a2);
+          Hh = add_bf_lo(n2, al * Hh);                     // mul then add, as the reference loop (:196)
+          Hh = add_bf_hi(n2, ah * Hh);
+          P *= al; P *= ah;
         };
+        if (CGF_PRELOAD && rbits == 0u && nvalid >= kTile) {
+          // ---- common case, half a tile (8 pairs) at a time: pull the
+          // accumulators out of TMEM, rounded to bf16 on the way (the GEMM output
+          // the reference materialises, :136-142), then the gate math from
+          // registers.  The slot goes back to the MMA warp as soon as the second
+          // half has been read.
 #pragma unroll 1
-        for (int c = 0; c < kTile / 8; ++c) {
-          const bool slow = ((rbits >> (c * 8)) & 0xffu) != 0u || c * 8 + 8 > nvalid;
-          if (slow) chunk1(c, TrueTag{});                  // rare (warp-uniform): own code path
-          else chunk1(c, FalseTag{});
-        }
-        // my half of the accumulators may be overwritten by the next MMA tile
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(t_empty + pr);
-        // ------------------------------------------------------ carry chain
-        const size_t widx = (((size_t)fam * p.ntt + tt) * p.B + b) * kMch + chl;
-        const size_t wstep = (size_t)p.B * kMch;           // one time tile back
-        float c0;
-        if (tt > 0 && tt + 1 < p.ntt) {                    // tile 0 publishes its state right away instead
-          st_relaxed_u64(p.agg_p + widx, pack_tagged(P, epoch));
-          st_relaxed_u64(p.agg_h + widx, pack_tagged(Hh, epoch));
-        }
-        if (tt == 0) {
-          c0 = p.h0 != nullptr ? p.h0[(size_t)b * p.E + ch] : 0.0f;
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t gx[8], ga[8], xv[8];
+            {
+              uint32_t dx[16], da[16], dt[16];
+              const uint32_t col = tm_acc + hh * 16;
+              tmem_ld8(col, *reinterpret_cast<uint32_t(*)[8]>(&dx[0]));
+              tmem_ld8(col + 8, *reinterpret_cast<uint32_t(*)[8]>(&dx[8]));
+              tmem_ld8(col + kMmaN, *reinterpret_cast<uint32_t(*)[8]>(&da[0]));
+              tmem_ld8(col + kMmaN + 8, *reinterpret_cast<uint32_t(*)[8]>(&da[8]));
+              tmem_ld8(col + 2 * kMmaN, *reinterpret_cast<uint32_t(*)[8]>(&dt[0]));
+              tmem_ld8(col + 2 * kMmaN + 8, *reinterpret_cast<uint32_t(*)[8]>(&dt[8]));
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                gx[i] = pack_bf2(__uint_as_float(dx[2 * i]), __uint_as_float(dx[2 * i + 1]));
+                ga[i] = pack_bf2(__uint_as_float(da[2 * i]), __uint_as_float(da[2 * i + 1]));
+                xv[i] = pack_bf2(__uint_as_float(dt[2 * i]), __uint_as_float(dt[2 * i + 1]));
+              }
+            }
+            if (hh == 1) {
+              release_slot();
+              if (twarp) CGF_EVENT(trole, 3);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              uint32_t st[8];
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                gate_step(xv[c * 4 + i], gx[c * 4 + i], ga[c * 4 + i], hh * 16 + c * 8 + 2 * i, FalseTag{}, st[i], st[4 + i]);
+              tmem_st8(tm_state + hh * 16 + c * 8, st);
+            }
+          }
         } else {
-          int j = tt - 1;
-          size_t src = widx - wstep;
-          unsigned long long pw;
-          const long long t_start = clock64();
-          unsigned polls = 0;
-          for (;;) {
-            pw = ld_relaxed_u64(p.pref + src);
-            if (__all_sync(0xffffffffu, (unsigned)pw == epoch)) break;
-            const bool agg = (unsigned)ld_relaxed_u64(p.agg_p + src) == epoch &&
-                             (unsigned)ld_relaxed_u64(p.agg_h + src) == epoch;
-            // (tile 0 never publishes an aggregate, only its state: j stays >= 0)
-            if (__all_sync(0xffffffffu, agg)) { --j; src -= wstep; continue; }
-            __nanosleep(20);
-            polls += 63;   // a poll here costs ~a microsecond: check the watchdog every 16 polls
-            if (__any_sync(0xffffffffu, watchdog_expired(t_start, p.err, 7, polls))) break;
-          }
-          c0 = tagged_value(pw);
-          for (int k = j + 1; k < tt; ++k) {               // fold the aggregates passed on the way, left to right
-            src += wstep;
-            c0 = fmaf(tagged_value(ld_relaxed_u64(p.agg_p + src)), c0,
-                      tagged_value(ld_relaxed_u64(p.agg_h + src)));
-          }
-        }
-        if (tt + 1 < p.ntt) st_relaxed_u64(p.pref + widx, pack_tagged(fmaf(P, c0, Hh), epoch));
-        // ------------------------------------------------------ pass 2 (replay)
-        float h = c0;
-        uint16_t* yp = p.y + ((size_t)b * p.T + t0) * p.E + ch;
-        const size_t E = (size_t)p.E;
+          // document starts or a ragged tail inside the tile (rare, warp-uniform):
+          // gates chunk by chunk out of TMEM
 #pragma unroll 1
-        for (int c = 0; c < kTile / 8; ++c) {
-          uint32_t st[8];
-          tmem_ld8(tm_state + c * 8, st);
-          tmem_wait_ld();
-          uint32_t o[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t a2 = st[i], n2 = st[4 + i];
-            const float y0 = add_bf_lo(n2, bf_lo(a2) * h);
-            const float y1 = add_bf_hi(n2, bf_hi(a2) * y0);
-            h = y1;
-            o[i] = pack_bf2(y0, y1);
-          }
-          uint16_t* yc = yp + (size_t)(c * 8) * E;
-          if (c * 8 + 8 <= nvalid) {
+          for (int c = 0; c < kTile / 8; ++c) {
+            uint32_t dx[8], da[8], dt[8], st[8];
+            tmem_ld8(tm_acc + c * 8, dx);
+            tmem_ld8(tm_acc + kMmaN + c * 8, da);
+            tmem_ld8(tm_acc + 2 * kMmaN + c * 8, dt);
+            tmem_wait_ld();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              st_u16(yc + (size_t)(2 * i) * E, o[i]);
-              st_u16(yc + (size_t)(2 * i + 1) * E, o[i] >> 16);
+              const uint32_t gxr = pack_bf2(__uint_as_float(dx[2 * i]), __uint_as_float(dx[2 * i + 1]));
+              const uint32_t gar = pack_bf2(__uint_as_float(da[2 * i]), __uint_as_float(da[2 * i + 1]));
+              const uint32_t xc = pack_bf2(__uint_as_float(dt[2 * i]), __uint_as_float(dt[2 * i + 1]));
+              gate_step(xc, gxr, gar, c * 8 + 2 * i, TrueTag{}, st[i], st[4 + i]);
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (c * 8 + 2 * i < nvalid) st_u16(yc + (size_t)(2 * i) * E, o[i]);
-              if (c * 8 + 2 * i + 1 < nvalid) st_u16(yc + (size_t)(2 * i + 1) * E, o[i] >> 16);
-            }
+            tmem_st8(tm_state + c * 8, st);
           }
+          release_slot();
         }
-        if (p.last_h != nullptr && tt == p.ntt - 1) p.last_h[(size_t)b * p.E + ch] = h;
+        tmem_wait_st();
+        if (twarp) CGF_EVENT(trole, 4);
+        // publish the tile's aggregate (tile 0 publishes its state right away in
+        // F instead) and queue the tile for F
+        pd.on = true; pd.tt = tt; pd.b = b; pd.nvalid = nvalid; pd.ch = ch; pd.P = P; pd.H = Hh;
+        pd.widx = (((size_t)fam * p.ntt + tt) * p.B + b) * kMch + chl;
+        pd.yp = p.y + ((size_t)b * p.T + t0) * p.E + ch;
+        if (tt > 0 && tt + 1 < p.ntt) {
+          st_relaxed_u64(p.agg_p + pd.widx, pack_tagged(P, epoch));
+          st_relaxed_u64(p.agg_h + pd.widx, pack_tagged(Hh, epoch));
+        }
+        if (twarp) CGF_EVENT(trole, 7);
       }
     }
+    if (pd.on) finish(request_pred());
   }
 
   // teardown: every role is done with TMEM

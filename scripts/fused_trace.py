@@ -1,0 +1,34 @@
+"""Timeline of one CTA of the fused kernel (needs a -DCGF_TRACE=1 build, see
+scripts/build_variants.py): per role, the clock64 of every pipeline event."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from cadence_gemma_b200 import _abi  # noqa: E402
+from scripts.fused_check import make  # noqa: E402
+
+B, T, E, H = 8, 2048, 2560, 10
+x, lru, seg, _ = make(B, T, E, H, resets=False)
+wpack = _abi.pack_gate_weights(lru.input_gate.w, lru.a_gate.w)
+ws = _abi.fused_workspace(x.device, B, T, E)
+for _ in range(3):
+  out = _abi.rglru_fused_fwd(x, wpack, lru.input_gate.b, lru.a_gate.b, lru.a_param, seg, H,
+                             arith_mode=2, debug=True, workspace=ws)
+torch.cuda.synchronize()
+tr = out[2].view(-1).view(torch.int64)[: 6 * 1024].view(6, 1024).cpu()
+names = ["producer", "mma", "wg0", "wg1", "wg2", "wg3"]
+t0 = None
+res = {}
+for r in range(6):
+  ev = [(int(v) >> 4, int(v) & 15) for v in tr[r].tolist() if v != 0]
+  if ev and (t0 is None or ev[0][0] < t0):
+    t0 = ev[0][0]
+  res[names[r]] = ev
+for k, ev in res.items():
+  res[k] = [(t - t0, c) for t, c in ev]
+json.dump(res, open("gpurun_out/fused_trace.json", "w"))
+for k, ev in res.items():
+  print(k, len(ev), ev[:40])
