@@ -37,6 +37,9 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(batch=8, seq_len=2048, width=2560, heads=10, temporal_width=4)
 GATHER_EVERY = int(os.environ.get("CG_BENCH_GATHER_EVERY", "18"))   # recurrent blocks per 2B prefill (common.py:90-101)
 METRIC = "rglru_conv1d_prefill_tokens_per_sec"
+# dram__bytes_read.sum + dram__bytes_write.sum of one fused-kernel launch at config 2
+# (ncu --set full, profiles/r1_rglru_fused_kernel_ncu_summary.txt)
+NCU_TRAFFIC_BYTES = 156298752
 UNIT = "tokens/s"
 
 
@@ -250,6 +253,7 @@ def own_arm(args, dtype):
   gather_out = (torch.empty(state_numel * world, dtype=torch.float32, device=dev)
                 if world > 1 else None)
 
+  fused = lru.uses_fused_kernel(x_dev)
   k_events = {"conv1d": [], "gate_gemm": [], "rglru": []}
   step_no = [0]
 
@@ -263,14 +267,19 @@ def own_arm(args, dtype):
       e0 = ev()
       xc, conv_state = conv(x, seg)
       e1 = ev()
-      gates = lru.gate_gemm(xc)
-      e2 = ev()
-      y, last_h = _abi.rglru_fwd(xc, None, None, lru.input_gate.b, lru.a_gate.b, lru.a_param,
-                                 seg, arith_mode=cg.get_arith_mode(), gemm_fused=gates,
-                                 block_width=w["width"] // w["heads"])
+      if fused:   # gate GEMMs + gates + scan: ONE tcgen05 kernel (no separate GEMM)
+        e2 = e1
+        y, last_h = lru(xc, seg)
+      else:
+        gates = lru.gate_gemm(xc)
+        e2 = ev()
+        y, last_h = _abi.rglru_fwd(xc, None, None, lru.input_gate.b, lru.a_gate.b, lru.a_param,
+                                   seg, arith_mode=cg.get_arith_mode(), gemm_fused=gates,
+                                   block_width=w["width"] // w["heads"])
       e3 = ev()
       k_events["conv1d"].append((e0, e1))
-      k_events["gate_gemm"].append((e1, e2))
+      if e2 is not e1:
+        k_events["gate_gemm"].append((e1, e2))
       k_events["rglru"].append((e2, e3))
     else:
       xc, conv_state = conv(x, seg)
@@ -323,7 +332,8 @@ def own_arm(args, dtype):
     launches = _abi.launch_count - launches0
     clocks = sampler.stop()
     ms_total = t_start.elapsed_time(t_end)
-    k_us = {k: statistics.mean(a.elapsed_time(b) * 1e3 for a, b in v) for k, v in k_events.items()}
+    k_us = {k: statistics.mean(a.elapsed_time(b) * 1e3 for a, b in v) if v else 0.0
+            for k, v in k_events.items()}
 
     # ---------------- end to end: pinned host buffers in, results out ------------
     x_pin = host["x_lin"].pin_memory()
@@ -331,18 +341,19 @@ def own_arm(args, dtype):
     y_pin = torch.empty_like(x_pin).pin_memory()
     h_pin = torch.empty((w["batch"], w["width"]), dtype=torch.float32).pin_memory()
     c_pin = torch.empty((w["batch"], w["temporal_width"] - 1, w["width"]), dtype=dtype).pin_memory()
-    x_stage, seg_stage = torch.empty_like(x_dev), torch.empty_like(seg_dev)
     h2d = x_pin.numel() * x_pin.element_size() + seg_pin.numel() * seg_pin.element_size()
     d2h = (y_pin.numel() * y_pin.element_size() + h_pin.numel() * 4 +
            c_pin.numel() * c_pin.element_size())
 
+    # the public host-buffer entry point: row chunks pipelined over three streams
+    # (upload c+1 | kernels c | download c-1), see cadence_gemma_b200/hostio.py
+    from cadence_gemma_b200.hostio import HostPrefill
+    e2e_chunks = int(os.environ.get("CG_BENCH_E2E_CHUNKS", "4"))
+    host_prefill = HostPrefill(conv, lru, w["batch"], w["seq_len"], chunks=e2e_chunks)
+
     def e2e_step():
-      x_stage.copy_(x_pin, non_blocking=True)
-      seg_stage.copy_(seg_pin, non_blocking=True)
-      y, last_h, conv_state = step(x_stage, seg_stage)
-      y_pin.copy_(y, non_blocking=True)
-      h_pin.copy_(last_h, non_blocking=True)
-      c_pin.copy_(conv_state, non_blocking=True)
+      host_prefill(x_pin, seg_pin, y_pin, h_pin, c_pin)
+      step_no[0] += 1
 
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(3):
@@ -380,23 +391,35 @@ def own_arm(args, dtype):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "ms_per_step": e2e_ms / e2e_steps},
+                "ms_per_step": e2e_ms / e2e_steps,
+                "how": f"HostPrefill: {e2e_chunks} row chunks pipelined over upload / kernel / download streams"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "cg::scan_kernel (RG-LRU gates + scan; events bracket the "
-                     "cg_rglru_fwd call incl. its small prologue launch)",
+        "roofline": {"bound": "hbm",
+                     "kernel": ("cg::fused::rglru_fused_kernel (tcgen05 gate GEMMs + gate math + scan in one "
+                                "launch; events bracket the cg_rglru_fused_fwd call incl. its small prologue "
+                                "launch)") if fused else
+                               ("cg::scan_kernel (RG-LRU gates + scan; events bracket the cg_rglru_fwd call "
+                                "incl. its small prologue launch)"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": k2_bytes,
-                     "us_per_launch": k2_mean_us, "traffic": None},
-        "kernels_us": {"conv1d": conv_us, "gate_gemm_cublas_fused": gemm_us, "rglru": k2_mean_us},
+                     "algorithmic_bytes_note": ("SURVEY 8(d) K2 figure: 4 x 2 B per element (x, pre_x, pre_a "
+                                                "in, y out).  The fused kernel keeps pre_x / pre_a in TMEM, "
+                                                "so it moves only about half of that (see `traffic`) and is "
+                                                "bound by the MUFU / issue rate of the gate math, not HBM"
+                                                if fused else "SURVEY 8(d) K2 figure: 4 x s bytes per element"),
+                     "us_per_launch": k2_mean_us, "traffic": NCU_TRAFFIC_BYTES if fused else None},
+        "kernels_us": ({"conv1d": conv_us, "rglru_fused_tcgen05": k2_mean_us} if fused else
+                       {"conv1d": conv_us, "gate_gemm_cublas_fused": gemm_us, "rglru": k2_mean_us}),
         "roofline_conv1d": {"bound": "hbm", "achieved": 2 * esize * nelem / (conv_us * 1e-6) / 1e9,
                             "peak": peak, "unit": "GB/s",
                             "frac": 2 * esize * nelem / (conv_us * 1e-6) / 1e9 / peak},
-        "roofline_conv1d_plus_rglru": {
-            "bound": "hbm", "achieved": 6 * esize * nelem / ((conv_us + k2_mean_us) * 1e-6) / 1e9,
+        "roofline_conv1d_plus_rglru": {   # whole block incl. the gate GEMMs, canonical 6 x s bytes
+            "bound": "hbm", "achieved": 6 * esize * nelem / ((conv_us + gemm_us + k2_mean_us) * 1e-6) / 1e9,
             "peak": peak, "unit": "GB/s",
-            "frac": 6 * esize * nelem / ((conv_us + k2_mean_us) * 1e-6) / 1e9 / peak},
+            "frac": 6 * esize * nelem / ((conv_us + gemm_us + k2_mean_us) * 1e-6) / 1e9 / peak},
         "arith_mode": cg.get_arith_mode(),
+        "fused_tcgen05_rglru": bool(fused),
     }
     if world == 1 and not args.no_cpu_baseline:
       threads = os.cpu_count() or 1

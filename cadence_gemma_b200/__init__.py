@@ -4,7 +4,8 @@ Public surface mirrors ``recurrentgemma.torch`` for this path
 (``recurrentgemma/torch/__init__.py:28-31``)."""
 from cadence_gemma_b200 import _abi
 from cadence_gemma_b200.layers import (BlockDiagonalLinear, Conv1D, RGLRU,
-                                       get_arith_mode, rnn_scan, set_arith_mode)
+                                       fused_enabled, get_arith_mode, rnn_scan,
+                                       set_arith_mode, set_fused)
 
 __all__ = ["BlockDiagonalLinear", "Conv1D", "RGLRU", "rnn_scan",
-           "set_arith_mode", "get_arith_mode", "_abi"]
+           "set_arith_mode", "get_arith_mode", "set_fused", "fused_enabled", "_abi"]

@@ -518,12 +518,13 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       } else if (__all_sync(0xffffffffu, (unsigned)early == epoch)) {
         c0 = tagged_value(early);
       } else {
-        // Decoupled look-back, kLook tiles per round trip.  Tiles [end, tt) are
-        // folded into (fp, fh): h(tt start) = fp * h(end start) + fh; folds run
-        // left to right only, so the result does not depend on timing.
+        // Decoupled look-back, kLook tiles per round trip: walk back over tiles
+        // whose aggregate is published until one with a published state is
+        // found, then apply the aggregates passed on the way one by one, left to
+        // right -- exactly the expression each of those tiles evaluates for its
+        // own state, so the carry does not depend on timing (bit-reproducible).
         constexpr int kLook = CGF_LOOK;
-        int end = tt;
-        float fp = 1.0f, fh = 0.0f;
+        int end = tt;                                    // tiles [end, tt): aggregate seen
         const long long t_start = clock64();
         unsigned polls = 0;
         c0 = 0.0f;
@@ -535,32 +536,43 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
             if (k < depth) {
               const size_t src = pd.widx - (size_t)(tt - end + k + 1) * wstep;
               wpf[k] = ld_relaxed_u64(p.pref + src);
-              wap[k] = ld_relaxed_u64(p.agg_p + src);
-              wah[k] = ld_relaxed_u64(p.agg_h + src);
+              if (k > 0 || kLook > 1) {
+                wap[k] = ld_relaxed_u64(p.agg_p + src);
+                wah[k] = ld_relaxed_u64(p.agg_h + src);
+              }
             } else {
               wpf[k] = wap[k] = wah[k] = 0ull;
             }
           }
           bool done = false;
-          int used = 0;                                  // aggregates consumed this round
+          int used = 0;                                  // aggregates accepted this round
 #pragma unroll
           for (int k = 0; k < kLook; ++k) {
             if (!done && k == used && k < depth) {
               if (__all_sync(0xffffffffu, (unsigned)wpf[k] == epoch)) {
-                c0 = fmaf(fp, tagged_value(wpf[k]), fh);
+                c0 = tagged_value(wpf[k]);
                 done = true;
-              } else if (__all_sync(0xffffffffu, (unsigned)wap[k] == epoch && (unsigned)wah[k] == epoch)) {
-                fh = fmaf(fp, tagged_value(wah[k]), fh);   // compose with the tile before
-                fp = fp * tagged_value(wap[k]);
-                used = k + 1;
+              } else {
+                if (kLook == 1) {                        // second round trip only when needed
+                  const size_t src = pd.widx - (size_t)(tt - end + 1) * wstep;
+                  wap[0] = ld_relaxed_u64(p.agg_p + src);
+                  wah[0] = ld_relaxed_u64(p.agg_h + src);
+                }
+                if (__all_sync(0xffffffffu, (unsigned)wap[k] == epoch && (unsigned)wah[k] == epoch))
+                  used = k + 1;
               }
             }
           }
-          if (done) break;
           end -= used;                                   // (tile 0 never publishes an aggregate: end stays > 0)
+          if (done) break;
           if (used == 0) __nanosleep(40);
           polls += 3;
           if (__any_sync(0xffffffffu, watchdog_expired(t_start, p.err, 7, polls))) break;
+        }
+        for (int k = end; k < tt; ++k) {                 // state(end-1) -> ... -> state(tt-1)
+          const size_t src = pd.widx - (size_t)(tt - k) * wstep;
+          c0 = fmaf(tagged_value(ld_relaxed_u64(p.agg_p + src)), c0,
+                    tagged_value(ld_relaxed_u64(p.agg_h + src)));
         }
       }
       if (tt + 1 < p.ntt) st_relaxed_u64(p.pref + pd.widx, pack_tagged(fmaf(pd.P, c0, pd.H), epoch));

@@ -17,6 +17,7 @@ CPU tensors or a missing library raise.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 from torch import nn
@@ -38,6 +39,23 @@ def set_arith_mode(mode: int) -> int:
 
 def get_arith_mode() -> int:
   return _arith_mode
+
+
+# The fused tensor-core kernel (gate GEMMs + gate math + scan in one launch,
+# cg_rglru_fused_fwd) is used whenever the shape allows it; CG_B200_FUSED=0 or
+# set_fused(False) forces the cuBLAS-GEMM + scan-kernel pair instead.
+_fused_enabled = os.environ.get("CG_B200_FUSED", "1") != "0"
+
+
+def set_fused(enabled: bool) -> bool:
+  """Enables / disables the fused tcgen05 RG-LRU path; returns the old setting."""
+  global _fused_enabled
+  old, _fused_enabled = _fused_enabled, bool(enabled)
+  return old
+
+
+def fused_enabled() -> bool:
+  return _fused_enabled
 
 
 def _forward_only(*tensors):
@@ -146,6 +164,22 @@ class RGLRU(nn.Module):
       self._wcat_key = key
     return self._wcat
 
+  def _packed_gate_weight(self) -> torch.Tensor:
+    """Gate weights as the shared-memory image the fused tcgen05 kernel reads
+    (cg_rglru_pack_gate_weights); rebuilt only when a gate weight changes."""
+    wx, wa = self.input_gate.w, self.a_gate.w
+    key = (wx.data_ptr(), wa.data_ptr(), wx._version, wa._version, wx.dtype, wx.device)
+    if getattr(self, "_wpack_key", None) != key:
+      self._wpack = _abi.pack_gate_weights(wx, wa)
+      self._wpack_key = key
+    return self._wpack
+
+  def uses_fused_kernel(self, x: torch.Tensor) -> bool:
+    """True if ``forward(x, ...)`` runs on the fused tensor-core kernel."""
+    return (_fused_enabled and x.is_cuda and x.shape[1] > 1 and
+            (_arith_mode & (_abi.ARITH_FP32 | _abi.ARITH_STRICT)) == 0 and
+            _abi.fused_supported(self.width, self.num_heads, x.dtype))
+
   def gate_gemm(self, x: torch.Tensor) -> torch.Tensor:
     """Both gate GEMMs (no bias) in one call -> [B*T, H, 2*bw]."""
     heads, bw = self.num_heads, self.width // self.num_heads
@@ -162,6 +196,11 @@ class RGLRU(nn.Module):
     assert segment_pos.shape == (bs, length)      # layers.py:344
     _forward_only(x, cache)
     with torch.no_grad():
+      if self.uses_fused_kernel(x):
+        return _abi.rglru_fused_fwd(
+            x, self._packed_gate_weight(), self.input_gate.b, self.a_gate.b,
+            self.a_param, segment_pos, self.num_heads, h0=cache,
+            return_cache=return_cache, arith_mode=_arith_mode)
       y, last_h = _abi.rglru_fwd(
           x, None, None, self.input_gate.b, self.a_gate.b, self.a_param,
           segment_pos, h0=cache, return_cache=return_cache,

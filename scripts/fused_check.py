@@ -76,8 +76,8 @@ def run_case(B, T, E, H, mode, variant, use_h0=True, debug=True):
   print(json.dumps(res), flush=True)
 
 
-def time_case(mode, variant, iters=20):
-  B, T, E, H = 8, 2048, 2560, 10
+def time_case(mode, variant, iters=20, B=8, T=2048):
+  E, H = 2560, 10
   x, lru, seg, _ = make(B, T, E, H, resets=False)
   wpack = _abi.pack_gate_weights(lru.input_gate.w, lru.a_gate.w)
   ws = _abi.fused_workspace(x.device, B, T, E)
@@ -97,7 +97,7 @@ def time_case(mode, variant, iters=20):
   torch.cuda.synchronize()
   us = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
   nelem = B * T * E
-  res = {"time": "cfg2", "mode": mode, "variant": variant, "us_median": us[len(us) // 2], "us_best": us[0],
+  res = {"time": [B, T], "mode": mode, "variant": variant, "us_median": us[len(us) // 2], "us_best": us[0],
          "alg_GBps_8B_per_elem": 8 * nelem / (us[len(us) // 2] * 1e-6) / 1e9,
          "watchdog": _abi.fused_watchdog_code(ws)}
   print(json.dumps(res), flush=True)
@@ -120,6 +120,9 @@ def main():
     run_case(8, 2048, 2560, 10, a.mode, a.variant, debug=False)
   elif a.case == "time":
     time_case(a.mode, a.variant)
+  elif a.case == "time_shapes":
+    for B, T in [(1, 2048), (2, 2048), (2, 8192), (32, 768), (8, 2048)]:
+      time_case(a.mode, a.variant, B=B, T=T)
 
 
 if __name__ == "__main__":

@@ -32,6 +32,8 @@ from oracle import ref_loader  # noqa: E402
 from tests.golden import fixture_io  # noqa: E402
 
 DTYPES = {"f32": torch.float32, "bf16": torch.bfloat16}
+# MAKE_GOLDEN_ONLY=substr[,substr]: regenerate only the RG-LRU fixtures whose name matches
+ONLY = [o for o in os.environ.get("MAKE_GOLDEN_ONLY", "").split(",") if o]
 
 
 def gen(seed):
@@ -144,7 +146,14 @@ def make_rglru(ref):
         (128, 1, 32, 1, "halves"), (256, 8, 64, 2, "halves"),
         (256, 8, 67, 2, "ragged_pad"), (128, 16, 128, 1, "halves"),
         (64, 2, 1, 3, "first"),
+        # head widths 128 / 256: the shapes the fused tensor-core kernel takes
+        (512, 2, 96, 2, "ragged_pad"), (256, 2, 70, 3, "halves"),
+        (512, 2, 160, 1, "halves"),
     ]:
+      if ONLY and not any(o in f"rglru_{tag}_e{width}_h{heads}_t{steps}_{segkind}" for o in ONLY):
+        continue
+      if width // heads >= 128 and heads > 1 and tag != "bf16":
+        continue   # fused-path shapes: bf16 only (the fp32 copies would add 6 MB)
       seed = seed_of(tag, width, heads, steps, segkind)
       g = gen(seed)
       torch.manual_seed(seed)
@@ -287,11 +296,14 @@ def make_griffin_tiny():
 
 def main():
   ref = ref_loader.load_reference()
-  make_rnn_scan(ref)
-  make_conv1d(ref)
-  make_rglru(ref)
-  make_recurrent_block(ref)
-  make_griffin_tiny()
+  if ONLY:
+    make_rglru(ref)
+  else:
+    make_rnn_scan(ref)
+    make_conv1d(ref)
+    make_rglru(ref)
+    make_recurrent_block(ref)
+    make_griffin_tiny()
   total = 0
   for f in sorted(os.listdir(fixture_io.GOLDEN_DIR)):
     if f.endswith(".npz"):

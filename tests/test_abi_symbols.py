@@ -31,6 +31,16 @@ def test_library_exports_every_declared_symbol():
   assert b"workspace" in loaded.cg_status_string(-5)
   assert loaded.cg_scan_workspace_bytes(8, 2048, 2560, 1) > 0
   assert loaded.cg_scan_workspace_bytes(0, 1, 1, 1) == 0
+  # fused tensor-core path: host-side shape logic only (no launches without a GPU)
+  assert loaded.cg_rglru_fused_supported(2560, 10, 1) == 1      # RecurrentGemma-2B, bf16
+  assert loaded.cg_rglru_fused_supported(4096, 16, 1) == 1      # 9B
+  assert loaded.cg_rglru_fused_supported(2560, 10, 0) == 0      # fp32 -> scan kernel
+  assert loaded.cg_rglru_fused_supported(256, 8, 1) == 0        # head width 32
+  # [E/128][2 gates][bw/64][128 x 128 B] + identity [2][128 x 128 B]
+  assert loaded.cg_rglru_gate_pack_bytes(2560, 10) == 20 * 2 * 4 * 16384 + 2 * 16384
+  assert loaded.cg_rglru_gate_pack_bytes(256, 8) == 0
+  assert loaded.cg_rglru_fused_workspace_bytes(8, 2048, 2560) > 3 * 8 * 8 * 64 * 2560
+  assert b"fused" in loaded.cg_status_string(-7)
 
 
 def test_shims_mirror_reference_api_and_have_no_cpu_fallback():

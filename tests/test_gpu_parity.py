@@ -343,7 +343,11 @@ def test_fused_gate_layout_equals_separate(dtype, width, heads):
     x = torch.randn(2, 75, width, device=DEV).to(dtype)
     seg = torch.arange(75, device=DEV)[None].repeat(2, 1)
     seg[1, 40:] -= 40
-    y_f, h_f = lru(x, seg)
+    old = cg.set_fused(False)     # this test is about the cuBLAS gate-GEMM layouts
+    try:
+      y_f, h_f = lru(x, seg)
+    finally:
+      cg.set_fused(old)
     y_s, h_s = abi.rglru_fwd(x, lru.input_gate.gemm(x), lru.a_gate.gemm(x), lru.input_gate.b,
                              lru.a_gate.b, lru.a_param, seg, arith_mode=cg.get_arith_mode())
     y_t, _ = abi.rglru_fwd(x, None, None, lru.input_gate.b, lru.a_gate.b, lru.a_param, seg,
@@ -366,3 +370,177 @@ def test_abi_argument_errors():
   with pytest.raises(AssertionError):   # decode wants exactly one token
     abi.conv1d_decode(torch.zeros(1, 2, 16, device=DEV), torch.zeros(4, 16, device=DEV),
                       torch.zeros(16, device=DEV), torch.zeros(1, 3, 16, device=DEV))
+
+
+# ----------------------------------------- fused tensor-core RG-LRU (tcgen05)
+def _fused_cases():
+  out = []
+  for case in fixture_io.cases("rglru_bf16"):
+    g = fixture_io.load(case)
+    width, heads = g["x"].shape[-1], g["input_gate_w"].shape[0]
+    if width // heads in (128, 256) and g["x"].shape[1] > 1:
+      out.append(case)
+  return out
+
+
+@pytest.mark.parametrize("mode", [REF, REF | FAST])
+@pytest.mark.parametrize("case", _fused_cases())
+def test_fused_rglru_golden(case, mode):
+  """cg_rglru_fused_fwd (gate GEMMs on tcgen05 + gates + scan) against the
+  reference's own outputs, incl. the GEMM: pre-activations must come out
+  bit-identical to the reference's bf16 einsum in >= 99.9 % of the elements."""
+  abi = _abi()
+  g = fixture_io.load(case)
+  heads = g["input_gate_w"].shape[0]
+  assert abi.fused_supported(g["x"].shape[-1], heads, torch.bfloat16)
+  wpack = abi.pack_gate_weights(cu(g["input_gate_w"]), cu(g["a_gate_w"]))
+  ws = abi.fused_workspace(torch.device(DEV), *g["x"].shape)
+  y, h, dbg = abi.rglru_fused_fwd(cu(g["x"]), wpack, cu(g["input_gate_b"]), cu(g["a_gate_b"]),
+                                  cu(g["a_param"]), cu(g["seg"]), heads, arith_mode=mode,
+                                  debug=True, workspace=ws)
+  assert abi.fused_watchdog_code(ws) == 0
+  # the debug planes hold round_bf16(x @ w) WITHOUT bias and the transposed x
+  bx = g["input_gate_b"].reshape(-1).float()
+  ba = g["a_gate_b"].reshape(-1).float()
+  pre_x = (dbg[0].cpu().float() + bx).to(torch.bfloat16)
+  pre_a = (dbg[1].cpu().float() + ba).to(torch.bfloat16)
+  assert identical_fraction(pre_x, g["pre_x"]) >= 0.999, case
+  assert identical_fraction(pre_a, g["pre_a"]) >= 0.999, case
+  assert_bitexact(dbg[2].cpu(), g["x"], case + " x through the identity MMA")
+  assert_close_bf16(y.cpu(), g["y"], f"{case} mode {mode}",
+                    min_identical=0.995 if mode == REF else 0.98)
+  assert normwise(h.cpu(), g["last_h"]) <= 1e-2
+  # no debug planes: same bits
+  y2, h2 = abi.rglru_fused_fwd(cu(g["x"]), wpack, cu(g["input_gate_b"]), cu(g["a_gate_b"]),
+                               cu(g["a_param"]), cu(g["seg"]), heads, arith_mode=mode,
+                               workspace=ws)
+  assert torch.equal(y2, y) and torch.equal(h2, h)
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 256, 1), (3, 200, 512, 2), (2, 33, 256, 2),
+                                   (1, 1000, 2560, 10), (5, 97, 1024, 4), (2, 31, 512, 4)])
+def test_fused_rglru_equals_unfused(shape):
+  """Fused kernel vs cuBLAS gate GEMM + scan kernel on the same inputs: ragged T,
+  both head widths, h0, random document starts (incl. t = 0 .. 31 boundaries)."""
+  import cadence_gemma_b200 as cg
+  abi = _abi()
+  bsz, steps, width, heads = shape
+  g = torch.Generator().manual_seed(sum(shape))
+  lru = cg.RGLRU(width, heads, device=DEV, dtype=torch.bfloat16)
+  bw = width // heads
+  with torch.no_grad():
+    lru.input_gate.w.copy_((torch.randn((heads, bw, bw), generator=g) * bw ** -0.5).to(torch.bfloat16))
+    lru.a_gate.w.copy_((torch.randn((heads, bw, bw), generator=g) * bw ** -0.5).to(torch.bfloat16))
+    lru.input_gate.b.copy_(torch.randn((heads, bw), generator=g).to(torch.bfloat16))
+    lru.a_gate.b.copy_(torch.randn((heads, bw), generator=g).to(torch.bfloat16))
+  x = torch.randn((bsz, steps, width), generator=g).to(torch.bfloat16).to(DEV)
+  seg = torch.arange(steps, dtype=torch.int32)[None].repeat(bsz, 1)
+  for b in range(bsz):
+    for cut in torch.randint(1, steps, (3,), generator=g).tolist():
+      seg[b, cut:] = torch.arange(steps - cut, dtype=torch.int32)
+  seg = seg.to(DEV)
+  h0 = torch.randn((bsz, width), generator=g).to(DEV)
+  for mode in (REF, REF | FAST):
+    old_mode = cg.set_arith_mode(mode)
+    try:
+      assert lru.uses_fused_kernel(x)
+      with torch.no_grad():
+        y_f, h_f = lru(x, seg, h0)
+        old = cg.set_fused(False)
+        try:
+          assert not lru.uses_fused_kernel(x)
+          y_u, h_u = lru(x, seg, h0)
+        finally:
+          cg.set_fused(old)
+    finally:
+      cg.set_arith_mode(old_mode)
+    assert identical_fraction(y_f, y_u) >= 0.999, (shape, mode, identical_fraction(y_f, y_u))
+    torch.testing.assert_close(y_f.float(), y_u.float(), rtol=1e-2, atol=3e-2)
+    assert normwise(h_f, h_u) <= 1e-5, (shape, mode, normwise(h_f, h_u))
+
+
+@pytest.mark.parametrize("steps,bsz", [(2048, 8), (8192, 2)])
+def test_fused_rglru_full_size_properties(steps, bsz):
+  """RecurrentGemma-2B shapes (configs 2 and 4): determinism, agreement with the
+  sequential device oracle, chunked continuation and reset isolation."""
+  import cadence_gemma_b200 as cg
+  abi = _abi()
+  width, heads = 2560, 10
+  p, x, _, _, seg = _full_inputs(bsz, steps, width, torch.bfloat16, 11, resets=7)
+  lru = cg.RGLRU(width, heads, device=DEV, dtype=torch.bfloat16)
+  with torch.no_grad():
+    lru.a_param.copy_(p.a_param)
+    lru.input_gate.b.copy_(p.input_gate_b)
+    lru.a_gate.b.copy_(p.a_gate_b)
+    y, h = lru(x, seg)
+    y2, h2 = lru(x, seg)
+    assert torch.equal(y, y2) and torch.equal(h, h2), "run-to-run determinism"
+    # sequential one-thread-per-channel kernel on the cuBLAS pre-activations
+    y_s, h_s = abi.rglru_fwd(x, None, None, lru.input_gate.b, lru.a_gate.b, lru.a_param, seg,
+                             arith_mode=cg.get_arith_mode() | STRICT,
+                             gemm_fused=lru.gate_gemm(x), block_width=width // heads)
+    assert identical_fraction(y, y_s) >= 0.97
+    torch.testing.assert_close(y.float(), y_s.float(), rtol=1e-2, atol=3e-2)
+    assert normwise(h, h_s) <= 1e-2
+    # continuation: prefill(T) == prefill(T1) ; prefill(T2, h0 = last_h)
+    cut = 1000
+    y1, h1 = lru(x[:, :cut].contiguous(), seg[:, :cut].contiguous())
+    y2, h2 = lru(x[:, cut:].contiguous(), seg[:, cut:].contiguous(), h1)
+    ycat = torch.cat([y1, y2], 1)
+    assert identical_fraction(ycat, y) >= 0.9999
+    assert normwise(h2, h) <= 1e-5
+    # reset isolation: a document start makes y independent of everything before
+    seg2 = seg.clone()
+    seg2[:, cut] = 0
+    ya, _ = lru(x, seg2)
+    xb = x.clone()
+    xb[:, :cut] = torch.randn_like(xb[:, :cut]) * 3
+    yb, _ = lru(xb, seg2)
+    assert torch.equal(ya[:, cut:], yb[:, cut:])
+  for ws in abi._fused_workspaces.values():
+    assert abi.fused_watchdog_code(ws) == 0
+
+
+def test_fused_rglru_argument_errors():
+  abi = _abi()
+  assert not abi.fused_supported(256, 8, torch.bfloat16)       # head width 32
+  assert not abi.fused_supported(2560, 10, torch.float32)      # fp32 takes the scan kernel
+  x = torch.zeros(1, 8, 256, device=DEV, dtype=torch.bfloat16)
+  w = torch.zeros(2, 128, 128, device=DEV, dtype=torch.bfloat16)
+  wpack = abi.pack_gate_weights(w, w)
+  seg = torch.zeros(1, 8, dtype=torch.int32, device=DEV)
+  ap = torch.zeros(256, device=DEV, dtype=torch.bfloat16)
+  with pytest.raises(AssertionError):     # fp32-in-registers mode is not a mode of the fused kernel
+    abi.rglru_fused_fwd(x, wpack, None, None, ap, seg, 2, arith_mode=FP32)
+  with pytest.raises(AssertionError):     # workspace too small
+    abi.rglru_fused_fwd(x, wpack, None, None, ap, seg, 2,
+                        workspace=torch.zeros(64, dtype=torch.uint8, device=DEV))
+
+
+def test_host_prefill_pipeline_matches_direct_call():
+  """The pipelined host-buffer entry point returns the bits of the direct call."""
+  import cadence_gemma_b200 as cg
+  from cadence_gemma_b200.hostio import HostPrefill
+  bsz, steps, width, heads = 8, 300, 512, 2
+  torch.manual_seed(3)
+  conv = cg.Conv1D(width, 4, device=DEV, dtype=torch.bfloat16)
+  lru = cg.RGLRU(width, heads, device=DEV, dtype=torch.bfloat16)
+  with torch.no_grad():
+    conv.b.normal_()
+    lru.input_gate.b.normal_()
+    lru.a_gate.b.normal_()
+  x = torch.randn(bsz, steps, width).to(torch.bfloat16).pin_memory()
+  seg = torch.arange(steps, dtype=torch.int32)[None].repeat(bsz, 1)
+  seg[:, 111:] -= 111
+  seg = seg.pin_memory()
+  y = torch.empty_like(x).pin_memory()
+  h = torch.empty(bsz, width).pin_memory()
+  c = torch.empty(bsz, 3, width, dtype=torch.bfloat16).pin_memory()
+  for chunks in (1, 4, 8):
+    y.zero_(); h.zero_(); c.zero_()
+    HostPrefill(conv, lru, bsz, steps, chunks=chunks)(x, seg, y, h, c)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+      xc, cs = conv(x.to(DEV), seg.to(DEV))
+      y_d, h_d = lru(xc, seg.to(DEV))
+    assert torch.equal(y, y_d.cpu()) and torch.equal(h, h_d.cpu()) and torch.equal(c, cs.cpu()), chunks

