@@ -54,18 +54,30 @@ def prefill_case(name, B, T, seg, dtype, iters=20):
       xc, _ = conv(x, seg)
       return lru(xc, seg)
     xc, _ = conv(x, seg)
-    gates = lru.gate_gemm(xc)
+    fused = lru.uses_fused_kernel(xc)
     t_full = timed(full, iters)
     t_conv = timed(lambda: conv(x, seg), iters)
-    t_gemm = timed(lambda: lru.gate_gemm(xc), iters)
-    t_lru = timed(lambda: _abi.rglru_fwd(xc, None, None, lru.input_gate.b, lru.a_gate.b,
-                                         lru.a_param, seg, arith_mode=cg.get_arith_mode(),
-                                         gemm_fused=gates, block_width=E // H), iters)
+    if fused:   # gate GEMMs + gates + scan in one tcgen05 kernel
+      t_gemm = 0.0
+      t_lru = timed(lambda: lru(xc, seg), iters)
+    else:
+      gates = lru.gate_gemm(xc)
+      t_gemm = timed(lambda: lru.gate_gemm(xc), iters)
+      t_lru = timed(lambda: _abi.rglru_fwd(xc, None, None, lru.input_gate.b, lru.a_gate.b,
+                                           lru.a_param, seg, arith_mode=cg.get_arith_mode(),
+                                           gemm_fused=gates, block_width=E // H), iters)
+    # the same step on the unfused pair of kernels, for comparison
+    old = cg.set_fused(False)
+    try:
+      t_full_unfused = timed(full, iters)
+    finally:
+      cg.set_fused(old)
   n = B * T * E
-  return dict(config=name, B=B, T=T, dtype=str(dtype), us_step=t_full, us_conv1d=t_conv,
+  return dict(config=name, B=B, T=T, dtype=str(dtype), fused_tcgen05=bool(fused), us_step=t_full,
+              us_step_unfused=t_full_unfused, us_conv1d=t_conv,
               us_gate_gemm=t_gemm, us_rglru=t_lru, tokens_per_s=B * T / t_full * 1e6,
               gbps_conv1d=2 * s * n / t_conv / 1e3, gbps_rglru=4 * s * n / t_lru / 1e3,
-              gbps_custom_kernels=6 * s * n / (t_conv + t_lru) / 1e3)
+              gbps_block=6 * s * n / (t_conv + t_gemm + t_lru) / 1e3)
 
 
 def decode_case(B, dtype, iters=200):
