@@ -39,7 +39,7 @@ GATHER_EVERY = int(os.environ.get("CG_BENCH_GATHER_EVERY", "18"))   # recurrent 
 METRIC = "rglru_conv1d_prefill_tokens_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of one fused-kernel launch at config 2
 # (ncu --set full, profiles/r1_rglru_fused_kernel_ncu_summary.txt)
-NCU_TRAFFIC_BYTES = 156298752
+NCU_TRAFFIC_BYTES = 155811840
 UNIT = "tokens/s"
 
 
@@ -207,6 +207,7 @@ def config_dict(args, where):
           "parallelism": (f"batch-sharded x{args.gpus}, no collective in the path; NCCL all-gather "
                           f"of last_h + conv cache once per {GATHER_EVERY} block steps (one 2B prefill)"),
           "l2": "working set 420 MB per step > 126 MB L2 (no explicit flush)",
+          "clock_ramp": "W warm-up steps plus 400 ms of untimed steps before the timed region",
           "device": where}
 
 
@@ -303,8 +304,18 @@ def own_arm(args, dtype):
     torch.cuda.synchronize()
 
   with torch.no_grad():
+    # W warm-up steps, then keep stepping until the GPU has been busy for
+    # CG_BENCH_RAMP_MS: a step is ~0.15 ms, so W steps alone end before the SM
+    # clocks have ramped up from idle on a fresh box (seen: 2x slower steps)
     for _ in range(max(args.warmup, 3)):
       out = step(x_dev, seg_dev)
+    torch.cuda.synchronize()
+    ramp_ms = float(os.environ.get("CG_BENCH_RAMP_MS", "400"))
+    t_ramp = time.perf_counter()
+    while (time.perf_counter() - t_ramp) * 1e3 < ramp_ms:
+      for _ in range(20):
+        out = step(x_dev, seg_dev)
+      torch.cuda.synchronize()
     if world > 1:
       # exercise the whole gather path once outside the timed region: NCCL sets
       # connections up lazily and CUDA loads the small copy/cast kernels lazily
