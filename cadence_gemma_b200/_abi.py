@@ -137,16 +137,19 @@ def scan_workspace(device, batch: int, steps: int, width: int, dtype) -> torch.T
 
 
 def conv1d_fwd(x, w, b, segment_pos, return_cache=True, mask_mode=MASK_FORK,
-               arith_mode=ARITH_REFERENCE):
+               arith_mode=ARITH_REFERENCE, out=None, cache_out=None):
   global launch_count
   _require_cuda(x, w, b, segment_pos)
   bsz, steps, width = x.shape
   tw = w.shape[0]
   x, w, b = x.contiguous(), w.contiguous(), b.contiguous()
   seg, is64, stride = _seg_args(segment_pos, bsz, steps)
-  y = torch.empty_like(x)
-  cache = (torch.empty((bsz, tw - 1, width), dtype=x.dtype, device=x.device)
-           if return_cache else None)
+  y = torch.empty_like(x) if out is None else out
+  cache = None
+  if return_cache:
+    cache = (torch.empty((bsz, tw - 1, width), dtype=x.dtype, device=x.device)
+             if cache_out is None else cache_out)
+  assert y.shape == x.shape and y.dtype == x.dtype and y.is_contiguous()
   with torch.cuda.device(x.device):
     rc = load().cg_conv1d_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(),
                               seg.data_ptr(), is64, stride, y.data_ptr(),
@@ -180,7 +183,7 @@ def conv1d_decode(x, w, b, cache, return_cache=True, arith_mode=ARITH_REFERENCE)
 
 def rglru_fwd(x, gemm_x, gemm_a, bias_x, bias_a, a_param, segment_pos, h0=None,
               return_cache=True, arith_mode=ARITH_REFERENCE, out=None,
-              gemm_fused=None, block_width=0):
+              gemm_fused=None, block_width=0, last_h_out=None):
   """Gate math + scan.
 
   Either ``gemm_x`` / ``gemm_a`` ([B,T,E], possibly row-strided views with unit
@@ -219,8 +222,10 @@ def rglru_fwd(x, gemm_x, gemm_a, bias_x, bias_a, a_param, segment_pos, h0=None,
     keep = (gemm_x, gemm_a)
   seg, is64, stride = _seg_args(segment_pos, bsz, steps)
   y = torch.empty_like(x) if out is None else out
-  last_h = (torch.empty((bsz, width), dtype=torch.float32, device=x.device)
-            if return_cache else None)
+  last_h = None
+  if return_cache:
+    last_h = (torch.empty((bsz, width), dtype=torch.float32, device=x.device)
+              if last_h_out is None else last_h_out)
   ws = scan_workspace(x.device, bsz, steps, width, x.dtype)
   bx = None if bias_x is None else bias_x.contiguous().view(-1)
   ba = None if bias_a is None else bias_a.contiguous().view(-1)
@@ -309,7 +314,7 @@ def fused_watchdog_code(ws: torch.Tensor) -> int:
 
 def rglru_fused_fwd(x, wpack, bias_x, bias_a, a_param, segment_pos, heads, h0=None,
                     return_cache=True, arith_mode=ARITH_FAST, out=None, debug=False,
-                    workspace=None):
+                    workspace=None, last_h_out=None):
   """RGLRU.forward (gate GEMMs included) on the fused tcgen05 kernel."""
   global launch_count
   _require_cuda(x, wpack, bias_x, bias_a, a_param, segment_pos, h0)
@@ -319,8 +324,10 @@ def rglru_fused_fwd(x, wpack, bias_x, bias_a, a_param, segment_pos, heads, h0=No
   x = x.contiguous()
   seg, is64, stride = _seg_args(segment_pos, bsz, steps)
   y = torch.empty_like(x) if out is None else out
-  last_h = (torch.empty((bsz, width), dtype=torch.float32, device=x.device)
-            if return_cache else None)
+  last_h = None
+  if return_cache:
+    last_h = (torch.empty((bsz, width), dtype=torch.float32, device=x.device)
+              if last_h_out is None else last_h_out)
   ws = fused_workspace(x.device, bsz, steps, width) if workspace is None else workspace
   bx = None if bias_x is None else bias_x.contiguous().view(-1)
   ba = None if bias_a is None else bias_a.contiguous().view(-1)

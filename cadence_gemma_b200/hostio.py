@@ -39,13 +39,21 @@ class HostPrefill:
     self.s_in = torch.cuda.Stream(dev)
     self.s_run = torch.cuda.Stream(dev)
     self.s_out = torch.cuda.Stream(dev)
-    # two device staging buffers per leg are enough: a chunk's buffer is reused
-    # two chunks later, after the consumer of its previous content has finished
-    self.x_dev = [torch.empty((self.rows, steps, width), dtype=dtype, device=dev) for _ in range(2)]
-    self.seg_dev = [torch.empty((self.rows, steps), dtype=torch.int32, device=dev) for _ in range(2)]
+    # Two device buffers per tensor are enough: a chunk's buffers are reused two
+    # chunks later, after the consumer of their previous content has finished.
+    # Everything is allocated here, once: no allocator traffic (and none of its
+    # cross-stream bookkeeping) on the hot path.
+    tw = conv.temporal_width if hasattr(conv, "temporal_width") else conv.w.shape[0]
+    mk = lambda shape, dt: [torch.empty(shape, dtype=dt, device=dev) for _ in range(2)]
+    self.x_dev = mk((self.rows, steps, width), dtype)
+    self.seg_dev = mk((self.rows, steps), torch.int32)
+    self.xc_dev = mk((self.rows, steps, width), dtype)
+    self.y_dev = mk((self.rows, steps, width), dtype)
+    self.h_dev = mk((self.rows, width), torch.float32)
+    self.c_dev = mk((self.rows, tw - 1, width), dtype)
     self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
     self.ev_run = [torch.cuda.Event() for _ in range(chunks)]
-    self.ev_free = [torch.cuda.Event() for _ in range(chunks)]
+    self.ev_out = [torch.cuda.Event() for _ in range(chunks)]
 
   @torch.no_grad()
   def __call__(self, x_host, seg_host, y_host, h_host=None, cache_host=None):
@@ -56,32 +64,32 @@ class HostPrefill:
     cur = torch.cuda.current_stream(self.device)
     for s in (self.s_in, self.s_run, self.s_out):
       s.wait_stream(cur)
-    keep = []
     for c in range(self.chunks):
       r0, r1 = c * self.rows, (c + 1) * self.rows
-      xb, sb = self.x_dev[c & 1], self.seg_dev[c & 1]
+      k = c & 1
       with torch.cuda.stream(self.s_in):
         if c >= 2:
-          self.s_in.wait_event(self.ev_free[c - 2])      # kernels of chunk c-2 have read the buffer
-        xb.copy_(x_host[r0:r1], non_blocking=True)
-        sb.copy_(seg_host[r0:r1], non_blocking=True)
+          self.s_in.wait_event(self.ev_run[c - 2])       # kernels of chunk c-2 have read x / seg
+        self.x_dev[k].copy_(x_host[r0:r1], non_blocking=True)
+        self.seg_dev[k].copy_(seg_host[r0:r1], non_blocking=True)
         self.ev_in[c].record(self.s_in)
       with torch.cuda.stream(self.s_run):
         self.s_run.wait_event(self.ev_in[c])
-        xc, conv_state = self.conv(xb, sb)
-        y, last_h = self.lru(xc, sb)
-        self.ev_free[c].record(self.s_run)
+        if c >= 2:
+          self.s_run.wait_event(self.ev_out[c - 2])      # chunk c-2 has been downloaded
+        self.conv.forward_into(self.x_dev[k], self.seg_dev[k], out=self.xc_dev[k],
+                               cache_out=self.c_dev[k])
+        self.lru.forward_into(self.xc_dev[k], self.seg_dev[k], out=self.y_dev[k],
+                              last_h_out=self.h_dev[k])
         self.ev_run[c].record(self.s_run)
       with torch.cuda.stream(self.s_out):
         self.s_out.wait_event(self.ev_run[c])
-        y_host[r0:r1].copy_(y, non_blocking=True)
+        y_host[r0:r1].copy_(self.y_dev[k], non_blocking=True)
         if h_host is not None:
-          h_host[r0:r1].copy_(last_h, non_blocking=True)
+          h_host[r0:r1].copy_(self.h_dev[k], non_blocking=True)
         if cache_host is not None:
-          cache_host[r0:r1].copy_(conv_state, non_blocking=True)
-      for t in (xc, conv_state, y, last_h):
-        t.record_stream(self.s_out)
-      keep.append((xc, y))
+          cache_host[r0:r1].copy_(self.c_dev[k], non_blocking=True)
+        self.ev_out[c].record(self.s_out)
     cur.wait_stream(self.s_out)
     cur.wait_stream(self.s_run)
     return y_host

@@ -190,6 +190,12 @@ class RGLRU(nn.Module):
 
   def forward(self, x, segment_pos, cache=None, return_cache=True):
     """Returns ``(y in x.dtype, last_h fp32 | None)``."""
+    return self.forward_into(x, segment_pos, cache, return_cache)
+
+  def forward_into(self, x, segment_pos, cache=None, return_cache=True, out=None,
+                   last_h_out=None):
+    """``forward`` writing into caller-provided ``out`` / ``last_h_out`` buffers
+    (no allocation on the hot path; used by ``hostio.HostPrefill``)."""
     bs, length, _ = x.shape
     if segment_pos.shape != (bs, length):
       segment_pos = segment_pos[None, :]
@@ -200,12 +206,13 @@ class RGLRU(nn.Module):
         return _abi.rglru_fused_fwd(
             x, self._packed_gate_weight(), self.input_gate.b, self.a_gate.b,
             self.a_param, segment_pos, self.num_heads, h0=cache,
-            return_cache=return_cache, arith_mode=_arith_mode)
+            return_cache=return_cache, arith_mode=_arith_mode, out=out,
+            last_h_out=last_h_out)
       y, last_h = _abi.rglru_fwd(
           x, None, None, self.input_gate.b, self.a_gate.b, self.a_param,
           segment_pos, h0=cache, return_cache=return_cache,
           arith_mode=_arith_mode, gemm_fused=self.gate_gemm(x),
-          block_width=self.width // self.num_heads)
+          block_width=self.width // self.num_heads, out=out, last_h_out=last_h_out)
     return y, last_h
 
   @classmethod
@@ -239,6 +246,11 @@ class Conv1D(nn.Module):
 
   def forward(self, x, segment_pos, cache=None, return_cache=True):
     """Returns ``(y, new_cache | None)``; decode when ``cache`` is given."""
+    return self.forward_into(x, segment_pos, cache, return_cache)
+
+  def forward_into(self, x, segment_pos, cache=None, return_cache=True, out=None,
+                   cache_out=None):
+    """``forward`` (prefill) writing into caller-provided buffers."""
     _forward_only(x, cache)
     mode = _arith_mode & (_abi.ARITH_FP32)
     with torch.no_grad():
@@ -247,7 +259,7 @@ class Conv1D(nn.Module):
                                   return_cache=return_cache, arith_mode=mode)
       return _abi.conv1d_fwd(x, self.w, self.b, segment_pos,
                              return_cache=return_cache, mask_mode=self.mask_mode,
-                             arith_mode=mode)
+                             arith_mode=mode, out=out, cache_out=cache_out)
 
   @classmethod
   def init_cache(cls, *, batch_size, width, dtype, conv1d_temporal_width=4,
