@@ -544,3 +544,51 @@ def test_host_prefill_pipeline_matches_direct_call():
       xc, cs = conv(x.to(DEV), seg.to(DEV))
       y_d, h_d = lru(xc, seg.to(DEV))
     assert torch.equal(y, y_d.cpu()) and torch.equal(h, h_d.cpu()) and torch.equal(c, cs.cpu()), chunks
+
+
+def test_fused_rglru_api_variants_and_cuda_graph():
+  """Module API corner cases on the fused path: 1-D / int64 / broadcast
+  segment_pos, no h0, return_cache=False, B = 1, and CUDA-graph capture of the
+  whole call (prologue + tcgen05 kernel; the tensor map travels as a kernel
+  parameter)."""
+  import cadence_gemma_b200 as cg
+  abi = _abi()
+  torch.manual_seed(9)
+  width, heads, steps = 512, 2, 130
+  lru = cg.RGLRU(width, heads, device=DEV, dtype=torch.bfloat16)
+  with torch.no_grad():
+    lru.input_gate.b.normal_()
+    lru.a_gate.b.normal_()
+    x = torch.randn(3, steps, width, device=DEV).to(torch.bfloat16)
+    seg = torch.cat([torch.arange(50), torch.arange(steps - 50)]).to(DEV)      # 1-D, int64
+    assert lru.uses_fused_kernel(x)
+    y1, h1 = lru(x, seg[None].repeat(3, 1))                                    # [B,T] int64
+    y2, h2 = lru(x, seg[None].repeat(3, 1).to(torch.int32))
+    assert torch.equal(y1, y2) and torch.equal(h1, h2)
+    y3, none = lru(x, seg[None].repeat(3, 1), return_cache=False)
+    assert none is None and torch.equal(y3, y1)
+    yb, hb = lru(x[1:2].contiguous(), seg)                                     # B = 1, 1-D positions (:342-344)
+    assert torch.equal(yb, y1[1:2]) and torch.equal(hb, h1[1:2])
+    with pytest.raises(AssertionError):                                        # 1-D positions need B = 1, as the reference
+      lru(x, seg)
+    # CUDA graph: capture once, replay on new inputs in the static buffers
+    xs, ys, hs = x.clone(), torch.empty_like(x), torch.empty_like(h1)
+    seg32 = seg[None].repeat(3, 1).to(torch.int32)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      lru.forward_into(xs, seg32, out=ys, last_h_out=hs)                       # warm (workspace, weights)
+      torch.cuda.synchronize()
+      g = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(g, stream=side):
+        lru.forward_into(xs, seg32, out=ys, last_h_out=hs)
+    torch.cuda.current_stream().wait_stream(side)
+    for k in range(3):
+      xn = torch.randn_like(x)
+      xs.copy_(xn)
+      g.replay()
+      torch.cuda.synchronize()
+      y_ref, h_ref = lru(xn, seg32)
+      assert torch.equal(ys, y_ref) and torch.equal(hs, h_ref), k
+  for ws in abi._fused_workspaces.values():
+    assert abi.fused_watchdog_code(ws) == 0
