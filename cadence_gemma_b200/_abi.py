@@ -38,7 +38,7 @@ SYMBOLS = {
     "cg_rglru_pack_gate_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "cg_rglru_fused_workspace_bytes": (_sz, [_i, _i, _i]),
     "cg_rglru_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp,
-                                _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+                                _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -314,12 +314,18 @@ def fused_watchdog_code(ws: torch.Tensor) -> int:
 
 def rglru_fused_fwd(x, wpack, bias_x, bias_a, a_param, segment_pos, heads, h0=None,
                     return_cache=True, arith_mode=ARITH_FAST, out=None, debug=False,
-                    workspace=None, last_h_out=None):
-  """RGLRU.forward (gate GEMMs included) on the fused tcgen05 kernel."""
+                    workspace=None, last_h_out=None, gate_mul=None):
+  """RGLRU.forward (gate GEMMs included) on the fused tcgen05 kernel.
+
+  ``gate_mul`` ([B,T,E], optional): return ``round(y * gate_mul)`` -- the gating
+  product of ``RecurrentBlock.forward`` (reference modules.py:651) folded in."""
   global launch_count
-  _require_cuda(x, wpack, bias_x, bias_a, a_param, segment_pos, h0)
+  _require_cuda(x, wpack, bias_x, bias_a, a_param, segment_pos, h0, gate_mul)
   bsz, steps, width = x.shape
   assert x.dtype == torch.bfloat16 and a_param.dtype == x.dtype
+  if gate_mul is not None:
+    assert gate_mul.shape == x.shape and gate_mul.dtype == x.dtype
+    gate_mul = gate_mul.contiguous()
   assert h0 is None or h0.dtype == torch.float32, "layers.py:170"
   x = x.contiguous()
   seg, is64, stride = _seg_args(segment_pos, bsz, steps)
@@ -339,7 +345,8 @@ def rglru_fused_fwd(x, wpack, bias_x, bias_a, a_param, segment_pos, heads, h0=No
                                    a_param.contiguous().data_ptr(), seg.data_ptr(), is64,
                                    stride, _ptr(h0c), y.data_ptr(), _ptr(last_h),
                                    ws.data_ptr(), ws.numel(), bsz, steps, width, heads,
-                                   dtype_code(x.dtype), arith_mode, _ptr(dbg), _stream(x))
+                                   dtype_code(x.dtype), arith_mode, _ptr(gate_mul), _ptr(dbg),
+                                   _stream(x))
   _check(rc, "cg_rglru_fused_fwd")
   launch_count += 2   # prologue + fused kernel
   if debug:

@@ -374,10 +374,10 @@ bool fused_shape_ok(int E, int H, int dtype) {
   return bw == 128 || bw == 256;
 }
 
-template <int KB, bool FAST, bool DBG>
+template <int KB, bool FAST, bool DBG, bool MUL>
 int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, cudaStream_t stream) {
   using Cfg = cg::fused::FusedCfg<KB>;
-  auto kernel = cg::fused::rglru_fused_kernel<KB, FAST, DBG>;
+  auto kernel = cg::fused::rglru_fused_kernel<KB, FAST, DBG, MUL>;
   static int sms = 0;
   if (sms == 0) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -393,12 +393,14 @@ int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, cudaS
 }
 
 template <int KB>
-int dispatch_fused(bool fast, bool dbg, const CUtensorMap& tmap, const cg::fused::FusedParams& p,
-                   cudaStream_t stream) {
-  if (dbg) return fast ? launch_fused<KB, true, true>(tmap, p, stream)
-                       : launch_fused<KB, false, true>(tmap, p, stream);
-  return fast ? launch_fused<KB, true, false>(tmap, p, stream)
-              : launch_fused<KB, false, false>(tmap, p, stream);
+int dispatch_fused(bool fast, bool dbg, bool mul, const CUtensorMap& tmap,
+                   const cg::fused::FusedParams& p, cudaStream_t stream) {
+  if (dbg) return fast ? launch_fused<KB, true, true, false>(tmap, p, stream)
+                       : launch_fused<KB, false, true, false>(tmap, p, stream);
+  if (mul) return fast ? launch_fused<KB, true, false, true>(tmap, p, stream)
+                       : launch_fused<KB, false, false, true>(tmap, p, stream);
+  return fast ? launch_fused<KB, true, false, false>(tmap, p, stream)
+              : launch_fused<KB, false, false, false>(tmap, p, stream);
 }
 
 }  // namespace
@@ -437,8 +439,8 @@ size_t cg_rglru_fused_workspace_bytes(int B, int T, int E) {
 int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, const void* bias_a,
                        const void* a_param, const void* seg, int seg_is_i64, long long seg_batch_stride,
                        const float* h0, void* y, float* last_h, void* workspace, size_t workspace_bytes,
-                       int B, int T, int E, int H, int dtype, int arith_mode, void* debug_out,
-                       cg_stream_t stream_) {
+                       int B, int T, int E, int H, int dtype, int arith_mode, const void* gate_mul,
+                       void* debug_out, cg_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!x || !wpack || !a_param || !seg || !y || !workspace) return CG_ERR_NULL;
   if (int rc = check_common(B, T, E, dtype)) return rc;
@@ -449,6 +451,7 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
   if (variant != 0) return CG_ERR_MODE;
   if (!aligned16(x) || !aligned16(wpack) || !aligned16(y) || !aligned16(workspace)) return CG_ERR_ALIGN;
   if (B > 65535) return CG_ERR_SHAPE;
+  if (gate_mul != nullptr && debug_out != nullptr) return CG_ERR_MODE;   // the debug build has no product path
   const int bw = E / H;
   const int tile_t = cg::fused::kTile;
   const Workspace ws_min = carve(workspace, B, T, E, cg::fused::kMch, tile_t);
@@ -492,6 +495,7 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
   p.words = words;
   p.h0 = h0; p.y = reinterpret_cast<uint16_t*>(y); p.last_h = last_h;
   p.epoch = ws.epoch; p.agg_p = ws.agg_p; p.agg_h = ws.agg_h; p.pref = ws.pref;
+  p.gate_mul = reinterpret_cast<const uint16_t*>(gate_mul);
   p.dbg = reinterpret_cast<uint16_t*>(debug_out);
   p.err = ws.counter + 2;   // third word of the scratch header
   p.B = B; p.T = T; p.E = E;
@@ -499,8 +503,9 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
   p.families = E / cg::fused::kMch;
   const bool fast = (mode & CG_ARITH_FAST) != 0;
   const bool dbg = debug_out != nullptr;
-  return bw == 256 ? dispatch_fused<4>(fast, dbg, tmap, p, stream)
-                   : dispatch_fused<2>(fast, dbg, tmap, p, stream);
+  const bool mul = gate_mul != nullptr;
+  return bw == 256 ? dispatch_fused<4>(fast, dbg, mul, tmap, p, stream)
+                   : dispatch_fused<2>(fast, dbg, mul, tmap, p, stream);
 }
 
 }  // extern "C"

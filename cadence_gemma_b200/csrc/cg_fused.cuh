@@ -101,6 +101,7 @@ struct FusedParams {
   unsigned long long* agg_p;       // [families][ntt][B][128]
   unsigned long long* agg_h;
   unsigned long long* pref;
+  const uint16_t* gate_mul;        // optional [B,T,E]: y <- round_bf16(y * gate_mul) (RecurrentBlock, modules.py:651)
   uint16_t* dbg;                   // optional [3][B][T][E]: rounded pre_x, pre_a, x^T
   int* err;                        // watchdog flag
   int B, T, E;
@@ -239,6 +240,11 @@ __device__ __forceinline__ float add_bf_hi(uint32_t packed, float c) {
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ uint32_t ld_u16(const uint16_t* p) {
+  uint16_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void st_u16(uint16_t* p, uint32_t v) {
   asm volatile("st.global.u16 [%0], %1;" :: "l"(p), "h"(static_cast<uint16_t>(v)) : "memory");
 }
@@ -323,7 +329,9 @@ __global__ void pack_gate_weights_kernel(const uint16_t* __restrict__ wx, const 
 // ---------------------------------------------------------------------------
 // (registers are allocated in units of four warps: 18 warps count as 20, which
 // caps the kernel at 96 registers per thread)
-template <int KB, bool FAST, bool DBG>
+// MUL: multiply the output by a second activation tensor on the way out (the
+// gating product of RecurrentBlock), SURVEY.md section 8(f) row F2.
+template <int KB, bool FAST, bool DBG, bool MUL>
 __global__ void __launch_bounds__(kThreads, 1)
 rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams p) {
   using Cfg = FusedCfg<KB>;
@@ -512,6 +520,16 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     auto finish = [&](unsigned long long early) {
       // `early`: the predecessor's state word, requested before stage A
       const int tt = pd.tt;
+      // gating-product operand of the first 8 steps, requested before the
+      // look-back so that its latency hides behind it
+      uint32_t gm[8];
+      const int E = p.E;
+      const uint16_t* gmp = nullptr;
+      if constexpr (MUL) {
+        gmp = p.gate_mul + (pd.yp - p.y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gm[i] = i < pd.nvalid ? ld_u16(gmp + i * E) : 0u;
+      }
       float c0;
       if (tt == 0) {
         c0 = p.h0 != nullptr ? p.h0[(size_t)pd.b * p.E + pd.ch] : 0.0f;
@@ -580,12 +598,17 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       // ---- pass 2 (replay): h = a*h + x~ from the true carry-in, mul then add as
       // the reference loop (:196); y leaves as bf16
       float h = c0;
-      const int E = p.E;
       const int nvalid = pd.nvalid;
 #pragma unroll 1
       for (int c = 0; c < kTile / 8; ++c) {
         uint32_t st[8];
         tmem_ld8(tm_state + c * 8, st);
+        uint32_t gn[8];                                  // operand of the next chunk, one chunk ahead
+        if constexpr (MUL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            gn[i] = (c + 1 < kTile / 8 && (c + 1) * 8 + i < nvalid) ? ld_u16(gmp + ((c + 1) * 8 + i) * E) : 0u;
+        }
         tmem_wait_ld();
         uint32_t o[4];
 #pragma unroll
@@ -595,6 +618,11 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           const float y1 = add_bf_hi(n2, bf_hi(a2) * y0);
           h = y1;
           o[i] = pack_bf2(y0, y1);
+          if constexpr (MUL) o[i] = bf2_mul(o[i], gm[2 * i] | (gm[2 * i + 1] << 16));   // r(r(h) * gate), :651
+        }
+        if constexpr (MUL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gm[i] = gn[i];
         }
         uint16_t* yc = pd.yp + (size_t)(c * 8) * E;
         if (c * 8 + 8 <= nvalid) {

@@ -41,13 +41,20 @@ def _fused_gate_gemm(lru, x):
   return out, bw
 
 
-def _rglru_forward(self, x, segment_pos, cache=None, return_cache=True):
+def _rglru_forward(self, x, segment_pos, cache=None, return_cache=True, gate_mul=None):
   bs, length, _ = x.shape
   if segment_pos.shape != (bs, length):
     segment_pos = segment_pos[None, :]
   assert segment_pos.shape == (bs, length)
   cg_layers._forward_only(x, cache)
   with torch.no_grad():
+    if cg_layers.uses_fused_kernel(self, x):
+      # gate GEMMs + gate math + scan in ONE tcgen05 kernel (cg_rglru_fused_fwd)
+      return _abi.rglru_fused_fwd(
+          x, cg_layers.packed_gate_weight(self), self.input_gate.b, self.a_gate.b,
+          self.a_param, segment_pos, self.num_heads, h0=cache, return_cache=return_cache,
+          arith_mode=cg_layers.get_arith_mode(), gate_mul=gate_mul)
+    assert gate_mul is None
     gates, bw = _fused_gate_gemm(self, x)
     return _abi.rglru_fwd(
         x, None, None, self.input_gate.b, self.a_gate.b, self.a_param, segment_pos,
@@ -66,8 +73,33 @@ def _conv1d_forward(self, x, segment_pos, cache=None, return_cache=True):
                            return_cache=return_cache, arith_mode=mode)
 
 
+def _recurrent_block_forward(self, x, segment_pos, cache=None, return_cache=True):
+  """RecurrentBlock.forward (reference modules.py:613-660) with the gating product
+  ``x * y`` (:651) folded into the fused RG-LRU kernel when that kernel runs."""
+  y = self.linear_y(x)
+  h = self.linear_x(x)
+  h, conv1d_state = self.conv_1d(
+      x=h, segment_pos=segment_pos,
+      cache=None if cache is None else cache.conv1d_state, return_cache=return_cache)
+  lru_cache = None if cache is None else cache.rg_lru_state
+  if cg_layers.uses_fused_kernel(self.rg_lru, h):
+    h, rg_lru_state = _rglru_forward(self.rg_lru, h, segment_pos, lru_cache, return_cache,
+                                     gate_mul=y)
+  else:
+    h, rg_lru_state = self.rg_lru(x=h, segment_pos=segment_pos, cache=lru_cache,
+                                  return_cache=return_cache)
+    h = h * y
+  out = self.linear_out(h)
+  if not return_cache:
+    return out, None
+  return out, _saved["modules"].RecurrentBlockCache(
+      conv1d_state=conv1d_state, rg_lru_state=rg_lru_state)
+
+
 def install(ref_layers, ref_modules=None) -> None:
-  """Patches the given reference modules in place (idempotent)."""
+  """Patches the given reference modules in place (idempotent).  With
+  ``ref_modules`` also ``RecurrentBlock.forward`` is rebound, so the gating
+  product rides on the fused RG-LRU kernel."""
   if "rnn_scan" in _saved:
     return
   _abi.load()   # fail loudly now if the library was not built
@@ -78,6 +110,10 @@ def install(ref_layers, ref_modules=None) -> None:
   ref_layers.rnn_scan = cg_layers.rnn_scan
   ref_layers.RGLRU.forward = _rglru_forward
   ref_layers.Conv1D.forward = _conv1d_forward
+  if ref_modules is not None and hasattr(ref_modules, "RecurrentBlock"):
+    _saved["modules"] = ref_modules
+    _saved["block_forward"] = ref_modules.RecurrentBlock.forward
+    ref_modules.RecurrentBlock.forward = _recurrent_block_forward
 
 
 def uninstall() -> None:
@@ -87,3 +123,5 @@ def uninstall() -> None:
   ref_layers.rnn_scan = _saved.pop("rnn_scan")
   ref_layers.RGLRU.forward = _saved.pop("rglru_forward")
   ref_layers.Conv1D.forward = _saved.pop("conv1d_forward")
+  if "modules" in _saved:
+    _saved.pop("modules").RecurrentBlock.forward = _saved.pop("block_forward")

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 
 import torch
 from torch import nn
@@ -81,6 +82,30 @@ def rnn_scan(x, a, reset, h0, acc_dtype=torch.float32):
     a = a.expand_as(x)
   mode = _arith_mode & _abi.ARITH_STRICT
   return _abi.rnn_scan_fwd(x, a, reset, h0, arith_mode=mode)
+
+
+_wpack_cache = weakref.WeakKeyDictionary()
+
+
+def packed_gate_weight(lru) -> torch.Tensor:
+  """Gate weights of an RGLRU-like module (ours or the reference's) as the
+  shared-memory image the fused tcgen05 kernel reads
+  (cg_rglru_pack_gate_weights); rebuilt only when a gate weight changes."""
+  wx, wa = lru.input_gate.w, lru.a_gate.w
+  key = (wx.data_ptr(), wa.data_ptr(), wx._version, wa._version, wx.dtype, wx.device)
+  hit = _wpack_cache.get(lru)
+  if hit is None or hit[0] != key:
+    hit = (key, _abi.pack_gate_weights(wx, wa))
+    _wpack_cache[lru] = hit
+  return hit[1]
+
+
+def uses_fused_kernel(lru, x: torch.Tensor) -> bool:
+  """True if the RG-LRU of module ``lru`` on input ``x`` runs on the fused
+  tensor-core kernel (bf16, head width 128 / 256, prefill, emulated modes)."""
+  return (_fused_enabled and x.is_cuda and x.shape[1] > 1 and
+          (_arith_mode & (_abi.ARITH_FP32 | _abi.ARITH_STRICT)) == 0 and
+          _abi.fused_supported(lru.width, lru.num_heads, x.dtype))
 
 
 class BlockDiagonalLinear(nn.Module):
@@ -164,21 +189,9 @@ class RGLRU(nn.Module):
       self._wcat_key = key
     return self._wcat
 
-  def _packed_gate_weight(self) -> torch.Tensor:
-    """Gate weights as the shared-memory image the fused tcgen05 kernel reads
-    (cg_rglru_pack_gate_weights); rebuilt only when a gate weight changes."""
-    wx, wa = self.input_gate.w, self.a_gate.w
-    key = (wx.data_ptr(), wa.data_ptr(), wx._version, wa._version, wx.dtype, wx.device)
-    if getattr(self, "_wpack_key", None) != key:
-      self._wpack = _abi.pack_gate_weights(wx, wa)
-      self._wpack_key = key
-    return self._wpack
-
   def uses_fused_kernel(self, x: torch.Tensor) -> bool:
     """True if ``forward(x, ...)`` runs on the fused tensor-core kernel."""
-    return (_fused_enabled and x.is_cuda and x.shape[1] > 1 and
-            (_arith_mode & (_abi.ARITH_FP32 | _abi.ARITH_STRICT)) == 0 and
-            _abi.fused_supported(self.width, self.num_heads, x.dtype))
+    return uses_fused_kernel(self, x)
 
   def gate_gemm(self, x: torch.Tensor) -> torch.Tensor:
     """Both gate GEMMs (no bias) in one call -> [B*T, H, 2*bw]."""
@@ -193,9 +206,12 @@ class RGLRU(nn.Module):
     return self.forward_into(x, segment_pos, cache, return_cache)
 
   def forward_into(self, x, segment_pos, cache=None, return_cache=True, out=None,
-                   last_h_out=None):
+                   last_h_out=None, gate_mul=None):
     """``forward`` writing into caller-provided ``out`` / ``last_h_out`` buffers
-    (no allocation on the hot path; used by ``hostio.HostPrefill``)."""
+    (no allocation on the hot path; used by ``hostio.HostPrefill``).
+
+    ``gate_mul`` (fused kernel only): return ``y * gate_mul`` rounded to bf16,
+    the gating product of ``RecurrentBlock.forward`` (modules.py:651)."""
     bs, length, _ = x.shape
     if segment_pos.shape != (bs, length):
       segment_pos = segment_pos[None, :]
@@ -204,10 +220,11 @@ class RGLRU(nn.Module):
     with torch.no_grad():
       if self.uses_fused_kernel(x):
         return _abi.rglru_fused_fwd(
-            x, self._packed_gate_weight(), self.input_gate.b, self.a_gate.b,
+            x, packed_gate_weight(self), self.input_gate.b, self.a_gate.b,
             self.a_param, segment_pos, self.num_heads, h0=cache,
             return_cache=return_cache, arith_mode=_arith_mode, out=out,
-            last_h_out=last_h_out)
+            last_h_out=last_h_out, gate_mul=gate_mul)
+      assert gate_mul is None, "the gating product is folded in only by the fused kernel"
       y, last_h = _abi.rglru_fwd(
           x, None, None, self.input_gate.b, self.a_gate.b, self.a_param,
           segment_pos, h0=cache, return_cache=return_cache,

@@ -3,7 +3,8 @@
 The reference block is kept as the boundary: two input projections, the
 temporal Conv1D, the RG-LRU, the gating product and the output projection.
 Only ``conv_1d`` and ``rg_lru`` run custom kernels; the three ``nn.Linear``
-stay cuBLAS GEMMs.  Parameter names / state-dict keys match the reference
+stay cuBLAS GEMMs.  On the fused tensor-core path the gating product ``x * y``
+(reference modules.py:651) is folded into the RG-LRU kernel's store.  Parameter names / state-dict keys match the reference
 (``linear_x``, ``linear_y``, ``linear_out``, ``conv_1d.{w,b}``,
 ``rg_lru.{a_param,input_gate.{w,b},a_gate.{w,b}}``), so reference checkpoints
 load with ``load_state_dict``.
@@ -62,11 +63,16 @@ class RecurrentBlock(nn.Module):
         x=h, segment_pos=segment_pos,
         cache=None if cache is None else cache.conv1d_state,
         return_cache=return_cache)
-    h, lru_state = self.rg_lru(
-        x=h, segment_pos=segment_pos,
-        cache=None if cache is None else cache.rg_lru_state,
-        return_cache=return_cache)
-    out = self.linear_out(h * gate)
+    lru_cache = None if cache is None else cache.rg_lru_state
+    if self.rg_lru.uses_fused_kernel(h):
+      # the gating product (reference :651) leaves the fused kernel already applied
+      h, lru_state = self.rg_lru.forward_into(h, segment_pos, lru_cache, return_cache,
+                                              gate_mul=gate)
+      out = self.linear_out(h)
+    else:
+      h, lru_state = self.rg_lru(x=h, segment_pos=segment_pos, cache=lru_cache,
+                                 return_cache=return_cache)
+      out = self.linear_out(h * gate)
     if not return_cache:
       return out, None
     return out, RecurrentBlockCache(rg_lru_state=lru_state, conv1d_state=conv_state)

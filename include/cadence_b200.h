@@ -168,6 +168,11 @@ int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset,
  *                              (every eager bf16 rounding point reproduced in both;
  *                              the GEMM accumulates in fp32 and rounds once to bf16
  *                              like the reference's einsum); variant 1 = 32-step tiles.
+ *                              gate_mul (nullable): [B,T,E] bf16; when given, the kernel
+ *                              returns round_bf16(y * gate_mul) -- the gating product of
+ *                              RecurrentBlock.forward (modules.py:651, `x = x * y`) folded
+ *                              into the store; last_h is
+ *                              unaffected.
  *                              debug_out (nullable): [3][B][T][E] bf16 -- the rounded
  *                              pre_x, pre_a and the transposed x the epilogue saw.
  */
@@ -181,8 +186,8 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x,
                        int seg_is_i64, long long seg_batch_stride,
                        const float* h0, void* y, float* last_h, void* workspace,
                        size_t workspace_bytes, int B, int T, int E, int H,
-                       int dtype, int arith_mode, void* debug_out,
-                       cg_stream_t stream);
+                       int dtype, int arith_mode, const void* gate_mul,
+                       void* debug_out, cg_stream_t stream);
 
 #ifdef __cplusplus
 }

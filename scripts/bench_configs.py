@@ -80,6 +80,35 @@ def prefill_case(name, B, T, seg, dtype, iters=20):
               gbps_block=6 * s * n / (t_conv + t_gemm + t_lru) / 1e3)
 
 
+def block_case(B, T, dtype, iters=20):
+  """Whole RecurrentBlock (reference modules.py:613-660) at 2B shapes: three cuBLAS
+  projections + the hot path, with / without the fused kernel and its folded
+  gating product."""
+  from cadence_gemma_b200.modules import RecurrentBlock
+  torch.manual_seed(0)
+  blk = RecurrentBlock(width=E, num_heads=H, lru_width=E, device=DEV, dtype=dtype)
+  with torch.no_grad():
+    blk.rg_lru.input_gate.b.normal_(); blk.rg_lru.a_gate.b.normal_()
+    x = torch.randn((B, T, E), device=DEV).to(dtype)
+    seg = torch.arange(T, dtype=torch.int32, device=DEV)[None].repeat(B, 1)
+    run = lambda: blk(x, seg)
+    t_fused = timed(run, iters)
+    def no_fold():   # fused kernel, gating product as a separate elementwise kernel
+      gate = blk.linear_y(x)
+      h, _ = blk.conv_1d(blk.linear_x(x), seg)
+      h, _ = blk.rg_lru(h, seg)
+      return blk.linear_out(h * gate)
+    t_nofold = timed(no_fold, iters)
+    old = cg.set_fused(False)
+    try:
+      t_unfused = timed(run, iters)
+    finally:
+      cg.set_fused(old)
+  return dict(config=f"RecurrentBlock 2B shape B={B} T={T}", dtype=str(dtype),
+              us_block_fused_folded=t_fused, us_block_fused_separate_product=t_nofold,
+              us_block_unfused=t_unfused, tokens_per_s=B * T / t_fused * 1e6)
+
+
 def decode_case(B, dtype, iters=200):
   conv, lru = modules(dtype)
   with torch.no_grad():
@@ -135,6 +164,8 @@ def main():
         seg4[b, cut:] = torch.arange(8192 - cut, dtype=torch.int32)
     out.append(prefill_case(f"4 long context T=8192 resets B={B}", B, 8192, seg4, bf, iters=8))
   out.append(prefill_case("sampler prefill B=1 T=2048", 1, 2048, ar(1, 2048), bf))
+  out.append(block_case(8, 2048, bf))
+  out.append(block_case(32, 768, bf))
   out.append(decode_case(32, bf))
   out.append(decode_case(256, bf))
   for r in out:

@@ -188,19 +188,26 @@ def make_rglru(ref):
 
 
 def make_recurrent_block(ref):
-  for tag, dtype in DTYPES.items():
-    seed = 4242 if tag == "f32" else 4243
+  # (fixture tag, dtype, width, heads, lru_width, steps); "bf16_h128" has head
+  # width 128: the block whose RG-LRU (and gating product) runs on the fused
+  # tensor-core kernel
+  for tag, dtype, width, heads, lru_width, steps in [
+      ("f32", torch.float32, 96, 4, 128, 48), ("bf16", torch.bfloat16, 96, 4, 128, 48),
+      ("bf16_h128", torch.bfloat16, 64, 2, 256, 80)]:
+    if ONLY and not any(o in f"recurrent_block_{tag}" for o in ONLY):
+      continue
+    seed = {"f32": 4242, "bf16": 4243}.get(tag, 4244)
     g = gen(seed)
     torch.manual_seed(seed)
-    blk = ref.modules.RecurrentBlock(width=96, num_heads=4, lru_width=128,
+    blk = ref.modules.RecurrentBlock(width=width, num_heads=heads, lru_width=lru_width,
                                      conv1d_temporal_width=4, dtype=dtype)
     with torch.no_grad():
       for p in (blk.rg_lru.input_gate.b, blk.rg_lru.a_gate.b, blk.conv_1d.b,
                 blk.linear_x.bias, blk.linear_y.bias):
         p.copy_((torch.randn(p.shape, generator=g) * 0.3).to(dtype))
       blk.conv_1d.w.copy_((torch.randn(blk.conv_1d.w.shape, generator=g) * 0.4).to(dtype))
-    bsz, steps = 2, 48
-    x = torch.randn((bsz, steps, 96), generator=g).to(dtype)
+    bsz = 2
+    x = torch.randn((bsz, steps, width), generator=g).to(dtype)
     seg = halves(steps, bsz)
     out = {"param." + k: v for k, v in blk.state_dict().items()}
     captured = {}
@@ -221,7 +228,7 @@ def make_recurrent_block(ref):
       out.update(x=x, seg=seg, y=y, rg_lru_state=cache.rg_lru_state,
                  conv1d_state=cache.conv1d_state, **captured)
       for i in range(2):
-        xs = torch.randn((bsz, 1, 96), generator=g).to(dtype)
+        xs = torch.randn((bsz, 1, width), generator=g).to(dtype)
         ys, cache = blk(xs, seg[:, -1:] + 1 + i, cache)
         out[f"step{i}_x"], out[f"step{i}_y"] = xs, ys
         out[f"step{i}_rg_lru_state"] = cache.rg_lru_state
@@ -298,6 +305,7 @@ def main():
   ref = ref_loader.load_reference()
   if ONLY:
     make_rglru(ref)
+    make_recurrent_block(ref)
   else:
     make_rnn_scan(ref)
     make_conv1d(ref)

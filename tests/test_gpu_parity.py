@@ -217,10 +217,15 @@ def test_recurrent_block_golden(case):
   from cadence_gemma_b200.modules import RecurrentBlock
   g = fixture_io.load(case)
   dtype = g["x"].dtype
-  blk = RecurrentBlock(width=96, num_heads=4, lru_width=128, device=DEV, dtype=dtype)
+  # shapes from the parameters (recurrent_block_bf16_h128 has head width 128: its
+  # RG-LRU and gating product run on the fused tensor-core kernel)
+  lru_width, width = g["param.linear_x.weight"].shape
+  heads = g["param.rg_lru.input_gate.w"].shape[0]
+  blk = RecurrentBlock(width=width, num_heads=heads, lru_width=lru_width, device=DEV, dtype=dtype)
   blk.load_state_dict({k[len("param."):]: v for k, v in g.items()
                        if k.startswith("param.")})
   bf = dtype == torch.bfloat16
+  assert blk.rg_lru.uses_fused_kernel(cu(g["conv_in"])) == (bf and lru_width // heads in (128, 256))
 
   def check(a, b, what):
     if bf:
@@ -592,3 +597,25 @@ def test_fused_rglru_api_variants_and_cuda_graph():
       assert torch.equal(ys, y_ref) and torch.equal(hs, h_ref), k
   for ws in abi._fused_workspaces.values():
     assert abi.fused_watchdog_code(ws) == 0
+
+
+@pytest.mark.parametrize("shape", [(2, 100, 512, 2), (3, 64, 256, 2), (1, 333, 2560, 10)])
+def test_fused_gating_product(shape):
+  """`x * y` of RecurrentBlock.forward (modules.py:651) folded
+  into the fused kernel's store == the separate bf16 multiply, bit for bit."""
+  import cadence_gemma_b200 as cg
+  bsz, steps, width, heads = shape
+  torch.manual_seed(sum(shape))
+  lru = cg.RGLRU(width, heads, device=DEV, dtype=torch.bfloat16)
+  with torch.no_grad():
+    lru.input_gate.b.normal_()
+    lru.a_gate.b.normal_()
+    x = torch.randn(bsz, steps, width, device=DEV).to(torch.bfloat16)
+    gate = torch.randn(bsz, steps, width, device=DEV).to(torch.bfloat16)
+    seg = torch.arange(steps, device=DEV, dtype=torch.int32)[None].repeat(bsz, 1)
+    seg[:, steps // 3:] -= steps // 3
+    h0 = torch.randn(bsz, width, device=DEV)
+    y, h = lru(x, seg, h0)
+    ym, hm = lru.forward_into(x, seg, h0, gate_mul=gate)
+    assert torch.equal(ym, y * gate)
+    assert torch.equal(hm, h)
