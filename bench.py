@@ -360,7 +360,8 @@ def own_arm(args, dtype):
     # (upload c+1 | kernels c | download c-1), see cadence_gemma_b200/hostio.py
     from cadence_gemma_b200.hostio import HostPrefill
     e2e_chunks = int(os.environ.get("CG_BENCH_E2E_CHUNKS", "4"))
-    host_prefill = HostPrefill(conv, lru, w["batch"], w["seq_len"], chunks=e2e_chunks)
+    e2e_graph = os.environ.get("CG_BENCH_E2E_GRAPH", "0") != "0"
+    host_prefill = HostPrefill(conv, lru, w["batch"], w["seq_len"], chunks=e2e_chunks, graph=e2e_graph)
 
     def e2e_step():
       host_prefill(x_pin, seg_pin, y_pin, h_pin, c_pin)

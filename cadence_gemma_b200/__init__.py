@@ -7,5 +7,7 @@ from cadence_gemma_b200.layers import (BlockDiagonalLinear, Conv1D, RGLRU,
                                        fused_enabled, get_arith_mode, rnn_scan,
                                        set_arith_mode, set_fused)
 
-__all__ = ["BlockDiagonalLinear", "Conv1D", "RGLRU", "rnn_scan",
+from cadence_gemma_b200.pipeline import recurrent_hot_path
+
+__all__ = ["recurrent_hot_path", "BlockDiagonalLinear", "Conv1D", "RGLRU", "rnn_scan",
            "set_arith_mode", "get_arith_mode", "set_fused", "fused_enabled", "_abi"]

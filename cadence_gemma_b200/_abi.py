@@ -38,7 +38,10 @@ SYMBOLS = {
     "cg_rglru_pack_gate_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "cg_rglru_fused_workspace_bytes": (_sz, [_i, _i, _i]),
     "cg_rglru_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp,
-                                _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+                                _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "cg_conv1d_stream_flags_bytes": (_sz, [_i, _i]),
+    "cg_conv1d_stream_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _i, _i, _i, _i,
+                                  _i, _i, _i, _vp]),
 }
 
 _lib = None
@@ -159,6 +162,26 @@ def conv1d_fwd(x, w, b, segment_pos, return_cache=True, mask_mode=MASK_FORK,
   _check(rc, "cg_conv1d_fwd")
   launch_count += 1
   return y, cache
+
+
+def conv1d_stream_fwd(x, w, b, segment_pos, flags, out, cache_out=None, mask_mode=MASK_FORK,
+                      arith_mode=ARITH_REFERENCE):
+  """Producer form of ``conv1d_fwd`` for the overlapped Conv1D -> RG-LRU pipeline
+  (``flags``: zeroed int32 [ceil(T/64) * B]); enqueued on the CURRENT stream."""
+  global launch_count
+  _require_cuda(x, w, b, segment_pos, flags, out)
+  bsz, steps, width = x.shape
+  assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape
+  assert flags.dtype == torch.int32 and flags.numel() * 4 >= load().cg_conv1d_stream_flags_bytes(bsz, steps)
+  seg, is64, stride = _seg_args(segment_pos, bsz, steps)
+  with torch.cuda.device(x.device):
+    rc = load().cg_conv1d_stream_fwd(x.data_ptr(), w.contiguous().data_ptr(), b.contiguous().data_ptr(),
+                                     seg.data_ptr(), is64, stride, out.data_ptr(), _ptr(cache_out),
+                                     flags.data_ptr(), bsz, steps, width, w.shape[0],
+                                     dtype_code(x.dtype), mask_mode, arith_mode, _stream(x))
+  _check(rc, "cg_conv1d_stream_fwd")
+  launch_count += 1
+  return out, cache_out
 
 
 def conv1d_decode(x, w, b, cache, return_cache=True, arith_mode=ARITH_REFERENCE):
@@ -314,7 +337,7 @@ def fused_watchdog_code(ws: torch.Tensor) -> int:
 
 def rglru_fused_fwd(x, wpack, bias_x, bias_a, a_param, segment_pos, heads, h0=None,
                     return_cache=True, arith_mode=ARITH_FAST, out=None, debug=False,
-                    workspace=None, last_h_out=None, gate_mul=None):
+                    workspace=None, last_h_out=None, gate_mul=None, conv_flags=None):
   """RGLRU.forward (gate GEMMs included) on the fused tcgen05 kernel.
 
   ``gate_mul`` ([B,T,E], optional): return ``round(y * gate_mul)`` -- the gating
@@ -345,8 +368,8 @@ def rglru_fused_fwd(x, wpack, bias_x, bias_a, a_param, segment_pos, heads, h0=No
                                    a_param.contiguous().data_ptr(), seg.data_ptr(), is64,
                                    stride, _ptr(h0c), y.data_ptr(), _ptr(last_h),
                                    ws.data_ptr(), ws.numel(), bsz, steps, width, heads,
-                                   dtype_code(x.dtype), arith_mode, _ptr(gate_mul), _ptr(dbg),
-                                   _stream(x))
+                                   dtype_code(x.dtype), arith_mode, _ptr(gate_mul),
+                                   _ptr(conv_flags), _ptr(dbg), _stream(x))
   _check(rc, "cg_rglru_fused_fwd")
   launch_count += 2   # prologue + fused kernel
   if debug:

@@ -187,6 +187,45 @@ int cg_conv1d_fwd(const void* x, const void* w, const void* b, const void* seg, 
   return (int)cudaGetLastError();
 }
 
+size_t cg_conv1d_stream_flags_bytes(int B, int T) {
+  if (B < 1 || T < 1) return 0;
+  return (size_t)B * ((T + 63) / 64) * sizeof(int);
+}
+
+int cg_conv1d_stream_fwd(const void* x, const void* w, const void* b, const void* seg, int seg_is_i64,
+                         long long seg_batch_stride, void* y, void* cache_out, int* flags, int B, int T,
+                         int E, int W, int dtype, int mask_mode, int arith_mode, cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !w || !b || !seg || !y || !flags) return CG_ERR_NULL;
+  if (int rc = check_common(B, T, E, dtype)) return rc;
+  if (mask_mode != CG_MASK_FORK && mask_mode != CG_MASK_UPSTREAM) return CG_ERR_MODE;
+  // producer form exists for the shapes the fused RG-LRU kernel takes: bf16, W = 4,
+  // reference rounding
+  if (dtype != CG_DTYPE_BF16 || W != 4 || (arith_mode & CG_ARITH_FP32) != 0) return CG_ERR_UNSUPPORTED;
+  if (E % 64 != 0) return CG_ERR_UNSUPPORTED;
+  if (!aligned16(x) || !aligned16(w) || !aligned16(b) || !aligned16(y) ||
+      (cache_out && !aligned16(cache_out)))
+    return CG_ERR_ALIGN;
+  ConvParams p{};
+  p.x = x; p.w = w; p.bias = b; p.seg = seg; p.seg_bstride = seg_batch_stride;
+  p.seg_is_i64 = seg_is_i64; p.y = y; p.cache_out = cache_out;
+  p.B = B; p.T = T; p.E = E; p.W = W; p.mask_mode = mask_mode;
+  constexpr int LC = 4;                       // 16 slots x 4 steps = one 64-step group per tile
+  const int ctiles = E / 64, tgroups = (T + 63) / 64;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 1) return (int)cudaErrorLaunchOutOfResources;
+  }
+  const long long ntiles = (long long)ctiles * tgroups * B;
+  // one small block per SM: they share the SMs with the fused RG-LRU CTAs
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  cg::conv1d_w4_stream_kernel<uint16_t, true, LC><<<grid, 128, 0, stream>>>(p, flags, ctiles, tgroups);
+  return (int)cudaGetLastError();
+}
+
 int cg_conv1d_decode(const void* x, const void* w, const void* b, const void* cache_in,
                      int cache_dtype, void* y, void* cache_out, int B, int E, int W, int dtype,
                      int arith_mode, cg_stream_t stream_) {
@@ -440,7 +479,7 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
                        const void* a_param, const void* seg, int seg_is_i64, long long seg_batch_stride,
                        const float* h0, void* y, float* last_h, void* workspace, size_t workspace_bytes,
                        int B, int T, int E, int H, int dtype, int arith_mode, const void* gate_mul,
-                       void* debug_out, cg_stream_t stream_) {
+                       const int* conv_flags, void* debug_out, cg_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!x || !wpack || !a_param || !seg || !y || !workspace) return CG_ERR_NULL;
   if (int rc = check_common(B, T, E, dtype)) return rc;
@@ -496,6 +535,8 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
   p.h0 = h0; p.y = reinterpret_cast<uint16_t*>(y); p.last_h = last_h;
   p.epoch = ws.epoch; p.agg_p = ws.agg_p; p.agg_h = ws.agg_h; p.pref = ws.pref;
   p.gate_mul = reinterpret_cast<const uint16_t*>(gate_mul);
+  p.conv_flags = conv_flags;
+  p.conv_need = (E + 63) / 64;
   p.dbg = reinterpret_cast<uint16_t*>(debug_out);
   p.err = ws.counter + 2;   // third word of the scratch header
   p.B = B; p.T = T; p.E = E;

@@ -32,18 +32,18 @@ struct ConvParams {
 // packed HMUL2/HADD2, for fp32 non-contracted FMUL/FADD, both bit-exact with
 // the reference.  !EMUL (bf16 only): fp32 accumulation, one final rounding.
 // ---------------------------------------------------------------------------
-template <typename IO, bool EMUL, int LC>
-__global__ void __launch_bounds__(128)
-conv1d_w4_kernel(const ConvParams p) {
+// One tile = 128 threads: channel tile `ctile` (8 lanes x 16 B), 16 time slots of
+// LC steps starting at slot block `tblock`, batch row b.  KEEP: plain stores (the
+// output is re-read from L2 right away by a concurrently running consumer)
+// instead of streaming (evict-first) ones.
+template <typename IO, bool EMUL, int LC, bool KEEP>
+__device__ __forceinline__ void conv1d_w4_tile(const ConvParams& p, int ctile, int tblock, int b) {
   constexpr int V = IoVec<IO>::V;
   constexpr bool BF = IoVec<IO>::kBf16;
   constexpr int EC = kCvl * V;
   const int cv = threadIdx.x & 7;
-  // blockIdx.x walks the channel tiles of a row first, so concurrently
-  // running blocks sweep whole rows (DRAM page locality)
-  const int tslot = blockIdx.y * (blockDim.x >> 3) + (threadIdx.x >> 3);
-  const int ch0 = blockIdx.x * EC + cv * V;
-  const int b = blockIdx.z;
+  const int tslot = tblock * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  const int ch0 = ctile * EC + cv * V;
   const int t0 = tslot * LC;
   if (ch0 >= p.E || t0 >= p.T) return;
   const IO* xb = reinterpret_cast<const IO*>(p.x) + (size_t)b * p.T * p.E + ch0;
@@ -126,7 +126,8 @@ conv1d_w4_kernel(const ConvParams p) {
         o[i] = __float_as_uint(__fadd_rn(acc, __uint_as_float(bb[i])));
       }
     }
-    stg_stream(yb + (size_t)t * p.E, make_uint4(o[0], o[1], o[2], o[3]));
+    if constexpr (KEEP) *reinterpret_cast<uint4*>(yb + (size_t)t * p.E) = make_uint4(o[0], o[1], o[2], o[3]);
+    else stg_stream(yb + (size_t)t * p.E, make_uint4(o[0], o[1], o[2], o[3]));
   }
 
   // new cache = last 3 input rows, left zero padded (:542-543); written by the
@@ -138,6 +139,37 @@ conv1d_w4_kernel(const ConvParams p) {
       const int ti = p.T - 3 + r;
       const uint4 v = ti >= 0 ? ldg_stream(xb + (size_t)ti * p.E) : zero;
       *reinterpret_cast<uint4*>(cb + (size_t)r * p.E) = v;
+    }
+  }
+}
+
+// Grid-mapped launch: blockIdx.x walks the channel tiles of a row first, so
+// concurrently running blocks sweep whole rows (DRAM page locality).
+template <typename IO, bool EMUL, int LC>
+__global__ void __launch_bounds__(128)
+conv1d_w4_kernel(const ConvParams p) {
+  conv1d_w4_tile<IO, EMUL, LC, false>(p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Producer form for the overlapped Conv1D -> RG-LRU pipeline: few persistent
+// blocks (they share the SMs with the fused RG-LRU kernel, which runs at the same
+// time on another stream) walk the tiles in TIME-MAJOR order -- the order in which
+// the consumer needs them -- and count finished tiles per (128-step group, batch
+// row) in `flags`; the consumer's TMA producer waits until all `ctiles` channel
+// tiles of a group are there.  flags must be zeroed before the launch.
+template <typename IO, bool EMUL, int LC>
+__global__ void __launch_bounds__(128, 8)
+conv1d_w4_stream_kernel(const ConvParams p, int* flags, int ctiles, int tgroups) {
+  const int ntiles = tgroups * p.B * ctiles;
+  for (int id = blockIdx.x; id < ntiles; id += gridDim.x) {
+    const int ct = id % ctiles;
+    const int r = id / ctiles;
+    const int b = r % p.B, g = r / p.B;
+    conv1d_w4_tile<IO, EMUL, LC, true>(p, ct, g, b);
+    __syncthreads();                 // every thread's stores are issued ...
+    if (threadIdx.x == 0) {
+      __threadfence();               // ... and visible device-wide before the count moves
+      atomicAdd(flags + g * p.B + b, 1);
     }
   }
 }

@@ -56,6 +56,14 @@
 #ifndef CGF_HINT_NS
 #define CGF_HINT_NS 20000
 #endif
+// CGF_P2PF: pass 2 requests the next chunk's state from TMEM before it replays
+// the current one; CGF_E: compile-time row pitch (experiment: immediate offsets)
+#ifndef CGF_P2PF
+#define CGF_P2PF 0
+#endif
+#ifndef CGF_E
+#define CGF_E 0
+#endif
 // CGF_TRACE: debug_out becomes a timeline buffer [6 roles][1024] of
 // (clock64 << 4 | event) words written by CTA 0 (scripts/fused_trace.py)
 #ifndef CGF_TRACE
@@ -101,6 +109,8 @@ struct FusedParams {
   unsigned long long* agg_p;       // [families][ntt][B][128]
   unsigned long long* agg_h;
   unsigned long long* pref;
+  const int* conv_flags;           // optional [ceil(T/64)][B]: channel tiles of x the Conv1D producer kernel has finished
+  int conv_need;                   // ... out of this many (E / 64)
   const uint16_t* gate_mul;        // optional [B,T,E]: y <- round_bf16(y * gate_mul) (RecurrentBlock, modules.py:651)
   uint16_t* dbg;                   // optional [3][B][T][E]: rounded pre_x, pre_a, x^T
   int* err;                        // watchdog flag
@@ -412,6 +422,25 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           CGF_EVENT(0, 1);
           mbar_wait(x_empty + stage, (use & 1) ^ 1, p.err, 2);
           CGF_EVENT(0, 2);
+          if (p.conv_flags != nullptr) {
+            // x is being written right now by the Conv1D producer kernel on another
+            // stream (conv1d_w4_stream_kernel): wait until every channel tile of
+            // the 64-step group(s) of this MMA tile is there, then order the
+            // generic-proxy view before the async-proxy (TMA) reads.
+            for (int hf = 0; hf < nhalf; ++hf) {
+              const int ticket = t1st + hf;
+              const int tt = ticket / p.B, b = ticket - tt * p.B;
+              const int* flag = p.conv_flags + (tt >> 1) * p.B + b;
+              const long long t0w = clock64();
+              unsigned polls = 0;
+              while (ld_acquire(flag) < p.conv_need) {
+                __nanosleep(100);
+                polls += 15;
+                if (watchdog_expired(t0w, p.err, 8, polls)) break;
+              }
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
           if (elect_one()) mbar_expect_tx(x_full + stage, nhalf * (Cfg::kXStageBytes / 2));
           for (int hf = 0; hf < nhalf; ++hf) {
             const int ticket = t1st + hf;
@@ -523,7 +552,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       // gating-product operand of the first 8 steps, requested before the
       // look-back so that its latency hides behind it
       uint32_t gm[8];
-      const int E = p.E;
+      const int E = CGF_E ? CGF_E : p.E;
       const uint16_t* gmp = nullptr;
       if constexpr (MUL) {
         gmp = p.gate_mul + (pd.yp - p.y);
@@ -599,17 +628,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       // the reference loop (:196); y leaves as bf16
       float h = c0;
       const int nvalid = pd.nvalid;
-#pragma unroll 1
-      for (int c = 0; c < kTile / 8; ++c) {
-        uint32_t st[8];
-        tmem_ld8(tm_state + c * 8, st);
-        uint32_t gn[8];                                  // operand of the next chunk, one chunk ahead
-        if constexpr (MUL) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            gn[i] = (c + 1 < kTile / 8 && (c + 1) * 8 + i < nvalid) ? ld_u16(gmp + ((c + 1) * 8 + i) * E) : 0u;
-        }
-        tmem_wait_ld();
+      auto replay_chunk = [&](int c, const uint32_t (&st)[8]) {
         uint32_t o[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -619,10 +638,6 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           h = y1;
           o[i] = pack_bf2(y0, y1);
           if constexpr (MUL) o[i] = bf2_mul(o[i], gm[2 * i] | (gm[2 * i + 1] << 16));   // r(r(h) * gate), :651
-        }
-        if constexpr (MUL) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) gm[i] = gn[i];
         }
         uint16_t* yc = pd.yp + (size_t)(c * 8) * E;
         if (c * 8 + 8 <= nvalid) {
@@ -638,7 +653,52 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
             if (c * 8 + 2 * i + 1 < nvalid) st_u16(yc + (2 * i + 1) * E, o[i] >> 16);
           }
         }
+      };
+      // gating-product operand of chunk c + 1: requested before chunk c is
+      // replayed, consumed one iteration later
+      uint32_t gn[8];
+      auto request_gate_mul = [&](int c) {
+        if constexpr (MUL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            gn[i] = (c + 1 < kTile / 8 && (c + 1) * 8 + i < nvalid) ? ld_u16(gmp + ((c + 1) * 8 + i) * E) : 0u;
+        }
+      };
+      auto next_gate_mul = [&]() {
+        if constexpr (MUL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gm[i] = gn[i];
+        }
+      };
+#if CGF_P2PF
+      {
+        uint32_t sa[8], sb[8];
+        tmem_ld8(tm_state, sa);
+#pragma unroll
+        for (int c = 0; c < kTile / 8; c += 2) {
+          tmem_wait_ld();
+          tmem_ld8(tm_state + (c + 1) * 8, sb);
+          request_gate_mul(c);
+          replay_chunk(c, sa);
+          next_gate_mul();
+          tmem_wait_ld();
+          if (c + 2 < kTile / 8) tmem_ld8(tm_state + (c + 2) * 8, sa);
+          request_gate_mul(c + 1);
+          replay_chunk(c + 1, sb);
+          next_gate_mul();
+        }
       }
+#else
+#pragma unroll 1
+      for (int c = 0; c < kTile / 8; ++c) {
+        uint32_t st[8];
+        tmem_ld8(tm_state + c * 8, st);
+        request_gate_mul(c);
+        tmem_wait_ld();
+        replay_chunk(c, st);
+        next_gate_mul();
+      }
+#endif
       if (p.last_h != nullptr && tt == p.ntt - 1) p.last_h[(size_t)pd.b * E + pd.ch] = h;
       pd.on = false;
       if (twarp) CGF_EVENT(trole, 6);

@@ -25,9 +25,14 @@ class HostPrefill:
     conv, lru: ``cadence_gemma_b200.Conv1D`` / ``RGLRU`` on a CUDA device.
     batch, steps: shape of the host activations ``[batch, steps, width]``.
     chunks: number of row chunks (must divide ``batch``).
+    graph: capture the whole three-stream pipeline (copies included) into a
+      CUDA graph on first use and replay it afterwards -- with many small
+      chunks the ~40 asynchronous calls of a step cost more host time than the
+      transfers take.  One graph per set of host buffers (re-captured when a
+      different buffer is passed).
   """
 
-  def __init__(self, conv, lru, batch: int, steps: int, chunks: int = 4):
+  def __init__(self, conv, lru, batch: int, steps: int, chunks: int = 4, graph: bool = False):
     assert batch % chunks == 0, (batch, chunks)
     self.conv, self.lru = conv, lru
     self.batch, self.steps, self.chunks = batch, steps, chunks
@@ -54,6 +59,8 @@ class HostPrefill:
     self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
     self.ev_run = [torch.cuda.Event() for _ in range(chunks)]
     self.ev_out = [torch.cuda.Event() for _ in range(chunks)]
+    self.use_graph = graph
+    self._graphs = {}
 
   @torch.no_grad()
   def __call__(self, x_host, seg_host, y_host, h_host=None, cache_host=None):
@@ -61,6 +68,28 @@ class HostPrefill:
     ``h_host [B,E]`` fp32, ``cache_host [B,W-1,E]`` (pinned, optional).
     Returns once all work is ENQUEUED; the caller's current stream waits for
     the last download."""
+    if not self.use_graph:
+      return self._enqueue(x_host, seg_host, y_host, h_host, cache_host)
+    key = tuple(None if t is None else t.data_ptr()
+                for t in (x_host, seg_host, y_host, h_host, cache_host))
+    g = self._graphs.get(key)
+    if g is None:
+      # warm up outside capture (workspaces, packed weights, lazy module loads)
+      self._enqueue(x_host, seg_host, y_host, h_host, cache_host)
+      torch.cuda.synchronize(self.device)
+      g = torch.cuda.CUDAGraph()
+      cap = torch.cuda.Stream(self.device)
+      cap.wait_stream(torch.cuda.current_stream(self.device))
+      with torch.cuda.graph(g, stream=cap):
+        self._enqueue(x_host, seg_host, y_host, h_host, cache_host)
+      torch.cuda.current_stream(self.device).wait_stream(cap)
+      if len(self._graphs) > 8:
+        self._graphs.clear()
+      self._graphs[key] = g
+    g.replay()
+    return y_host
+
+  def _enqueue(self, x_host, seg_host, y_host, h_host, cache_host):
     cur = torch.cuda.current_stream(self.device)
     for s in (self.s_in, self.s_run, self.s_out):
       s.wait_stream(cur)

@@ -17,7 +17,7 @@ from typing import NamedTuple
 import torch
 from torch import nn
 
-from cadence_gemma_b200 import layers
+from cadence_gemma_b200 import layers, pipeline
 
 
 class RecurrentBlockCache(NamedTuple):
@@ -59,20 +59,16 @@ class RecurrentBlock(nn.Module):
     """Returns ``(out, RecurrentBlockCache | None)`` (reference :613-660)."""
     gate = self.linear_y(x)              # y branch (no GELU in this fork, :634)
     h = self.linear_x(x)                 # x branch
-    h, conv_state = self.conv_1d(
-        x=h, segment_pos=segment_pos,
-        cache=None if cache is None else cache.conv1d_state,
-        return_cache=return_cache)
-    lru_cache = None if cache is None else cache.rg_lru_state
-    if self.rg_lru.uses_fused_kernel(h):
-      # the gating product (reference :651) leaves the fused kernel already applied
-      h, lru_state = self.rg_lru.forward_into(h, segment_pos, lru_cache, return_cache,
-                                              gate_mul=gate)
-      out = self.linear_out(h)
-    else:
-      h, lru_state = self.rg_lru(x=h, segment_pos=segment_pos, cache=lru_cache,
-                                 return_cache=return_cache)
-      out = self.linear_out(h * gate)
+    # Conv1D -> RG-LRU as one overlapped pipeline where the fused kernel applies
+    # (pipeline.py); the gating product (reference :651) is then folded into the
+    # RG-LRU kernel's store as well
+    fold = self.rg_lru.uses_fused_kernel(h)
+    h, conv_state, lru_state = pipeline.recurrent_hot_path(
+        self.conv_1d, self.rg_lru, h, segment_pos,
+        conv_cache=None if cache is None else cache.conv1d_state,
+        lru_cache=None if cache is None else cache.rg_lru_state,
+        return_cache=return_cache, gate_mul=gate if fold else None)
+    out = self.linear_out(h if fold else h * gate)
     if not return_cache:
       return out, None
     return out, RecurrentBlockCache(rg_lru_state=lru_state, conv1d_state=conv_state)

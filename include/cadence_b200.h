@@ -173,6 +173,7 @@ int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset,
  *                              RecurrentBlock.forward (modules.py:651, `x = x * y`) folded
  *                              into the store; last_h is
  *                              unaffected.
+ *                              conv_flags (nullable): see cg_conv1d_stream_fwd below.
  *                              debug_out (nullable): [3][B][T][E] bf16 -- the rounded
  *                              pre_x, pre_a and the transposed x the epilogue saw.
  */
@@ -187,7 +188,29 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x,
                        const float* h0, void* y, float* last_h, void* workspace,
                        size_t workspace_bytes, int B, int T, int E, int H,
                        int dtype, int arith_mode, const void* gate_mul,
-                       void* debug_out, cg_stream_t stream);
+                       const int* conv_flags, void* debug_out,
+                       cg_stream_t stream);
+
+/*
+ * Overlapped Conv1D -> RG-LRU (bf16, W = 4, E % 64 == 0): the producer form of
+ * cg_conv1d_fwd.  A few persistent blocks walk x in time-major order and count
+ * finished [64 steps x 64 channels] tiles per (64-step group, batch row) in
+ * `flags` ([ceil(T/64)][B] int32, cg_conv1d_stream_flags_bytes); a
+ * cg_rglru_fused_fwd call that is given the same `flags` as `conv_flags` and the
+ * conv output `y` as its `x` may be enqueued on ANOTHER stream and runs at the
+ * same time: its TMA producer waits per tile until the rows it needs are there.
+ * The Conv1D traffic then hides under the (compute-bound) RG-LRU kernel.
+ * Protocol: zero `flags` on the consumer's stream, fork (event) to the
+ * producer's stream, enqueue cg_conv1d_stream_fwd there FIRST, then
+ * cg_rglru_fused_fwd on the consumer's stream, join.  The producer never waits
+ * for the consumer, so the pair cannot deadlock.
+ */
+size_t cg_conv1d_stream_flags_bytes(int B, int T);
+int cg_conv1d_stream_fwd(const void* x, const void* w, const void* b,
+                         const void* seg, int seg_is_i64,
+                         long long seg_batch_stride, void* y, void* cache_out,
+                         int* flags, int B, int T, int E, int W, int dtype,
+                         int mask_mode, int arith_mode, cg_stream_t stream);
 
 #ifdef __cplusplus
 }

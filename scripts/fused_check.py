@@ -103,6 +103,44 @@ def time_case(mode, variant, iters=20, B=8, T=2048):
   print(json.dumps(res), flush=True)
 
 
+def overlap_case(B=8, T=2048, iters=30):
+  """Conv1D -> RG-LRU: sequential kernels vs the overlapped producer / consumer pipeline."""
+  E, H = 2560, 10
+  x, lru, seg, _ = make(B, T, E, H, resets=False)
+  conv = cg.Conv1D(E, 4, device=x.device, dtype=torch.bfloat16)
+  with torch.no_grad():
+    conv.w.normal_(0, 0.4); conv.b.normal_(0, 0.2)
+
+  def seq():
+    xc, cs = conv(x, seg)
+    return lru(xc, seg)
+
+  from cadence_gemma_b200 import pipeline
+  pipeline.set_overlap(True)
+
+  def ovl():
+    return cg.recurrent_hot_path(conv, lru, x, seg)
+
+  res = {"overlap": [B, T]}
+  with torch.no_grad():
+    for name, fn in (("sequential_us", seq), ("overlapped_us", ovl)):
+      for _ in range(5):
+        fn()
+      torch.cuda.synchronize()
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      for _ in range(iters):
+        fn()
+      b.record()
+      torch.cuda.synchronize()
+      res[name] = a.elapsed_time(b) * 1e3 / iters
+    y1, h1 = seq()
+    y2, _, h2 = ovl()
+    res["identical"] = bool(torch.equal(y1, y2) and torch.equal(h1, h2))
+  res["watchdog"] = [_abi.fused_watchdog_code(w) for w in _abi._fused_workspaces.values()]
+  print(json.dumps(res), flush=True)
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--case", default="small")
@@ -120,6 +158,10 @@ def main():
     run_case(8, 2048, 2560, 10, a.mode, a.variant, debug=False)
   elif a.case == "time":
     time_case(a.mode, a.variant)
+  elif a.case == "overlap":
+    overlap_case()
+    overlap_case(32, 768)
+    overlap_case(2, 8192)
   elif a.case == "time_shapes":
     for B, T in [(1, 2048), (2, 2048), (2, 8192), (32, 768), (8, 2048)]:
       time_case(a.mode, a.variant, B=B, T=T)

@@ -619,3 +619,48 @@ def test_fused_gating_product(shape):
     ym, hm = lru.forward_into(x, seg, h0, gate_mul=gate)
     assert torch.equal(ym, y * gate)
     assert torch.equal(hm, h)
+
+
+@pytest.mark.parametrize("shape", [(8, 2048, 2560, 10), (3, 200, 512, 2), (2, 33, 256, 2), (1, 1000, 2560, 10)])
+def test_overlapped_conv_rglru_pipeline_equals_sequential(shape):
+  """Conv1D as a producer kernel on a side stream under the fused RG-LRU kernel
+  (pipeline.recurrent_hot_path) == the two kernels one after the other, bit for
+  bit, run after run (the flag protocol must not let the consumer read rows that
+  are not there yet)."""
+  import cadence_gemma_b200 as cg
+  from cadence_gemma_b200 import pipeline
+  bsz, steps, width, heads = shape
+  torch.manual_seed(sum(shape))
+  conv = cg.Conv1D(width, 4, device=DEV, dtype=torch.bfloat16)
+  lru = cg.RGLRU(width, heads, device=DEV, dtype=torch.bfloat16)
+  with torch.no_grad():
+    conv.w.normal_(0, 0.4)
+    conv.b.normal_(0, 0.2)
+    lru.input_gate.b.normal_()
+    lru.a_gate.b.normal_()
+    x = torch.randn(bsz, steps, width, device=DEV).to(torch.bfloat16)
+    seg = torch.arange(steps, device=DEV, dtype=torch.int32)[None].repeat(bsz, 1)
+    seg[:, steps // 2:] -= steps // 2
+    h0 = torch.randn(bsz, width, device=DEV)
+    xc, cs_ref = conv(x, seg)
+    y_ref, h_ref = lru(xc, seg, h0)
+    gate = torch.randn_like(x)
+    # default: sequential kernels through the same entry point
+    assert not pipeline.can_overlap(conv, lru, x)
+    y, cs, h = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0)
+    assert torch.equal(y, y_ref) and torch.equal(h, h_ref) and torch.equal(cs, cs_ref)
+    old = pipeline.set_overlap(True)
+    try:
+      assert pipeline.can_overlap(conv, lru, x)
+      for it in range(12):
+        # poison what the producer is about to write, so that a premature read shows
+        y, cs, h = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0,
+                                         conv_out=torch.full_like(x, float("nan")))
+        assert torch.equal(y, y_ref) and torch.equal(h, h_ref) and torch.equal(cs, cs_ref), it
+      y, _, _ = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0, gate_mul=gate)
+      assert torch.equal(y, y_ref * gate)
+    finally:
+      pipeline.set_overlap(old)
+  abi = _abi()
+  for ws in abi._fused_workspaces.values():
+    assert abi.fused_watchdog_code(ws) == 0
