@@ -39,6 +39,9 @@ SYMBOLS = {
     "cg_rglru_fused_workspace_bytes": (_sz, [_i, _i, _i]),
     "cg_rglru_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp,
                                 _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "cg_recurrent_decode_supported": (_i, [_i, _i, _i, _i]),
+    "cg_recurrent_decode_step": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll,
+                                      _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cg_conv1d_stream_flags_bytes": (_sz, [_i, _i]),
     "cg_conv1d_stream_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _i, _i, _i, _i,
                                   _i, _i, _i, _vp]),
@@ -375,3 +378,46 @@ def rglru_fused_fwd(x, wpack, bias_x, bias_a, a_param, segment_pos, heads, h0=No
   if debug:
     return y, last_h, dbg
   return y, last_h
+
+
+# ---------------------------------------------------------------------------
+# Fused decode step (conv step + gate GEMVs + gates + h = a*h0 + x~, one launch)
+# ---------------------------------------------------------------------------
+def decode_supported(width: int, heads: int, temporal_width: int, dtype) -> bool:
+  if dtype != torch.bfloat16:
+    return False
+  return bool(load().cg_recurrent_decode_supported(width, heads, temporal_width, DTYPE_BF16))
+
+
+def recurrent_decode_step(x, conv_w, conv_b, conv_cache, wx, wa, bias_x, bias_a, a_param,
+                          segment_pos, h0=None, gate_mul=None, return_cache=True,
+                          arith_mode=ARITH_FAST):
+  """One decode step of Conv1D -> RG-LRU.  Returns ``(y, new_conv_cache | None, last_h | None)``."""
+  global launch_count
+  _require_cuda(x, conv_w, conv_b, conv_cache, wx, wa, a_param, segment_pos, h0, gate_mul)
+  bsz, steps, width = x.shape
+  heads, bw, _ = wx.shape
+  assert steps == 1, "layers.py:566: decode takes exactly one token"
+  assert conv_cache.shape == (bsz, conv_w.shape[0] - 1, width), "layers.py:565"
+  assert h0 is None or h0.dtype == torch.float32, "layers.py:170"
+  x, conv_cache = x.contiguous(), conv_cache.contiguous()
+  wx, wa = wx.contiguous(), wa.contiguous()
+  seg, is64, stride = _seg_args(segment_pos, bsz, 1)
+  y = torch.empty_like(x)
+  new_cache = torch.empty_like(conv_cache) if return_cache else None
+  last_h = (torch.empty((bsz, width), dtype=torch.float32, device=x.device)
+            if return_cache else None)
+  bx = None if bias_x is None else bias_x.contiguous().view(-1)
+  ba = None if bias_a is None else bias_a.contiguous().view(-1)
+  h0c = None if h0 is None else h0.contiguous()
+  gm = None if gate_mul is None else gate_mul.contiguous()
+  with torch.cuda.device(x.device):
+    rc = load().cg_recurrent_decode_step(
+        x.data_ptr(), conv_w.contiguous().data_ptr(), conv_b.contiguous().data_ptr(),
+        conv_cache.data_ptr(), dtype_code(conv_cache.dtype), wx.data_ptr(), wa.data_ptr(),
+        _ptr(bx), _ptr(ba), a_param.contiguous().data_ptr(), seg.data_ptr(), is64, stride,
+        _ptr(h0c), _ptr(gm), y.data_ptr(), _ptr(new_cache), _ptr(last_h), bsz, width, heads,
+        conv_w.shape[0], dtype_code(x.dtype), arith_mode & ARITH_FAST, _stream(x))
+  _check(rc, "cg_recurrent_decode_step")
+  launch_count += 1
+  return y, new_cache, last_h

@@ -12,6 +12,7 @@
 #include "cg_conv1d.cuh"
 #include "cg_scan.cuh"
 #include "cg_fused.cuh"
+#include "cg_decode.cuh"
 
 namespace {
 
@@ -547,6 +548,55 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
   const bool mul = gate_mul != nullptr;
   return bw == 256 ? dispatch_fused<4>(fast, dbg, mul, tmap, p, stream)
                    : dispatch_fused<2>(fast, dbg, mul, tmap, p, stream);
+}
+
+
+int cg_recurrent_decode_supported(int E, int H, int W, int dtype) {
+  if (dtype != CG_DTYPE_BF16 || W != 4 || H < 1 || E < 1 || E % H != 0) return 0;
+  const int bw = E / H;
+  return (bw % 64 == 0 && bw <= cg::kDecMaxBw) ? 1 : 0;
+}
+
+int cg_recurrent_decode_step(const void* x, const void* conv_w, const void* conv_b, const void* cache_in,
+                             int cache_dtype, const void* wx, const void* wa, const void* bias_x,
+                             const void* bias_a, const void* a_param, const void* seg, int seg_is_i64,
+                             long long seg_batch_stride, const float* h0, const void* gate_mul, void* y,
+                             void* cache_out, float* last_h, int B, int E, int H, int W, int dtype,
+                             int arith_mode, cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !conv_w || !conv_b || !cache_in || !wx || !wa || !a_param || !seg || !y) return CG_ERR_NULL;
+  if (int rc = check_common(B, 1, E, dtype)) return rc;
+  if (cache_dtype != CG_DTYPE_F32 && cache_dtype != CG_DTYPE_BF16) return CG_ERR_DTYPE;
+  if (!cg_recurrent_decode_supported(E, H, W, dtype)) return CG_ERR_UNSUPPORTED;
+  if ((arith_mode & ~CG_ARITH_FAST) != 0) return CG_ERR_MODE;       // reference rounding, exact or fast math
+  if (cache_out == cache_in) return CG_ERR_MODE;                    // several CTAs read the cache rows
+  if ((B + cg::kDecBT - 1) / cg::kDecBT > 65535) return CG_ERR_SHAPE;
+  cg::DecodeParams p{};
+  p.x = reinterpret_cast<const uint16_t*>(x);
+  p.conv_w = reinterpret_cast<const uint16_t*>(conv_w);
+  p.conv_b = reinterpret_cast<const uint16_t*>(conv_b);
+  p.cache_in = cache_in; p.cache_is_bf16 = cache_dtype == CG_DTYPE_BF16;
+  p.wx = reinterpret_cast<const uint16_t*>(wx); p.wa = reinterpret_cast<const uint16_t*>(wa);
+  p.bias_x = reinterpret_cast<const uint16_t*>(bias_x); p.bias_a = reinterpret_cast<const uint16_t*>(bias_a);
+  p.a_param = reinterpret_cast<const uint16_t*>(a_param);
+  p.seg = seg; p.seg_is_i64 = seg_is_i64; p.seg_bstride = seg_batch_stride;
+  p.h0 = h0; p.gate_mul = reinterpret_cast<const uint16_t*>(gate_mul);
+  p.y = reinterpret_cast<uint16_t*>(y); p.cache_out = cache_out; p.last_h = last_h;
+  p.B = B; p.E = E; p.H = H; p.bw = E / H;
+  dim3 grid(H * (p.bw / 64), (B + cg::kDecBT - 1) / cg::kDecBT);
+  size_t smem = (size_t)2 * p.bw * 128;                  // both gates' [bw x 64] bf16 slice ...
+  if (smem < 32768) smem = 32768;                        // ... later reused for the partial sums
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(cg::recurrent_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         2 * cg::kDecMaxBw * 128);
+    cudaFuncSetAttribute(cg::recurrent_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         2 * cg::kDecMaxBw * 128);
+    configured = true;
+  }
+  if (arith_mode & CG_ARITH_FAST) cg::recurrent_decode_kernel<true><<<grid, 256, smem, stream>>>(p);
+  else cg::recurrent_decode_kernel<false><<<grid, 256, smem, stream>>>(p);
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

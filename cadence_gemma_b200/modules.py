@@ -62,7 +62,8 @@ class RecurrentBlock(nn.Module):
     # Conv1D -> RG-LRU as one overlapped pipeline where the fused kernel applies
     # (pipeline.py); the gating product (reference :651) is then folded into the
     # RG-LRU kernel's store as well
-    fold = self.rg_lru.uses_fused_kernel(h)
+    fold = self.rg_lru.uses_fused_kernel(h) or pipeline.can_fuse_decode(
+        self.conv_1d, self.rg_lru, h, None if cache is None else cache.conv1d_state)
     h, conv_state, lru_state = pipeline.recurrent_hot_path(
         self.conv_1d, self.rg_lru, h, segment_pos,
         conv_cache=None if cache is None else cache.conv1d_state,

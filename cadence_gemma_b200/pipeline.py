@@ -33,6 +33,11 @@ import torch
 from cadence_gemma_b200 import _abi, layers
 
 _overlap = os.environ.get("CG_B200_OVERLAP", "0") != "0"
+# One-launch decode step (cg_recurrent_decode_step).  It more than halves the cost
+# of an EAGER decode step (30 us vs 76 us per block at B = 32: three launches and
+# their host overhead become one); inside a CUDA graph, where launch overhead is
+# gone, the three small kernels are ~5 us faster at B = 32 -- switch it off there.
+_fused_decode = os.environ.get("CG_B200_FUSED_DECODE", "1") != "0"
 _side_streams: dict = {}
 _flag_buffers: dict = {}
 
@@ -50,6 +55,22 @@ def set_overlap(enabled: bool) -> bool:
   global _overlap
   old, _overlap = _overlap, bool(enabled)
   return old
+
+
+def set_fused_decode(enabled: bool) -> bool:
+  """Switches the one-launch decode step; returns the old setting."""
+  global _fused_decode
+  old, _fused_decode = _fused_decode, bool(enabled)
+  return old
+
+
+def can_fuse_decode(conv, lru, x, conv_cache) -> bool:
+  """True if a decode step (T == 1, conv cache given) runs as ONE fused launch
+  (``cg_recurrent_decode_step``)."""
+  return (_fused_decode and layers.fused_enabled() and conv_cache is not None and x.is_cuda and x.shape[1] == 1 and
+          (layers.get_arith_mode() & (_abi.ARITH_FP32 | _abi.ARITH_STRICT)) == 0 and
+          conv_cache.dtype in (torch.bfloat16, torch.float32) and
+          _abi.decode_supported(lru.width, lru.num_heads, conv.w.shape[0], x.dtype))
 
 
 def can_overlap(conv, lru, x, conv_cache=None) -> bool:
@@ -73,6 +94,17 @@ def recurrent_hot_path(conv, lru, x, segment_pos, conv_cache=None, lru_cache=Non
   caller-provided buffers.
   """
   layers._forward_only(x, conv_cache, lru_cache)
+  if can_fuse_decode(conv, lru, x, conv_cache):
+    # decode step: conv step + gate GEMVs + gates + h = a*h0 + x~ in ONE launch
+    bsz = x.shape[0]
+    if segment_pos.shape != (bsz, 1):
+      segment_pos = segment_pos[None, :]
+    assert segment_pos.shape == (bsz, 1)              # layers.py:344
+    y, conv_state, h = _abi.recurrent_decode_step(
+        x, conv.w, conv.b, conv_cache, lru.input_gate.w, lru.a_gate.w, lru.input_gate.b,
+        lru.a_gate.b, lru.a_param, segment_pos, h0=lru_cache, gate_mul=gate_mul,
+        return_cache=return_cache, arith_mode=layers.get_arith_mode())
+    return y, conv_state, h
   if not can_overlap(conv, lru, x, conv_cache):
     xc, conv_state = conv(x, segment_pos, conv_cache, return_cache)
     if gate_mul is not None and not layers.uses_fused_kernel(lru, xc):

@@ -212,6 +212,31 @@ int cg_conv1d_stream_fwd(const void* x, const void* w, const void* b,
                          int* flags, int B, int T, int E, int W, int dtype,
                          int mask_mode, int arith_mode, cg_stream_t stream);
 
+/*
+ * Fused decode step of the recurrent hot path (T == 1, caches given, bf16,
+ * W == 4, head width a multiple of 64 up to 256): the Conv1D step with its cache
+ * roll (layers.py:478-483, :542), both BlockDiagonalLinear gate GEMVs (:133-142),
+ * the gate math (:345-365) and rnn_scan's sampling branch h = a*h0 + x~
+ * (:175-182) in ONE launch instead of three (conv step, cuBLAS batched GEMV,
+ * gate step).  SURVEY.md section 8(b) / 8(f) row F3.
+ *   x [B,1,E] = linear_x output; conv_w [4,E], conv_b [E];
+ *   cache_in / cache_out [B,3,E] in cache_dtype (cache_out nullable, must NOT
+ *   alias cache_in); wx, wa [H,bw,bw] in the reference layout (y = x @ w[h]);
+ *   h0 [B,E] fp32 or NULL; gate_mul [B,1,E] or NULL (modules.py:651 folded in);
+ *   y [B,1,E]; last_h [B,E] fp32 or NULL.
+ *   arith_mode: CG_ARITH_REFERENCE or CG_ARITH_FAST.
+ */
+int cg_recurrent_decode_supported(int E, int H, int W, int dtype);
+int cg_recurrent_decode_step(const void* x, const void* conv_w, const void* conv_b,
+                             const void* cache_in, int cache_dtype,
+                             const void* wx, const void* wa, const void* bias_x,
+                             const void* bias_a, const void* a_param,
+                             const void* seg, int seg_is_i64,
+                             long long seg_batch_stride, const float* h0,
+                             const void* gate_mul, void* y, void* cache_out,
+                             float* last_h, int B, int E, int H, int W, int dtype,
+                             int arith_mode, cg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

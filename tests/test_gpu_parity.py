@@ -664,3 +664,49 @@ def test_overlapped_conv_rglru_pipeline_equals_sequential(shape):
   abi = _abi()
   for ws in abi._fused_workspaces.values():
     assert abi.fused_watchdog_code(ws) == 0
+
+
+@pytest.mark.parametrize("shape", [(32, 2560, 10), (5, 512, 2), (8, 256, 4), (1, 256, 2), (3, 1024, 4)])
+@pytest.mark.parametrize("cache_dtype", [torch.bfloat16, torch.float32])
+def test_fused_decode_step_equals_three_kernel_path(shape, cache_dtype):
+  """cg_recurrent_decode_step (conv step + gate GEMVs + gates + h = a*h0 + x~ in one
+  launch) vs conv1d_decode -> cuBLAS GEMV -> gate step: conv cache bit-exact, y and
+  last_h equal up to the GEMV summation order; document starts, odd batch sizes,
+  fp32 conv cache, missing h0, folded gating product."""
+  import cadence_gemma_b200 as cg
+  from cadence_gemma_b200 import pipeline
+  bsz, width, heads = shape
+  torch.manual_seed(sum(shape))
+  conv = cg.Conv1D(width, 4, device=DEV, dtype=torch.bfloat16)
+  lru = cg.RGLRU(width, heads, device=DEV, dtype=torch.bfloat16)
+  with torch.no_grad():
+    conv.w.normal_(0, 0.4)
+    conv.b.normal_(0, 0.2)
+    lru.input_gate.b.normal_()
+    lru.a_gate.b.normal_()
+    x = torch.randn(bsz, 1, width, device=DEV).to(torch.bfloat16)
+    cache = torch.randn(bsz, 3, width, device=DEV).to(cache_dtype)
+    h0 = torch.randn(bsz, width, device=DEV)
+    seg = torch.full((bsz, 1), 17, device=DEV, dtype=torch.int32)
+    if bsz > 2:
+      seg[1, 0] = 0                        # a document start at this decode step
+    assert pipeline.can_fuse_decode(conv, lru, x, cache)
+    for h_in in (h0, None):
+      y, cs, h = cg.recurrent_hot_path(conv, lru, x, seg, conv_cache=cache, lru_cache=h_in)
+      old = cg.set_fused(False)
+      try:
+        assert not pipeline.can_fuse_decode(conv, lru, x, cache)
+        y_u, cs_u, h_u = cg.recurrent_hot_path(conv, lru, x, seg, conv_cache=cache, lru_cache=h_in)
+      finally:
+        cg.set_fused(old)
+      assert cs.dtype == cache_dtype and torch.equal(cs, cs_u)
+      assert identical_fraction(y, y_u) >= 0.995, identical_fraction(y, y_u)
+      torch.testing.assert_close(y.float(), y_u.float(), rtol=1e-2, atol=3e-2)
+      assert normwise(h, h_u) <= 1e-2
+    gate = torch.randn_like(x)
+    y_g, _, _ = cg.recurrent_hot_path(conv, lru, x, seg, conv_cache=cache, lru_cache=h0, gate_mul=gate)
+    y_p, _, _ = cg.recurrent_hot_path(conv, lru, x, seg, conv_cache=cache, lru_cache=h0)
+    assert torch.equal(y_g, y_p * gate)
+    y_n, cs_n, h_n = cg.recurrent_hot_path(conv, lru, x, seg, conv_cache=cache, lru_cache=h0,
+                                           return_cache=False)
+    assert cs_n is None and h_n is None and torch.equal(y_n, y_p)
