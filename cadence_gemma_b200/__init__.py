@@ -5,9 +5,9 @@ Public surface mirrors ``recurrentgemma.torch`` for this path
 from cadence_gemma_b200 import _abi
 from cadence_gemma_b200.layers import (BlockDiagonalLinear, Conv1D, RGLRU,
                                        fused_enabled, get_arith_mode, rnn_scan,
-                                       set_arith_mode, set_fused)
+                                       set_arith_mode, set_fold_gate, set_fused)
 
 from cadence_gemma_b200.pipeline import recurrent_hot_path
 
 __all__ = ["recurrent_hot_path", "BlockDiagonalLinear", "Conv1D", "RGLRU", "rnn_scan",
-           "set_arith_mode", "get_arith_mode", "set_fused", "fused_enabled", "_abi"]
+           "set_arith_mode", "get_arith_mode", "set_fused", "set_fold_gate", "fused_enabled", "_abi"]

@@ -82,7 +82,7 @@ def _recurrent_block_forward(self, x, segment_pos, cache=None, return_cache=True
       x=h, segment_pos=segment_pos,
       cache=None if cache is None else cache.conv1d_state, return_cache=return_cache)
   lru_cache = None if cache is None else cache.rg_lru_state
-  if cg_layers.uses_fused_kernel(self.rg_lru, h):
+  if cg_layers.fold_gate_enabled() and cg_layers.uses_fused_kernel(self.rg_lru, h):
     h, rg_lru_state = _rglru_forward(self.rg_lru, h, segment_pos, lru_cache, return_cache,
                                      gate_mul=y)
   else:

@@ -59,6 +59,25 @@ def fused_enabled() -> bool:
   return _fused_enabled
 
 
+# Folding RecurrentBlock's gating product `x * y` (reference modules.py:651) into
+# the fused kernel's store (its `gate_mul` operand) is implemented
+# and tested, but OFF by default: the operand arrives transposed to the kernel's
+# thread layout (one 2-byte load per element in the latency-bound replay pass),
+# which costs the kernel more (+50 us at config 2) than the separate elementwise
+# multiply it saves (~40 us).  CG_B200_FOLD_GATE=1 / set_fold_gate(True) enable it.
+_fold_gate = os.environ.get("CG_B200_FOLD_GATE", "0") != "0"
+
+
+def set_fold_gate(enabled: bool) -> bool:
+  global _fold_gate
+  old, _fold_gate = _fold_gate, bool(enabled)
+  return old
+
+
+def fold_gate_enabled() -> bool:
+  return _fold_gate
+
+
 def _forward_only(*tensors):
   if torch.is_grad_enabled() and any(
       t is not None and t.requires_grad for t in tensors):

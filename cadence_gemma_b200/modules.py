@@ -59,11 +59,12 @@ class RecurrentBlock(nn.Module):
     """Returns ``(out, RecurrentBlockCache | None)`` (reference :613-660)."""
     gate = self.linear_y(x)              # y branch (no GELU in this fork, :634)
     h = self.linear_x(x)                 # x branch
-    # Conv1D -> RG-LRU as one overlapped pipeline where the fused kernel applies
-    # (pipeline.py); the gating product (reference :651) is then folded into the
-    # RG-LRU kernel's store as well
-    fold = self.rg_lru.uses_fused_kernel(h) or pipeline.can_fuse_decode(
-        self.conv_1d, self.rg_lru, h, None if cache is None else cache.conv1d_state)
+    # Conv1D -> RG-LRU through the hot-path entry point (pipeline.py).  The gating
+    # product (reference :651) rides on the one-launch decode step; folding it
+    # into the prefill kernel's store is optional (layers.set_fold_gate)
+    fold = (layers.fold_gate_enabled() and self.rg_lru.uses_fused_kernel(h)) or \
+        pipeline.can_fuse_decode(self.conv_1d, self.rg_lru, h,
+                                 None if cache is None else cache.conv1d_state)
     h, conv_state, lru_state = pipeline.recurrent_hot_path(
         self.conv_1d, self.rg_lru, h, segment_pos,
         conv_cache=None if cache is None else cache.conv1d_state,

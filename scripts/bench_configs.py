@@ -92,13 +92,12 @@ def block_case(B, T, dtype, iters=20):
     x = torch.randn((B, T, E), device=DEV).to(dtype)
     seg = torch.arange(T, dtype=torch.int32, device=DEV)[None].repeat(B, 1)
     run = lambda: blk(x, seg)
-    t_fused = timed(run, iters)
-    def no_fold():   # fused kernel, gating product as a separate elementwise kernel
-      gate = blk.linear_y(x)
-      h, _ = blk.conv_1d(blk.linear_x(x), seg)
-      h, _ = blk.rg_lru(h, seg)
-      return blk.linear_out(h * gate)
-    t_nofold = timed(no_fold, iters)
+    t_nofold = timed(run, iters)      # default: gating product as a separate elementwise kernel
+    oldf = cg.set_fold_gate(True)     # optional: folded into the fused kernel's store
+    try:
+      t_fused = timed(run, iters)
+    finally:
+      cg.set_fold_gate(oldf)
     old = cg.set_fused(False)
     try:
       t_unfused = timed(run, iters)

@@ -236,6 +236,16 @@ def test_recurrent_block_golden(case):
   with torch.no_grad():
     y, cache = blk(cu(g["x"]), cu(g["seg"]))
     check(y, g["y"], case + " y")
+    if blk.rg_lru.uses_fused_kernel(cu(g["conv_in"])):
+      # the optional folding of the gating product into the fused kernel's store
+      #  gives the same bits as the separate multiply
+      import cadence_gemma_b200 as cg
+      old = cg.set_fold_gate(True)
+      try:
+        y_f, cache_f = blk(cu(g["x"]), cu(g["seg"]))
+      finally:
+        cg.set_fold_gate(old)
+      assert torch.equal(y_f, y) and torch.equal(cache_f.rg_lru_state, cache.rg_lru_state)
     assert cache.rg_lru_state.dtype == torch.float32
     assert normwise(cache.rg_lru_state.cpu(), g["rg_lru_state"]) <= (3e-2 if bf else 5e-5)
     check(cache.conv1d_state, g["conv1d_state"], case + " conv state")
