@@ -415,7 +415,8 @@ bool fused_shape_ok(int E, int H, int dtype) {
 }
 
 template <int KB, bool FAST, bool DBG, bool MUL>
-int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, cudaStream_t stream) {
+int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int grid_limit,
+                 cudaStream_t stream) {
   using Cfg = cg::fused::FusedCfg<KB>;
   auto kernel = cg::fused::rglru_fused_kernel<KB, FAST, DBG, MUL>;
   static int sms = 0;
@@ -428,19 +429,22 @@ int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, cudaS
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms < 1) return (int)cudaErrorLaunchOutOfResources;
   }
-  kernel<<<sms, cg::fused::kThreads, Cfg::kSmemBytes, stream>>>(tmap, p);
+  // one persistent CTA per SM; grid_limit > 0 (test hook) runs with fewer CTAs than
+  // column families, which exercises the family loop (weight reload) of a CTA
+  const int grid = grid_limit > 0 && grid_limit < sms ? grid_limit : sms;
+  kernel<<<grid, cg::fused::kThreads, Cfg::kSmemBytes, stream>>>(tmap, p);
   return (int)cudaGetLastError();
 }
 
 template <int KB>
 int dispatch_fused(bool fast, bool dbg, bool mul, const CUtensorMap& tmap,
-                   const cg::fused::FusedParams& p, cudaStream_t stream) {
-  if (dbg) return fast ? launch_fused<KB, true, true, false>(tmap, p, stream)
-                       : launch_fused<KB, false, true, false>(tmap, p, stream);
-  if (mul) return fast ? launch_fused<KB, true, false, true>(tmap, p, stream)
-                       : launch_fused<KB, false, false, true>(tmap, p, stream);
-  return fast ? launch_fused<KB, true, false, false>(tmap, p, stream)
-              : launch_fused<KB, false, false, false>(tmap, p, stream);
+                   const cg::fused::FusedParams& p, int grid_limit, cudaStream_t stream) {
+  if (dbg) return fast ? launch_fused<KB, true, true, false>(tmap, p, grid_limit, stream)
+                       : launch_fused<KB, false, true, false>(tmap, p, grid_limit, stream);
+  if (mul) return fast ? launch_fused<KB, true, false, true>(tmap, p, grid_limit, stream)
+                       : launch_fused<KB, false, false, true>(tmap, p, grid_limit, stream);
+  return fast ? launch_fused<KB, true, false, false>(tmap, p, grid_limit, stream)
+              : launch_fused<KB, false, false, false>(tmap, p, grid_limit, stream);
 }
 
 }  // namespace
@@ -488,7 +492,7 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
   const int mode = arith_mode & 7;
   const int variant = (arith_mode >> 8) & 0xff;
   if ((arith_mode & ~0xff07) != 0 || (mode & (CG_ARITH_FP32 | CG_ARITH_STRICT)) != 0) return CG_ERR_MODE;
-  if (variant != 0) return CG_ERR_MODE;
+  if (variant > 64) return CG_ERR_MODE;   // variant v > 0: at most v CTAs (test hook, see launch_fused)
   if (!aligned16(x) || !aligned16(wpack) || !aligned16(y) || !aligned16(workspace)) return CG_ERR_ALIGN;
   if (B > 65535) return CG_ERR_SHAPE;
   if (gate_mul != nullptr && debug_out != nullptr) return CG_ERR_MODE;   // the debug build has no product path
@@ -546,8 +550,8 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
   const bool fast = (mode & CG_ARITH_FAST) != 0;
   const bool dbg = debug_out != nullptr;
   const bool mul = gate_mul != nullptr;
-  return bw == 256 ? dispatch_fused<4>(fast, dbg, mul, tmap, p, stream)
-                   : dispatch_fused<2>(fast, dbg, mul, tmap, p, stream);
+  return bw == 256 ? dispatch_fused<4>(fast, dbg, mul, tmap, p, variant, stream)
+                   : dispatch_fused<2>(fast, dbg, mul, tmap, p, variant, stream);
 }
 
 

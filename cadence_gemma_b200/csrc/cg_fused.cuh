@@ -56,13 +56,11 @@
 #ifndef CGF_HINT_NS
 #define CGF_HINT_NS 20000
 #endif
-// CGF_P2PF: pass 2 requests the next chunk's state from TMEM before it replays
-// the current one; CGF_E: compile-time row pitch (experiment: immediate offsets)
-#ifndef CGF_P2PF
-#define CGF_P2PF 0
-#endif
-#ifndef CGF_E
-#define CGF_E 0
+// CGF_INTERLEAVE: the replay pass of the previous tile runs inside the gate loop
+// of the current one (same basic block: the compiler fills the gate math's MUFU
+// latencies with the replay's FMA / store work) instead of before it
+#ifndef CGF_INTERLEAVE
+#define CGF_INTERLEAVE 0   // measured: no gain (110.8 vs 109.8 us), the kernel is throughput-bound
 #endif
 // CGF_TRACE: debug_out becomes a timeline buffer [6 roles][1024] of
 // (clock64 << 4 | event) words written by CTA 0 (scripts/fused_trace.py)
@@ -546,30 +544,21 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     };
 
     // F: carry chain + pass 2 of the pending tile
-    auto finish = [&](unsigned long long early) {
-      // `early`: the predecessor's state word, requested before stage A
+    // carry-in of the pending tile by decoupled look-back; publishes its state
+    auto resolve_carry = [&](unsigned long long early) -> float {
+      // `early`: the predecessor's state word, requested before the accumulator wait
       const int tt = pd.tt;
-      // gating-product operand of the first 8 steps, requested before the
-      // look-back so that its latency hides behind it
-      uint32_t gm[8];
-      const int E = CGF_E ? CGF_E : p.E;
-      const uint16_t* gmp = nullptr;
-      if constexpr (MUL) {
-        gmp = p.gate_mul + (pd.yp - p.y);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) gm[i] = i < pd.nvalid ? ld_u16(gmp + i * E) : 0u;
-      }
       float c0;
       if (tt == 0) {
         c0 = p.h0 != nullptr ? p.h0[(size_t)pd.b * p.E + pd.ch] : 0.0f;
       } else if (__all_sync(0xffffffffu, (unsigned)early == epoch)) {
         c0 = tagged_value(early);
       } else {
-        // Decoupled look-back, kLook tiles per round trip: walk back over tiles
-        // whose aggregate is published until one with a published state is
-        // found, then apply the aggregates passed on the way one by one, left to
-        // right -- exactly the expression each of those tiles evaluates for its
-        // own state, so the carry does not depend on timing (bit-reproducible).
+        // Walk back over tiles whose aggregate is published until one with a
+        // published state is found (kLook tiles per round trip), then apply the
+        // aggregates passed on the way one by one, left to right -- exactly the
+        // expression each of those tiles evaluates for its own state, so the
+        // carry does not depend on timing (bit-reproducible).
         constexpr int kLook = CGF_LOOK;
         int end = tt;                                    // tiles [end, tt): aggregate seen
         const long long t_start = clock64();
@@ -624,84 +613,73 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       }
       if (tt + 1 < p.ntt) st_relaxed_u64(p.pref + pd.widx, pack_tagged(fmaf(pd.P, c0, pd.H), epoch));
       if (twarp) CGF_EVENT(trole, 5);
-      // ---- pass 2 (replay): h = a*h + x~ from the true carry-in, mul then add as
-      // the reference loop (:196); y leaves as bf16
-      float h = c0;
-      const int nvalid = pd.nvalid;
-      auto replay_chunk = [&](int c, const uint32_t (&st)[8]) {
-        uint32_t o[4];
+      return c0;
+    };
+    // replay of 8 steps of the pending tile: h = a*h + x~ from the true carry, mul
+    // then add as the reference loop (:196); y leaves as bf16 (2-byte stores: a
+    // warp writes 64 contiguous bytes per row)
+    auto replay_chunk = [&](int c, const uint32_t (&st)[8], float& h, const uint32_t* gm) {
+      const int E = p.E;
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t a2 = st[i], n2 = st[4 + i];
+        const float y0 = add_bf_lo(n2, bf_lo(a2) * h);
+        const float y1 = add_bf_hi(n2, bf_hi(a2) * y0);
+        h = y1;
+        o[i] = pack_bf2(y0, y1);
+        if constexpr (MUL) o[i] = bf2_mul(o[i], gm[2 * i] | (gm[2 * i + 1] << 16));   // r(r(h) * gate), :651
+      }
+      uint16_t* yc = pd.yp + (size_t)(c * 8) * E;
+      if (c * 8 + 8 <= pd.nvalid) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint32_t a2 = st[i], n2 = st[4 + i];
-          const float y0 = add_bf_lo(n2, bf_lo(a2) * h);
-          const float y1 = add_bf_hi(n2, bf_hi(a2) * y0);
-          h = y1;
-          o[i] = pack_bf2(y0, y1);
-          if constexpr (MUL) o[i] = bf2_mul(o[i], gm[2 * i] | (gm[2 * i + 1] << 16));   // r(r(h) * gate), :651
+          st_u16(yc + (2 * i) * E, o[i]);
+          st_u16(yc + (2 * i + 1) * E, o[i] >> 16);
         }
-        uint16_t* yc = pd.yp + (size_t)(c * 8) * E;
-        if (c * 8 + 8 <= nvalid) {
+      } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            st_u16(yc + (2 * i) * E, o[i]);
-            st_u16(yc + (2 * i + 1) * E, o[i] >> 16);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (c * 8 + 2 * i < nvalid) st_u16(yc + (2 * i) * E, o[i]);
-            if (c * 8 + 2 * i + 1 < nvalid) st_u16(yc + (2 * i + 1) * E, o[i] >> 16);
-          }
-        }
-      };
-      // gating-product operand of chunk c + 1: requested before chunk c is
-      // replayed, consumed one iteration later
-      uint32_t gn[8];
-      auto request_gate_mul = [&](int c) {
-        if constexpr (MUL) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            gn[i] = (c + 1 < kTile / 8 && (c + 1) * 8 + i < nvalid) ? ld_u16(gmp + ((c + 1) * 8 + i) * E) : 0u;
-        }
-      };
-      auto next_gate_mul = [&]() {
-        if constexpr (MUL) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) gm[i] = gn[i];
-        }
-      };
-#if CGF_P2PF
-      {
-        uint32_t sa[8], sb[8];
-        tmem_ld8(tm_state, sa);
-#pragma unroll
-        for (int c = 0; c < kTile / 8; c += 2) {
-          tmem_wait_ld();
-          tmem_ld8(tm_state + (c + 1) * 8, sb);
-          request_gate_mul(c);
-          replay_chunk(c, sa);
-          next_gate_mul();
-          tmem_wait_ld();
-          if (c + 2 < kTile / 8) tmem_ld8(tm_state + (c + 2) * 8, sa);
-          request_gate_mul(c + 1);
-          replay_chunk(c + 1, sb);
-          next_gate_mul();
+        for (int i = 0; i < 4; ++i) {
+          if (c * 8 + 2 * i < pd.nvalid) st_u16(yc + (2 * i) * E, o[i]);
+          if (c * 8 + 2 * i + 1 < pd.nvalid) st_u16(yc + (2 * i + 1) * E, o[i] >> 16);
         }
       }
-#else
+    };
+    auto retire_pending = [&](float h) {                 // the pending tile is complete
+      if (p.last_h != nullptr && pd.tt == p.ntt - 1) p.last_h[(size_t)pd.b * p.E + pd.ch] = h;
+      pd.on = false;
+      if (twarp) CGF_EVENT(trole, 6);
+    };
+    // F: carry chain + the whole replay pass of the pending tile
+    auto finish = [&](unsigned long long early) {
+      const int E = p.E;
+      // gating-product operand of the first 8 steps, requested before the
+      // look-back so that its latency hides behind it
+      uint32_t gm[8], gn[8];
+      const uint16_t* gmp = nullptr;
+      if constexpr (MUL) {
+        gmp = p.gate_mul + (pd.yp - p.y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gm[i] = i < pd.nvalid ? ld_u16(gmp + i * E) : 0u;
+      }
+      float h = resolve_carry(early);
 #pragma unroll 1
       for (int c = 0; c < kTile / 8; ++c) {
         uint32_t st[8];
         tmem_ld8(tm_state + c * 8, st);
-        request_gate_mul(c);
+        if constexpr (MUL) {                             // operand of chunk c + 1, one chunk ahead
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            gn[i] = (c + 1 < kTile / 8 && (c + 1) * 8 + i < pd.nvalid) ? ld_u16(gmp + ((c + 1) * 8 + i) * E) : 0u;
+        }
         tmem_wait_ld();
-        replay_chunk(c, st);
-        next_gate_mul();
+        replay_chunk(c, st, h, gm);
+        if constexpr (MUL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gm[i] = gn[i];
+        }
       }
-#endif
-      if (p.last_h != nullptr && tt == p.ntt - 1) p.last_h[(size_t)pd.b * E + pd.ch] = h;
-      pd.on = false;
-      if (twarp) CGF_EVENT(trole, 6);
+      retire_pending(h);
     };
     auto request_pred = [&]() -> unsigned long long {    // state word of the pending tile's predecessor
       return (pd.on && pd.tt > 0) ? ld_relaxed_u64(p.pref + pd.widx - wstep) : 0ull;
@@ -727,15 +705,22 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         mbar_wait(t_full + pr, use & 1, p.err, 6);
         if (twarp) CGF_EVENT(trole, 2);
         tc_fence_after();
-        if (pd.on) finish(early);                          // F(k-1)
         if (ticket >= ntiles) {                            // odd tile count: nothing in my half
           release_slot();
+          if (pd.on) finish(early);
           continue;
         }
         const int tt = ticket / p.B, b = ticket - tt * p.B;
         const int t0 = tt * kTile;
         const unsigned rbits = p.reset_bits[(long long)b * p.bits_bstride + tt];   // kTile == 32: one word
         const int nvalid = p.T - t0;                       // >= 1; >= kTile for a full tile
+        const bool fast_tile = CGF_PRELOAD && rbits == 0u && nvalid >= kTile;
+        // F(k-1): before the new tile -- or, for a common-case tile, only the carry
+        // now and the replay inside the gate loop below
+        const bool weave = CGF_INTERLEAVE && !MUL && fast_tile && pd.on;
+        float ph = 0.0f;                                   // running state of the pending tile's replay
+        if (weave) ph = resolve_carry(early);
+        else if (pd.on) finish(early);
         float P = 1.0f, Hh = 0.0f;
         // gates for one bf16x2 pair of steps (t, t+1) -> (a, x~); the tile's
         // transform h -> P*h + H is accumulated on the way
@@ -774,7 +759,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           Hh = add_bf_hi(n2, ah * Hh);
           P *= al; P *= ah;
         };
-        if (CGF_PRELOAD && rbits == 0u && nvalid >= kTile) {
+        if (fast_tile) {
           // ---- common case, half a tile (8 pairs) at a time: pull the
           // accumulators out of TMEM, rounded to bf16 on the way (the GEMM output
           // the reference materialises, :136-142), then the gate math from
@@ -804,6 +789,14 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
               release_slot();
               if (twarp) CGF_EVENT(trole, 3);
             }
+            // the pending tile's (a, x~) of these 16 steps leave my state columns
+            // before this tile's take their place
+            uint32_t os[2][8];
+            if (weave) {
+              tmem_ld8(tm_state + hh * 16, os[0]);
+              tmem_ld8(tm_state + hh * 16 + 8, os[1]);
+              tmem_wait_ld();
+            }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               uint32_t st[8];
@@ -811,8 +804,10 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
               for (int i = 0; i < 4; ++i)
                 gate_step(xv[c * 4 + i], gx[c * 4 + i], ga[c * 4 + i], hh * 16 + c * 8 + 2 * i, FalseTag{}, st[i], st[4 + i]);
               tmem_st8(tm_state + hh * 16 + c * 8, st);
+              if (weave) replay_chunk(hh * 2 + c, os[c], ph, nullptr);
             }
           }
+          if (weave) retire_pending(ph);
         } else {
           // document starts or a ragged tail inside the tile (rare, warp-uniform):
           // gates chunk by chunk out of TMEM

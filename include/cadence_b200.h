@@ -167,7 +167,9 @@ int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset,
  *                              arith_mode: CG_ARITH_REFERENCE or CG_ARITH_FAST
  *                              (every eager bf16 rounding point reproduced in both;
  *                              the GEMM accumulates in fp32 and rounds once to bf16
- *                              like the reference's einsum); variant 1 = 32-step tiles.
+ *                              like the reference's einsum); CG_ARITH_VARIANT(v), v in 1..64 limits
+ *                              the launch to v CTAs (a test hook: fewer CTAs than column
+ *                              families exercises the per-CTA family loop).
  *                              gate_mul (nullable): [B,T,E] bf16; when given, the kernel
  *                              returns round_bf16(y * gate_mul) -- the gating product of
  *                              RecurrentBlock.forward (modules.py:651, `x = x * y`) folded

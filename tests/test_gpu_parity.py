@@ -720,3 +720,29 @@ def test_fused_decode_step_equals_three_kernel_path(shape, cache_dtype):
     y_n, cs_n, h_n = cg.recurrent_hot_path(conv, lru, x, seg, conv_cache=cache, lru_cache=h0,
                                            return_cache=False)
     assert cs_n is None and h_n is None and torch.equal(y_n, y_p)
+
+
+@pytest.mark.parametrize("ctas", [1, 3, 7])
+def test_fused_rglru_family_loop_small_grid(ctas):
+  """Fewer CTAs than column families (as on a device with few SMs): a CTA then
+  walks several families in turn, reloading the gate weights -- same bits as the
+  full grid."""
+  abi = _abi()
+  torch.manual_seed(ctas)
+  bsz, steps, width, heads = 3, 150, 1024, 4          # 8 families of 128 channels
+  wx = (torch.randn(heads, 256, 256, device=DEV) / 16).to(torch.bfloat16)
+  wa = (torch.randn(heads, 256, 256, device=DEV) / 16).to(torch.bfloat16)
+  bx = torch.randn(width, device=DEV).to(torch.bfloat16)
+  ba = torch.randn(width, device=DEV).to(torch.bfloat16)
+  ap = torch.randn(width, device=DEV).to(torch.bfloat16)
+  x = torch.randn(bsz, steps, width, device=DEV).to(torch.bfloat16)
+  seg = torch.arange(steps, device=DEV, dtype=torch.int32)[None].repeat(bsz, 1)
+  seg[:, 70:] -= 70
+  h0 = torch.randn(bsz, width, device=DEV)
+  wpack = abi.pack_gate_weights(wx, wa)
+  ws = abi.fused_workspace(torch.device(DEV), bsz, steps, width)
+  y_ref, h_ref = abi.rglru_fused_fwd(x, wpack, bx, ba, ap, seg, heads, h0=h0, arith_mode=FAST, workspace=ws)
+  y, h = abi.rglru_fused_fwd(x, wpack, bx, ba, ap, seg, heads, h0=h0, arith_mode=FAST | (ctas << 8),
+                             workspace=ws)
+  assert abi.fused_watchdog_code(ws) == 0
+  assert torch.equal(y, y_ref) and torch.equal(h, h_ref)
