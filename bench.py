@@ -359,22 +359,43 @@ def own_arm(args, dtype):
     # the public host-buffer entry point: row chunks pipelined over three streams
     # (upload c+1 | kernels c | download c-1), see cadence_gemma_b200/hostio.py
     from cadence_gemma_b200.hostio import HostPrefill
-    e2e_chunks = int(os.environ.get("CG_BENCH_E2E_CHUNKS", "4"))
+    e2e_chunks = int(os.environ.get("CG_BENCH_E2E_CHUNKS", "1"))
     e2e_graph = os.environ.get("CG_BENCH_E2E_GRAPH", "0") != "0"
     host_prefill = HostPrefill(conv, lru, w["batch"], w["seq_len"], chunks=e2e_chunks, graph=e2e_graph)
 
+    # back-to-back batches are streamed (HostPrefill.submit): every step still
+    # uploads its inputs and downloads its results inside the timed region, but
+    # the upload of step n+1 overlaps the download of step n (PCIe full duplex).
+    # Two sets of host result buffers alternate, as a double-buffered consumer would.
+    e2e_stream = os.environ.get("CG_BENCH_E2E_STREAM", "1") != "0" and not e2e_graph
+    outs = [(y_pin, h_pin, c_pin),
+            (torch.empty_like(y_pin).pin_memory(), torch.empty_like(h_pin).pin_memory(),
+             torch.empty_like(c_pin).pin_memory())]
+    e2e_done = []
+
     def e2e_step():
-      host_prefill(x_pin, seg_pin, y_pin, h_pin, c_pin)
+      yo, ho, co = outs[step_no[0] & 1]
+      if e2e_stream:
+        e2e_done.append(host_prefill.submit(x_pin, seg_pin, yo, ho, co))
+      else:
+        host_prefill(x_pin, seg_pin, yo, ho, co)
       step_no[0] += 1
+
+    def e2e_join():                                      # results of every submitted step are on the host
+      for ev in e2e_done:
+        torch.cuda.current_stream().wait_event(ev)
+      e2e_done.clear()
 
     e2e_steps = max(3, min(args.steps, 20))
     for _ in range(3):
       e2e_step()
+    e2e_join()
     sync_all()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record()
     for _ in range(e2e_steps):
       e2e_step()
+    e2e_join()
     if world > 1:
       torch.cuda.current_stream().wait_stream(comm_stream)
     e_end.record()
@@ -404,7 +425,9 @@ def own_arm(args, dtype):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": e2e_ms / e2e_steps,
-                "how": f"HostPrefill: {e2e_chunks} row chunks pipelined over upload / kernel / download streams"},
+                "how": (f"HostPrefill: {e2e_chunks} row chunks pipelined over upload / kernel / download "
+                        "streams" + ("; consecutive steps streamed with submit() (upload of step n+1 under "
+                                     "the download of step n)" if e2e_stream else ""))},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm",
                      "kernel": ("cg::fused::rglru_fused_kernel (tcgen05 gate GEMMs + gate math + scan in one "

@@ -46,18 +46,26 @@ __device__ __forceinline__ uint32_t bf2_sub(uint32_t a, uint32_t b) {
 }
 
 // ------------------------------------------------------------- transcendentals
+// CG_ABLATE_MUFU (timing experiments only, results are WRONG): 1 = no MUFU.SQRT,
+// 2 = no MUFU.EX2, 4 = no MUFU.RCP
+#ifndef CG_ABLATE_MUFU
+#define CG_ABLATE_MUFU 0
+#endif
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
+  if (CG_ABLATE_MUFU & 2) return x * 0.125f + 0.5f;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
+  if (CG_ABLATE_MUFU & 4) return 1.0f - x * 0.01f;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
+  if (CG_ABLATE_MUFU & 1) return x * 0.75f;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }

@@ -62,6 +62,11 @@
 #ifndef CGF_INTERLEAVE
 #define CGF_INTERLEAVE 0   // measured: no gain (110.8 vs 109.8 us), the kernel is throughput-bound
 #endif
+// CGF_ABLATE (timing experiments only, results are WRONG): 1 = no look-back,
+// 2 = no y stores, 4 = no replay pass at all
+#ifndef CGF_ABLATE
+#define CGF_ABLATE 0
+#endif
 // CGF_TRACE: debug_out becomes a timeline buffer [6 roles][1024] of
 // (clock64 << 4 | event) words written by CTA 0 (scripts/fused_trace.py)
 #ifndef CGF_TRACE
@@ -549,7 +554,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       // `early`: the predecessor's state word, requested before the accumulator wait
       const int tt = pd.tt;
       float c0;
-      if (tt == 0) {
+      if (tt == 0 || (CGF_ABLATE & 1)) {
         c0 = p.h0 != nullptr ? p.h0[(size_t)pd.b * p.E + pd.ch] : 0.0f;
       } else if (__all_sync(0xffffffffu, (unsigned)early == epoch)) {
         c0 = tagged_value(early);
@@ -631,6 +636,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         if constexpr (MUL) o[i] = bf2_mul(o[i], gm[2 * i] | (gm[2 * i + 1] << 16));   // r(r(h) * gate), :651
       }
       uint16_t* yc = pd.yp + (size_t)(c * 8) * E;
+      if ((CGF_ABLATE & 2) && o[0] != 0x12345678u) return;
       if (c * 8 + 8 <= pd.nvalid) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -664,7 +670,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       }
       float h = resolve_carry(early);
 #pragma unroll 1
-      for (int c = 0; c < kTile / 8; ++c) {
+      for (int c = 0; c < ((CGF_ABLATE & 4) ? 0 : kTile / 8); ++c) {
         uint32_t st[8];
         tmem_ld8(tm_state + c * 8, st);
         if constexpr (MUL) {                             // operand of chunk c + 1, one chunk ahead

@@ -56,11 +56,13 @@ class HostPrefill:
     self.y_dev = mk((self.rows, steps, width), dtype)
     self.h_dev = mk((self.rows, width), torch.float32)
     self.c_dev = mk((self.rows, tw - 1, width), dtype)
-    self.ev_in = [torch.cuda.Event() for _ in range(chunks)]
-    self.ev_run = [torch.cuda.Event() for _ in range(chunks)]
-    self.ev_out = [torch.cuda.Event() for _ in range(chunks)]
+    self.ev_in = [torch.cuda.Event() for _ in range(2)]       # one per device-buffer slot
+    self.ev_run = [torch.cuda.Event() for _ in range(2)]
+    self.ev_out = [torch.cuda.Event() for _ in range(2)]
+    self._g = 0                                               # chunks enqueued so far
     self.use_graph = graph
     self._graphs = {}
+    self._streamed = False          # the previous call was a submit(): its chunks may still be in flight
 
   @torch.no_grad()
   def __call__(self, x_host, seg_host, y_host, h_host=None, cache_host=None):
@@ -81,6 +83,7 @@ class HostPrefill:
       cap = torch.cuda.Stream(self.device)
       cap.wait_stream(torch.cuda.current_stream(self.device))
       with torch.cuda.graph(g, stream=cap):
+        self._g = 0                                      # no dependency on events recorded outside the capture
         self._enqueue(x_host, seg_host, y_host, h_host, cache_host)
       torch.cuda.current_stream(self.device).wait_stream(cap)
       if len(self._graphs) > 8:
@@ -89,36 +92,65 @@ class HostPrefill:
     g.replay()
     return y_host
 
-  def _enqueue(self, x_host, seg_host, y_host, h_host, cache_host):
+  def submit(self, x_host, seg_host, y_host, h_host=None, cache_host=None):
+    """Streaming form of ``__call__`` for back-to-back batches: enqueues the
+    batch on the three pipeline streams WITHOUT joining them with the caller's
+    stream, so the upload of batch n+1 runs under the kernels and the download
+    of batch n (PCIe is full duplex: a batch then costs max(H2D, D2H), with no
+    pipeline fill / drain per batch).  The device buffers are shared between
+    consecutive batches; the reuse dependencies are carried by the per-slot
+    events across calls.  Returns a CUDA event that fires when ``y_host`` /
+    ``h_host`` / ``cache_host`` of THIS batch are complete
+    (``event.synchronize()`` or ``stream.wait_event(event)``).  The host input
+    buffers must already hold their data when this is called."""
+    self._enqueue(x_host, seg_host, y_host, h_host, cache_host, join=False)
+    done = torch.cuda.Event()
+    done.record(self.s_out)
+    return done
+
+  def _enqueue(self, x_host, seg_host, y_host, h_host, cache_host, join=True):
     cur = torch.cuda.current_stream(self.device)
-    for s in (self.s_in, self.s_run, self.s_out):
-      s.wait_stream(cur)
+    if join:
+      if self._streamed:                                 # drain submitted batches first
+        cur.wait_stream(self.s_out)
+        cur.wait_stream(self.s_run)
+        self._streamed = False
+      for s in (self.s_in, self.s_run, self.s_out):
+        s.wait_stream(cur)
+    # The g-th chunk ever enqueued works in device-buffer slot g & 1, across
+    # calls: before a slot is overwritten, the kernels that read it (upload
+    # side) and the download that read it (kernel side) must have finished --
+    # the per-slot events carry that from one chunk, and one call, to the next.
     for c in range(self.chunks):
       r0, r1 = c * self.rows, (c + 1) * self.rows
-      k = c & 1
+      k = self._g & 1
+      reuse = self._g >= 2
+      self._g += 1
       with torch.cuda.stream(self.s_in):
-        if c >= 2:
-          self.s_in.wait_event(self.ev_run[c - 2])       # kernels of chunk c-2 have read x / seg
+        if reuse:
+          self.s_in.wait_event(self.ev_run[k])           # kernels of the slot's last chunk have read x / seg
         self.x_dev[k].copy_(x_host[r0:r1], non_blocking=True)
         self.seg_dev[k].copy_(seg_host[r0:r1], non_blocking=True)
-        self.ev_in[c].record(self.s_in)
+        self.ev_in[k].record(self.s_in)
       with torch.cuda.stream(self.s_run):
-        self.s_run.wait_event(self.ev_in[c])
-        if c >= 2:
-          self.s_run.wait_event(self.ev_out[c - 2])      # chunk c-2 has been downloaded
+        self.s_run.wait_event(self.ev_in[k])
+        if reuse:
+          self.s_run.wait_event(self.ev_out[k])          # the slot's last results have been downloaded
         self.conv.forward_into(self.x_dev[k], self.seg_dev[k], out=self.xc_dev[k],
                                cache_out=self.c_dev[k])
         self.lru.forward_into(self.xc_dev[k], self.seg_dev[k], out=self.y_dev[k],
                               last_h_out=self.h_dev[k])
-        self.ev_run[c].record(self.s_run)
+        self.ev_run[k].record(self.s_run)
       with torch.cuda.stream(self.s_out):
-        self.s_out.wait_event(self.ev_run[c])
+        self.s_out.wait_event(self.ev_run[k])
         y_host[r0:r1].copy_(self.y_dev[k], non_blocking=True)
         if h_host is not None:
           h_host[r0:r1].copy_(self.h_dev[k], non_blocking=True)
         if cache_host is not None:
           cache_host[r0:r1].copy_(self.c_dev[k], non_blocking=True)
-        self.ev_out[c].record(self.s_out)
-    cur.wait_stream(self.s_out)
-    cur.wait_stream(self.s_run)
+        self.ev_out[k].record(self.s_out)
+    self._streamed = not join
+    if join:
+      cur.wait_stream(self.s_out)
+      cur.wait_stream(self.s_run)
     return y_host

@@ -1,33 +1,17 @@
-"""Per-phase mean cycles from gpurun_out/fused_trace.json (scripts/fused_trace.py)."""
+"""Mean cycles between consecutive pipeline events of gpurun_out/fused_trace.json
+(scripts/fused_trace.py), per role, keyed by (previous event -> next event)."""
+import collections
 import json
-import statistics
 import sys
 
 r = json.load(open(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/fused_trace.json"))
-for wg in ["wg0", "wg1", "wg2", "wg3"]:
-  tiles, cur = [], {}
-  for t, c in r[wg]:
-    cur[c] = t
-    if c == 6:
-      tiles.append(cur)
-      cur = {}
-  d = lambda a, b: statistics.mean(x[b] - x[a] for x in tiles[2:] if a in x and b in x)
-  per = statistics.mean(tiles[i + 1][1] - tiles[i][1] for i in range(2, len(tiles) - 1))
-  print(f"{wg}: wait t_full {d(1,2):6.0f} accload {d(2,3):6.0f} gate {d(3,4):6.0f} lookback {d(4,5):6.0f} "
-        f"pass2 {d(5,6):6.0f} period {per:6.0f} tiles {len(tiles)}")
-tiles, cur = [], {}
-for t, c in r["mma"]:
-  cur[c] = t
-  if c == 4:
-    tiles.append(cur)
-    cur = {}
-d = lambda a, b: statistics.mean(x[b] - x[a] for x in tiles[2:])
-per = statistics.mean(tiles[i + 1][1] - tiles[i][1] for i in range(2, len(tiles) - 1))
-print(f"mma: wait x_full {d(1,2):6.0f} wait t_empty {d(2,3):6.0f} issue {d(3,4):6.0f} period {per:6.0f}")
-tiles, cur = [], {}
-for t, c in r["producer"]:
-  cur[c] = t
-  if c == 2:
-    tiles.append(cur)
-    cur = {}
-print("producer wait x_empty", statistics.mean(x[2] - x[1] for x in tiles[2:]), "end", r["wg0"][-1][0])
+for role, ev in r.items():
+  ev = ev[len(ev) // 6:len(ev) - len(ev) // 6]          # steady state only
+  acc = collections.defaultdict(list)
+  for (t0, c0), (t1, c1) in zip(ev, ev[1:]):
+    acc[(c0, c1)].append(t1 - t0)
+  first = [t for t, c in ev if c == ev[0][1]]
+  period = (first[-1] - first[0]) / max(1, len(first) - 1)
+  parts = "  ".join(f"{a}->{b}: {sum(v) / len(v):6.0f} (n={len(v)})" for (a, b), v in sorted(acc.items()))
+  print(f"{role:9s} period {period:7.0f}  {parts}")
+print("end", max(ev[-1][0] for ev in r.values() if ev))

@@ -561,6 +561,44 @@ def test_host_prefill_pipeline_matches_direct_call():
     assert torch.equal(y, y_d.cpu()) and torch.equal(h, h_d.cpu()) and torch.equal(c, cs.cpu()), chunks
 
 
+def test_host_prefill_streaming_submit_overlaps_batches_correctly():
+  """submit(): consecutive batches share the device buffers and overlap on the
+  three streams; every batch must still return the bits of the direct call, and
+  a blocking __call__ after submitted batches must drain them first."""
+  import cadence_gemma_b200 as cg
+  from cadence_gemma_b200.hostio import HostPrefill
+  bsz, steps, width, heads = 4, 260, 512, 2
+  torch.manual_seed(5)
+  conv = cg.Conv1D(width, 4, device=DEV, dtype=torch.bfloat16)
+  lru = cg.RGLRU(width, heads, device=DEV, dtype=torch.bfloat16)
+  with torch.no_grad():
+    conv.b.normal_()
+    lru.input_gate.b.normal_()
+    lru.a_gate.b.normal_()
+  seg = torch.arange(steps, dtype=torch.int32)[None].repeat(bsz, 1)
+  seg[:, 77:] -= 77
+  seg = seg.pin_memory()
+  nb = 5
+  xs = [torch.randn(bsz, steps, width).to(torch.bfloat16).pin_memory() for _ in range(nb)]
+  ys = [torch.zeros_like(xs[0]).pin_memory() for _ in range(nb)]
+  hs = [torch.zeros(bsz, width).pin_memory() for _ in range(nb)]
+  cs = [torch.zeros(bsz, 3, width, dtype=torch.bfloat16).pin_memory() for _ in range(nb)]
+  for chunks in (1, 2, 4):
+    hp = HostPrefill(conv, lru, bsz, steps, chunks=chunks)
+    for t in ys + hs + cs:
+      t.zero_()
+    events = [hp.submit(xs[i], seg, ys[i], hs[i], cs[i]) for i in range(nb - 1)]
+    hp(xs[-1], seg, ys[-1], hs[-1], cs[-1])              # blocking form after streamed ones
+    for e in events:
+      e.synchronize()
+    torch.cuda.synchronize()
+    for i in range(nb):
+      with torch.no_grad():
+        xc, cd = conv(xs[i].to(DEV), seg.to(DEV))
+        y_d, h_d = lru(xc, seg.to(DEV))
+      assert torch.equal(ys[i], y_d.cpu()) and torch.equal(hs[i], h_d.cpu()) and torch.equal(cs[i], cd.cpu()), (chunks, i)
+
+
 def test_fused_rglru_api_variants_and_cuda_graph():
   """Module API corner cases on the fused path: 1-D / int64 / broadcast
   segment_pos, no h0, return_cache=False, B = 1, and CUDA-graph capture of the
