@@ -33,6 +33,8 @@ SYMBOLS = {
                           _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "cg_rnn_scan_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i,
                              _i, _i, _vp]),
+    "cg_rnn_scan_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i,
+                             _i, _vp]),
     "cg_rglru_fused_supported": (_i, [_i, _i, _i]),
     "cg_rglru_gate_pack_bytes": (_sz, [_i, _i]),
     "cg_rglru_pack_gate_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -287,6 +289,32 @@ def rnn_scan_fwd(x, a, reset, h0=None, arith_mode=ARITH_REFERENCE):
   _check(rc, "cg_rnn_scan_fwd")
   launch_count += 1 if (arith_mode & ARITH_STRICT) else 2
   return y, h_last
+
+
+def rnn_scan_bwd(gy, g_last, a, h, reset, h0=None, need_dh0=True):
+  """Backward of ``rnn_scan`` (cg_rnn_scan_bwd): returns ``(dx, da, dh0 | None)``.
+
+  ``gy`` grad of y, ``g_last`` fp32 grad of last_h or None, ``a`` / ``reset`` /
+  ``h0`` the forward's inputs, ``h`` the forward's output y."""
+  global launch_count
+  _require_cuda(gy, a, h, reset, h0, g_last)
+  bsz, steps, width = gy.shape
+  assert a.shape == gy.shape and h.shape == gy.shape and a.dtype == gy.dtype and h.dtype == gy.dtype
+  gy, a, h = gy.contiguous(), a.contiguous(), h.contiguous()
+  rs = reset.to(torch.uint8).contiguous()
+  assert rs.shape == (bsz, steps)
+  glc = None if g_last is None else g_last.to(torch.float32).contiguous()
+  h0c = None if h0 is None else h0.contiguous()
+  dx, da = torch.empty_like(gy), torch.empty_like(gy)
+  dh0 = torch.empty((bsz, width), dtype=torch.float32, device=gy.device) if need_dh0 else None
+  ws = scan_workspace(gy.device, bsz, steps, width, gy.dtype)
+  with torch.cuda.device(gy.device):
+    rc = load().cg_rnn_scan_bwd(gy.data_ptr(), _ptr(glc), a.data_ptr(), h.data_ptr(), rs.data_ptr(),
+                                _ptr(h0c), dx.data_ptr(), da.data_ptr(), _ptr(dh0), ws.data_ptr(),
+                                ws.numel(), bsz, steps, width, dtype_code(gy.dtype), _stream(gy))
+  _check(rc, "cg_rnn_scan_bwd")
+  launch_count += 2
+  return dx, da, dh0
 
 
 # ---------------------------------------------------------------------------

@@ -382,6 +382,40 @@ int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset, co
             : dispatch_geometry<float, 1, 1>(variant, p, workspace, workspace_bytes, stream);
 }
 
+int cg_rnn_scan_bwd(const void* gy, const float* g_last_h, const void* a, const void* h,
+                    const unsigned char* reset, const float* h0, void* dx, void* da, float* dh0,
+                    void* workspace, size_t workspace_bytes, int B, int T, int E, int dtype,
+                    cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!gy || !a || !h || !reset || !dx || !da || !workspace) return CG_ERR_NULL;
+  if (int rc = check_common(B, T, E, dtype)) return rc;
+  if (B > 65535) return CG_ERR_SHAPE;
+  const bool bf = dtype == CG_DTYPE_BF16;
+  const int V = bf ? 8 : 4;
+  if (E % V != 0) return CG_ERR_ALIGN;
+  if (!aligned16(gy) || !aligned16(a) || !aligned16(h) || !aligned16(dx) || !aligned16(da) ||
+      (h0 && !aligned16(h0)) || (g_last_h && !aligned16(g_last_h)) || (dh0 && !aligned16(dh0)) ||
+      !aligned16(workspace))
+    return CG_ERR_ALIGN;
+  const Workspace ws_min = carve(workspace, B, T, E, cg::kCvl * V, kMinSuperChunk);
+  if (ws_min.total > workspace_bytes) return CG_ERR_WORKSPACE;
+  ScanParams p{};
+  p.x = gy; p.a = a; p.reset = reset; p.h0 = h0; p.hprev = h; p.g_last = g_last_h;
+  p.y = dx; p.da = da; p.last_h = dh0;
+  p.B = B; p.T = T; p.E = E;
+  {
+    const int words = (T + 31) / 32;
+    cg::PrologueParams q{};                     // ticket reset + new epoch (the bitmask is not used here)
+    q.counter = ws_min.counter; q.epoch = ws_min.epoch;
+    q.reset = reset; q.reset_bits = ws_min.reset_bits; q.rows = B; q.T = T; q.words_per_row = words;
+    cg::scan_prologue_kernel<<<(B * words * 32 + 127) / 128, 128, 0, stream>>>(q);
+    if (cudaError_t err = cudaGetLastError()) return (int)err;
+    p.reset_bits = ws_min.reset_bits; p.bits_bstride = words;
+  }
+  return bf ? launch_scan<uint16_t, 2, 0, 8, 4, 1, 3>(p, workspace, workspace_bytes, stream)
+            : launch_scan<float, 2, 1, 8, 4, 1, 3>(p, workspace, workspace_bytes, stream);
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------

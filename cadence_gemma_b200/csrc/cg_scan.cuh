@@ -59,6 +59,10 @@ struct ScanParams {
   // plain scan inputs (KIND 1): x above, plus
   const void* a;                 // [B,T,E]
   const unsigned char* reset;    // [B,T]
+  // backward of the plain scan (KIND 2): x = grad of y, a / reset as forward, plus
+  const void* hprev;             // [B,T,E] forward output y (h_t in the I/O dtype); h0 above = forward h0
+  const float* g_last;           // [B,E] grad of last_h or null
+  void* da;                      // [B,T,E] grad of a; `y` above receives grad of x; last_h receives grad of h0
   // state
   const float* h0;   // [B,E] or null
   void* y;           // [B,T,E]
@@ -158,7 +162,11 @@ __device__ __forceinline__ void gate_f32(float xc, float gxr, float gar, float b
   a_out = e;
 }
 
-// KIND: 0 = RG-LRU (gates fused), 1 = plain rnn_scan(x, a, reset, h0).
+// KIND: 0 = RG-LRU (gates fused), 1 = plain rnn_scan(x, a, reset, h0),
+// 2 = backward of the plain scan: the same recurrence run over reversed time,
+//   dh_t = a_{t+1} * dh_{t+1} + gy_t,   dx_t = dh_t,   da_t = dh_t * h_{t-1}
+// (autograd of the reference loop, layers.py:187-199: mul then add in fp32,
+// casts at the ends).  Logical step tau of the scan is physical row T-1-tau.
 // ARITH: CG_ARITH_* bits 0 (fp32 in registers) and 1 (fast math).
 template <typename IO, int KIND, int ARITH>
 struct ScanTraits {
@@ -166,15 +174,15 @@ struct ScanTraits {
   static constexpr bool BF = IoVec<IO>::kBf16;
   static constexpr bool FAST = (ARITH & 2) != 0;
   // (a, x~) are exactly bf16 -> kept packed between the two passes
-  static constexpr bool PACKED = BF && (KIND == 1 || (ARITH & 1) == 0);
+  static constexpr bool PACKED = BF && (KIND >= 1 || (ARITH & 1) == 0);
   static constexpr int EC = kCvl * V;          // channels per tile (128 B rows)
   static constexpr int CPL = EC / 32;          // channels per lane in the carry warp
   // 16-byte staging slots per (step, lane): inputs x, g1, g2 (or x, a); the
   // (x~, a) state overwrites them in place (fp32 state of 8 channels needs 4)
-  static constexpr int NT = KIND == 1 ? 2 : ((BF && !PACKED) ? 4 : 3);
+  static constexpr int NT = KIND == 1 ? 2 : ((BF && !PACKED) ? 4 : 3);   // KIND 2: gy, a, h_prev
   // With 3 slots the third one (gemm_a) is dead after pass 1: the segment
   // transforms live there instead of in a separate shared array.
-  static constexpr bool ALIAS = NT == 3;
+  static constexpr bool ALIAS = NT == 3 && KIND == 0;
 };
 
 // STAGES staging buffers per CTA: with 2, item i+1 streams in while item i is
@@ -256,6 +264,27 @@ scan_kernel(const ScanParams p) {
   // only cp.async.wait_group.  One commit group per item.
   auto issue_loads = [&](const Coord& c, int buf) {
     const int nv = valid_steps(c);
+    if constexpr (KIND == 2) {
+      if (nv > 0) {
+        // reversed time: logical step tau reads gy[t], a[t+1] (1 at tau == 0: the
+        // incoming grad of last_h enters with coefficient one) and h[t-1], t = T-1-tau
+        const int ch0 = c.e0 + cv * V;
+        const int tau0 = (c.sc * NW + warp) * TC + seg_id * L;
+        const size_t rowb = (size_t)c.b * p.T;
+        uint4* dst = stage + (size_t)buf * STAGE_U4 + (size_t)warp * L * NT * 32 + lane;
+        const uint32_t one = BF ? kOne2 : 0x3f800000u;
+        for (int j = 0; j < nv; ++j) {
+          const int t = p.T - 1 - (tau0 + j);
+          cp_async16(dst, reinterpret_cast<const IO*>(p.x) + (rowb + t) * p.E + ch0);
+          if (t + 1 < p.T) cp_async16(dst + 32, reinterpret_cast<const IO*>(p.a) + (rowb + t + 1) * p.E + ch0);
+          else dst[32] = make_uint4(one, one, one, one);
+          if (t > 0) cp_async16(dst + 64, reinterpret_cast<const IO*>(p.hprev) + (rowb + t - 1) * p.E + ch0);
+          dst += NT * 32;
+        }
+      }
+      cp_async_commit();
+      return;
+    }
     if (nv > 0) {
       const int ch0 = c.e0 + cv * V;
       const size_t row = (size_t)c.b * p.T + (c.sc * NW + warp) * TC + seg_id * L;
@@ -280,7 +309,7 @@ scan_kernel(const ScanParams p) {
   // L2 prefetch of an item's input rows (one 128-byte row per lane and tensor),
   // issued as soon as the item is known: the later cp.async then hit L2.
   auto prefetch_l2 = [&](const Coord& c) {
-    if (c.item >= p.nitems || lane >= TC) return;
+    if (KIND == 2 || c.item >= p.nitems || lane >= TC) return;
     const int t = (c.sc * NW + warp) * TC + lane;
     if (t >= p.T) return;
     const size_t row = (size_t)c.b * p.T + t;
@@ -308,6 +337,14 @@ scan_kernel(const ScanParams p) {
     if (valid_steps(c) == 0) return;
     const int ch0 = c.e0 + cv * V;
     const int t_first = (c.sc * NW + warp) * TC + seg_id * L;
+    if constexpr (KIND == 2) {
+      // coefficient of logical step tau is a[t+1] * ~reset[t+1], t = T-1-tau
+      for (int j = 0; j < L; ++j) {
+        const int tn = p.T - (t_first + j);              // t + 1
+        if (tn >= 1 && tn < p.T && p.reset[(size_t)c.b * p.T + tn] != 0) meta_rs |= 1u << j;
+      }
+      return;
+    }
     meta_rs = (p.reset_bits[(long long)c.b * p.bits_bstride + (t_first >> 5)] >> (t_first & 31)) &
               ((1u << L) - 1u);
     if constexpr (KIND == 0) {
@@ -531,7 +568,8 @@ scan_kernel(const ScanParams p) {
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
           const int ch = e0 + lane * CPL + i;
-          c0[i] = (p.h0 != nullptr && ch < p.E) ? p.h0[(size_t)b * p.E + ch] : 0.0f;
+          const float* init = KIND == 2 ? p.g_last : p.h0;   // backward: the scan starts from grad(last_h)
+          c0[i] = (init != nullptr && ch < p.E) ? init[(size_t)b * p.E + ch] : 0.0f;
         }
       } else {
 #pragma unroll
@@ -644,6 +682,33 @@ scan_kernel(const ScanParams p) {
 
     // ---------------------------------------------------------- pass 2 (replay)
     IO* yrow = reinterpret_cast<IO*>(p.y) + (row0 + t_first) * p.E + ch0;
+    // KIND 2: grad of a for the physical step t: dh_t * h_{t-1} (h_{-1} = h0),
+    // zero at a document start (a was multiplied by ~reset, :173)
+    auto grad_a = [&](int j, const float (&dh)[V], const uint4& vhp) -> uint4 {
+      const int t = p.T - 1 - (t_first + j);
+      float hp[V];
+      if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) hp[i] = p.h0 != nullptr ? p.h0[(size_t)b * p.E + ch0 + i] : 0.0f;
+      } else if constexpr (BF) {
+        const uint32_t w[4] = {vhp.x, vhp.y, vhp.z, vhp.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { hp[2 * i] = bf_lo(w[i]); hp[2 * i + 1] = bf_hi(w[i]); }
+      } else {
+        hp[0] = __uint_as_float(vhp.x); hp[1] = __uint_as_float(vhp.y);
+        hp[2] = __uint_as_float(vhp.z); hp[3] = __uint_as_float(vhp.w);
+      }
+      float g[V];
+      const bool rz = p.reset[row0 + t] != 0;
+#pragma unroll
+      for (int i = 0; i < V; ++i) g[i] = rz ? 0.0f : __fmul_rn(dh[i], hp[i]);
+      if constexpr (BF)
+        return make_uint4(pack_bf2(g[0], g[1]), pack_bf2(g[2], g[3]), pack_bf2(g[4 % V], g[5 % V]),
+                          pack_bf2(g[6 % V], g[7 % V]));
+      else
+        return make_uint4(__float_as_uint(g[0]), __float_as_uint(g[1]), __float_as_uint(g[2]),
+                          __float_as_uint(g[3]));
+    };
     auto step2 = [&](int j) {
       uint4 out;
       if constexpr (PACKED) {
@@ -687,12 +752,29 @@ scan_kernel(const ScanParams p) {
                            __float_as_uint(h[2]), __float_as_uint(h[3]));
         }
       }
-      stg_stream(yrow + (size_t)j * p.E, out);
+      if constexpr (KIND == 2) {
+        const size_t off = ((row0 + p.T - 1 - (t_first + j)) * p.E + ch0);
+        stg_stream(reinterpret_cast<IO*>(p.y) + off, out);
+        stg_stream(reinterpret_cast<IO*>(p.da) + off, grad_a(j, h, my[(j * NT + 2) * 32]));
+      } else {
+        stg_stream(yrow + (size_t)j * p.E, out);
+      }
     };
 #pragma unroll 2
     for (int j = 0; j < nvalid; ++j) step2(j);
     // hidden state after the last valid step (padding steps are identities)
     if (p.last_h != nullptr && sc == p.nchunks - 1 && my_seg == NSEG - 1 && ch0 < p.E) {
+      if constexpr (KIND == 2) {
+        // grad of h0 = a_0 * ~reset_0 * dh_0 (h is dh_0 here: the scan ended at t = 0)
+        const bool rz = p.reset[row0] != 0;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float a0;
+          if constexpr (BF) a0 = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(p.a)[row0 * p.E + ch0 + i] << 16);
+          else a0 = reinterpret_cast<const float*>(p.a)[row0 * p.E + ch0 + i];
+          h[i] = rz ? 0.0f : __fmul_rn(a0, h[i]);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < V; i += 4)
         *reinterpret_cast<float4*>(p.last_h + (size_t)b * p.E + ch0 + i) =

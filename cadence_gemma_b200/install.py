@@ -46,7 +46,11 @@ def _rglru_forward(self, x, segment_pos, cache=None, return_cache=True, gate_mul
   if segment_pos.shape != (bs, length):
     segment_pos = segment_pos[None, :]
   assert segment_pos.shape == (bs, length)
-  cg_layers._forward_only(x, cache)
+  if cg_layers._wants_grad(x, cache, *self.parameters()):
+    # training: the reference's own forward builds the autograd graph; its scan
+    # is the patched module-global rnn_scan = the differentiable kernel pair
+    assert gate_mul is None
+    return _saved["rglru_forward"](self, x, segment_pos, cache, return_cache)
   with torch.no_grad():
     if cg_layers.uses_fused_kernel(self, x):
       # gate GEMMs + gate math + scan in ONE tcgen05 kernel (cg_rglru_fused_fwd)
@@ -82,7 +86,8 @@ def _recurrent_block_forward(self, x, segment_pos, cache=None, return_cache=True
       x=h, segment_pos=segment_pos,
       cache=None if cache is None else cache.conv1d_state, return_cache=return_cache)
   lru_cache = None if cache is None else cache.rg_lru_state
-  if cg_layers.fold_gate_enabled() and cg_layers.uses_fused_kernel(self.rg_lru, h):
+  if (cg_layers.fold_gate_enabled() and cg_layers.uses_fused_kernel(self.rg_lru, h) and
+      not cg_layers._wants_grad(h, y, lru_cache, *self.rg_lru.parameters())):
     h, rg_lru_state = _rglru_forward(self.rg_lru, h, segment_pos, lru_cache, return_cache,
                                      gate_mul=y)
   else:

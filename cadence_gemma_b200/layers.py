@@ -11,8 +11,14 @@ call signatures and return conventions as the reference
   * ``Conv1D``               layers.py:389-676
 
 The arithmetic runs in ``libcadence_b200.so`` through the C ABI
-(``include/cadence_b200.h``).  Forward only; there is no CPU / eager fallback:
-CPU tensors or a missing library raise.
+(``include/cadence_b200.h``).  There is no CPU fallback: CPU tensors or a
+missing library raise.
+
+Gradients: ``rnn_scan`` is differentiable --
+its backward is the reverse-time scan kernel ``cg_rnn_scan_bwd`` -- and
+``RGLRU.forward`` called with grad enabled builds the reference's autograd
+graph (gate math as ATen ops, clipped-sqrt gradient, layers.py:224-238) around
+it, so ``training/train.py`` can run on it.  ``Conv1D`` is forward only.
 """
 from __future__ import annotations
 
@@ -86,19 +92,68 @@ def _forward_only(*tensors):
         "torch.no_grad() (there is no autograd or eager fallback)")
 
 
+def _wants_grad(*tensors) -> bool:
+  return torch.is_grad_enabled() and any(
+      t is not None and t.requires_grad for t in tensors)
+
+
+class _RnnScanFn(torch.autograd.Function):
+  """``rnn_scan`` with the reverse-time scan kernel as its backward: the
+  gradients autograd derives from the reference loop (layers.py:173, :187-199)."""
+
+  @staticmethod
+  def forward(ctx, x, a, reset, h0):
+    y, last_h = _abi.rnn_scan_fwd(x, a, reset, h0, arith_mode=_arith_mode & _abi.ARITH_STRICT)
+    ctx.has_h0 = h0 is not None
+    ctx.save_for_backward(a, y, reset, h0 if h0 is not None else y.new_empty(0))
+    return y, last_h
+
+  @staticmethod
+  def backward(ctx, gy, g_last):
+    a, y, reset, h0 = ctx.saved_tensors
+    if gy is None:
+      gy = torch.zeros_like(y)
+    want_h0 = ctx.has_h0 and ctx.needs_input_grad[3]
+    dx, da, dh0 = _abi.rnn_scan_bwd(gy, g_last, a, y, reset, h0 if ctx.has_h0 else None,
+                                    need_dh0=want_h0)
+    return dx, da, None, dh0
+
+
+class SqrtBoundDerivative(torch.autograd.Function):
+  """``sqrt`` whose gradient is bounded by ``_MAX_SQRT_GRADIENT`` (reference
+  layers.py:224-238): d/dx sqrt(x) = 1 / sqrt(max(4 x, 1 / bound^2))."""
+
+  @staticmethod
+  def forward(ctx, x):
+    ctx.save_for_backward(x)
+    return torch.sqrt(x)
+
+  @staticmethod
+  def backward(ctx, grad_output):
+    (x,) = ctx.saved_tensors
+    return grad_output / torch.sqrt(torch.clip(4.0 * x, min=1.0 / (_MAX_SQRT_GRADIENT ** 2)))
+
+
+_MAX_SQRT_GRADIENT = 1000.0
+
+
 def rnn_scan(x, a, reset, h0, acc_dtype=torch.float32):
   """Linear recurrence h_t = a_t h_{t-1} + x_t (reference layers.py:146-199).
 
-  Returns ``(y in x.dtype, h_last in fp32)``.
+  Returns ``(y in x.dtype, h_last in fp32)``.  Differentiable in ``x``, ``a``
+  and ``h0`` (backward = ``cg_rnn_scan_bwd``).
   """
   assert x.ndim == 3
   assert a.shape == x.shape[-a.ndim:]
   assert a.dtype == x.dtype
   assert acc_dtype == torch.float32, "only fp32 accumulation is implemented"
   assert h0 is None or h0.dtype == acc_dtype
-  _forward_only(x, a, h0)
   if a.shape != x.shape:
     a = a.expand_as(x)
+  if _wants_grad(x, a, h0):
+    if x.shape[1] == 1 and h0 is None:      # :177-178: the output IS x (views, no arithmetic)
+      return x, x[:, 0].type(acc_dtype)
+    return _RnnScanFn.apply(x, a, reset, h0)
   mode = _arith_mode & _abi.ARITH_STRICT
   return _abi.rnn_scan_fwd(x, a, reset, h0, arith_mode=mode)
 
@@ -164,6 +219,10 @@ class BlockDiagonalLinear(nn.Module):
 
   def forward(self, x: torch.Tensor) -> torch.Tensor:
     heads, bw = self.num_blocks, self.block_width
+    if _wants_grad(x, self.w, self.b):          # autograd path: no out= variant
+      x2 = x.reshape(-1, heads, bw)
+      y = torch.bmm(x2.transpose(0, 1), self.w).transpose(0, 1) + self.b
+      return y.reshape(x.shape)
     y = self.gemm(x).view(*x.shape[:-1], heads, bw) + self.b
     return y.view(x.shape)
 
@@ -235,7 +294,9 @@ class RGLRU(nn.Module):
     if segment_pos.shape != (bs, length):
       segment_pos = segment_pos[None, :]
     assert segment_pos.shape == (bs, length)      # layers.py:344
-    _forward_only(x, cache)
+    if _wants_grad(x, cache, *self.parameters()):
+      assert out is None and last_h_out is None and gate_mul is None
+      return self._forward_autograd(x, segment_pos, cache, return_cache)
     with torch.no_grad():
       if self.uses_fused_kernel(x):
         return _abi.rglru_fused_fwd(
@@ -250,6 +311,23 @@ class RGLRU(nn.Module):
           arith_mode=_arith_mode, gemm_fused=self.gate_gemm(x),
           block_width=self.width // self.num_heads, out=out, last_h_out=last_h_out)
     return y, last_h
+
+  def _forward_autograd(self, x, segment_pos, cache, return_cache):
+    """Training path (grad enabled and x / cache / a parameter requires grad):
+    the reference's op sequence (layers.py:345-371) as ATen ops, so autograd
+    sees the same graph, around the differentiable scan kernels."""
+    reset = segment_pos == 0
+    gate_x = torch.sigmoid(self.input_gate(x))
+    gate_a = torch.sigmoid(self.a_gate(x))
+    log_a = -8.0 * gate_a * nn.functional.softplus(self.a_param)
+    a = torch.exp(log_a)
+    a_square = torch.exp(2 * log_a)
+    gated_x = x * gate_x
+    multiplier = SqrtBoundDerivative.apply(1 - a_square)
+    multiplier = reset[..., None] + ~reset[..., None] * multiplier
+    normalized_x = gated_x * multiplier.type(x.dtype)
+    y, last_h = rnn_scan(normalized_x, a, reset, cache)
+    return (y, last_h) if return_cache else (y, None)
 
   @classmethod
   def init_cache(cls, batch_size, width, device=None):

@@ -145,6 +145,27 @@ int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset,
                     int arith_mode, cg_stream_t stream);
 
 /*
+ * Backward of rnn_scan: what torch autograd derives from the reference loop
+ * (layers.py:173, :187-199) -- SURVEY.md section 8(f) row F4; the JAX VJP
+ * jax/pallas.py:785-839 is the same recurrence.  One chunked scan over
+ * reversed time:
+ *     dh_t = a_{t+1} * ~reset_{t+1} * dh_{t+1} + gy_t      (dh_T = g_last_h)
+ *     dx_t = dh_t        da_t = ~reset_t * dh_t * h_{t-1}  (h_{-1} = h0)
+ *     dh0  = a_0 * ~reset_0 * dh_0
+ * fp32 mul then add as autograd does; dx / da leave in `dtype`.
+ *   gy [B,T,E] grad of y (`dtype`); g_last_h [B,E] fp32 grad of last_h or NULL;
+ *   a, reset, h0 as given to the forward; h [B,T,E] = the forward's y (`dtype`;
+ *   for bf16 the reference keeps fp32 h_t for this product, so da differs from
+ *   it by at most the bf16 rounding of h);
+ *   dx, da [B,T,E] in `dtype`; dh0 [B,E] fp32 or NULL.
+ * Workspace as cg_rnn_scan_fwd.
+ */
+int cg_rnn_scan_bwd(const void* gy, const float* g_last_h, const void* a, const void* h,
+                    const unsigned char* reset, const float* h0, void* dx, void* da,
+                    float* dh0, void* workspace, size_t workspace_bytes, int B, int T,
+                    int E, int dtype, cg_stream_t stream);
+
+/*
  * Fused tensor-core RG-LRU (bf16): the two BlockDiagonalLinear gate GEMMs
  * (layers.py:133-142, :348-349), the gate math (:350-365) and rnn_scan
  * (:146-199, :366-371) in ONE kernel -- tcgen05 MMAs with TMEM accumulators,

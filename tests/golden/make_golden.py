@@ -301,9 +301,58 @@ def make_griffin_tiny():
   fixture_io.save("griffin_tiny_f32_t128", out)
 
 
+def make_grads(ref):
+  """Gradients torch autograd derives from the reference's rnn_scan / RGLRU
+  (the training path, training/train.py): pins the backward scan kernel
+  (SURVEY.md section 8(f) row F4)."""
+  for tag, dtype in DTYPES.items():
+    for name, (bsz, steps, width, with_h0) in {
+        "t37_h0": (2, 37, 48, True), "t37_noh0": (2, 37, 48, False),
+        "t1_h0": (3, 1, 40, True), "t1_noh0": (3, 1, 40, False),
+        "t300_h0": (2, 300, 72, True),
+    }.items():
+      g = gen(seed_of("grad", tag, name))
+      x = torch.randn((bsz, steps, width), generator=g).to(dtype).requires_grad_()
+      a = (0.5 + 0.4999 * torch.rand((bsz, steps, width), generator=g)).to(dtype).requires_grad_()
+      reset = torch.rand((bsz, steps), generator=g) < 0.1
+      reset[0, 0] = True
+      h0 = torch.randn((bsz, width), generator=g).requires_grad_() if with_h0 else None
+      gy = torch.randn((bsz, steps, width), generator=g).to(dtype)
+      gh = torch.randn((bsz, width), generator=g)
+      y, h_last = ref.layers.rnn_scan(x, a, reset, h0)
+      torch.autograd.backward([y, h_last], [gy, gh])
+      fixture_io.save(f"grad_rnn_scan_{tag}_{name}", dict(
+          x=x, a=a, reset=reset, h0=h0, gy=gy, gh=gh, y=y, h_last=h_last,
+          dx=x.grad, da=a.grad, dh0=None if h0 is None else h0.grad))
+    for width, heads, steps, bsz, segkind, with_cache in [
+        (128, 4, 48, 2, "halves", False), (256, 2, 70, 2, "ragged_pad", True)]:
+      seed = seed_of("grad", tag, width, heads, steps, segkind)
+      g = gen(seed)
+      torch.manual_seed(seed)
+      lru = ref.layers.RGLRU(width=width, num_heads=heads, dtype=dtype)
+      with torch.no_grad():
+        lru.input_gate.b.copy_(torch.randn(lru.input_gate.b.shape, generator=g).to(dtype))
+        lru.a_gate.b.copy_(torch.randn(lru.a_gate.b.shape, generator=g).to(dtype))
+      x = torch.randn((bsz, steps, width), generator=g).to(dtype).requires_grad_()
+      seg = halves(steps, bsz) if segkind == "halves" else ragged_segments(bsz, steps, seed, pad=3)
+      cache = torch.randn((bsz, width), generator=g).requires_grad_() if with_cache else None
+      gy = torch.randn((bsz, steps, width), generator=g).to(dtype)
+      gh = torch.randn((bsz, width), generator=g)
+      y, last_h = lru(x, seg, cache)
+      torch.autograd.backward([y, last_h], [gy, gh])
+      out = dict(x=x, seg=seg, cache=cache, gy=gy, gh=gh, y=y, last_h=last_h, dx=x.grad,
+                 dcache=None if cache is None else cache.grad)
+      for k, v in lru.named_parameters():
+        out["param." + k] = v.data
+        out["grad." + k] = v.grad
+      fixture_io.save(f"grad_rglru_{tag}_e{width}_h{heads}_t{steps}_{segkind}", out)
+
+
 def main():
   ref = ref_loader.load_reference()
-  if ONLY:
+  if ONLY == ["grad"]:
+    make_grads(ref)
+  elif ONLY:
     make_rglru(ref)
     make_recurrent_block(ref)
   else:
@@ -312,6 +361,7 @@ def main():
     make_rglru(ref)
     make_recurrent_block(ref)
     make_griffin_tiny()
+    make_grads(ref)
   total = 0
   for f in sorted(os.listdir(fixture_io.GOLDEN_DIR)):
     if f.endswith(".npz"):

@@ -70,6 +70,110 @@ def test_rnn_scan_api_matches_reference_contract():
     cg.rnn_scan(x.cpu(), a.cpu(), rs.cpu(), None)
 
 
+# ------------------------------------------------- gradients
+def _grad_close(got, want, what, bf16_identical=0.97):
+  got, want = got.cpu(), want.cpu()
+  assert got.dtype == want.dtype and got.shape == want.shape, (what, got.dtype, want.dtype)
+  if got.dtype == torch.bfloat16:
+    assert_close_bf16(got, want, what, min_identical=bf16_identical)
+  else:
+    assert_close_f32(got, want, what)
+
+
+@pytest.mark.parametrize("case", fixture_io.cases("grad_rnn_scan_"))
+def test_rnn_scan_backward_golden(case):
+  """cg_rnn_scan_bwd against the gradients autograd derives from the reference
+  loop.  fp32: 1e-5 normwise.  bf16: dx to bf16 rounding; da is formed from the
+  bf16 forward output instead of the reference's fp32 h_t (documented in
+  include/cadence_b200.h), hence the lower bit-identical floor."""
+  import cadence_gemma_b200 as cg
+  g = fixture_io.load(case)
+  x = cu(g["x"]).requires_grad_()
+  a = cu(g["a"]).requires_grad_()
+  h0 = cu(g["h0"]).requires_grad_() if "h0" in g else None
+  with torch.enable_grad():
+    y, h = cg.rnn_scan(x, a, cu(g["reset"]), h0)
+    torch.autograd.backward([y, h], [cu(g["gy"]), cu(g["gh"])])
+  _close(y.detach(), g["y"], case + " y", min_identical=0.995)
+  _grad_close(x.grad, g["dx"], case + " dx", 0.995)
+  if "da" in g:
+    _grad_close(a.grad, g["da"], case + " da", 0.5)
+  else:                                   # T == 1 without h0 (:177-178): a does not reach the output
+    assert a.grad is None or not a.grad.any()
+  if h0 is not None:
+    assert_close_f32(h0.grad.cpu(), g["dh0"], case + " dh0")
+  # direct ABI call, grad of last_h absent and dh0 not wanted
+  abi = _abi()
+  dx, da, dh0 = abi.rnn_scan_bwd(cu(g["gy"]), None, a.detach(), y.detach(), cu(g["reset"]),
+                                 None if h0 is None else h0.detach(), need_dh0=False)
+  assert dh0 is None and torch.isfinite(dx.float()).all() and torch.isfinite(da.float()).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_rnn_scan_backward_full_size_vs_sequential(dtype):
+  """Config-2 sized backward scan (many chunks, look-back across CTAs) against a
+  sequential reverse loop in fp32 torch ops on the device, and run-to-run
+  determinism."""
+  abi = _abi()
+  torch.manual_seed(11)
+  bsz, steps, width = 4, 2048, 2560
+  a = (0.6 + 0.3999 * torch.rand(bsz, steps, width, device=DEV)).to(dtype)
+  gy = torch.randn(bsz, steps, width, device=DEV).to(dtype)
+  h = torch.randn(bsz, steps, width, device=DEV).to(dtype)
+  reset = torch.rand(bsz, steps, device=DEV) < 0.002
+  reset[:, 0] = True
+  h0 = torch.randn(bsz, width, device=DEV)
+  gl = torch.randn(bsz, width, device=DEV)
+  dx, da, dh0 = abi.rnn_scan_bwd(gy, gl, a, h, reset, h0)
+  dx2, da2, dh02 = abi.rnn_scan_bwd(gy, gl, a, h, reset, h0)
+  assert torch.equal(dx, dx2) and torch.equal(da, da2) and torch.equal(dh0, dh02)
+  am = (a * ~reset[..., None]).float()
+  dh = gl.clone()
+  want_dx = torch.empty(bsz, steps, width, device=DEV)
+  for t in range(steps - 1, -1, -1):
+    dh = dh + gy[:, t].float() if t == steps - 1 else am[:, t + 1] * dh + gy[:, t].float()
+    want_dx[:, t] = dh
+  hprev = torch.cat([h0[:, None], h[:, :-1].float()], dim=1)
+  want_da = (want_dx * hprev) * ~reset[..., None]
+  want_dh0 = am[:, 0] * want_dx[:, 0]
+  if dtype == torch.float32:
+    assert normwise(dx, want_dx) <= 1e-5 and normwise(da, want_da) <= 1e-5
+  else:
+    assert_close_bf16(dx.cpu(), want_dx.to(dtype).cpu(), "dx", min_identical=0.995)
+    assert_close_bf16(da.cpu(), want_da.to(dtype).cpu(), "da", min_identical=0.995)
+  assert normwise(dh0, want_dh0) <= 1e-5
+
+
+@pytest.mark.parametrize("case", fixture_io.cases("grad_rglru_"))
+def test_rglru_training_path_golden(case):
+  """RGLRU.forward with grad enabled: the reference's autograd graph around the
+  differentiable scan kernels; gradients of x, the cache and every parameter
+  against the reference's."""
+  import cadence_gemma_b200 as cg
+  g = fixture_io.load(case)
+  dtype = g["x"].dtype
+  heads, bw, _ = g["param.input_gate.w"].shape
+  lru = cg.RGLRU(heads * bw, heads, device=DEV, dtype=dtype)
+  lru.load_state_dict({k[6:]: v for k, v in g.items() if k.startswith("param.")})
+  x = cu(g["x"]).requires_grad_()
+  cache = cu(g["cache"]).requires_grad_() if "cache" in g else None
+  with torch.enable_grad():
+    y, last_h = lru(x, cu(g["seg"]), cache)
+    torch.autograd.backward([y, last_h], [cu(g["gy"]), cu(g["gh"])])
+  bf = dtype == torch.bfloat16
+  _close(y.detach(), g["y"], case + " y", min_identical=0.99)
+  tol = 4e-2 if bf else 2e-5
+  assert normwise(x.grad.float().cpu(), g["dx"].float()) <= tol, case
+  if cache is not None:
+    assert normwise(cache.grad.cpu(), g["dcache"]) <= (2e-2 if bf else 2e-5), case
+  for name, prm in lru.named_parameters():
+    nw = normwise(prm.grad.float().cpu(), g["grad." + name].float())
+    assert nw <= (6e-2 if bf else 1e-4), (case, name, nw)
+  with torch.no_grad():                       # the inference path is untouched by training mode
+    y2, _ = lru(x.detach(), cu(g["seg"]), None if cache is None else cache.detach())
+  _close(y2, g["y"], case + " y (no_grad)", min_identical=0.99)
+
+
 # -------------------------------------------------------------------- conv1d
 @pytest.mark.parametrize("case", fixture_io.cases("conv1d_"))
 def test_conv1d_golden(case):

@@ -34,6 +34,25 @@ def test_rnn_scan(case):
   assert_bitexact(h, g["h_last"], case + " C h")
 
 
+@pytest.mark.parametrize("case", fixture_io.cases("grad_rnn_scan_"))
+def test_rnn_scan_gradients(case):
+  """Autograd through the port's loop == autograd through the reference's
+  (the oracle of the backward scan kernel)."""
+  g = fixture_io.load(case)
+  x = g["x"].clone().requires_grad_()
+  a = g["a"].clone().requires_grad_()
+  h0 = g["h0"].clone().requires_grad_() if "h0" in g else None
+  y, h = torch_port.rnn_scan(x, a, g["reset"], h0)
+  torch.autograd.backward([y, h], [g["gy"], g["gh"]])
+  assert_bitexact(x.grad, g["dx"], case + " dx")
+  if "da" in g:
+    assert_bitexact(a.grad, g["da"], case + " da")
+  else:                                   # T == 1 without h0 returns x itself (:177-178): a is unused
+    assert a.grad is None
+  if h0 is not None:
+    assert_bitexact(h0.grad, g["dh0"], case + " dh0")
+
+
 # ------------------------------------------------------------------ conv1d
 @pytest.mark.parametrize("case", fixture_io.cases("conv1d_"))
 def test_conv1d(case):
