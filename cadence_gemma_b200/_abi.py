@@ -33,6 +33,9 @@ SYMBOLS = {
                           _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
     "cg_rnn_scan_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i,
                              _i, _i, _vp]),
+    "cg_conv1d_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cg_conv1d_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i,
+                           _i, _i, _vp]),
     "cg_rnn_scan_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i,
                              _i, _vp]),
     "cg_rglru_fused_supported": (_i, [_i, _i, _i]),
@@ -167,6 +170,28 @@ def conv1d_fwd(x, w, b, segment_pos, return_cache=True, mask_mode=MASK_FORK,
   _check(rc, "cg_conv1d_fwd")
   launch_count += 1
   return y, cache
+
+
+def conv1d_bwd(gy, x, w, segment_pos, mask_mode=MASK_FORK):
+  """Backward of the Conv1D prefill (cg_conv1d_bwd): returns ``(dx, dw, db)``."""
+  global launch_count
+  _require_cuda(gy, x, w, segment_pos)
+  bsz, steps, width = x.shape
+  assert gy.shape == x.shape and gy.dtype == x.dtype and w.dtype == x.dtype
+  gy, x, w = gy.contiguous(), x.contiguous(), w.contiguous()
+  seg, is64, stride = _seg_args(segment_pos, bsz, steps)
+  dx = torch.empty_like(x)
+  dw = torch.empty_like(w)
+  db = torch.empty((width,), dtype=x.dtype, device=x.device)
+  nbytes = load().cg_conv1d_bwd_workspace_bytes(bsz, steps, width)
+  ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+  with torch.cuda.device(x.device):
+    rc = load().cg_conv1d_bwd(gy.data_ptr(), x.data_ptr(), w.data_ptr(), seg.data_ptr(), is64, stride,
+                              dx.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(),
+                              bsz, steps, width, w.shape[0], dtype_code(x.dtype), mask_mode, _stream(x))
+  _check(rc, "cg_conv1d_bwd")
+  launch_count += 2
+  return dx, dw, db
 
 
 def conv1d_stream_fwd(x, w, b, segment_pos, flags, out, cache_out=None, mask_mode=MASK_FORK,

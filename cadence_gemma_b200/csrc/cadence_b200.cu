@@ -188,6 +188,49 @@ int cg_conv1d_fwd(const void* x, const void* w, const void* b, const void* seg, 
   return (int)cudaGetLastError();
 }
 
+namespace {
+constexpr int kConvBwdLC = 4;
+inline int conv_bwd_tblocks(int T) { return ((T + kConvBwdLC - 1) / kConvBwdLC + 15) / 16; }
+}  // namespace
+
+size_t cg_conv1d_bwd_workspace_bytes(int B, int T, int E) {
+  if (B < 1 || T < 1 || E < 1) return 0;
+  return (size_t)B * conv_bwd_tblocks(T) * 5 * E * sizeof(float);
+}
+
+int cg_conv1d_bwd(const void* gy, const void* x, const void* w, const void* seg, int seg_is_i64,
+                  long long seg_batch_stride, void* dx, void* dw, void* db, void* workspace,
+                  size_t workspace_bytes, int B, int T, int E, int W, int dtype, int mask_mode,
+                  cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!gy || !x || !w || !seg || !dx || !dw || !db || !workspace) return CG_ERR_NULL;
+  if (int rc = check_common(B, T, E, dtype)) return rc;
+  if (mask_mode != CG_MASK_FORK && mask_mode != CG_MASK_UPSTREAM) return CG_ERR_MODE;
+  if (W != 4) return CG_ERR_UNSUPPORTED;            // the temporal width of every Griffin preset
+  if (B > 65535) return CG_ERR_SHAPE;
+  const bool bf = dtype == CG_DTYPE_BF16;
+  const int V = bf ? 8 : 4;
+  if (E % V != 0) return CG_ERR_ALIGN;
+  if (!aligned16(gy) || !aligned16(x) || !aligned16(w) || !aligned16(dx) || !aligned16(workspace))
+    return CG_ERR_ALIGN;
+  if (cg_conv1d_bwd_workspace_bytes(B, T, E) > workspace_bytes) return CG_ERR_WORKSPACE;
+  cg::ConvBwdParams p{};
+  p.gy = gy; p.x = x; p.w = w; p.seg = seg; p.seg_bstride = seg_batch_stride; p.seg_is_i64 = seg_is_i64;
+  p.dx = dx; p.partial = reinterpret_cast<float*>(workspace);
+  p.B = B; p.T = T; p.E = E; p.mask_mode = mask_mode;
+  const int tblocks = conv_bwd_tblocks(T);
+  if (tblocks > 65535) return CG_ERR_SHAPE;
+  dim3 grid((E + 8 * V - 1) / (8 * V), tblocks, B);
+  if (bf) cg::conv1d_w4_bwd_kernel<uint16_t, kConvBwdLC><<<grid, 128, 0, stream>>>(p);
+  else cg::conv1d_w4_bwd_kernel<float, kConvBwdLC><<<grid, 128, 0, stream>>>(p);
+  if (cudaError_t err = cudaGetLastError()) return (int)err;
+  const int nparts = B * tblocks;
+  const int rgrid = (5 * E + 127) / 128;
+  if (bf) cg::conv1d_bwd_reduce_kernel<uint16_t><<<rgrid, 128, 0, stream>>>(p.partial, nparts, E, dw, db);
+  else cg::conv1d_bwd_reduce_kernel<float><<<rgrid, 128, 0, stream>>>(p.partial, nparts, E, dw, db);
+  return (int)cudaGetLastError();
+}
+
 size_t cg_conv1d_stream_flags_bytes(int B, int T) {
   if (B < 1 || T < 1) return 0;
   return (size_t)B * ((T + 63) / 64) * sizeof(int);

@@ -175,6 +175,194 @@ conv1d_w4_stream_kernel(const ConvParams p, int* flags, int ctiles, int tgroups)
 }
 
 // ---------------------------------------------------------------------------
+// Backward of the W == 4 prefill (what autograd derives from layers.py:484-546;
+// training path).  With m_s(t) the document mask
+// of tap s at output step t (the forward's m1..m3):
+//   dx[u]    = sum_s w[3-s] * gy[u+s] * m_s(u+s)
+//   dw[3-s]  = sum_{b,t} gy[t] * x[t-s] * m_s(t)        db = sum_{b,t} gy[t]
+// Same tiling as the forward: thread = 16-byte channel vector x LC steps.  dx is
+// accumulated in the tensor dtype in autograd's order (bit-exact with the
+// reference); the parameter gradients are summed in fp32 and reduced
+// in a fixed order (registers -> shared memory over the block's 16 time slots
+// -> one partial row per block -> conv1d_bwd_reduce_kernel): bit-reproducible.
+// ---------------------------------------------------------------------------
+struct ConvBwdParams {
+  const void* gy;     // [B,T,E]
+  const void* x;      // [B,T,E] forward input
+  const void* w;      // [4,E]
+  const void* seg;
+  long long seg_bstride;
+  int seg_is_i64;
+  void* dx;           // [B,T,E]
+  float* partial;     // [B * tblocks][5][E] fp32: dw[0..3], db per block
+  int B, T, E;
+  int mask_mode;
+};
+
+template <typename IO>
+__device__ __forceinline__ void widen_vec(const uint4& v, float (&f)[IoVec<IO>::V]) {
+  if constexpr (IoVec<IO>::kBf16) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f[2 * i] = bf_lo(w[i]); f[2 * i + 1] = bf_hi(w[i]); }
+  } else {
+    f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
+  }
+}
+
+template <typename IO, int LC>
+__global__ void __launch_bounds__(128)
+conv1d_w4_bwd_kernel(const ConvBwdParams p) {
+  constexpr int V = IoVec<IO>::V;
+  constexpr bool BF = IoVec<IO>::kBf16;
+  constexpr int EC = kCvl * V;
+  __shared__ float red[16][kCvl][5 * V + 1];
+  const int cv = threadIdx.x & 7;
+  const int slot = threadIdx.x >> 3;
+  const int tslot = blockIdx.y * 16 + slot;
+  const int b = blockIdx.z;
+  const int ch0 = blockIdx.x * EC + cv * V;
+  const int t0 = tslot * LC;
+  const bool live = ch0 < p.E && t0 < p.T;
+  float acc[5][V];
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[k][i] = 0.0f;
+
+  if (live) {
+    const IO* gb = reinterpret_cast<const IO*>(p.gy) + (size_t)b * p.T * p.E + ch0;
+    const IO* xb = reinterpret_cast<const IO*>(p.x) + (size_t)b * p.T * p.E + ch0;
+    IO* dxb = reinterpret_cast<IO*>(p.dx) + (size_t)b * p.T * p.E + ch0;
+    const long long seg0 = (long long)b * p.seg_bstride;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    uint4 gr[LC + 3], xr[LC + 3];   // gr[r] = gy[t0 + r], xr[r] = x[t0 - 3 + r]
+#pragma unroll
+    for (int r = 0; r < LC + 3; ++r) {
+      const int tg = t0 + r, tx = t0 - 3 + r;
+      gr[r] = tg < p.T ? ldg_stream(gb + (size_t)tg * p.E) : zero;
+      xr[r] = (tx >= 0 && tx < p.T) ? ldg_stream(xb + (size_t)tx * p.E) : zero;
+    }
+    // nb bit r = (segment_pos[t0 - 2 + r] != 0), r < LC + 5 (steps t0-2 .. t0+LC+2)
+    unsigned nb = 0;
+#pragma unroll
+    for (int r = 0; r < LC + 5; ++r) {
+      const int t = t0 - 2 + r;
+      if (t >= 0 && t < p.T)
+        nb |= (load_seg(p.seg, p.seg_is_i64 != 0, seg0 + t) != 0 ? 1u : 0u) << r;
+    }
+    // masks of output step t (as the forward): bit 0 seg[t-2], bit 1 seg[t-1], bit 2 seg[t]
+    auto masks = [&](int t, bool& m1, bool& m2, bool& m3) {
+      const unsigned w3 = nb >> (t - t0);
+      if (p.mask_mode == 0) { m1 = true; m2 = true; m3 = (w3 & 1u) != 0; }
+      else { m1 = (w3 & 4u) != 0; m2 = (w3 & 6u) == 6u; m3 = (w3 & 7u) == 7u; }
+    };
+    // taps as loaded (packed bf16x2 pairs or fp32 words): wq[k][i]
+    uint32_t wq[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const IO*>(p.w) + (size_t)k * p.E + ch0);
+      wq[k][0] = v.x; wq[k][1] = v.y; wq[k][2] = v.z; wq[k][3] = v.w;
+    }
+    // one product / one sum in the tensor dtype, rounded as the eager op is
+    auto mul_io = [](uint32_t u, uint32_t v) -> uint32_t {
+      if constexpr (BF) return bf2_mul(u, v);
+      else return __float_as_uint(__fmul_rn(__uint_as_float(u), __uint_as_float(v)));
+    };
+    auto add_io = [](uint32_t u, uint32_t v) -> uint32_t {
+      if constexpr (BF) return bf2_add(u, v);
+      else return __float_as_uint(__fadd_rn(__uint_as_float(u), __uint_as_float(v)));
+    };
+
+#pragma unroll
+    for (int j = 0; j < LC; ++j) {
+      const int t = t0 + j;
+      if (t >= p.T) break;
+      const uint32_t g0[4] = {gr[j].x, gr[j].y, gr[j].z, gr[j].w};
+      const uint32_t g1[4] = {gr[j + 1].x, gr[j + 1].y, gr[j + 1].z, gr[j + 1].w};
+      const uint32_t g2[4] = {gr[j + 2].x, gr[j + 2].y, gr[j + 2].z, gr[j + 2].w};
+      const uint32_t g3[4] = {gr[j + 3].x, gr[j + 3].y, gr[j + 3].z, gr[j + 3].w};
+      // ---- dx[t]: taps of the output steps t .. t+3 that read x[t].  Autograd
+      // accumulates the four contributions in the tensor dtype, last tap first
+      // (tap 3, 2, 1, 0), each product rounded: reproduced exactly.
+      bool a1, a2, a3, b1, b2, b3, c1, c2, c3;
+      masks(t + 1, a1, a2, a3); masks(t + 2, b1, b2, b3); masks(t + 3, c1, c2, c3);
+      uint32_t o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint32_t v = c3 ? mul_io(g3[i], wq[0][i]) : 0u;          // gy rows beyond T were loaded as zero
+        v = add_io(v, b2 ? mul_io(g2[i], wq[1][i]) : 0u);
+        v = add_io(v, a1 ? mul_io(g1[i], wq[2][i]) : 0u);
+        o[i] = add_io(v, mul_io(g0[i], wq[3][i]));
+      }
+      stg_stream(dxb + (size_t)t * p.E, make_uint4(o[0], o[1], o[2], o[3]));
+      // ---- parameter gradients of output step t: products rounded to the
+      // tensor dtype (the eager mul of autograd), summed in fp32
+      bool m1, m2, m3;
+      masks(t, m1, m2, m3);
+      const uint4 zr = make_uint4(0, 0, 0, 0);
+      const uint4 r0 = xr[j + 3], r1 = m1 ? xr[j + 2] : zr, r2 = m2 ? xr[j + 1] : zr, r3 = m3 ? xr[j] : zr;
+      const uint32_t x0[4] = {r0.x, r0.y, r0.z, r0.w}, x1[4] = {r1.x, r1.y, r1.z, r1.w};
+      const uint32_t x2[4] = {r2.x, r2.y, r2.z, r2.w}, x3[4] = {r3.x, r3.y, r3.z, r3.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t q3 = mul_io(g0[i], x0[i]), q2 = mul_io(g0[i], x1[i]);
+        const uint32_t q1 = mul_io(g0[i], x2[i]), q0 = mul_io(g0[i], x3[i]);
+        if constexpr (BF) {
+          acc[3][2 * i] += bf_lo(q3); acc[3][2 * i + 1] += bf_hi(q3);
+          acc[2][2 * i] += bf_lo(q2); acc[2][2 * i + 1] += bf_hi(q2);
+          acc[1][2 * i] += bf_lo(q1); acc[1][2 * i + 1] += bf_hi(q1);
+          acc[0][2 * i] += bf_lo(q0); acc[0][2 * i + 1] += bf_hi(q0);
+          acc[4][2 * i] += bf_lo(g0[i]); acc[4][2 * i + 1] += bf_hi(g0[i]);
+        } else {
+          acc[3][i] += __uint_as_float(q3); acc[2][i] += __uint_as_float(q2);
+          acc[1][i] += __uint_as_float(q1); acc[0][i] += __uint_as_float(q0);
+          acc[4][i] += __uint_as_float(g0[i]);
+        }
+      }
+    }
+  }
+  // ---- block reduction over the 16 time slots, fixed order
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) red[slot][cv][k * V + i] = acc[k][i];
+  __syncthreads();
+  float* out = p.partial + ((size_t)(b * gridDim.y + blockIdx.y) * 5) * p.E;
+  for (int idx = threadIdx.x; idx < kCvl * 5 * V; idx += blockDim.x) {
+    const int c = idx / (5 * V), r = idx - c * (5 * V);
+    const int k = r / V, i = r - k * V;
+    const int ch = blockIdx.x * EC + c * V + i;
+    if (ch >= p.E) continue;
+    float sum = 0.0f;
+#pragma unroll
+    for (int sl = 0; sl < 16; ++sl) sum += red[sl][c][r];
+    out[(size_t)k * p.E + ch] = sum;
+  }
+}
+
+// dw[k][e] / db[e] = sum of the per-block partials, in block order.
+template <typename IO>
+__global__ void conv1d_bwd_reduce_kernel(const float* __restrict__ partial, int nparts, int E,
+                                         void* __restrict__ dw, void* __restrict__ db) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 5 * E) return;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;   // four interleaved chains, combined in a fixed order
+  int q = 0;
+  for (; q + 3 < nparts; q += 4) {
+    s0 += partial[(size_t)q * 5 * E + idx];
+    s1 += partial[(size_t)(q + 1) * 5 * E + idx];
+    s2 += partial[(size_t)(q + 2) * 5 * E + idx];
+    s3 += partial[(size_t)(q + 3) * 5 * E + idx];
+  }
+  for (; q < nparts; ++q) s0 += partial[(size_t)q * 5 * E + idx];
+  const float sum = (s0 + s1) + (s2 + s3);
+  if (idx < 4 * E) store_io<IO>(dw, idx, sum);
+  else store_io<IO>(db, idx - 4 * E, sum);
+}
+
+// ---------------------------------------------------------------------------
 // Generic temporal width (W != 4): one thread per output element.  Slow path,
 // kept for API completeness (the reference's tests also run W = 8).
 // Reproduces the accumulated in-place masking of the returned cache

@@ -67,8 +67,11 @@ def _rglru_forward(self, x, segment_pos, cache=None, return_cache=True, gate_mul
 
 
 def _conv1d_forward(self, x, segment_pos, cache=None, return_cache=True):
-  cg_layers._forward_only(x, cache)
   mode = cg_layers.get_arith_mode() & _abi.ARITH_FP32
+  if cg_layers._wants_grad(x, cache, self.w, self.b):
+    if cache is not None:
+      raise RuntimeError("Conv1D decode steps (cache given) are forward-only; call under torch.no_grad()")
+    return cg_layers._Conv1DFn.apply(x, self.w, self.b, segment_pos, _abi.MASK_FORK, mode, return_cache)
   with torch.no_grad():
     if cache is not None:
       return _abi.conv1d_decode(x, self.w, self.b, cache,

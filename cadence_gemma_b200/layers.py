@@ -18,7 +18,8 @@ Gradients: ``rnn_scan`` is differentiable --
 its backward is the reverse-time scan kernel ``cg_rnn_scan_bwd`` -- and
 ``RGLRU.forward`` called with grad enabled builds the reference's autograd
 graph (gate math as ATen ops, clipped-sqrt gradient, layers.py:224-238) around
-it, so ``training/train.py`` can run on it.  ``Conv1D`` is forward only.
+it; the ``Conv1D`` prefill is differentiable too (``cg_conv1d_bwd``), so
+``training/train.py`` can run on the kernels.  Decode steps are forward only.
 """
 from __future__ import annotations
 
@@ -82,14 +83,6 @@ def set_fold_gate(enabled: bool) -> bool:
 
 def fold_gate_enabled() -> bool:
   return _fold_gate
-
-
-def _forward_only(*tensors):
-  if torch.is_grad_enabled() and any(
-      t is not None and t.requires_grad for t in tensors):
-    raise RuntimeError(
-        "cadence_gemma_b200 kernels are forward-only; call under "
-        "torch.no_grad() (there is no autograd or eager fallback)")
 
 
 def _wants_grad(*tensors) -> bool:
@@ -334,6 +327,28 @@ class RGLRU(nn.Module):
     return torch.zeros((batch_size, width), dtype=torch.float32, device=device)
 
 
+class _Conv1DFn(torch.autograd.Function):
+  """Conv1D prefill with ``cg_conv1d_bwd`` as its backward.  The returned cache
+  (a copy of the last input rows) is not differentiable."""
+
+  @staticmethod
+  def forward(ctx, x, w, b, segment_pos, mask_mode, arith_mode, return_cache):
+    y, cache = _abi.conv1d_fwd(x, w, b, segment_pos, return_cache=return_cache,
+                               mask_mode=mask_mode, arith_mode=arith_mode)
+    ctx.save_for_backward(x, w, segment_pos)
+    ctx.mask_mode = mask_mode
+    if cache is None:
+      return y, None
+    ctx.mark_non_differentiable(cache)
+    return y, cache
+
+  @staticmethod
+  def backward(ctx, gy, _g_cache):
+    x, w, segment_pos = ctx.saved_tensors
+    dx, dw, db = _abi.conv1d_bwd(gy, x, w, segment_pos, mask_mode=ctx.mask_mode)
+    return dx, dw, db, None, None, None, None
+
+
 class Conv1D(nn.Module):
   """Depth-wise causal temporal convolution (reference layers.py:389-676)."""
 
@@ -365,8 +380,14 @@ class Conv1D(nn.Module):
   def forward_into(self, x, segment_pos, cache=None, return_cache=True, out=None,
                    cache_out=None):
     """``forward`` (prefill) writing into caller-provided buffers."""
-    _forward_only(x, cache)
     mode = _arith_mode & (_abi.ARITH_FP32)
+    if _wants_grad(x, cache, self.w, self.b):
+      # training path: differentiable prefill (temporal width 4); decoding with a
+      # cache is an inference-only operation
+      if cache is not None:
+        raise RuntimeError("Conv1D decode steps (cache given) are forward-only; call under torch.no_grad()")
+      assert out is None and cache_out is None
+      return _Conv1DFn.apply(x, self.w, self.b, segment_pos, self.mask_mode, mode, return_cache)
     with torch.no_grad():
       if cache is not None:
         return _abi.conv1d_decode(x, self.w, self.b, cache,

@@ -81,10 +81,25 @@ def can_overlap(conv, lru, x, conv_cache=None) -> bool:
           layers.uses_fused_kernel(lru, x))
 
 
-@torch.no_grad()
 def recurrent_hot_path(conv, lru, x, segment_pos, conv_cache=None, lru_cache=None,
                        return_cache=True, gate_mul=None, out=None, last_h_out=None,
                        conv_out=None, conv_cache_out=None):
+  """``Conv1D.forward -> RGLRU.forward`` of one recurrent block.  With grad enabled
+  and anything that requires grad this is the differentiable sequence of the two
+  modules (training path); otherwise the inference kernels below."""
+  if layers._wants_grad(x, conv_cache, lru_cache, gate_mul, *conv.parameters(), *lru.parameters()):
+    assert out is None and last_h_out is None and conv_out is None and conv_cache_out is None
+    xc, conv_state = conv(x, segment_pos, conv_cache, return_cache)
+    y, h = lru(xc, segment_pos, lru_cache, return_cache)
+    return (y if gate_mul is None else y * gate_mul), conv_state, h
+  return _recurrent_hot_path_inference(conv, lru, x, segment_pos, conv_cache, lru_cache, return_cache,
+                                       gate_mul, out, last_h_out, conv_out, conv_cache_out)
+
+
+@torch.no_grad()
+def _recurrent_hot_path_inference(conv, lru, x, segment_pos, conv_cache=None, lru_cache=None,
+                                  return_cache=True, gate_mul=None, out=None, last_h_out=None,
+                                  conv_out=None, conv_cache_out=None):
   """Returns ``(y, conv1d_state | None, rg_lru_state | None)``.
 
   ``conv`` / ``lru``: ``Conv1D`` / ``RGLRU`` modules (ours or the reference's
@@ -93,7 +108,6 @@ def recurrent_hot_path(conv, lru, x, segment_pos, conv_cache=None, lru_cache=Non
   only).  ``out`` / ``last_h_out`` / ``conv_out`` / ``conv_cache_out``: optional
   caller-provided buffers.
   """
-  layers._forward_only(x, conv_cache, lru_cache)
   if can_fuse_decode(conv, lru, x, conv_cache):
     # decode step: conv step + gate GEMVs + gates + h = a*h0 + x~ in ONE launch
     bsz = x.shape[0]

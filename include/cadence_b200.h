@@ -145,6 +145,24 @@ int cg_rnn_scan_fwd(const void* x, const void* a, const unsigned char* reset,
                     int arith_mode, cg_stream_t stream);
 
 /*
+ * Backward of the Conv1D prefill (W == 4; other widths: CG_ERR_UNSUPPORTED): the
+ * gradients autograd derives from layers.py:484-546 with the forward's
+ * document mask m_s(t) of tap s at output step t (mask_mode as cg_conv1d_fwd):
+ *     dx[u]   = sum_s w[3-s] * gy[u+s] * m_s(u+s)
+ *     dw[3-s] = sum_{b,t} gy[t] * x[t-s] * m_s(t)          db = sum_{b,t} gy[t]
+ * dx is accumulated in `dtype` in autograd's order (tap 3 first, every product
+ * and sum rounded: bit-exact with the reference); dw / db are summed in fp32 in
+ * a fixed order (bit-reproducible) and rounded once.  gy, x, dx [B,T,E]; w, dw [4,E]; db [E].
+ * workspace: cg_conv1d_bwd_workspace_bytes(B,T,E) bytes, no initialisation needed.
+ * SURVEY.md section 8(f) row F4 (training path).
+ */
+size_t cg_conv1d_bwd_workspace_bytes(int B, int T, int E);
+int cg_conv1d_bwd(const void* gy, const void* x, const void* w, const void* seg,
+                  int seg_is_i64, long long seg_batch_stride, void* dx, void* dw,
+                  void* db, void* workspace, size_t workspace_bytes, int B, int T,
+                  int E, int W, int dtype, int mask_mode, cg_stream_t stream);
+
+/*
  * Backward of rnn_scan: what torch autograd derives from the reference loop
  * (layers.py:173, :187-199) -- SURVEY.md section 8(f) row F4; the JAX VJP
  * jax/pallas.py:785-839 is the same recurrence.  One chunked scan over

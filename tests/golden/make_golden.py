@@ -348,9 +348,54 @@ def make_grads(ref):
       fixture_io.save(f"grad_rglru_{tag}_e{width}_h{heads}_t{steps}_{segkind}", out)
 
 
+def make_grads_block(ref):
+  """Conv1D and whole-RecurrentBlock gradients (autograd through the reference)."""
+  for tag, dtype in DTYPES.items():
+    for steps, width, bsz, segkind in [(33, 64, 3, "ragged"), (5, 32, 2, "halves"), (150, 64, 2, "ragged_pad")]:
+      seed = seed_of("gradconv", tag, steps, segkind)
+      g = gen(seed)
+      torch.manual_seed(seed)
+      conv = ref.layers.Conv1D(width=width, temporal_width=4, dtype=dtype)
+      with torch.no_grad():
+        conv.w.copy_((torch.randn(conv.w.shape, generator=g) * 0.5).to(dtype))
+        conv.b.copy_((torch.randn(conv.b.shape, generator=g) * 0.1).to(dtype))
+      x = torch.randn((bsz, steps, width), generator=g).to(dtype).requires_grad_()
+      seg = {"halves": lambda: halves(steps, bsz), "ragged": lambda: ragged_segments(bsz, steps, seed),
+             "ragged_pad": lambda: ragged_segments(bsz, steps, seed, pad=5)}[segkind]()
+      gy = torch.randn((bsz, steps, width), generator=g).to(dtype)
+      y, _ = conv(x * 1.0, seg)          # a non-leaf: the reference masks its input in place (D2)
+      y.backward(gy)
+      fixture_io.save(f"grad_conv1d_{tag}_t{steps}_{segkind}", dict(
+          w=conv.w.data, b=conv.b.data, x=x, seg=seg, gy=gy, y=y, dx=x.grad, dw=conv.w.grad,
+          db=conv.b.grad))
+    seed = seed_of("gradblock", tag)
+    g = gen(seed)
+    torch.manual_seed(seed)
+    blk = ref.modules.RecurrentBlock(width=64, num_heads=2, lru_width=256,
+                                     conv1d_temporal_width=4, dtype=dtype)
+    with torch.no_grad():
+      for p in (blk.rg_lru.input_gate.b, blk.rg_lru.a_gate.b, blk.conv_1d.b,
+                blk.linear_x.bias, blk.linear_y.bias):
+        p.copy_((torch.randn(p.shape, generator=g) * 0.3).to(dtype))
+      blk.conv_1d.w.copy_((torch.randn(blk.conv_1d.w.shape, generator=g) * 0.4).to(dtype))
+    bsz, steps = 2, 80
+    x = torch.randn((bsz, steps, 64), generator=g).to(dtype).requires_grad_()
+    seg = halves(steps, bsz)
+    gy = torch.randn((bsz, steps, 64), generator=g).to(dtype)
+    y, _ = blk(x, seg)
+    y.backward(gy)
+    out = dict(x=x, seg=seg, gy=gy, y=y, dx=x.grad)
+    for k, v in blk.named_parameters():
+      out["param." + k] = v.data
+      out["grad." + k] = v.grad
+    fixture_io.save(f"grad_recurrent_block_{tag}", out)
+
+
 def main():
   ref = ref_loader.load_reference()
-  if ONLY == ["grad"]:
+  if ONLY == ["gradblock"]:
+    make_grads_block(ref)
+  elif ONLY == ["grad"]:
     make_grads(ref)
   elif ONLY:
     make_rglru(ref)
@@ -362,6 +407,7 @@ def main():
     make_recurrent_block(ref)
     make_griffin_tiny()
     make_grads(ref)
+    make_grads_block(ref)
   total = 0
   for f in sorted(os.listdir(fixture_io.GOLDEN_DIR)):
     if f.endswith(".npz"):

@@ -174,6 +174,94 @@ def test_rglru_training_path_golden(case):
   _close(y2, g["y"], case + " y (no_grad)", min_identical=0.99)
 
 
+@pytest.mark.parametrize("case", fixture_io.cases("grad_conv1d_"))
+def test_conv1d_backward_golden(case):
+  """cg_conv1d_bwd (dx, dw, db) against autograd through the reference Conv1D,
+  fork mask included; second run bit-identical (fixed-order reductions)."""
+  import cadence_gemma_b200 as cg
+  g = fixture_io.load(case)
+  dtype = g["x"].dtype
+  conv = cg.Conv1D(g["x"].shape[-1], 4, device=DEV, dtype=dtype)
+  conv.load_state_dict({"w": g["w"], "b": g["b"]})
+  x = cu(g["x"]).requires_grad_()
+  with torch.enable_grad():
+    y, cache = conv(x, cu(g["seg"]))
+    assert not cache.requires_grad
+    y.backward(cu(g["gy"]))
+  assert_bitexact(y.detach().cpu(), g["y"], case + " y")
+  bf = dtype == torch.bfloat16
+  assert_bitexact(x.grad.cpu(), g["dx"], case + " dx")        # autograd's bf16 / fp32 accumulation order
+  for got, key in ((conv.w.grad, "dw"), (conv.b.grad, "db")):
+    if bf:
+      assert_close_bf16(got.cpu(), g[key], f"{case} {key}", min_identical=0.9)
+    else:
+      assert_close_f32(got.cpu(), g[key], f"{case} {key}", tol=2e-5)
+  abi = _abi()
+  r1 = abi.conv1d_bwd(cu(g["gy"]), x.detach(), conv.w.detach(), cu(g["seg"]))
+  r2 = abi.conv1d_bwd(cu(g["gy"]), x.detach(), conv.w.detach(), cu(g["seg"]))
+  assert all(torch.equal(u, v) for u, v in zip(r1, r2))
+
+
+@pytest.mark.parametrize("mask_mode", [0, 1])
+def test_conv1d_backward_full_size_vs_torch_autograd(mask_mode):
+  """Config-2 sized Conv1D backward against torch autograd over an fp32
+  restatement of the masked convolution on the device (both mask modes)."""
+  abi = _abi()
+  torch.manual_seed(21)
+  bsz, steps, width = 4, 2048, 2560
+  x = torch.randn(bsz, steps, width, device=DEV).bfloat16()
+  gy = torch.randn(bsz, steps, width, device=DEV).bfloat16()
+  w = (torch.randn(4, width, device=DEV) * 0.5).bfloat16()
+  seg = torch.arange(steps, device=DEV, dtype=torch.int32)[None].repeat(bsz, 1)
+  for b in range(bsz):
+    cut = 100 + 333 * b
+    seg[b, cut:] -= cut
+    seg[b, cut + 1] = 0                           # adjacent document starts
+  dx, dw, db = abi.conv1d_bwd(gy, x, w, seg, mask_mode=mask_mode)
+  xf = x.float().requires_grad_()
+  wf = w.float().requires_grad_()
+  nz = (seg != 0)
+  with torch.enable_grad():
+    y = torch.zeros(bsz, steps, width, device=DEV)
+    for s in range(4):
+      xs = torch.nn.functional.pad(xf, (0, 0, s, 0))[:, :steps]
+      m = torch.ones(bsz, steps, dtype=torch.bool, device=DEV)
+      lo = 1 if mask_mode == 1 else 3              # fork: only tap 3 looks at seg[t-2]
+      if s >= lo:
+        for j in ((range(1, s + 1)) if mask_mode == 1 else [1]):
+          # seg[t - s + j] != 0
+          shifted = torch.nn.functional.pad(nz, (s - j, 0), value=True)[:, :steps]
+          m = m & shifted
+      y = y + xs * wf[3 - s] * m[..., None]
+    y.backward(gy.float())
+  assert_close_bf16(dx.cpu(), xf.grad.bfloat16().cpu(), "dx", min_identical=0.5)   # bf16 accumulation vs fp32
+  assert normwise(dw.float(), wf.grad) <= 1e-2
+  assert normwise(db.float(), gy.float().sum((0, 1))) <= 1e-2
+
+
+@pytest.mark.parametrize("case", fixture_io.cases("grad_recurrent_block_"))
+def test_recurrent_block_training_golden(case):
+  """One training step's gradients through the RecurrentBlock mirror (linear_x /
+  linear_y / linear_out by cuBLAS autograd, Conv1D and the scan by our backward
+  kernels) against the reference block's autograd."""
+  from cadence_gemma_b200.modules import RecurrentBlock
+  g = fixture_io.load(case)
+  dtype = g["x"].dtype
+  blk = RecurrentBlock(width=64, num_heads=2, lru_width=256, conv1d_temporal_width=4,
+                       device=DEV, dtype=dtype)
+  blk.load_state_dict({k[6:]: v for k, v in g.items() if k.startswith("param.")})
+  x = cu(g["x"]).requires_grad_()
+  with torch.enable_grad():
+    y, _ = blk(x, cu(g["seg"]))
+    y.backward(cu(g["gy"]))
+  bf = dtype == torch.bfloat16
+  assert normwise(y.detach().float().cpu(), g["y"].float()) <= (2e-2 if bf else 2e-5)
+  assert normwise(x.grad.float().cpu(), g["dx"].float()) <= (5e-2 if bf else 5e-5)
+  for name, prm in blk.named_parameters():
+    nw = normwise(prm.grad.float().cpu(), g["grad." + name].float())
+    assert nw <= (8e-2 if bf else 2e-4), (case, name, nw)
+
+
 # -------------------------------------------------------------------- conv1d
 @pytest.mark.parametrize("case", fixture_io.cases("conv1d_"))
 def test_conv1d_golden(case):
