@@ -190,7 +190,10 @@ int cg_conv1d_fwd(const void* x, const void* w, const void* b, const void* seg, 
 
 namespace {
 constexpr int kConvBwdLC = 4;
-inline int conv_bwd_tblocks(int T) { return ((T + kConvBwdLC - 1) / kConvBwdLC + 15) / 16; }
+inline int conv_bwd_tblocks(int T) {      // CTAs along time: kConvBwdSpan blocks of 16 slots x LC steps each
+  const int blocks = ((T + kConvBwdLC - 1) / kConvBwdLC + 15) / 16;
+  return (blocks + cg::kConvBwdSpan - 1) / cg::kConvBwdSpan;
+}
 }  // namespace
 
 size_t cg_conv1d_bwd_workspace_bytes(int B, int T, int E) {

@@ -186,6 +186,8 @@ conv1d_w4_stream_kernel(const ConvParams p, int* flags, int ctiles, int tgroups)
 // in a fixed order (registers -> shared memory over the block's 16 time slots
 // -> one partial row per block -> conv1d_bwd_reduce_kernel): bit-reproducible.
 // ---------------------------------------------------------------------------
+constexpr int kConvBwdSpan = 8;
+
 struct ConvBwdParams {
   const void* gy;     // [B,T,E]
   const void* x;      // [B,T,E] forward input
@@ -220,18 +222,21 @@ conv1d_w4_bwd_kernel(const ConvBwdParams p) {
   __shared__ float red[16][kCvl][5 * V + 1];
   const int cv = threadIdx.x & 7;
   const int slot = threadIdx.x >> 3;
-  const int tslot = blockIdx.y * 16 + slot;
   const int b = blockIdx.z;
   const int ch0 = blockIdx.x * EC + cv * V;
-  const int t0 = tslot * LC;
-  const bool live = ch0 < p.E && t0 < p.T;
   float acc[5][V];
 #pragma unroll
   for (int k = 0; k < 5; ++k)
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[k][i] = 0.0f;
 
-  if (live) {
+  // kConvBwdSpan consecutive time blocks (16 slots x LC steps each) per CTA: the
+  // parameter-gradient partials stay in registers across them
+#pragma unroll 1
+  for (int q = 0; q < kConvBwdSpan; ++q) {
+    const int tslot = (blockIdx.y * kConvBwdSpan + q) * 16 + slot;
+    const int t0 = tslot * LC;
+    if (ch0 >= p.E || t0 >= p.T) break;
     const IO* gb = reinterpret_cast<const IO*>(p.gy) + (size_t)b * p.T * p.E + ch0;
     const IO* xb = reinterpret_cast<const IO*>(p.x) + (size_t)b * p.T * p.E + ch0;
     IO* dxb = reinterpret_cast<IO*>(p.dx) + (size_t)b * p.T * p.E + ch0;

@@ -92,6 +92,7 @@ class HostPrefill:
     g.replay()
     return y_host
 
+  @torch.no_grad()
   def submit(self, x_host, seg_host, y_host, h_host=None, cache_host=None):
     """Streaming form of ``__call__`` for back-to-back batches: enqueues the
     batch on the three pipeline streams WITHOUT joining them with the caller's

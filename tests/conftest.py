@@ -22,3 +22,13 @@ def pytest_collection_modifyitems(config, items):
   for item in items:
     if "gpu" in item.keywords:
       item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _inference_by_default():
+  """Parity tests exercise the inference kernels: autograd is off unless a test
+  turns it on (``torch.enable_grad()``) -- with grad enabled the modules take
+  their differentiable training path instead."""
+  import torch
+  with torch.no_grad():
+    yield

@@ -62,12 +62,13 @@ def test_shims_mirror_reference_api_and_have_no_cpu_fallback():
         call()
   # training path: still no CPU fallback; decode steps stay forward-only
   xg = torch.randn(1, 8, 64, requires_grad=True)
-  with pytest.raises(RuntimeError, match="no CPU"):
-    conv(xg, seg)
-  with pytest.raises(RuntimeError, match="no CPU"):
-    lru(xg, seg)
-  with pytest.raises(RuntimeError, match="forward-only"):
-    conv(xg[:, :1], seg[:, :1], torch.zeros(1, 3, 64))
+  with torch.enable_grad():
+    with pytest.raises(RuntimeError, match="no CPU"):
+      conv(xg, seg)
+    with pytest.raises(RuntimeError, match="no CPU"):
+      lru(xg, seg)
+    with pytest.raises(RuntimeError, match="forward-only"):
+      conv(xg[:, :1], seg[:, :1], torch.zeros(1, 3, 64))
 
 
 def test_recurrent_block_mirror_state_dict_keys():

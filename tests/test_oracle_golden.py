@@ -42,8 +42,9 @@ def test_rnn_scan_gradients(case):
   x = g["x"].clone().requires_grad_()
   a = g["a"].clone().requires_grad_()
   h0 = g["h0"].clone().requires_grad_() if "h0" in g else None
-  y, h = torch_port.rnn_scan(x, a, g["reset"], h0)
-  torch.autograd.backward([y, h], [g["gy"], g["gh"]])
+  with torch.enable_grad():
+    y, h = torch_port.rnn_scan(x, a, g["reset"], h0)
+    torch.autograd.backward([y, h], [g["gy"], g["gh"]])
   assert_bitexact(x.grad, g["dx"], case + " dx")
   if "da" in g:
     assert_bitexact(a.grad, g["da"], case + " da")
