@@ -334,8 +334,11 @@ def own_arm(args, dtype):
     launches0 = _abi.launch_count
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
-    for _ in range(args.steps):
-      out = step(x_dev, seg_dev, record=True)
+    # per-kernel CUDA events bracket every CG_BENCH_EVENT_EVERY-th step of the timed
+    # region (each bracket costs ~1-2 us of stream time, so not every step)
+    ev_every = max(1, min(args.steps, int(os.environ.get("CG_BENCH_EVENT_EVERY", "5"))))
+    for i in range(args.steps):
+      out = step(x_dev, seg_dev, record=(i % ev_every == ev_every // 2))
     if world > 1:
       torch.cuda.current_stream().wait_stream(comm_stream)
     t_end.record()

@@ -512,7 +512,21 @@ int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int g
   // one persistent CTA per SM; grid_limit > 0 (test hook) runs with fewer CTAs than
   // column families, which exercises the family loop (weight reload) of a CTA
   const int grid = grid_limit > 0 && grid_limit < sms ? grid_limit : sms;
-  kernel<<<grid, cg::fused::kThreads, Cfg::kSmemBytes, stream>>>(tmap, p);
+  // programmatic dependent launch behind the prologue kernel (see the
+  // griddepcontrol.wait in the epilogue warps): set-up and operand loads start
+  // while the prologue is still running
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(cg::fused::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmap, p);
+  if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();
 }
 
@@ -591,7 +605,19 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
     q.reset_bits = ws_min.reset_bits;
     q.rows = seg_batch_stride == 0 ? 1 : B; q.T = T; q.words_per_row = words;
     const int n = E > q.rows * words * 32 ? E : q.rows * words * 32;
-    cg::scan_prologue_kernel<<<(n + 127) / 128, 128, 0, stream>>>(q);
+    // programmatic dependent of whatever precedes it on the stream: behind our
+    // Conv1D kernel (which triggers early) it runs under that kernel's tail; it
+    // reads nothing the convolution writes and does not complete before it
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((n + 127) / 128);
+    cfg.blockDim = dim3(128);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaError_t err = cudaLaunchKernelEx(&cfg, cg::scan_prologue_kernel, q)) return (int)err;
     if (cudaError_t err = cudaGetLastError()) return (int)err;
   }
   EncodeTiledFn encode = encode_tiled_fn();

@@ -148,6 +148,10 @@ __device__ __forceinline__ void conv1d_w4_tile(const ConvParams& p, int ctile, i
 template <typename IO, bool EMUL, int LC>
 __global__ void __launch_bounds__(128)
 conv1d_w4_kernel(const ConvParams p) {
+  // programmatic dependent launch: once every block of this grid has started, a
+  // PDL consumer (the RG-LRU prologue, then the fused kernel's set-up) may begin;
+  // consumers order themselves after this grid's stores with griddepcontrol.wait
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   conv1d_w4_tile<IO, EMUL, LC, false>(p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 

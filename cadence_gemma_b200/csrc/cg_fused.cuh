@@ -258,8 +258,25 @@ __device__ __forceinline__ uint32_t ld_u16(const uint16_t* p) {
   asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
   return v;
 }
+// y stores.  CGF_YST: 0 = default policy, 1 = .cs (streaming / evict-first), 2 = .wt
+// (write-through), 3 = L2::evict_first cache-hint policy.  The 84 MB of y a
+// config-2 launch writes would otherwise sit dirty in the 126 MB L2 and be
+// written back under the NEXT kernel, which then pays for it.
+#ifndef CGF_YST
+#define CGF_YST 0   // measured: no policy changes the step time (149-153 us for all four)
+#endif
 __device__ __forceinline__ void st_u16(uint16_t* p, uint32_t v) {
+#if CGF_YST == 1
+  asm volatile("st.global.cs.u16 [%0], %1;" :: "l"(p), "h"(static_cast<uint16_t>(v)) : "memory");
+#elif CGF_YST == 2
+  asm volatile("st.global.wt.u16 [%0], %1;" :: "l"(p), "h"(static_cast<uint16_t>(v)) : "memory");
+#elif CGF_YST == 3
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" :: "l"(p), "h"(static_cast<uint16_t>(v)), "l"(pol) : "memory");
+#else
   asm volatile("st.global.u16 [%0], %1;" :: "l"(p), "h"(static_cast<uint16_t>(v)) : "memory");
+#endif
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -415,6 +432,10 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
             bulk_load(sI + off, p.ident + off, kKBlockBytes, w_full);
         }
         __syncwarp();
+        // x is written by the kernel(s) before the prologue in stream order; as a
+        // programmatic dependent this grid may be running before they are done.
+        // The weights above do not depend on them, the X boxes below do.
+        if (witer == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
         ++witer;
         const int c_head = (fam / CBS) * (KB * 64);
 #pragma unroll 1
@@ -525,6 +546,10 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     //          my TMEM state columns; the slot goes back to the MMA warp half way
     //          through, so the MMAs of the pair's next tile run under G and F;
     //          publish the tile's aggregate.
+    // The launch is a programmatic dependent of the prologue kernel (epoch bump,
+    // -8*softplus, reset bitmask): barrier / TMEM set-up above and the producer's
+    // weight and X loads overlap the prologue; its outputs are read only below.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int wg = warp >> 2;
     const uint32_t pr = wg >> 1, hf = wg & 1;
     const int chl = (warp & 3) * 32 + lane;           // TMEM lane = channel inside the column

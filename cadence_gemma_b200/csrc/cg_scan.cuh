@@ -808,6 +808,10 @@ struct PrologueParams {
 };
 
 __global__ void scan_prologue_kernel(const PrologueParams q) {
+  // programmatic dependent launch: a consumer launched with the PDL attribute
+  // (the fused RG-LRU kernel) may start its own set-up now; it orders itself
+  // after this grid's writes with griddepcontrol.wait.  No-op otherwise.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && q.counter != nullptr) { *q.counter = 0; *q.epoch = *q.epoch + 1u; }
   if (q.a_param != nullptr && i < q.E) {
@@ -831,6 +835,11 @@ __global__ void scan_prologue_kernel(const PrologueParams q) {
     const unsigned bits = __ballot_sync(0xffffffffu, rs);
     if ((threadIdx.x & 31) == 0) q.reset_bits[r * q.words_per_row + (t >> 5)] = bits;
   }
+  // When launched as a programmatic dependent (fused path) this grid may have run
+  // under the tail of its predecessor (the Conv1D kernel, whose output it does
+  // not read).  It must not COMPLETE before the predecessor has: the fused kernel
+  // takes "prologue complete" to mean "x complete".  No-op for a plain launch.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------
