@@ -42,6 +42,7 @@ SYMBOLS = {
     "cg_rglru_gate_pack_bytes": (_sz, [_i, _i]),
     "cg_rglru_pack_gate_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "cg_rglru_fused_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cg_rglru_fused_schedule": (_i, [_i, _i, _i, _i, _i, _vp, _i]),
     "cg_rglru_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp,
                                 _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "cg_recurrent_decode_supported": (_i, [_i, _i, _i, _i]),

@@ -569,6 +569,19 @@ int cg_rglru_pack_gate_weights(const void* wx, const void* wa, void* wpack, int 
   return (int)cudaGetLastError();
 }
 
+int cg_rglru_fused_schedule(int ctas, int families, int pairs, int cta, int balance, int* segments,
+                            int max_segments) {
+  if (ctas < 1 || families < 1 || pairs < 0 || cta < 0 || cta >= ctas) return CG_ERR_SHAPE;
+  const cg::fused::Schedule sched(cta, ctas, families, pairs, balance < 0 ? CGF_BALANCE != 0 : balance != 0);
+  const int n = sched.nseg();
+  for (int i = 0; i < n && i < max_segments && segments != nullptr; ++i) {
+    const cg::fused::Seg sg = sched.get(i);
+    segments[4 * i] = sg.fam; segments[4 * i + 1] = sg.j0;
+    segments[4 * i + 2] = sg.stride; segments[4 * i + 3] = sg.count;
+  }
+  return n;
+}
+
 size_t cg_rglru_fused_workspace_bytes(int B, int T, int E) {
   if (B < 1 || T < 1 || E < 1) return 0;
   return carve(nullptr, B, T, E, cg::fused::kMch, cg::fused::kTile).total;

@@ -355,6 +355,101 @@ __global__ void pack_gate_weights_kernel(const uint16_t* __restrict__ wx, const 
 
 
 // ---------------------------------------------------------------------------
+// Work schedule, identical in every role of a CTA.  The ticket pairs (= MMA
+// tiles) of a family are numbered j = 0 .. npairs-1 in time-major order; a CTA
+// works through SEGMENTS (family, first pair, stride, count), in order, and
+// reloads the gate weights when the family changes.
+//   G < families           CTA i takes families i, i+G, ... completely (test hook)
+//   G = d * families       d CTAs per family share its pairs round-robin
+//   G = d * families + r   (148 SMs, 20 families: d = 7, r = 8): round-robin with d or
+//       d + 1 CTAs per family, or, with CGF_BALANCE:
+//       d dedicated CTAs per family plus r FLOATERS.  The pair sequence of every
+//       family is cut into S equal parts; in h of them a floater joins as member
+//       d + 1 (S = families / gcd, h = r / gcd).  Floater k spends its s-th part
+//       on family (k*S + s) / h, so every CTA gets ~npairs * families / G pairs
+//       instead of npairs / d on the d-CTA families and npairs / (d+1) on the
+//       others (-5 % on the critical path at config 2).  Every CTA visits the
+//       parts in increasing order and a floater's part index equals the family's
+//       part index, so all look-back dependencies point to work that is running
+//       or done: no cycles.
+// ---------------------------------------------------------------------------
+// Measured (config 2, A/B in one run): 116 us balanced vs 105.6 us round-robin.
+// The floater couples the families it visits: a family helped in part q reaches
+// part q+1 earlier than the family the floater goes to next, the round-robin
+// chain of the new family cannot pass the floater's pairs, and the lags add up.
+// Kept (off) with its coverage test; row-disjoint shares are the next thing to try.
+#ifndef CGF_BALANCE
+#define CGF_BALANCE 0
+#endif
+struct Seg { int fam, j0, stride, count; };
+struct Schedule {
+  int mode;        // 0 = whole families, 1 = round-robin, 2 = balanced with floaters
+  int cta, G, nfam, npairs;
+  int d, S, h;     // mode 2
+  __host__ __device__ __forceinline__ static int gcd(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+  __host__ __device__ __forceinline__ Schedule(int cta_, int G_, int nfam_, int npairs_,
+                                              bool balance = CGF_BALANCE != 0)
+      : cta(cta_), G(G_), nfam(nfam_), npairs(npairs_), d(0), S(1), h(0) {
+    if (G < nfam) { mode = 0; return; }
+    mode = 1;
+    d = G / nfam;
+    const int r = G - d * nfam;
+    if (balance && r != 0) {
+      const int g = gcd(nfam, r);
+      S = nfam / g; h = r / g;
+      if (npairs >= 2 * S * (d + 1)) mode = 2;
+    }
+  }
+  __host__ __device__ __forceinline__ int nseg() const {
+    if (mode == 0) return cta < nfam ? (nfam - 1 - cta) / G + 1 : 0;
+    return mode == 1 ? 1 : S;
+  }
+  __host__ __device__ __forceinline__ static int count_from(int j0, int end, int stride) {
+    return j0 < end ? (end - j0 + stride - 1) / stride : 0;
+  }
+  __host__ __device__ __forceinline__ Seg get(int s) const {
+    Seg sg;
+    if (mode == 0) {
+      sg.fam = cta + s * G; sg.j0 = 0; sg.stride = 1; sg.count = npairs;
+    } else if (mode == 1) {
+      sg.fam = cta % nfam;
+      const int rank = cta / nfam;
+      sg.stride = (G - 1 - sg.fam) / nfam + 1;
+      sg.j0 = rank;
+      sg.count = count_from(rank, npairs, sg.stride);
+    } else {
+      const int b0 = (int)((long long)s * npairs / S), b1 = (int)((long long)(s + 1) * npairs / S);
+      if (cta < nfam * d) {                          // dedicated: member `rank` of its family
+        sg.fam = cta % nfam;
+        const int rank = cta / nfam;
+        // is a floater with this family in part q?  family f owns global slices [f*h, f*h + h)
+        auto members = [&](int q) {
+          bool helped = false;
+          for (int u = sg.fam * h; u < sg.fam * h + h; ++u) helped = helped || (u % S == q);
+          return d + (helped ? 1 : 0);
+        };
+        // the members that get one pair more than the others in a part (its length
+        // is not a multiple of the member count) rotate from part to part
+        int start = 0;
+        for (int q = 0; q < s; ++q) {
+          const int len = (int)((long long)(q + 1) * npairs / S) - (int)((long long)q * npairs / S);
+          start += len % members(q);
+        }
+        sg.stride = members(s);
+        sg.j0 = b0 + ((rank - start) % d + d) % d;
+      } else {                                       // floater: member d of family (k*S + s) / h
+        const int k = cta - nfam * d;
+        sg.fam = (k * S + s) / h;
+        sg.stride = d + 1;
+        sg.j0 = b0 + d;
+      }
+      sg.count = count_from(sg.j0, b1, sg.stride);
+    }
+    return sg;
+  }
+};
+
+// ---------------------------------------------------------------------------
 // The fused kernel.  KB = head width / 64 (K blocks of the gate GEMMs).
 // ---------------------------------------------------------------------------
 // (registers are allocated in units of four warps: 18 warps count as 20, which
@@ -399,27 +494,26 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
 
-  // family schedule of this CTA (identical in every role).  Tiles of a family
-  // are ticketed time-major (ticket = tt * B + b) and handed out two at a time:
-  // ticket pair j -> CTA (j % nc) of the family, as its MMA tile number j / nc.
-  const int G = gridDim.x, nfam = p.families;
-  const bool spread = G >= nfam;                  // several CTAs share one family
-  const int fam_step = spread ? nfam : G;
-  const int rank = spread ? blockIdx.x / nfam : 0;
+  // work schedule of this CTA (identical in every role), see Schedule above.
+  // Ticket = tt * B + b (time-major); pair j = tickets 2j, 2j + 1 = one MMA tile.
+  const int nfam = p.families;
   const int ntiles = p.ntt * p.B;
   const int npairs = (ntiles + 1) >> 1;
-  auto family_ctas = [&](int fam) { return spread ? (G - 1 - fam) / nfam + 1 : 1; };
-  auto my_mma_tiles = [&](int nc) { return rank < npairs ? (npairs - rank + nc - 1) / nc : 0; };
+  const Schedule sched(blockIdx.x, gridDim.x, nfam, npairs);
+  const int nsegs = sched.nseg();
 
   if (warp == kEpiWarps) {
     // ===================================================== TMA producer
     {
       uint32_t mq = 0, witer = 0;
       int tn = 0; (void)tn;
-      for (int fam = blockIdx.x % nfam; fam < nfam; fam += fam_step) {
-        const int nc = family_ctas(fam);
-        const int nm = my_mma_tiles(nc);
-        if (nm == 0) continue;
+      int cur_fam = -1;
+      for (int sgi = 0; sgi < nsegs; ++sgi) {
+        const Seg sg = sched.get(sgi);
+        if (sg.count == 0) continue;
+        const int fam = sg.fam;
+        if (fam != cur_fam) {
+        cur_fam = fam;
         if (witer > 0) mbar_wait(w_empty, (witer - 1) & 1, p.err, 1);
         const unsigned char* wsrc = p.wpack + (size_t)fam * Cfg::kWBytes;
         if (elect_one()) {
@@ -437,10 +531,11 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         // The weights above do not depend on them, the X boxes below do.
         if (witer == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
         ++witer;
+        }
         const int c_head = (fam / CBS) * (KB * 64);
 #pragma unroll 1
-        for (int m = 0; m < nm; ++m, ++mq) {
-          const int t1st = 2 * (rank + m * nc);
+        for (int m = 0; m < sg.count; ++m, ++mq) {
+          const int t1st = 2 * (sg.j0 + m * sg.stride);
           const int nhalf = t1st + 1 < ntiles ? 2 : 1;
           const uint32_t stage = mq & 1u, use = mq >> 1;
           CGF_EVENT(0, 1);
@@ -486,14 +581,24 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     {
       uint32_t mq = 0, witer = 0;
       int tn = 0; (void)tn;
-      for (int fam = blockIdx.x % nfam; fam < nfam; fam += fam_step) {
-        const int nm = my_mma_tiles(family_ctas(fam));
-        if (nm == 0) continue;
+      int cur_fam = -1;
+      for (int sgi = 0; sgi < nsegs; ++sgi) {
+        const Seg sg = sched.get(sgi);
+        if (sg.count == 0) continue;
+        const int fam = sg.fam;
+        if (fam != cur_fam) {
+          if (cur_fam >= 0) {                            // the old family's weights may be overwritten
+            if (elect_one()) umma_commit(w_empty);
+            __syncwarp();
+          }
+          cur_fam = fam;
+          mbar_wait(w_full, witer & 1, p.err, 3);
+          tc_fence_after();
+          ++witer;
+        }
         const int cb = fam % CBS;
-        mbar_wait(w_full, witer & 1, p.err, 3);
-        tc_fence_after();
 #pragma unroll 1
-        for (int m = 0; m < nm; ++m, ++mq) {
+        for (int m = 0; m < sg.count; ++m, ++mq) {
           const uint32_t pr = mq & 1u, use = mq >> 1;      // warpgroup pair == X stage
           CGF_EVENT(1, 1);
           mbar_wait(x_full + pr, use & 1, p.err, 4);
@@ -529,9 +634,6 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           __syncwarp();
           CGF_EVENT(1, 4);
         }
-        if (elect_one()) umma_commit(w_empty);
-        __syncwarp();
-        ++witer;
       }
     }
     __syncwarp();
@@ -716,20 +818,25 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       return (pd.on && pd.tt > 0) ? ld_relaxed_u64(p.pref + pd.widx - wstep) : 0ull;
     };
 
-    for (int fam = blockIdx.x % nfam; fam < nfam; fam += fam_step) {
-      const int nc = family_ctas(fam);
-      const int nm = my_mma_tiles(nc);
-      if (nm == 0) continue;
-      const int ch = fam * kMch + chl;
-      uint32_t bx2 = 0, ba2 = 0;
-      if (p.bias_x != nullptr) { const uint32_t v = p.bias_x[ch]; bx2 = v | (v << 16); }
-      if (p.bias_a != nullptr) { const uint32_t v = p.bias_a[ch]; ba2 = v | (v << 16); }
-      uint32_t sp2 = p.neg8sp_bf[ch]; sp2 |= sp2 << 16;
+    int cur_fam = -1, ch = 0;
+    uint32_t bx2 = 0, ba2 = 0, sp2 = 0;
+    for (int sgi = 0; sgi < nsegs; ++sgi) {
+      const Seg sg = sched.get(sgi);
+      if (sg.count == 0) continue;
+      const int fam = sg.fam;
+      if (fam != cur_fam) {                                // per-channel constants of the new family
+        cur_fam = fam;
+        ch = fam * kMch + chl;
+        bx2 = 0; ba2 = 0;
+        if (p.bias_x != nullptr) { const uint32_t v = p.bias_x[ch]; bx2 = v | (v << 16); }
+        if (p.bias_a != nullptr) { const uint32_t v = p.bias_a[ch]; ba2 = v | (v << 16); }
+        sp2 = p.neg8sp_bf[ch]; sp2 |= sp2 << 16;
+      }
 #pragma unroll 1
-      for (int m = 0; m < nm; ++m, ++mq) {
+      for (int m = 0; m < sg.count; ++m, ++mq) {
         if ((mq & 1u) != pr) continue;
         const uint32_t use = mq >> 1;
-        const int ticket = 2 * (rank + m * nc) + (int)hf;
+        const int ticket = 2 * (sg.j0 + m * sg.stride) + (int)hf;
         if (twarp) CGF_EVENT(trole, 8);
         const unsigned long long early = request_pred();
         if (twarp) CGF_EVENT(trole, 1);

@@ -222,6 +222,14 @@ int cg_rglru_fused_supported(int E, int H, int dtype);
 size_t cg_rglru_gate_pack_bytes(int E, int H);
 int cg_rglru_pack_gate_weights(const void* wx, const void* wa, void* wpack,
                                int E, int H, int dtype, cg_stream_t stream);
+/* Introspection (host only, no GPU needed): the work schedule the fused kernel
+ * uses for a grid of `ctas` CTAs, `families` 128-channel families and `pairs`
+ * MMA tiles per family.  balance: 1 = with floater CTAs, 0 = plain round-robin,
+ * -1 = what the kernel was built to use.  Writes up to max_segments rows
+ * {family, first pair, stride, count} of CTA `cta` and returns its number of
+ * segments (tests check that every pair is covered exactly once). */
+int cg_rglru_fused_schedule(int ctas, int families, int pairs, int cta, int balance,
+                            int* segments, int max_segments);
 size_t cg_rglru_fused_workspace_bytes(int B, int T, int E);
 int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x,
                        const void* bias_a, const void* a_param, const void* seg,

@@ -101,3 +101,47 @@ def test_install_patches_reference_entry_points():
   finally:
     install.uninstall()
   assert (ref.layers.rnn_scan, ref.layers.RGLRU.forward, ref.layers.Conv1D.forward) == orig
+
+
+@pytest.mark.parametrize("ctas,families,pairs", [
+    (148, 20, 256),    # config 2: 7 dedicated CTAs per family + 8 floaters
+    (148, 20, 384),    # config 3 (B=32, T=768)
+    (148, 20, 2048),   # config 4 (B=16, T=8192)
+    (148, 20, 37),     # too few pairs to balance: plain round-robin
+    (148, 8, 300),     # 18 per family + 4 floaters, S = 2
+    (148, 4, 64),      # divides evenly
+    (132, 20, 256),    # another SM count
+    (3, 20, 10),       # fewer CTAs than families (test hook): whole families
+    (148, 32, 501),    # 9B shape (E = 4096), odd pair count
+])
+@pytest.mark.parametrize("balance", [0, 1, -1])
+def test_fused_schedule_covers_every_pair_once_and_is_balanced(ctas, families, pairs, balance):
+  """The fused kernel's work schedule (floater CTAs when the SM count is not a
+  multiple of the family count), evaluated on the host through the C ABI."""
+  import ctypes
+  from cadence_gemma_b200 import _abi
+  lib = _abi.load()
+  seen = [[0] * pairs for _ in range(families)]
+  load = []
+  for cta in range(ctas):
+    buf = (ctypes.c_int * (4 * 64))()
+    n = lib.cg_rglru_fused_schedule(ctas, families, pairs, cta, balance, ctypes.cast(buf, ctypes.c_void_p), 64)
+    assert 0 <= n <= 64
+    total, last = 0, (-1, -1)
+    for i in range(n):
+      fam, j0, stride, count = buf[4 * i:4 * i + 4]
+      assert 0 <= fam < families and stride >= 1 and count >= 0
+      for m in range(count):
+        j = j0 + m * stride
+        assert 0 <= j < pairs
+        seen[fam][j] += 1
+      if count:
+        # a CTA moves forward in time inside a family; it never returns to a family it left
+        assert (fam, j0) > last or fam != last[0]
+        last = (fam, j0 + (count - 1) * stride)
+      total += count
+    load.append(total)
+  assert all(c == 1 for row in seen for c in row)
+  if ctas >= families and balance == 1:
+    ideal = families * pairs / ctas
+    assert max(load) <= ideal + 3 or pairs < 80, (max(load), ideal)
