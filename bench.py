@@ -444,7 +444,8 @@ def own_arm(args, dtype):
                      "algorithmic_bytes_note": ("SURVEY 8(d) K2 figure: 4 x 2 B per element (x, pre_x, pre_a "
                                                 "in, y out).  The fused kernel keeps pre_x / pre_a in TMEM, "
                                                 "so it moves only about half of that (see `traffic`) and is "
-                                                "bound by the MUFU / issue rate of the gate math, not HBM"
+                                                "bound by the instruction issue rate of the epilogue (gate math + scan, "
+                                                "51 instructions per element; ablations in DESIGN.md section 9), not HBM"
                                                 if fused else "SURVEY 8(d) K2 figure: 4 x s bytes per element"),
                      "us_per_launch": k2_mean_us, "traffic": NCU_TRAFFIC_BYTES if fused else None},
         "kernels_us": ({"conv1d": conv_us, "rglru_fused_tcgen05": k2_mean_us} if fused else
