@@ -230,7 +230,9 @@ def own_arm(args, dtype):
     # and keep NCCL's footprint on the SMs (shared with the kernels) small
     if os.environ.get("CG_BENCH_NCCL_CHANNELS", "2") != "0":
       os.environ.setdefault("NCCL_MAX_NCHANNELS", os.environ.get("CG_BENCH_NCCL_CHANNELS", "2"))
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    # fail fast: a collective that does not complete is an error here, not a 10 minute wait
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
   _abi.load()
 
   w = WORKLOAD
@@ -263,7 +265,7 @@ def own_arm(args, dtype):
     e.record()
     return e
 
-  def step(x, seg, record=False):
+  def step(x, seg, record=False, gather=True):
     if record:   # same calls as the module API makes, with events between the kernels
       e0 = ev()
       xc, conv_state = conv(x, seg)
@@ -286,7 +288,7 @@ def own_arm(args, dtype):
       xc, conv_state = conv(x, seg)
       y, last_h = lru(xc, seg)
     step_no[0] += 1
-    if world > 1 and GATHER_EVERY > 0 and step_no[0] % GATHER_EVERY == 0:
+    if gather and world > 1 and GATHER_EVERY > 0 and step_no[0] % GATHER_EVERY == 0:
       # merged cache for the host: one all-gather of the small per-row states
       # per model prefill (18 recurrent blocks), on a side stream
       gather_in[: last_h.numel()].copy_(last_h.view(-1))
@@ -313,8 +315,10 @@ def own_arm(args, dtype):
     ramp_ms = float(os.environ.get("CG_BENCH_RAMP_MS", "400"))
     t_ramp = time.perf_counter()
     while (time.perf_counter() - t_ramp) * 1e3 < ramp_ms:
+      # wall-clock bounded, so the ranks run DIFFERENT numbers of these steps: no
+      # collective inside (a gather here once left two ranks in different collectives)
       for _ in range(20):
-        out = step(x_dev, seg_dev)
+        out = step(x_dev, seg_dev, gather=False)
       torch.cuda.synchronize()
     if world > 1:
       # exercise the whole gather path once outside the timed region: NCCL sets
