@@ -458,8 +458,16 @@ int cg_rnn_scan_bwd(const void* gy, const float* g_last_h, const void* a, const 
     if (cudaError_t err = cudaGetLastError()) return (int)err;
     p.reset_bits = ws_min.reset_bits; p.bits_bstride = words;
   }
-  return bf ? launch_scan<uint16_t, 2, 0, 8, 4, 1, 3>(p, workspace, workspace_bytes, stream)
-            : launch_scan<float, 2, 1, 8, 4, 1, 3>(p, workspace, workspace_bytes, stream);
+  // geometry (steps per lane, warps per CTA, stages, min CTAs / SM), see dispatch_geometry
+#ifndef CG_BWD_L
+#define CG_BWD_L 8
+#define CG_BWD_NW 4
+#define CG_BWD_ST 1
+#define CG_BWD_MINB 3
+#endif
+#define CG_BWD_GEOM CG_BWD_L, CG_BWD_NW, CG_BWD_ST, CG_BWD_MINB
+  return bf ? launch_scan<uint16_t, 2, 0, CG_BWD_GEOM>(p, workspace, workspace_bytes, stream)
+            : launch_scan<float, 2, 1, CG_BWD_GEOM>(p, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

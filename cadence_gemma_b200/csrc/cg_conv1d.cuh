@@ -217,8 +217,11 @@ __device__ __forceinline__ void widen_vec(const uint4& v, float (&f)[IoVec<IO>::
   }
 }
 
+#ifndef CG_CONVBWD_MINB
+#define CG_CONVBWD_MINB 1
+#endif
 template <typename IO, int LC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, CG_CONVBWD_MINB)
 conv1d_w4_bwd_kernel(const ConvBwdParams p) {
   constexpr int V = IoVec<IO>::V;
   constexpr bool BF = IoVec<IO>::kBf16;

@@ -52,8 +52,10 @@ def main():
     n = B * T * E
     us = timed(lambda: _abi.rnn_scan_bwd(gy, gl, a, h, reset, h0))
     out[f"rnn_scan_bwd_{name}"] = {"us": us, "GBps": 5 * s * n / us / 1e3, "frac": 5 * s * n / us / 1e3 / peak}
-    us = timed(lambda: _abi.rnn_scan_fwd(x, a, reset, h0, arith_mode=0))
-    out[f"rnn_scan_fwd_{name}"] = {"us": us, "GBps": 3 * s * n / us / 1e3, "frac": 3 * s * n / us / 1e3 / peak}
+    for variant in ([0] if "--variants" not in sys.argv else range(6)):
+      us = timed(lambda: _abi.rnn_scan_fwd(x, a, reset, h0, arith_mode=variant << 8))
+      key = f"rnn_scan_fwd_{name}" + (f"_v{variant}" if variant else "")
+      out[key] = {"us": us, "GBps": 3 * s * n / us / 1e3, "frac": 3 * s * n / us / 1e3 / peak}
     us = timed(lambda: _abi.conv1d_bwd(gy, x, w, seg))
     out[f"conv1d_bwd_{name}"] = {"us": us, "GBps": 3 * s * n / us / 1e3, "frac": 3 * s * n / us / 1e3 / peak}
   print(json.dumps(out))
