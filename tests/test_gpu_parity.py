@@ -791,6 +791,50 @@ def test_host_prefill_streaming_submit_overlaps_batches_correctly():
       assert torch.equal(ys[i], y_d.cpu()) and torch.equal(hs[i], h_d.cpu()) and torch.equal(cs[i], cd.cpu()), (chunks, i)
 
 
+def test_back_to_back_steps_with_programmatic_dependent_launch_are_ordered():
+  """Conv1D -> prologue -> fused RG-LRU kernel are chained by programmatic
+  dependent launches (the consumers start under their producer's tail).  Many
+  unsynchronised steps on alternating inputs, with buffers reused across steps,
+  must give exactly the results of fully synchronised single steps."""
+  import cadence_gemma_b200 as cg
+  torch.manual_seed(17)
+  bsz, steps, width, heads = 8, 2048, 2560, 10
+  conv = cg.Conv1D(width, 4, device=DEV, dtype=torch.bfloat16)
+  lru = cg.RGLRU(width, heads, device=DEV, dtype=torch.bfloat16)
+  with torch.no_grad():
+    conv.w.normal_(0, 0.4)
+    conv.b.normal_(0, 0.2)
+    lru.input_gate.b.normal_()
+    lru.a_gate.b.normal_()
+  seg = torch.arange(steps, dtype=torch.int32, device=DEV)[None].repeat(bsz, 1)
+  seg[:, 777:] -= 777
+  xs = [torch.randn(bsz, steps, width, device=DEV).bfloat16() for _ in range(3)]
+  want = []
+  for x in xs:                                   # synchronised reference runs
+    xc, cs = conv(x, seg)
+    torch.cuda.synchronize()
+    y, h = lru(xc, seg)
+    torch.cuda.synchronize()
+    want.append((y.clone(), h.clone(), cs.clone()))
+  xc_buf = torch.empty_like(xs[0])
+  y_bufs = [torch.empty_like(xs[0]) for _ in range(3)]
+  h_bufs = [torch.empty(bsz, width, device=DEV) for _ in range(3)]
+  c_bufs = [torch.empty(bsz, 3, width, device=DEV, dtype=torch.bfloat16) for _ in range(3)]
+  for it in range(30):                           # no host sync; xc_buf is reused every step
+    k = it % 3
+    conv.forward_into(xs[k], seg, out=xc_buf, cache_out=c_bufs[k])
+    lru.forward_into(xc_buf, seg, out=y_bufs[k], last_h_out=h_bufs[k])
+    if it % 7 == 3:                              # an unrelated kernel in between now and then
+      xc_buf.mul_(1.0)
+  torch.cuda.synchronize()
+  for k in range(3):
+    assert torch.equal(y_bufs[k], want[k][0]) and torch.equal(h_bufs[k], want[k][1]), k
+    assert torch.equal(c_bufs[k], want[k][2]), k
+  abi = _abi()
+  for ws in abi._fused_workspaces.values():
+    assert abi.fused_watchdog_code(ws) == 0
+
+
 def test_fused_rglru_api_variants_and_cuda_graph():
   """Module API corner cases on the fused path: 1-D / int64 / broadcast
   segment_pos, no h0, return_cache=False, B = 1, and CUDA-graph capture of the
