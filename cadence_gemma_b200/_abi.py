@@ -36,6 +36,10 @@ SYMBOLS = {
     "cg_conv1d_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
     "cg_conv1d_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i,
                            _i, _i, _vp]),
+    "cg_rglru_gates_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "cg_rglru_gates_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cg_rglru_gates_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                _i, _i, _i, _i, _vp]),
     "cg_rnn_scan_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i,
                              _i, _vp]),
     "cg_rglru_fused_supported": (_i, [_i, _i, _i]),
@@ -315,6 +319,50 @@ def rnn_scan_fwd(x, a, reset, h0=None, arith_mode=ARITH_REFERENCE):
   _check(rc, "cg_rnn_scan_fwd")
   launch_count += 1 if (arith_mode & ARITH_STRICT) else 2
   return y, h_last
+
+
+def rglru_gates_fwd(x, pre_x, pre_a, a_param, reset):
+  """Gate math of the RG-LRU for the training path (cg_rglru_gates_fwd):
+  returns ``(a, normalized_x)``, the inputs of ``rnn_scan``."""
+  global launch_count
+  _require_cuda(x, pre_x, pre_a, a_param, reset)
+  bsz, steps, width = x.shape
+  assert pre_x.shape == x.shape and pre_a.shape == x.shape
+  assert pre_x.dtype == x.dtype and pre_a.dtype == x.dtype and a_param.dtype == x.dtype
+  x, pre_x, pre_a, ap = x.contiguous(), pre_x.contiguous(), pre_a.contiguous(), a_param.contiguous()
+  rs = reset.to(torch.uint8).contiguous()
+  a, nx = torch.empty_like(x), torch.empty_like(x)
+  with torch.cuda.device(x.device):
+    rc = load().cg_rglru_gates_fwd(x.data_ptr(), pre_x.data_ptr(), pre_a.data_ptr(), ap.data_ptr(),
+                                   rs.data_ptr(), a.data_ptr(), nx.data_ptr(), bsz, steps, width,
+                                   dtype_code(x.dtype), _stream(x))
+  _check(rc, "cg_rglru_gates_fwd")
+  launch_count += 1
+  return a, nx
+
+
+def rglru_gates_bwd(x, pre_x, pre_a, a_param, reset, d_nx, d_a):
+  """Backward of ``rglru_gates_fwd`` (cg_rglru_gates_bwd): returns
+  ``(dx, d_pre_x, d_pre_a, d_a_param)``."""
+  global launch_count
+  _require_cuda(x, pre_x, pre_a, a_param, reset, d_nx, d_a)
+  bsz, steps, width = x.shape
+  x, pre_x, pre_a, ap = x.contiguous(), pre_x.contiguous(), pre_a.contiguous(), a_param.contiguous()
+  d_nx, d_a = d_nx.contiguous(), d_a.contiguous()
+  assert d_nx.dtype == x.dtype and d_a.dtype == x.dtype
+  rs = reset.to(torch.uint8).contiguous()
+  dx, dpx, dpa = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+  dap = torch.empty_like(ap)
+  ws = torch.empty(load().cg_rglru_gates_bwd_workspace_bytes(bsz, steps, width), dtype=torch.uint8,
+                   device=x.device)
+  with torch.cuda.device(x.device):
+    rc = load().cg_rglru_gates_bwd(x.data_ptr(), pre_x.data_ptr(), pre_a.data_ptr(), ap.data_ptr(),
+                                   rs.data_ptr(), d_nx.data_ptr(), d_a.data_ptr(), dx.data_ptr(),
+                                   dpx.data_ptr(), dpa.data_ptr(), dap.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), bsz, steps, width, dtype_code(x.dtype), _stream(x))
+  _check(rc, "cg_rglru_gates_bwd")
+  launch_count += 2
+  return dx, dpx, dpa, dap
 
 
 def rnn_scan_bwd(gy, g_last, a, h, reset, h0=None, need_dh0=True):

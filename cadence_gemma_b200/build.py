@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libcadence_b200.so")
 SOURCES = ["cadence_b200.cu"]
-HEADERS = ["cg_common.cuh", "cg_scan.cuh", "cg_conv1d.cuh", "cg_fused.cuh",
+HEADERS = ["cg_common.cuh", "cg_scan.cuh", "cg_conv1d.cuh", "cg_fused.cuh", "cg_decode.cuh", "cg_train.cuh",
            os.path.join("..", "..", "include", "cadence_b200.h")]
 
 NVCC_FLAGS = [

@@ -13,6 +13,7 @@
 #include "cg_scan.cuh"
 #include "cg_fused.cuh"
 #include "cg_decode.cuh"
+#include "cg_train.cuh"
 
 namespace {
 
@@ -468,6 +469,81 @@ int cg_rnn_scan_bwd(const void* gy, const float* g_last_h, const void* a, const 
 #define CG_BWD_GEOM CG_BWD_L, CG_BWD_NW, CG_BWD_ST, CG_BWD_MINB
   return bf ? launch_scan<uint16_t, 2, 0, CG_BWD_GEOM>(p, workspace, workspace_bytes, stream)
             : launch_scan<float, 2, 1, CG_BWD_GEOM>(p, workspace, workspace_bytes, stream);
+}
+
+int cg_rglru_gates_fwd(const void* x, const void* pre_x, const void* pre_a, const void* a_param,
+                       const unsigned char* reset, void* a, void* nx, int B, int T, int E, int dtype,
+                       cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !pre_x || !pre_a || !a_param || !reset || !a || !nx) return CG_ERR_NULL;
+  if (int rc = check_common(B, T, E, dtype)) return rc;
+  const bool bf = dtype == CG_DTYPE_BF16;
+  const int V = bf ? 8 : 4;
+  if (E % V != 0) return CG_ERR_ALIGN;
+  if (!aligned16(x) || !aligned16(pre_x) || !aligned16(pre_a) || !aligned16(a) || !aligned16(nx) ||
+      !aligned16(a_param))
+    return CG_ERR_ALIGN;
+  cg::GateParams p{};
+  p.x = x; p.pre_x = pre_x; p.pre_a = pre_a; p.a_param = a_param; p.reset = reset; p.a = a; p.nx = nx;
+  p.N = (long long)B * T; p.E = E;
+  const long long threads = p.N * (E / V);
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  if (bf) cg::rglru_gates_fwd_kernel<uint16_t><<<grid, 256, 0, stream>>>(p);
+  else cg::rglru_gates_fwd_kernel<float><<<grid, 256, 0, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+size_t cg_rglru_gates_bwd_workspace_bytes(int B, int T, int E) {
+  if (B < 1 || T < 1 || E < 1) return 0;
+  const long long n = (long long)B * T;
+  return (size_t)((n + cg::kTrainRows - 1) / cg::kTrainRows) * E * sizeof(float);
+}
+
+int cg_rglru_gates_bwd(const void* x, const void* pre_x, const void* pre_a, const void* a_param,
+                       const unsigned char* reset, const void* d_nx, const void* d_a, void* dx,
+                       void* d_pre_x, void* d_pre_a, void* d_a_param, void* workspace,
+                       size_t workspace_bytes, int B, int T, int E, int dtype, cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!x || !pre_x || !pre_a || !a_param || !reset || !d_nx || !d_a || !dx || !d_pre_x || !d_pre_a ||
+      !d_a_param || !workspace)
+    return CG_ERR_NULL;
+  if (int rc = check_common(B, T, E, dtype)) return rc;
+  const bool bf = dtype == CG_DTYPE_BF16;
+  const int V = bf ? 8 : 4;
+  if (E % V != 0) return CG_ERR_ALIGN;
+  if (!aligned16(x) || !aligned16(pre_x) || !aligned16(pre_a) || !aligned16(d_nx) || !aligned16(d_a) ||
+      !aligned16(dx) || !aligned16(d_pre_x) || !aligned16(d_pre_a) || !aligned16(workspace))
+    return CG_ERR_ALIGN;
+  if (cg_rglru_gates_bwd_workspace_bytes(B, T, E) > workspace_bytes) return CG_ERR_WORKSPACE;
+  cg::GateParams p{};
+  p.x = x; p.pre_x = pre_x; p.pre_a = pre_a; p.a_param = a_param; p.reset = reset;
+  p.d_nx = d_nx; p.d_a = d_a; p.dx = dx; p.d_pre_x = d_pre_x; p.d_pre_a = d_pre_a;
+  p.partial = reinterpret_cast<float*>(workspace);
+  p.N = (long long)B * T; p.E = E;
+  const long long nparts = (p.N + cg::kTrainRows - 1) / cg::kTrainRows;
+  if (nparts > 0x7fffffffLL) return CG_ERR_SHAPE;
+  dim3 grid((E + 8 * V - 1) / (8 * V), 1, 1);
+  // blockIdx.y is limited to 65535: large N goes through several launches of <= 65535 row groups
+  for (long long first = 0; first < nparts; first += 65535) {
+    const long long cnt = nparts - first < 65535 ? nparts - first : 65535;
+    cg::GateParams q = p;
+    const size_t roff = (size_t)first * cg::kTrainRows;
+    auto adv = [&](const void* ptr) -> const void* {
+      return reinterpret_cast<const char*>(ptr) + roff * E * (bf ? 2 : 4);
+    };
+    q.x = adv(p.x); q.pre_x = adv(p.pre_x); q.pre_a = adv(p.pre_a); q.d_nx = adv(p.d_nx); q.d_a = adv(p.d_a);
+    q.dx = const_cast<void*>(adv(p.dx)); q.d_pre_x = const_cast<void*>(adv(p.d_pre_x));
+    q.d_pre_a = const_cast<void*>(adv(p.d_pre_a));
+    q.reset = p.reset + roff; q.partial = p.partial + (size_t)first * E; q.N = p.N - (long long)roff;
+    grid.y = (unsigned)cnt;
+    if (bf) cg::rglru_gates_bwd_kernel<uint16_t><<<grid, 128, 0, stream>>>(q);
+    else cg::rglru_gates_bwd_kernel<float><<<grid, 128, 0, stream>>>(q);
+    if (cudaError_t err = cudaGetLastError()) return (int)err;
+  }
+  const int rgrid = (E + 127) / 128;
+  if (bf) cg::column_reduce_kernel<uint16_t><<<rgrid, 128, 0, stream>>>(p.partial, (int)nparts, E, d_a_param);
+  else cg::column_reduce_kernel<float><<<rgrid, 128, 0, stream>>>(p.partial, (int)nparts, E, d_a_param);
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

@@ -16,9 +16,9 @@ missing library raise.
 
 Gradients: ``rnn_scan`` is differentiable --
 its backward is the reverse-time scan kernel ``cg_rnn_scan_bwd`` -- and
-``RGLRU.forward`` called with grad enabled builds the reference's autograd
-graph (gate math as ATen ops, clipped-sqrt gradient, layers.py:224-238) around
-it; the ``Conv1D`` prefill is differentiable too (``cg_conv1d_bwd``), so
+``RGLRU.forward`` called with grad enabled runs gate math + scan forward and
+backward on the training kernels (``_RGLRUFn``: ``cg_rglru_gates_fwd/bwd`` with the
+clipped-sqrt gradient of layers.py:224-238, ``cg_rnn_scan_fwd/bwd``); the ``Conv1D`` prefill is differentiable too (``cg_conv1d_bwd``), so
 ``training/train.py`` can run on the kernels.  Decode steps are forward only.
 """
 from __future__ import annotations
@@ -110,6 +110,45 @@ class _RnnScanFn(torch.autograd.Function):
     dx, da, dh0 = _abi.rnn_scan_bwd(gy, g_last, a, y, reset, h0 if ctx.has_h0 else None,
                                     need_dh0=want_h0)
     return dx, da, None, dh0
+
+
+class _RGLRUFn(torch.autograd.Function):
+  """RG-LRU after the gate GEMMs, on the training kernels: forward = gate math
+  (``cg_rglru_gates_fwd``) + scan (``cg_rnn_scan_fwd``); backward = reverse scan
+  (``cg_rnn_scan_bwd``) + gate backward (``cg_rglru_gates_bwd``, incl. the
+  clipped square-root gradient).  Saves the pre-activations, ``a`` and ``y``."""
+
+  @staticmethod
+  def forward(ctx, x, pre_x, pre_a, a_param, reset, h0):
+    a, nx = _abi.rglru_gates_fwd(x, pre_x, pre_a, a_param, reset)
+    y, last_h = _abi.rnn_scan_fwd(nx, a, reset, h0, arith_mode=0)
+    ctx.has_h0 = h0 is not None
+    ctx.save_for_backward(x, pre_x, pre_a, a_param, reset, a, y,
+                          h0 if h0 is not None else y.new_empty(0))
+    return y, last_h
+
+  @staticmethod
+  def backward(ctx, gy, g_last):
+    x, pre_x, pre_a, a_param, reset, a, y, h0 = ctx.saved_tensors
+    if gy is None:
+      gy = torch.zeros_like(y)
+    want_h0 = ctx.has_h0 and ctx.needs_input_grad[5]
+    d_nx, d_a, dh0 = _abi.rnn_scan_bwd(gy, g_last, a, y, reset, h0 if ctx.has_h0 else None,
+                                       need_dh0=want_h0)
+    dx, dpx, dpa, dap = _abi.rglru_gates_bwd(x, pre_x, pre_a, a_param, reset, d_nx, d_a)
+    return dx, dpx, dpa, dap, None, dh0
+
+
+_train_kernels = os.environ.get("CG_B200_TRAIN_KERNELS", "1") != "0"
+
+
+def set_train_kernels(enabled: bool) -> bool:
+  """Training path of ``RGLRU.forward``: True (default) = gate math forward and
+  backward on our kernels (``_RGLRUFn``); False = the reference's ATen op sequence
+  under autograd around the differentiable scan.  Returns the previous setting."""
+  global _train_kernels
+  prev, _train_kernels = _train_kernels, bool(enabled)
+  return prev
 
 
 class SqrtBoundDerivative(torch.autograd.Function):
@@ -310,6 +349,10 @@ class RGLRU(nn.Module):
     the reference's op sequence (layers.py:345-371) as ATen ops, so autograd
     sees the same graph, around the differentiable scan kernels."""
     reset = segment_pos == 0
+    if _train_kernels and not (x.shape[1] == 1 and cache is None):
+      # gate GEMMs by cuBLAS under autograd; everything after them on our kernels
+      y, last_h = _RGLRUFn.apply(x, self.input_gate(x), self.a_gate(x), self.a_param, reset, cache)
+      return (y, last_h) if return_cache else (y, None)
     gate_x = torch.sigmoid(self.input_gate(x))
     gate_a = torch.sigmoid(self.a_gate(x))
     log_a = -8.0 * gate_a * nn.functional.softplus(self.a_param)

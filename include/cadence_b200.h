@@ -163,6 +163,28 @@ int cg_conv1d_bwd(const void* gy, const void* x, const void* w, const void* seg,
                   int E, int W, int dtype, int mask_mode, cg_stream_t stream);
 
 /*
+ * Training path of the RG-LRU gate math.
+ *   cg_rglru_gates_fwd: layers.py:348-365 from x and the gate pre-activations
+ *     (BlockDiagonalLinear outputs, bias included) to the scan's inputs
+ *     a = exp(-8 sigmoid(pre_a) softplus(a_param)) and
+ *     nx = x sigmoid(pre_x) sqrt(1 - a^2) (multiplier 1 where reset != 0), with the
+ *     reference's eager bf16 rounding points.  All [B,T,E] in `dtype`, reset [B,T].
+ *   cg_rglru_gates_bwd: what autograd derives from those lines, including the
+ *     clipped square-root gradient (layers.py:224-238): from d_nx = grad(nx) and
+ *     d_a = grad(a) (the outputs of cg_rnn_scan_bwd) to dx, d_pre_x, d_pre_a
+ *     [B,T,E] and d_a_param [E] (fixed-order reduction).  fp32 in registers, gates
+ *     recomputed from the saved pre-activations.
+ */
+int cg_rglru_gates_fwd(const void* x, const void* pre_x, const void* pre_a, const void* a_param,
+                       const unsigned char* reset, void* a, void* nx, int B, int T, int E,
+                       int dtype, cg_stream_t stream);
+size_t cg_rglru_gates_bwd_workspace_bytes(int B, int T, int E);
+int cg_rglru_gates_bwd(const void* x, const void* pre_x, const void* pre_a, const void* a_param,
+                       const unsigned char* reset, const void* d_nx, const void* d_a, void* dx,
+                       void* d_pre_x, void* d_pre_a, void* d_a_param, void* workspace,
+                       size_t workspace_bytes, int B, int T, int E, int dtype, cg_stream_t stream);
+
+/*
  * Backward of rnn_scan: what torch autograd derives from the reference loop
  * (layers.py:173, :187-199) -- SURVEY.md section 8(f) row F4; the JAX VJP
  * jax/pallas.py:785-839 is the same recurrence.  One chunked scan over

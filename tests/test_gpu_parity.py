@@ -144,11 +144,23 @@ def test_rnn_scan_backward_full_size_vs_sequential(dtype):
   assert normwise(dh0, want_dh0) <= 1e-5
 
 
+@pytest.mark.parametrize("train_kernels", [True, False])
 @pytest.mark.parametrize("case", fixture_io.cases("grad_rglru_"))
-def test_rglru_training_path_golden(case):
-  """RGLRU.forward with grad enabled: the reference's autograd graph around the
-  differentiable scan kernels; gradients of x, the cache and every parameter
-  against the reference's."""
+def test_rglru_training_path_golden(case, train_kernels):
+  """RGLRU.forward with grad enabled -- gate math and scan forward / backward on
+  the training kernels (train_kernels) or the reference's ATen op sequence around
+  the differentiable scan: gradients of x, the cache and every parameter against
+  the reference's autograd."""
+  import cadence_gemma_b200 as cg
+  from cadence_gemma_b200 import layers
+  prev = layers.set_train_kernels(train_kernels)
+  try:
+    _rglru_training_golden(case)
+  finally:
+    layers.set_train_kernels(prev)
+
+
+def _rglru_training_golden(case):
   import cadence_gemma_b200 as cg
   g = fixture_io.load(case)
   dtype = g["x"].dtype
@@ -237,6 +249,47 @@ def test_conv1d_backward_full_size_vs_torch_autograd(mask_mode):
   assert_close_bf16(dx.cpu(), xf.grad.bfloat16().cpu(), "dx", min_identical=0.5)   # bf16 accumulation vs fp32
   assert normwise(dw.float(), wf.grad) <= 1e-2
   assert normwise(db.float(), gy.float().sum((0, 1))) <= 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gate_kernels_vs_aten_autograd_full_size(dtype):
+  """cg_rglru_gates_fwd / _bwd at a config-2 sized problem against the reference's
+  ATen op sequence (layers.py:348-365, clipped sqrt gradient :224-238) evaluated
+  under torch autograd on the device."""
+  from cadence_gemma_b200 import layers
+  abi = _abi()
+  torch.manual_seed(31)
+  bsz, steps, width = 4, 1024, 2560
+  bf = dtype == torch.bfloat16
+  x = torch.randn(bsz, steps, width, device=DEV).to(dtype).requires_grad_()
+  px = (torch.randn(bsz, steps, width, device=DEV) * 1.5).to(dtype).requires_grad_()
+  pa = (torch.randn(bsz, steps, width, device=DEV) * 1.5).to(dtype).requires_grad_()
+  ap = (torch.rand(width, device=DEV) * -7 + 1).to(dtype).requires_grad_()
+  reset = torch.rand(bsz, steps, device=DEV) < 0.01
+  d_nx = torch.randn(bsz, steps, width, device=DEV).to(dtype)
+  d_a = (torch.randn(bsz, steps, width, device=DEV) * ~reset[..., None]).to(dtype)
+  with torch.enable_grad():
+    gate_x, gate_a = torch.sigmoid(px), torch.sigmoid(pa)
+    log_a = -8.0 * gate_a * torch.nn.functional.softplus(ap)
+    a_ref = torch.exp(log_a)
+    mult = layers.SqrtBoundDerivative.apply(1 - torch.exp(2 * log_a))
+    mult = reset[..., None] + ~reset[..., None] * mult
+    nx_ref = (x * gate_x) * mult.type(dtype)
+    torch.autograd.backward([nx_ref, a_ref], [d_nx, d_a])
+  a, nx = abi.rglru_gates_fwd(x.detach(), px.detach(), pa.detach(), ap.detach(), reset)
+  if bf:   # same eager rounding points; libdevice expf vs ATen's: a few flips
+    assert identical_fraction(a, a_ref.detach()) >= 0.999 and identical_fraction(nx, nx_ref.detach()) >= 0.995
+  else:
+    assert normwise(a, a_ref.detach()) <= 1e-5 and normwise(nx, nx_ref.detach()) <= 1e-5
+  dx, dpx, dpa, dap = abi.rglru_gates_bwd(x.detach(), px.detach(), pa.detach(), ap.detach(), reset, d_nx, d_a)
+  # bf16: the forward's saved tensors carry the eager rounding (the kernel reproduces
+  # it), the chain rule itself runs in fp32 in the kernel and in bf16 in ATen
+  tol = 3e-2 if bf else 2e-5
+  for got, want, name in ((dx, x.grad, "dx"), (dpx, px.grad, "dpx"), (dpa, pa.grad, "dpa")):
+    assert normwise(got.float(), want.float()) <= tol, (name, normwise(got.float(), want.float()))
+  assert normwise(dap.float(), ap.grad.float()) <= (5e-2 if bf else 1e-4)
+  r2 = abi.rglru_gates_bwd(x.detach(), px.detach(), pa.detach(), ap.detach(), reset, d_nx, d_a)
+  assert all(torch.equal(u, v) for u, v in zip((dx, dpx, dpa, dap), r2))
 
 
 @pytest.mark.parametrize("case", fixture_io.cases("grad_recurrent_block_"))
