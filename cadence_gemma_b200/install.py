@@ -47,9 +47,15 @@ def _rglru_forward(self, x, segment_pos, cache=None, return_cache=True, gate_mul
     segment_pos = segment_pos[None, :]
   assert segment_pos.shape == (bs, length)
   if cg_layers._wants_grad(x, cache, *self.parameters()):
-    # training: the reference's own forward builds the autograd graph; its scan
-    # is the patched module-global rnn_scan = the differentiable kernel pair
     assert gate_mul is None
+    if cg_layers._train_kernels and not (length == 1 and cache is None):
+      # training kernels: the module's own gate GEMMs (autograd), then gate math +
+      # scan forward / backward on our kernels
+      y, last_h = cg_layers._RGLRUFn.apply(x, self.input_gate(x), self.a_gate(x), self.a_param,
+                                           segment_pos == 0, cache)
+      return (y, last_h) if return_cache else (y, None)
+    # otherwise the reference's own forward builds the autograd graph; its scan is
+    # the patched module-global rnn_scan = the differentiable kernel pair
     return _saved["rglru_forward"](self, x, segment_pos, cache, return_cache)
   with torch.no_grad():
     if cg_layers.uses_fused_kernel(self, x):

@@ -58,6 +58,29 @@ def main():
       out[key] = {"us": us, "GBps": 3 * s * n / us / 1e3, "frac": 3 * s * n / us / 1e3 / peak}
     us = timed(lambda: _abi.conv1d_bwd(gy, x, w, seg))
     out[f"conv1d_bwd_{name}"] = {"us": us, "GBps": 3 * s * n / us / 1e3, "frac": 3 * s * n / us / 1e3 / peak}
+  # one training step (forward + backward) of the RG-LRU module and of the whole
+  # recurrent block at 2B shapes: training kernels vs the ATen op sequence around
+  # the differentiable scan
+  import cadence_gemma_b200 as cg
+  from cadence_gemma_b200 import layers
+  from cadence_gemma_b200.modules import RecurrentBlock
+  dtype = torch.bfloat16
+  lru = cg.RGLRU(E, 10, device=dev, dtype=dtype)
+  blk = RecurrentBlock(width=2560, num_heads=10, lru_width=E, conv1d_temporal_width=4, device=dev, dtype=dtype)
+  seg = torch.arange(T, dtype=torch.int32, device=dev)[None].repeat(B, 1)
+  xin = torch.randn(B, T, E, device=dev).to(dtype).requires_grad_()
+  gyo = torch.randn(B, T, E, device=dev).to(dtype)
+
+  def train_step(mod):
+    with torch.enable_grad():
+      y, _ = mod(xin, seg)
+      y.backward(gyo)
+
+  for flag, tag in ((True, "kernels"), (False, "aten")):
+    prev = layers.set_train_kernels(flag)
+    out[f"rglru_train_step_{tag}_us"] = timed(lambda: train_step(lru), iters=5)
+    out[f"recurrent_block_train_step_{tag}_us"] = timed(lambda: train_step(blk), iters=5)
+    layers.set_train_kernels(prev)
   print(json.dumps(out))
 
 
