@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
-  text = open(os.path.join(ROOT, "include", "cadence_b200.h")).read()
+  with open(os.path.join(ROOT, "include", "cadence_b200.h")) as f:
+    text = f.read()
   text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
   return sorted(set(re.findall(r"\b(cg_[a-z0-9_]+)\s*\(", text)))
 
