@@ -214,6 +214,39 @@ def uses_fused_kernel(lru, x: torch.Tensor) -> bool:
           _abi.fused_supported(lru.width, lru.num_heads, x.dtype))
 
 
+class _BlockDiagonalLinearFn(torch.autograd.Function):
+  """``x @ blockdiag(w) + b`` for the training path: strided-batched cuBLAS GEMMs
+  that read and write the flat ``[..., H*bw]`` layout directly, forward and
+  backward (autograd through ``einsum`` / ``bmm`` + ``transpose`` materialises a
+  permuted copy of every activation-sized tensor)."""
+
+  @staticmethod
+  def forward(ctx, x, w, b):
+    heads, bw, _ = w.shape
+    x2 = x.reshape(-1, heads, bw)
+    out = torch.empty_like(x2)
+    torch.bmm(x2.transpose(0, 1), w, out=out.transpose(0, 1))
+    out += b                                   # r(r(x @ w) + b), layers.py:139
+    ctx.save_for_backward(x2, w)
+    return out.view(x.shape)
+
+  @staticmethod
+  def backward(ctx, gy):
+    x2, w = ctx.saved_tensors
+    heads, bw, _ = w.shape
+    gy2 = gy.reshape(-1, heads, bw)
+    dx = dw = db = None
+    if ctx.needs_input_grad[0]:
+      dx2 = torch.empty_like(x2)
+      torch.bmm(gy2.transpose(0, 1), w.transpose(1, 2), out=dx2.transpose(0, 1))
+      dx = dx2.view(gy.shape)
+    if ctx.needs_input_grad[1]:
+      dw = torch.bmm(x2.transpose(0, 1).transpose(1, 2), gy2.transpose(0, 1))
+    if ctx.needs_input_grad[2]:
+      db = gy2.sum(0)
+    return dx, dw, db
+
+
 class BlockDiagonalLinear(nn.Module):
   """Block-diagonal linear layer (reference layers.py:81-142)."""
 
@@ -251,10 +284,8 @@ class BlockDiagonalLinear(nn.Module):
 
   def forward(self, x: torch.Tensor) -> torch.Tensor:
     heads, bw = self.num_blocks, self.block_width
-    if _wants_grad(x, self.w, self.b):          # autograd path: no out= variant
-      x2 = x.reshape(-1, heads, bw)
-      y = torch.bmm(x2.transpose(0, 1), self.w).transpose(0, 1) + self.b
-      return y.reshape(x.shape)
+    if _wants_grad(x, self.w, self.b):          # training path
+      return _BlockDiagonalLinearFn.apply(x, self.w, self.b)
     y = self.gemm(x).view(*x.shape[:-1], heads, bw) + self.b
     return y.view(x.shape)
 
