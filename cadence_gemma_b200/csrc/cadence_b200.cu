@@ -87,7 +87,17 @@ int launch_scan(ScanParams p, void* workspace, size_t workspace_bytes, cudaStrea
     resident = per_sm * sms;
   }
   const int grid = p.nitems < resident ? p.nitems : resident;
-  kernel<<<grid, NW * 32, smem, stream>>>(p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NW * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // behind the prologue, see scan_kernel
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, p)) return (int)e;
   return (int)cudaGetLastError();
 }
 

@@ -216,6 +216,10 @@ scan_kernel(const ScanParams p) {
   constexpr int NSEG = NW * kSegs;           // time segments per item
   constexpr int STAGE_U4 = NW * L * NT * 32; // uint4 per staging buffer
 
+  // launched as a programmatic dependent of the prologue kernel (ticket reset,
+  // epoch, reset bitmask): block scheduling overlaps the prologue, everything
+  // below reads its outputs
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint4* stage = reinterpret_cast<uint4*>(smem_raw);
   constexpr bool ALIAS = Tr::ALIAS;
@@ -414,7 +418,11 @@ scan_kernel(const ScanParams p) {
         const int j = kind * (V / 4) + (ch % V) / 4;
         return reinterpret_cast<float*>(stage_buf + ((w * L + j) * NT + 2) * 32 + sg * 8 + ch / V) + (ch & 3);
       } else {
-        return (kind ? s_h : s_p) + sgm * EC + ch;
+        // [segment][4-channel group of the vector][lane cv][4]: the eight lanes of a
+        // quarter warp (one 128-bit access each) cover 32 consecutive banks; the
+        // plain [segment][channel] layout is a 2-way conflict for 8-channel vectors
+        const int c = ch / V, i = ch % V;
+        return (kind ? s_h : s_p) + sgm * EC + (i >> 2) * (kCvl * 4) + c * 4 + (i & 3);
       }
     };
 
