@@ -354,7 +354,11 @@ def own_arm(args, dtype):
             for k, v in k_events.items()}
 
     # ---------------- end to end: pinned host buffers in, results out ------------
-    x_pin = host["x_lin"].pin_memory()
+    # the host buffers of this rank live on the memory node of its GPU
+    from cadence_gemma_b200.hostio import bind_host_thread_to_device
+    prev_affinity = (bind_host_thread_to_device(local_rank)
+                     if os.environ.get("CG_BENCH_NUMA_BIND", "1") != "0" else None)
+    x_pin = host["x_lin"].clone().pin_memory()
     seg_pin = host["segment_pos"].pin_memory()
     y_pin = torch.empty_like(x_pin).pin_memory()
     h_pin = torch.empty((w["batch"], w["width"]), dtype=torch.float32).pin_memory()
@@ -465,6 +469,12 @@ def own_arm(args, dtype):
         "fused_tcgen05_rglru": bool(fused),
     }
     if world == 1 and not args.no_cpu_baseline:
+      if prev_affinity is not None:     # the CPU baseline uses every host core again
+        for tid in os.listdir("/proc/self/task"):       # worker threads inherit the bound mask
+          try:
+            os.sched_setaffinity(int(tid), prev_affinity)
+          except OSError:
+            pass
       threads = os.cpu_count() or 1
       host0 = make_host_inputs(dtype, seed=1)
       times, cpu_out = run_cpu_port(host0, 3, 1, threads)

@@ -18,6 +18,34 @@ from __future__ import annotations
 import torch
 
 
+def bind_host_thread_to_device(device_index: int):
+  """Binds the calling thread to the CPU cores next to GPU ``device_index`` (NVML's
+  ideal CPU affinity), so that pinned host buffers allocated afterwards are placed
+  on that GPU's memory node and the copy engines do not pull them across the
+  socket interconnect -- with one process per GPU on a multi-socket host the
+  host legs of ``HostPrefill`` otherwise share one socket's memory and one
+  inter-socket link.  Returns the previous affinity set (restore it with
+  ``os.sched_setaffinity(0, previous)``) or None if NVML is unavailable."""
+  import os
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+    handle = None
+    for i in range(pynvml.nvmlDeviceGetCount()):
+      h = pynvml.nvmlDeviceGetHandleByIndex(i)
+      if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:     # CUDA_VISIBLE_DEVICES remapping
+        handle = h
+        break
+    if handle is None:
+      handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+    previous = os.sched_getaffinity(0)
+    pynvml.nvmlDeviceSetCpuAffinity(handle)
+    return previous
+  except Exception:   # no NVML / not permitted: placement stays with the OS default
+    return None
+
+
 class HostPrefill:
   """Pipelined prefill of one recurrent block's hot path from host buffers.
 
