@@ -59,6 +59,9 @@
 // CGF_INTERLEAVE: the replay pass of the previous tile runs inside the gate loop
 // of the current one (same basic block: the compiler fills the gate math's MUFU
 // latencies with the replay's FMA / store work) instead of before it
+#ifndef CGF_WAIT_LATE
+#define CGF_WAIT_LATE 0
+#endif
 #ifndef CGF_INTERLEAVE
 #define CGF_INTERLEAVE 0   // measured: no gain (110.8 vs 109.8 us), the kernel is throughput-bound
 #endif
@@ -840,6 +843,10 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         if (twarp) CGF_EVENT(trole, 8);
         const unsigned long long early = request_pred();
         if (twarp) CGF_EVENT(trole, 1);
+        // CGF_WAIT_LATE: the pending tile needs nothing from the new accumulators --
+        // finish it first, so that a late MMA costs no idle time in this warpgroup
+        const bool pend_first = CGF_WAIT_LATE && !CGF_INTERLEAVE && pd.on;
+        if (pend_first) finish(early);
         mbar_wait(t_full + pr, use & 1, p.err, 6);
         if (twarp) CGF_EVENT(trole, 2);
         tc_fence_after();

@@ -26,6 +26,7 @@ def make(B, T, E, H, seed=0, resets=True):
   bw = E // H
   dev = torch.device("cuda")
   x = torch.randn((B, T, E), generator=g).to(torch.bfloat16).to(dev)
+  torch.manual_seed(seed)                  # a_param comes from reset_parameters (global generator)
   lru = cg.RGLRU(E, H, device=dev, dtype=torch.bfloat16)
   with torch.no_grad():
     lru.input_gate.w.copy_((torch.randn((H, bw, bw), generator=g) * bw ** -0.5).to(torch.bfloat16))
@@ -72,6 +73,9 @@ def run_case(B, T, E, H, mode, variant, use_h0=True, debug=True):
     res["pre_a"] = stats(dbg[1], g4[:, :, :, 1].reshape(B, T, E))
     res["x_t"] = stats(dbg[2], x)
   res["y"] = stats(y, y_ref)
+  csum = lambda t: int(t.contiguous().view(torch.int16).to(torch.int64).sum().item())
+  res["checksum"] = {"y_fused": csum(y), "y_unfused": csum(y_ref), "gates_gemm": csum(gates),
+                     "h_fused": float(last_h.double().sum().item()), "h_unfused": float(h_ref.double().sum().item())}
   res["last_h"] = stats(last_h, h_ref)
   print(json.dumps(res), flush=True)
 
