@@ -46,6 +46,8 @@ def _rglru_forward(self, x, segment_pos, cache=None, return_cache=True, gate_mul
   if segment_pos.shape != (bs, length):
     segment_pos = segment_pos[None, :]
   assert segment_pos.shape == (bs, length)
+  if cg_layers._empty_batch(x):
+    return cg_layers._empty_rglru(x, self.width, return_cache)
   if cg_layers._wants_grad(x, cache, *self.parameters()):
     assert gate_mul is None
     if cg_layers._train_kernels and not (length == 1 and cache is None):
@@ -74,6 +76,8 @@ def _rglru_forward(self, x, segment_pos, cache=None, return_cache=True, gate_mul
 
 def _conv1d_forward(self, x, segment_pos, cache=None, return_cache=True):
   mode = cg_layers.get_arith_mode() & _abi.ARITH_FP32
+  if cg_layers._empty_batch(x):
+    return cg_layers._empty_conv1d(x, self.temporal_width, cache, return_cache)
   if cg_layers._wants_grad(x, cache, self.w, self.b):
     if cache is not None:
       raise RuntimeError("Conv1D decode steps (cache given) are forward-only; call under torch.no_grad()")

@@ -85,6 +85,32 @@ def fold_gate_enabled() -> bool:
   return _fold_gate
 
 
+def _empty_batch(x) -> bool:
+  """True for ``[0, T >= 1, E]`` activations (e.g. a rank whose batch shard holds no
+  rows).  The reference runs its ops over zero rows and returns empty tensors
+  (probe: ``rnn_scan`` / ``RGLRU`` / ``Conv1D`` with B = 0 give ``y [0,T,E]``,
+  ``last_h [0,E]`` fp32, conv cache ``[0,W-1,E]``); there is nothing to launch.
+  T = 0 stays an error, as in the reference (``x[:, 0]`` raises, layers.py:178)."""
+  return x.shape[0] == 0 and x.shape[1] >= 1
+
+
+def _empty_rglru(x, width, return_cache, out=None, last_h_out=None):
+  y = out if out is not None else torch.empty_like(x)
+  if not return_cache:
+    return y, None
+  return y, (last_h_out if last_h_out is not None else x.new_zeros((0, width), dtype=torch.float32))
+
+
+def _empty_conv1d(x, temporal_width, cache, return_cache, out=None, cache_out=None):
+  y = out if out is not None else torch.empty_like(x)
+  if not return_cache:
+    return y, None
+  if cache_out is not None:
+    return y, cache_out
+  return y, x.new_zeros((0, temporal_width - 1, x.shape[2]),
+                        dtype=x.dtype if cache is None else cache.dtype)   # decode keeps the cache's dtype (:542)
+
+
 def _wants_grad(*tensors) -> bool:
   return torch.is_grad_enabled() and any(
       t is not None and t.requires_grad for t in tensors)
@@ -182,6 +208,8 @@ def rnn_scan(x, a, reset, h0, acc_dtype=torch.float32):
   assert h0 is None or h0.dtype == acc_dtype
   if a.shape != x.shape:
     a = a.expand_as(x)
+  if _empty_batch(x):
+    return x.clone(), x.new_zeros((0, x.shape[2]), dtype=acc_dtype)
   if _wants_grad(x, a, h0):
     if x.shape[1] == 1 and h0 is None:      # :177-178: the output IS x (views, no arithmetic)
       return x, x[:, 0].type(acc_dtype)
@@ -357,6 +385,8 @@ class RGLRU(nn.Module):
     if segment_pos.shape != (bs, length):
       segment_pos = segment_pos[None, :]
     assert segment_pos.shape == (bs, length)      # layers.py:344
+    if _empty_batch(x):
+      return _empty_rglru(x, self.width, return_cache, out, last_h_out)
     if _wants_grad(x, cache, *self.parameters()):
       assert out is None and last_h_out is None and gate_mul is None
       return self._forward_autograd(x, segment_pos, cache, return_cache)
@@ -455,6 +485,8 @@ class Conv1D(nn.Module):
                    cache_out=None):
     """``forward`` (prefill) writing into caller-provided buffers."""
     mode = _arith_mode & (_abi.ARITH_FP32)
+    if _empty_batch(x):
+      return _empty_conv1d(x, self.temporal_width, cache, return_cache, out, cache_out)
     if _wants_grad(x, cache, self.w, self.b):
       # training path: differentiable prefill (temporal width 4); decoding with a
       # cache is an inference-only operation

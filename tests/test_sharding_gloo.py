@@ -73,7 +73,7 @@ def _worker(rank, world, port, batch, ok):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("batch", [4, 5])
+@pytest.mark.parametrize("batch", [4, 5, 1])   # 1: rank 1 owns an empty shard
 def test_sharded_equals_unsharded_world2(batch):
   world = 2
   ok = mp.get_context("spawn").Array("i", [0] * world)
