@@ -59,12 +59,16 @@
 // CGF_INTERLEAVE: the replay pass of the previous tile runs inside the gate loop
 // of the current one (same basic block: the compiler fills the gate math's MUFU
 // latencies with the replay's FMA / store work) instead of before it
+#ifndef CGF_LATE_WAIT_ST
+#define CGF_LATE_WAIT_ST 0
+#endif
 #ifndef CGF_WAIT_LATE
 #define CGF_WAIT_LATE 0
 #endif
 #ifndef CGF_INTERLEAVE
 #define CGF_INTERLEAVE 0   // measured: no gain (110.8 vs 109.8 us), the kernel is throughput-bound
 #endif
+static_assert(!(CGF_LATE_WAIT_ST && CGF_INTERLEAVE), "the woven replay reads the state columns without that wait");
 // CGF_ABLATE (timing experiments only, results are WRONG): 1 = no look-back,
 // 2 = no y stores, 4 = no replay pass at all
 #ifndef CGF_ABLATE
@@ -799,6 +803,9 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         for (int i = 0; i < 8; ++i) gm[i] = i < pd.nvalid ? ld_u16(gmp + i * E) : 0u;
       }
       float h = resolve_carry(early);
+      // CGF_LATE_WAIT_ST: the tile's state stores are awaited here, right before they
+      // are read back, instead of right after they were issued
+      if (CGF_LATE_WAIT_ST) tmem_wait_st();
 #pragma unroll 1
       for (int c = 0; c < ((CGF_ABLATE & 4) ? 0 : kTile / 8); ++c) {
         uint32_t st[8];
@@ -974,7 +981,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           }
           release_slot();
         }
-        tmem_wait_st();
+        if (!CGF_LATE_WAIT_ST) tmem_wait_st();
         if (twarp) CGF_EVENT(trole, 4);
         // publish the tile's aggregate (tile 0 publishes its state right away in
         // F instead) and queue the tile for F
