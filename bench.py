@@ -39,7 +39,7 @@ GATHER_EVERY = int(os.environ.get("CG_BENCH_GATHER_EVERY", "18"))   # recurrent 
 METRIC = "rglru_conv1d_prefill_tokens_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of one fused-kernel launch at config 2
 # (ncu --set full, profiles/r1_rglru_fused_kernel_ncu_summary.txt)
-NCU_TRAFFIC_BYTES = 164182016   # 94.04 MB read + 70.14 MB written
+NCU_TRAFFIC_BYTES = 161748480   # 94.05 MB read + 67.70 MB written (profiles/r1_rglru_fused_kernel_ncu_summary.txt)
 UNIT = "tokens/s"
 
 
@@ -452,8 +452,9 @@ def own_arm(args, dtype):
                      "algorithmic_bytes_note": ("SURVEY 8(d) K2 figure: 4 x 2 B per element (x, pre_x, pre_a "
                                                 "in, y out).  The fused kernel keeps pre_x / pre_a in TMEM, "
                                                 "so it moves only about half of that (see `traffic`) and is "
-                                                "bound by the instruction issue rate of the epilogue (gate math + scan, "
-                                                "51 instructions per element; ablations in DESIGN.md section 9), not HBM"
+                                                "bound by the SM-wide issue / MUFU throughput of the epilogue (gate math "
+                                                "+ scan: 51 instructions, 5 of them MUFU, per element; ablations in "
+                                                "DESIGN.md section 9), not HBM"
                                                 if fused else "SURVEY 8(d) K2 figure: 4 x s bytes per element"),
                      "us_per_launch": k2_mean_us, "traffic": NCU_TRAFFIC_BYTES if fused else None},
         "kernels_us": ({"conv1d": conv_us, "rglru_fused_tcgen05": k2_mean_us} if fused else
