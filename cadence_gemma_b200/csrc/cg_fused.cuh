@@ -50,8 +50,12 @@
 #ifndef CGF_PRELOAD
 #define CGF_PRELOAD 1
 #endif
+// look-back depth per round trip: 2 = the predecessor's state word plus the aggregates /
+// state of the tile before it in ONE round trip.  Measured (us, fused kernel alone):
+// B=2,T=8192 141.6 -> 129.4; B=8,T=2048 107.0 -> 107.0; B=32,T=768 144.3 -> 144.0-145.9;
+// depth 4: 131.4 / 111.1 / 146.0 (more loads per poll than the chain is long)
 #ifndef CGF_LOOK
-#define CGF_LOOK 1
+#define CGF_LOOK 2
 #endif
 #ifndef CGF_HINT_NS
 #define CGF_HINT_NS 20000
