@@ -112,6 +112,28 @@ def _stream(t: torch.Tensor):
   return torch.cuda.current_stream(t.device).cuda_stream
 
 
+class _NoSwitch:
+  """Stand-in for ``torch.cuda.device`` when the tensor already lives on the current
+  device: the device-guard context costs several microseconds per call, which is
+  what a small-batch prefill (host-bound: ~15 us of Python per kernel) is made of."""
+  __slots__ = ()
+
+  def __enter__(self):
+    return None
+
+  def __exit__(self, *exc):
+    return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on_device(device):
+  if device.index is None or device.index == torch.cuda.current_device():
+    return _NO_SWITCH
+  return torch.cuda.device(device)
+
+
 def _require_cuda(*tensors):
   for t in tensors:
     if t is not None and not t.is_cuda:
@@ -166,7 +188,7 @@ def conv1d_fwd(x, w, b, segment_pos, return_cache=True, mask_mode=MASK_FORK,
     cache = (torch.empty((bsz, tw - 1, width), dtype=x.dtype, device=x.device)
              if cache_out is None else cache_out)
   assert y.shape == x.shape and y.dtype == x.dtype and y.is_contiguous()
-  with torch.cuda.device(x.device):
+  with _on_device(x.device):
     rc = load().cg_conv1d_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(),
                               seg.data_ptr(), is64, stride, y.data_ptr(),
                               _ptr(cache), bsz, steps, width, tw,
@@ -190,7 +212,7 @@ def conv1d_bwd(gy, x, w, segment_pos, mask_mode=MASK_FORK):
   db = torch.empty((width,), dtype=x.dtype, device=x.device)
   nbytes = load().cg_conv1d_bwd_workspace_bytes(bsz, steps, width)
   ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-  with torch.cuda.device(x.device):
+  with _on_device(x.device):
     rc = load().cg_conv1d_bwd(gy.data_ptr(), x.data_ptr(), w.data_ptr(), seg.data_ptr(), is64, stride,
                               dx.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(),
                               bsz, steps, width, w.shape[0], dtype_code(x.dtype), mask_mode, _stream(x))
@@ -209,7 +231,7 @@ def conv1d_stream_fwd(x, w, b, segment_pos, flags, out, cache_out=None, mask_mod
   assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape
   assert flags.dtype == torch.int32 and flags.numel() * 4 >= load().cg_conv1d_stream_flags_bytes(bsz, steps)
   seg, is64, stride = _seg_args(segment_pos, bsz, steps)
-  with torch.cuda.device(x.device):
+  with _on_device(x.device):
     rc = load().cg_conv1d_stream_fwd(x.data_ptr(), w.contiguous().data_ptr(), b.contiguous().data_ptr(),
                                      seg.data_ptr(), is64, stride, out.data_ptr(), _ptr(cache_out),
                                      flags.data_ptr(), bsz, steps, width, w.shape[0],
@@ -229,7 +251,7 @@ def conv1d_decode(x, w, b, cache, return_cache=True, arith_mode=ARITH_REFERENCE)
   x, w, b, cache = x.contiguous(), w.contiguous(), b.contiguous(), cache.contiguous()
   y = torch.empty_like(x)
   new_cache = torch.empty_like(cache) if return_cache else None
-  with torch.cuda.device(x.device):
+  with _on_device(x.device):
     rc = load().cg_conv1d_decode(x.data_ptr(), w.data_ptr(), b.data_ptr(),
                                  cache.data_ptr(), dtype_code(cache.dtype),
                                  y.data_ptr(), _ptr(new_cache), bsz, width, tw,
@@ -288,7 +310,7 @@ def rglru_fwd(x, gemm_x, gemm_a, bias_x, bias_a, a_param, segment_pos, h0=None,
   bx = None if bias_x is None else bias_x.contiguous().view(-1)
   ba = None if bias_a is None else bias_a.contiguous().view(-1)
   h0c = None if h0 is None else h0.contiguous()
-  with torch.cuda.device(x.device):
+  with _on_device(x.device):
     rc = load().cg_rglru_fwd(x.data_ptr(), px, pa, ldx, gbw, _ptr(bx), _ptr(ba),
                              a_param.contiguous().data_ptr(), seg.data_ptr(), is64,
                              stride, _ptr(h0c), y.data_ptr(), _ptr(last_h),
@@ -311,7 +333,7 @@ def rnn_scan_fwd(x, a, reset, h0=None, arith_mode=ARITH_REFERENCE):
   h_last = torch.empty((bsz, width), dtype=torch.float32, device=x.device)
   ws = scan_workspace(x.device, bsz, steps, width, x.dtype)
   h0c = None if h0 is None else h0.contiguous()
-  with torch.cuda.device(x.device):
+  with _on_device(x.device):
     rc = load().cg_rnn_scan_fwd(x.data_ptr(), a.data_ptr(), rs.data_ptr(),
                                 _ptr(h0c), y.data_ptr(), h_last.data_ptr(),
                                 ws.data_ptr(), ws.numel(), bsz, steps, width,
@@ -332,7 +354,7 @@ def rglru_gates_fwd(x, pre_x, pre_a, a_param, reset):
   x, pre_x, pre_a, ap = x.contiguous(), pre_x.contiguous(), pre_a.contiguous(), a_param.contiguous()
   rs = reset.to(torch.uint8).contiguous()
   a, nx = torch.empty_like(x), torch.empty_like(x)
-  with torch.cuda.device(x.device):
+  with _on_device(x.device):
     rc = load().cg_rglru_gates_fwd(x.data_ptr(), pre_x.data_ptr(), pre_a.data_ptr(), ap.data_ptr(),
                                    rs.data_ptr(), a.data_ptr(), nx.data_ptr(), bsz, steps, width,
                                    dtype_code(x.dtype), _stream(x))
@@ -355,7 +377,7 @@ def rglru_gates_bwd(x, pre_x, pre_a, a_param, reset, d_nx, d_a):
   dap = torch.empty_like(ap)
   ws = torch.empty(load().cg_rglru_gates_bwd_workspace_bytes(bsz, steps, width), dtype=torch.uint8,
                    device=x.device)
-  with torch.cuda.device(x.device):
+  with _on_device(x.device):
     rc = load().cg_rglru_gates_bwd(x.data_ptr(), pre_x.data_ptr(), pre_a.data_ptr(), ap.data_ptr(),
                                    rs.data_ptr(), d_nx.data_ptr(), d_a.data_ptr(), dx.data_ptr(),
                                    dpx.data_ptr(), dpa.data_ptr(), dap.data_ptr(), ws.data_ptr(),
@@ -382,7 +404,7 @@ def rnn_scan_bwd(gy, g_last, a, h, reset, h0=None, need_dh0=True):
   dx, da = torch.empty_like(gy), torch.empty_like(gy)
   dh0 = torch.empty((bsz, width), dtype=torch.float32, device=gy.device) if need_dh0 else None
   ws = scan_workspace(gy.device, bsz, steps, width, gy.dtype)
-  with torch.cuda.device(gy.device):
+  with _on_device(gy.device):
     rc = load().cg_rnn_scan_bwd(gy.data_ptr(), _ptr(glc), a.data_ptr(), h.data_ptr(), rs.data_ptr(),
                                 _ptr(h0c), dx.data_ptr(), da.data_ptr(), _ptr(dh0), ws.data_ptr(),
                                 ws.numel(), bsz, steps, width, dtype_code(gy.dtype), _stream(gy))
@@ -412,7 +434,7 @@ def pack_gate_weights(wx: torch.Tensor, wa: torch.Tensor) -> torch.Tensor:
   assert nbytes > 0, "shape not supported by the fused path"
   out = torch.empty(nbytes, dtype=torch.uint8, device=wx.device)
   wx, wa = wx.detach().contiguous(), wa.detach().contiguous()
-  with torch.cuda.device(wx.device):
+  with _on_device(wx.device):
     rc = load().cg_rglru_pack_gate_weights(wx.data_ptr(), wa.data_ptr(), out.data_ptr(),
                                            width, heads, dtype_code(wx.dtype), _stream(wx))
   _check(rc, "cg_rglru_pack_gate_weights")
@@ -468,7 +490,7 @@ def rglru_fused_fwd(x, wpack, bias_x, bias_a, a_param, segment_pos, heads, h0=No
   h0c = None if h0 is None else h0.contiguous()
   dbg = (torch.zeros((3, bsz, steps, width), dtype=x.dtype, device=x.device)
          if debug else None)
-  with torch.cuda.device(x.device):
+  with _on_device(x.device):
     rc = load().cg_rglru_fused_fwd(x.data_ptr(), wpack.data_ptr(), _ptr(bx), _ptr(ba),
                                    a_param.contiguous().data_ptr(), seg.data_ptr(), is64,
                                    stride, _ptr(h0c), y.data_ptr(), _ptr(last_h),
@@ -513,7 +535,7 @@ def recurrent_decode_step(x, conv_w, conv_b, conv_cache, wx, wa, bias_x, bias_a,
   ba = None if bias_a is None else bias_a.contiguous().view(-1)
   h0c = None if h0 is None else h0.contiguous()
   gm = None if gate_mul is None else gate_mul.contiguous()
-  with torch.cuda.device(x.device):
+  with _on_device(x.device):
     rc = load().cg_recurrent_decode_step(
         x.data_ptr(), conv_w.contiguous().data_ptr(), conv_b.contiguous().data_ptr(),
         conv_cache.data_ptr(), dtype_code(conv_cache.dtype), wx.data_ptr(), wa.data_ptr(),
