@@ -39,7 +39,7 @@ GATHER_EVERY = int(os.environ.get("CG_BENCH_GATHER_EVERY", "18"))   # recurrent 
 METRIC = "rglru_conv1d_prefill_tokens_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of one fused-kernel launch at config 2
 # (ncu --set full, profiles/r1_rglru_fused_kernel_ncu_summary.txt)
-NCU_TRAFFIC_BYTES = 161748480   # 94.05 MB read + 67.70 MB written (profiles/r1_rglru_fused_kernel_ncu_summary.txt)
+NCU_TRAFFIC_BYTES = 162999296   # 94.71 MB read + 68.29 MB written (profiles/r1_rglru_fused_kernel_ncu_summary.txt)
 UNIT = "tokens/s"
 
 
