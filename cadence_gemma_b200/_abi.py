@@ -46,16 +46,20 @@ SYMBOLS = {
     "cg_rglru_gate_pack_bytes": (_sz, [_i, _i]),
     "cg_rglru_pack_gate_weights": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "cg_rglru_fused_workspace_bytes": (_sz, [_i, _i, _i]),
-    "cg_rglru_fused_schedule": (_i, [_i, _i, _i, _i, _i, _vp, _i]),
     "cg_rglru_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp,
-                                _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+                                _vp, _sz, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "cg_recurrent_prefill_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "cg_recurrent_decode_supported": (_i, [_i, _i, _i, _i]),
     "cg_recurrent_decode_step": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll,
                                       _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "cg_conv1d_stream_flags_bytes": (_sz, [_i, _i]),
-    "cg_conv1d_stream_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _i, _i, _i, _i,
-                                  _i, _i, _i, _vp]),
 }
+# include/cadence_b200_experimental.h (development taps, not part of the drop-in surface)
+EXPERIMENTAL_SYMBOLS = {
+    "cg_recurrent_prefill_debug": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _vp, _vp, _vp, _vp,
+                                        _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+}
+ABI_VERSION = 2
 
 _lib = None
 _lock = threading.Lock()
@@ -78,11 +82,13 @@ def load():
             f"{LIB_PATH} is missing: run `python -m cadence_gemma_b200.build` "
             "(there is no CPU / eager fallback for the recurrent hot path)")
       lib = ctypes.CDLL(LIB_PATH)
-      for name, (restype, argtypes) in SYMBOLS.items():
+      for name, (restype, argtypes) in {**SYMBOLS, **EXPERIMENTAL_SYMBOLS}.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = restype, argtypes
-      if lib.cg_abi_version() != 1:
-        raise CadenceAbiError("libcadence_b200.so ABI version mismatch")
+      if lib.cg_abi_version() != ABI_VERSION:
+        raise CadenceAbiError(
+            f"libcadence_b200.so ABI version {lib.cg_abi_version()} != {ABI_VERSION}: rebuild "
+            "(python -m cadence_gemma_b200.build --force)")
       _lib = lib
   return _lib
 
@@ -157,21 +163,30 @@ def _seg_args(segment_pos: torch.Tensor, batch: int, steps: int):
 
 
 # ---------------------------------------------------------------------------
+# Scratch buffers: ONE grow-only buffer per (device, stream, kind).  The kernels tag
+# every exchange word with a per-launch epoch, so a buffer can be reused across
+# shapes; it is never freed or replaced by a smaller one while the process lives,
+# and a buffer that had to grow is kept alive next to its successor (a captured
+# CUDA graph may still hold its address -- ADVICE r1).
 _workspaces: dict = {}
+_retired_workspaces: list = []
+
+
+def _grow_only_workspace(kind: str, device, nbytes: int) -> torch.Tensor:
+  key = (kind, device, torch.cuda.current_stream(device).cuda_stream)
+  ws = _workspaces.get(key)
+  if ws is None or ws.numel() < nbytes:
+    if ws is not None:
+      _retired_workspaces.append(ws)
+    ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)   # zero-filled ONCE (header contract)
+    _workspaces[key] = ws
+  return ws
 
 
 def scan_workspace(device, batch: int, steps: int, width: int, dtype) -> torch.Tensor:
-  """Cached scratch buffer per (device, stream, shape), zero-filled once."""
-  key = (device, torch.cuda.current_stream(device).cuda_stream, batch, steps,
-         width, dtype)
-  ws = _workspaces.get(key)
-  if ws is None:
-    nbytes = load().cg_scan_workspace_bytes(batch, steps, width, dtype_code(dtype))
-    ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-    if len(_workspaces) > 64:
-      _workspaces.clear()
-    _workspaces[key] = ws
-  return ws
+  """Scratch of the scan kernels for the current stream (grow-only, zero-filled once)."""
+  nbytes = load().cg_scan_workspace_bytes(batch, steps, width, dtype_code(dtype))
+  return _grow_only_workspace("scan", device, nbytes)
 
 
 def conv1d_fwd(x, w, b, segment_pos, return_cache=True, mask_mode=MASK_FORK,
@@ -219,26 +234,6 @@ def conv1d_bwd(gy, x, w, segment_pos, mask_mode=MASK_FORK):
   _check(rc, "cg_conv1d_bwd")
   launch_count += 2
   return dx, dw, db
-
-
-def conv1d_stream_fwd(x, w, b, segment_pos, flags, out, cache_out=None, mask_mode=MASK_FORK,
-                      arith_mode=ARITH_REFERENCE):
-  """Producer form of ``conv1d_fwd`` for the overlapped Conv1D -> RG-LRU pipeline
-  (``flags``: zeroed int32 [ceil(T/64) * B]); enqueued on the CURRENT stream."""
-  global launch_count
-  _require_cuda(x, w, b, segment_pos, flags, out)
-  bsz, steps, width = x.shape
-  assert x.is_contiguous() and out.is_contiguous() and out.shape == x.shape
-  assert flags.dtype == torch.int32 and flags.numel() * 4 >= load().cg_conv1d_stream_flags_bytes(bsz, steps)
-  seg, is64, stride = _seg_args(segment_pos, bsz, steps)
-  with _on_device(x.device):
-    rc = load().cg_conv1d_stream_fwd(x.data_ptr(), w.contiguous().data_ptr(), b.contiguous().data_ptr(),
-                                     seg.data_ptr(), is64, stride, out.data_ptr(), _ptr(cache_out),
-                                     flags.data_ptr(), bsz, steps, width, w.shape[0],
-                                     dtype_code(x.dtype), mask_mode, arith_mode, _stream(x))
-  _check(rc, "cg_conv1d_stream_fwd")
-  launch_count += 1
-  return out, cache_out
 
 
 def conv1d_decode(x, w, b, cache, return_cache=True, arith_mode=ARITH_REFERENCE):
@@ -442,37 +437,45 @@ def pack_gate_weights(wx: torch.Tensor, wa: torch.Tensor) -> torch.Tensor:
   return out
 
 
-_fused_workspaces: dict = {}
-
-
 def fused_workspace(device, batch: int, steps: int, width: int) -> torch.Tensor:
-  key = (device, torch.cuda.current_stream(device).cuda_stream, batch, steps, width)
-  ws = _fused_workspaces.get(key)
-  if ws is None:
-    nbytes = load().cg_rglru_fused_workspace_bytes(batch, steps, width)
-    ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
-    if len(_fused_workspaces) > 64:
-      _fused_workspaces.clear()
-    _fused_workspaces[key] = ws
-  return ws
-
-
-def fused_watchdog_code(ws: torch.Tensor) -> int:
-  """Non-zero after a launch whose kernel-side watchdog fired (synchronises)."""
-  return int(ws[8:12].view(torch.int32).item())
+  """Scratch of the fused tensor-core kernels for the current stream (grow-only)."""
+  nbytes = load().cg_rglru_fused_workspace_bytes(batch, steps, width)
+  return _grow_only_workspace("fused", device, nbytes)
 
 
 def rglru_fused_fwd(x, wpack, bias_x, bias_a, a_param, segment_pos, heads, h0=None,
                     return_cache=True, arith_mode=ARITH_FAST, out=None, debug=False,
-                    workspace=None, last_h_out=None, gate_mul=None, conv_flags=None):
+                    workspace=None, last_h_out=None, gate_mul=None):
   """RGLRU.forward (gate GEMMs included) on the fused tcgen05 kernel.
 
   ``gate_mul`` ([B,T,E], optional): return ``round(y * gate_mul)`` -- the gating
-  product of ``RecurrentBlock.forward`` (reference modules.py:651) folded in."""
+  product of ``RecurrentBlock.forward`` (reference modules.py:651) folded in.
+  ``debug`` (tests): also return the pre-activation / x taps (experimental ABI)."""
+  res = recurrent_prefill_fwd(x, None, None, wpack, bias_x, bias_a, a_param, segment_pos, heads, h0=h0,
+                              return_cache=return_cache, arith_mode=arith_mode, out=out, debug=debug,
+                              workspace=workspace, last_h_out=last_h_out, gate_mul=gate_mul)
+  return (res[0], res[2]) + tuple(res[3:])
+
+
+def recurrent_prefill_fwd(x, conv_w, conv_b, wpack, bias_x, bias_a, a_param, segment_pos, heads,
+                          h0=None, return_cache=True, mask_mode=MASK_FORK, arith_mode=ARITH_FAST,
+                          out=None, conv_cache_out=None, last_h_out=None, gate_mul=None, debug=False,
+                          workspace=None):
+  """``Conv1D.forward -> RGLRU.forward`` (prefill) in ONE fused kernel
+  (``cg_recurrent_prefill_fwd``): ``x`` is the convolution's INPUT, the temporal
+  convolution runs inside the tcgen05 kernel.  With ``conv_w is None`` ``x`` is
+  the convolution's output and the call is ``cg_rglru_fused_fwd``.
+
+  Returns ``(y, conv_cache | None, last_h | None[, debug taps])``."""
   global launch_count
-  _require_cuda(x, wpack, bias_x, bias_a, a_param, segment_pos, h0, gate_mul)
+  _require_cuda(x, conv_w, conv_b, wpack, bias_x, bias_a, a_param, segment_pos, h0, gate_mul)
   bsz, steps, width = x.shape
   assert x.dtype == torch.bfloat16 and a_param.dtype == x.dtype
+  conv = conv_w is not None
+  if conv:
+    assert conv_w.shape == (4, width) and conv_b.shape == (width,), "fused prefill: temporal width 4"
+    assert conv_w.dtype == x.dtype and conv_b.dtype == x.dtype
+    conv_w, conv_b = conv_w.contiguous(), conv_b.contiguous()
   if gate_mul is not None:
     assert gate_mul.shape == x.shape and gate_mul.dtype == x.dtype
     gate_mul = gate_mul.contiguous()
@@ -480,28 +483,49 @@ def rglru_fused_fwd(x, wpack, bias_x, bias_a, a_param, segment_pos, heads, h0=No
   x = x.contiguous()
   seg, is64, stride = _seg_args(segment_pos, bsz, steps)
   y = torch.empty_like(x) if out is None else out
-  last_h = None
+  assert y.shape == x.shape and y.dtype == x.dtype and y.is_contiguous()
+  last_h = conv_cache = None
   if return_cache:
     last_h = (torch.empty((bsz, width), dtype=torch.float32, device=x.device)
               if last_h_out is None else last_h_out)
+    if conv:
+      conv_cache = (torch.empty((bsz, 3, width), dtype=x.dtype, device=x.device)
+                    if conv_cache_out is None else conv_cache_out)
+      assert conv_cache.shape == (bsz, 3, width) and conv_cache.dtype == x.dtype and conv_cache.is_contiguous()
   ws = fused_workspace(x.device, bsz, steps, width) if workspace is None else workspace
   bx = None if bias_x is None else bias_x.contiguous().view(-1)
   ba = None if bias_a is None else bias_a.contiguous().view(-1)
   h0c = None if h0 is None else h0.contiguous()
-  dbg = (torch.zeros((3, bsz, steps, width), dtype=x.dtype, device=x.device)
-         if debug else None)
+  ap = a_param.contiguous()
+  lib = load()
   with _on_device(x.device):
-    rc = load().cg_rglru_fused_fwd(x.data_ptr(), wpack.data_ptr(), _ptr(bx), _ptr(ba),
-                                   a_param.contiguous().data_ptr(), seg.data_ptr(), is64,
-                                   stride, _ptr(h0c), y.data_ptr(), _ptr(last_h),
-                                   ws.data_ptr(), ws.numel(), bsz, steps, width, heads,
-                                   dtype_code(x.dtype), arith_mode, _ptr(gate_mul),
-                                   _ptr(conv_flags), _ptr(dbg), _stream(x))
-  _check(rc, "cg_rglru_fused_fwd")
+    if debug:
+      assert gate_mul is None
+      dbg = torch.zeros((3, bsz, steps, width), dtype=x.dtype, device=x.device)
+      rc = lib.cg_recurrent_prefill_debug(x.data_ptr(), _ptr(conv_w), _ptr(conv_b), wpack.data_ptr(),
+                                          _ptr(bx), _ptr(ba), ap.data_ptr(), seg.data_ptr(), is64, stride,
+                                          _ptr(h0c), y.data_ptr(), _ptr(conv_cache), _ptr(last_h),
+                                          ws.data_ptr(), ws.numel(), bsz, steps, width, heads,
+                                          dtype_code(x.dtype), mask_mode, arith_mode, dbg.data_ptr(), _stream(x))
+      what = "cg_recurrent_prefill_debug"
+    elif conv:
+      rc = lib.cg_recurrent_prefill_fwd(x.data_ptr(), conv_w.data_ptr(), conv_b.data_ptr(), wpack.data_ptr(),
+                                        _ptr(bx), _ptr(ba), ap.data_ptr(), seg.data_ptr(), is64, stride,
+                                        _ptr(h0c), _ptr(gate_mul), y.data_ptr(), _ptr(conv_cache), _ptr(last_h),
+                                        ws.data_ptr(), ws.numel(), bsz, steps, width, heads, 4,
+                                        dtype_code(x.dtype), mask_mode, arith_mode, _stream(x))
+      what = "cg_recurrent_prefill_fwd"
+    else:
+      rc = lib.cg_rglru_fused_fwd(x.data_ptr(), wpack.data_ptr(), _ptr(bx), _ptr(ba), ap.data_ptr(),
+                                  seg.data_ptr(), is64, stride, _ptr(h0c), y.data_ptr(), _ptr(last_h),
+                                  ws.data_ptr(), ws.numel(), bsz, steps, width, heads,
+                                  dtype_code(x.dtype), arith_mode, _ptr(gate_mul), _stream(x))
+      what = "cg_rglru_fused_fwd"
+  _check(rc, what)
   launch_count += 2   # prologue + fused kernel
   if debug:
-    return y, last_h, dbg
-  return y, last_h
+    return y, conv_cache, last_h, dbg
+  return y, conv_cache, last_h
 
 
 # ---------------------------------------------------------------------------

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "cg_common.cuh"
 #include "cg_conv1d.cuh"
 #include "cg_scan.cuh"
@@ -24,6 +26,11 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 constexpr int kMinSuperChunk = 64;  // smallest NW * 4 * L of any compiled geometry
+
+// Per-device launch state: cudaFuncSetAttribute, occupancy and the SM count belong
+// to a device, not to the process (a process may drive several GPUs).
+constexpr int kMaxDevices = 64;
+struct DeviceSlot { std::once_flag once; int sms = 0; cudaError_t err = cudaSuccess; };
 
 // scratch layout: [ticket, epoch | 256 B][agg_p][agg_h][pref][neg8sp]
 // The exchange arrays hold 64-bit {value, epoch} words; the scratch must be
@@ -72,20 +79,27 @@ int launch_scan(ScanParams p, void* workspace, size_t workspace_bytes, cudaStrea
   p.counter = ws.counter; p.epoch = ws.epoch;
   p.agg_p = ws.agg_p; p.agg_h = ws.agg_h; p.pref = ws.pref;
   auto kernel = cg::scan_kernel<IO, KIND, ARITH, L, NW, STAGES, MINB>;
-  static int resident = 0;   // CTAs that fit on the device; queried once per process
-  if (resident == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+  // CTAs that fit on the device: function attributes and the occupancy belong to a
+  // device, so they are set up once per device (a process may drive several GPUs)
+  static DeviceSlot slots[kMaxDevices];
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev)) return (int)e;
+  if (dev < 0 || dev >= kMaxDevices) return (int)cudaErrorInvalidDevice;
+  DeviceSlot& slot = slots[dev];
+  std::call_once(slot.once, [&] {
+    slot.err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (slot.err != cudaSuccess) return;
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
+    int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NW * 32, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1 || sms < 1) return (int)cudaErrorLaunchOutOfResources;
-    resident = per_sm * sms;
-  }
+    slot.err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NW * 32, smem);
+    if (slot.err != cudaSuccess) return;
+    if (per_sm < 1 || sms < 1) { slot.err = cudaErrorLaunchOutOfResources; return; }
+    slot.sms = per_sm * sms;   // resident CTAs
+  });
+  if (slot.err != cudaSuccess) return (int)slot.err;
+  const int resident = slot.sms;
   const int grid = p.nitems < resident ? p.nitems : resident;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -242,45 +256,6 @@ int cg_conv1d_bwd(const void* gy, const void* x, const void* w, const void* seg,
   const int rgrid = (5 * E + 127) / 128;
   if (bf) cg::conv1d_bwd_reduce_kernel<uint16_t><<<rgrid, 128, 0, stream>>>(p.partial, nparts, E, dw, db);
   else cg::conv1d_bwd_reduce_kernel<float><<<rgrid, 128, 0, stream>>>(p.partial, nparts, E, dw, db);
-  return (int)cudaGetLastError();
-}
-
-size_t cg_conv1d_stream_flags_bytes(int B, int T) {
-  if (B < 1 || T < 1) return 0;
-  return (size_t)B * ((T + 63) / 64) * sizeof(int);
-}
-
-int cg_conv1d_stream_fwd(const void* x, const void* w, const void* b, const void* seg, int seg_is_i64,
-                         long long seg_batch_stride, void* y, void* cache_out, int* flags, int B, int T,
-                         int E, int W, int dtype, int mask_mode, int arith_mode, cg_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (!x || !w || !b || !seg || !y || !flags) return CG_ERR_NULL;
-  if (int rc = check_common(B, T, E, dtype)) return rc;
-  if (mask_mode != CG_MASK_FORK && mask_mode != CG_MASK_UPSTREAM) return CG_ERR_MODE;
-  // producer form exists for the shapes the fused RG-LRU kernel takes: bf16, W = 4,
-  // reference rounding
-  if (dtype != CG_DTYPE_BF16 || W != 4 || (arith_mode & CG_ARITH_FP32) != 0) return CG_ERR_UNSUPPORTED;
-  if (E % 64 != 0) return CG_ERR_UNSUPPORTED;
-  if (!aligned16(x) || !aligned16(w) || !aligned16(b) || !aligned16(y) ||
-      (cache_out && !aligned16(cache_out)))
-    return CG_ERR_ALIGN;
-  ConvParams p{};
-  p.x = x; p.w = w; p.bias = b; p.seg = seg; p.seg_bstride = seg_batch_stride;
-  p.seg_is_i64 = seg_is_i64; p.y = y; p.cache_out = cache_out;
-  p.B = B; p.T = T; p.E = E; p.W = W; p.mask_mode = mask_mode;
-  constexpr int LC = 4;                       // 16 slots x 4 steps = one 64-step group per tile
-  const int ctiles = E / 64, tgroups = (T + 63) / 64;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms < 1) return (int)cudaErrorLaunchOutOfResources;
-  }
-  const long long ntiles = (long long)ctiles * tgroups * B;
-  // one small block per SM: they share the SMs with the fused RG-LRU CTAs
-  const int grid = (int)(ntiles < sms ? ntiles : sms);
-  cg::conv1d_w4_stream_kernel<uint16_t, true, LC><<<grid, 128, 0, stream>>>(p, flags, ctiles, tgroups);
   return (int)cudaGetLastError();
 }
 
@@ -588,21 +563,23 @@ bool fused_shape_ok(int E, int H, int dtype) {
   return bw == 128 || bw == 256;
 }
 
-template <int KB, bool FAST, bool DBG, bool MUL>
+template <int KB, bool FAST, bool DBG, bool MUL, bool CONV>
 int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int grid_limit,
                  cudaStream_t stream) {
   using Cfg = cg::fused::FusedCfg<KB>;
-  auto kernel = cg::fused::rglru_fused_kernel<KB, FAST, DBG, MUL>;
-  static int sms = 0;
-  if (sms == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)Cfg::kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms < 1) return (int)cudaErrorLaunchOutOfResources;
-  }
+  auto kernel = cg::fused::rglru_fused_kernel<KB, FAST, DBG, MUL, CONV>;
+  static DeviceSlot slots[kMaxDevices];
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev)) return (int)e;
+  if (dev < 0 || dev >= kMaxDevices) return (int)cudaErrorInvalidDevice;
+  DeviceSlot& slot = slots[dev];
+  std::call_once(slot.once, [&] {
+    slot.err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
+    if (slot.err == cudaSuccess) slot.err = cudaDeviceGetAttribute(&slot.sms, cudaDevAttrMultiProcessorCount, dev);
+  });
+  if (slot.err != cudaSuccess) return (int)slot.err;
+  const int sms = slot.sms;
+  if (sms < 1) return (int)cudaErrorLaunchOutOfResources;
   // one persistent CTA per SM; grid_limit > 0 (test hook) runs with fewer CTAs than
   // column families, which exercises the family loop (weight reload) of a CTA
   const int grid = grid_limit > 0 && grid_limit < sms ? grid_limit : sms;
@@ -624,69 +601,24 @@ int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int g
   return (int)cudaGetLastError();
 }
 
-template <int KB>
+template <int KB, bool CONV>
 int dispatch_fused(bool fast, bool dbg, bool mul, const CUtensorMap& tmap,
                    const cg::fused::FusedParams& p, int grid_limit, cudaStream_t stream) {
-  if (dbg) return fast ? launch_fused<KB, true, true, false>(tmap, p, grid_limit, stream)
-                       : launch_fused<KB, false, true, false>(tmap, p, grid_limit, stream);
-  if (mul) return fast ? launch_fused<KB, true, false, true>(tmap, p, grid_limit, stream)
-                       : launch_fused<KB, false, false, true>(tmap, p, grid_limit, stream);
-  return fast ? launch_fused<KB, true, false, false>(tmap, p, grid_limit, stream)
-              : launch_fused<KB, false, false, false>(tmap, p, grid_limit, stream);
+  if (dbg) return fast ? launch_fused<KB, true, true, false, CONV>(tmap, p, grid_limit, stream)
+                       : launch_fused<KB, false, true, false, CONV>(tmap, p, grid_limit, stream);
+  if (mul) return fast ? launch_fused<KB, true, false, true, CONV>(tmap, p, grid_limit, stream)
+                       : launch_fused<KB, false, false, true, CONV>(tmap, p, grid_limit, stream);
+  return fast ? launch_fused<KB, true, false, false, CONV>(tmap, p, grid_limit, stream)
+              : launch_fused<KB, false, false, false, CONV>(tmap, p, grid_limit, stream);
 }
 
-}  // namespace
-
-extern "C" {
-
-int cg_rglru_fused_supported(int E, int H, int dtype) { return fused_shape_ok(E, H, dtype) ? 1 : 0; }
-
-size_t cg_rglru_gate_pack_bytes(int E, int H) {
-  if (!fused_shape_ok(E, H, CG_DTYPE_BF16)) return 0;
-  const size_t bw = (size_t)E / H;
-  // [E/128 families][2 gates][bw/64 K blocks][128 rows][128 B] + identity [2][128][128 B]
-  return (size_t)(E / 128) * 2 * (bw / 64) * cg::fused::kKBlockBytes + 2 * cg::fused::kKBlockBytes;
-}
-
-int cg_rglru_pack_gate_weights(const void* wx, const void* wa, void* wpack, int E, int H, int dtype,
-                               cg_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (!wx || !wa || !wpack) return CG_ERR_NULL;
-  if (!fused_shape_ok(E, H, dtype)) return CG_ERR_UNSUPPORTED;
-  if (!aligned16(wpack)) return CG_ERR_ALIGN;
-  const int bw = E / H;
-  const size_t wbytes = cg_rglru_gate_pack_bytes(E, H) - 2 * cg::fused::kKBlockBytes;
-  const long long chunks = (long long)(wbytes / 16) + 2 * 128 * 8;
-  cg::fused::pack_gate_weights_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const uint16_t*>(wx), reinterpret_cast<const uint16_t*>(wa),
-      reinterpret_cast<unsigned char*>(wpack), reinterpret_cast<unsigned char*>(wpack) + wbytes, H, bw);
-  return (int)cudaGetLastError();
-}
-
-int cg_rglru_fused_schedule(int ctas, int families, int pairs, int cta, int balance, int* segments,
-                            int max_segments) {
-  if (ctas < 1 || families < 1 || pairs < 0 || cta < 0 || cta >= ctas) return CG_ERR_SHAPE;
-  const cg::fused::Schedule sched(cta, ctas, families, pairs, balance < 0 ? CGF_BALANCE != 0 : balance != 0);
-  const int n = sched.nseg();
-  for (int i = 0; i < n && i < max_segments && segments != nullptr; ++i) {
-    const cg::fused::Seg sg = sched.get(i);
-    segments[4 * i] = sg.fam; segments[4 * i + 1] = sg.j0;
-    segments[4 * i + 2] = sg.stride; segments[4 * i + 3] = sg.count;
-  }
-  return n;
-}
-
-size_t cg_rglru_fused_workspace_bytes(int B, int T, int E) {
-  if (B < 1 || T < 1 || E < 1) return 0;
-  return carve(nullptr, B, T, E, cg::fused::kMch, cg::fused::kTile).total;
-}
-
-int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, const void* bias_a,
-                       const void* a_param, const void* seg, int seg_is_i64, long long seg_batch_stride,
-                       const float* h0, void* y, float* last_h, void* workspace, size_t workspace_bytes,
-                       int B, int T, int E, int H, int dtype, int arith_mode, const void* gate_mul,
-                       const int* conv_flags, void* debug_out, cg_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+// Shared body of cg_rglru_fused_fwd (x = Conv1D output) and cg_recurrent_prefill_fwd
+// (x = Conv1D INPUT, convolution inside the kernel when conv_w != nullptr).
+int fused_forward(const void* x, const void* conv_w, const void* conv_b, void* conv_cache_out, int mask_mode,
+                  const void* wpack, const void* bias_x, const void* bias_a, const void* a_param,
+                  const void* seg, int seg_is_i64, long long seg_batch_stride, const float* h0, void* y,
+                  float* last_h, void* workspace, size_t workspace_bytes, int B, int T, int E, int H,
+                  int dtype, int arith_mode, const void* gate_mul, void* debug_out, cudaStream_t stream) {
   if (!x || !wpack || !a_param || !seg || !y || !workspace) return CG_ERR_NULL;
   if (int rc = check_common(B, T, E, dtype)) return rc;
   if (!fused_shape_ok(E, H, dtype)) return CG_ERR_UNSUPPORTED;
@@ -695,26 +627,31 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
   if ((arith_mode & ~0xff07) != 0 || (mode & (CG_ARITH_FP32 | CG_ARITH_STRICT)) != 0) return CG_ERR_MODE;
   if (variant > 64) return CG_ERR_MODE;   // variant v > 0: at most v CTAs (test hook, see launch_fused)
   if (!aligned16(x) || !aligned16(wpack) || !aligned16(y) || !aligned16(workspace)) return CG_ERR_ALIGN;
+  const bool conv = conv_w != nullptr;
+  if (conv) {
+    if (!conv_b) return CG_ERR_NULL;
+    if (mask_mode != CG_MASK_FORK && mask_mode != CG_MASK_UPSTREAM) return CG_ERR_MODE;
+    if (!aligned16(conv_w) || !aligned16(conv_b) || (conv_cache_out && !aligned16(conv_cache_out))) return CG_ERR_ALIGN;
+  }
   if (B > 65535) return CG_ERR_SHAPE;
   if (gate_mul != nullptr && debug_out != nullptr) return CG_ERR_MODE;   // the debug build has no product path
   const int bw = E / H;
   const int tile_t = cg::fused::kTile;
-  const Workspace ws_min = carve(workspace, B, T, E, cg::fused::kMch, tile_t);
-  if (ws_min.total > workspace_bytes) return CG_ERR_WORKSPACE;
-  const Workspace& ws = ws_min;
+  const Workspace ws = carve(workspace, B, T, E, cg::fused::kMch, tile_t);
+  if (ws.total > workspace_bytes) return CG_ERR_WORKSPACE;
   const int words = (T + 31) / 32;
   {   // epoch bump, -8*softplus(a_param), reset bitmask (shared with the unfused path)
     cg::PrologueParams q{};
-    q.a_param = a_param; q.neg8sp = ws_min.neg8sp; q.neg8sp_bf = ws_min.neg8sp_bf;
+    q.a_param = a_param; q.neg8sp = ws.neg8sp; q.neg8sp_bf = ws.neg8sp_bf;
     q.E = E; q.is_bf16 = 1; q.emulate = 1;
-    q.counter = ws_min.counter; q.epoch = ws_min.epoch;
+    q.counter = ws.counter; q.epoch = ws.epoch;
     q.seg = seg; q.seg_is_i64 = seg_is_i64; q.seg_bstride = seg_batch_stride;
-    q.reset_bits = ws_min.reset_bits;
+    q.reset_bits = ws.reset_bits;
     q.rows = seg_batch_stride == 0 ? 1 : B; q.T = T; q.words_per_row = words;
     const int n = E > q.rows * words * 32 ? E : q.rows * words * 32;
-    // programmatic dependent of whatever precedes it on the stream: behind our
-    // Conv1D kernel (which triggers early) it runs under that kernel's tail; it
-    // reads nothing the convolution writes and does not complete before it
+    // programmatic dependent of whatever precedes it on the stream (the kernel that
+    // produces x): it runs under that kernel's tail if that kernel triggers early;
+    // it reads nothing that kernel writes and does not complete before it
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((n + 127) / 128);
     cfg.blockDim = dim3(128);
@@ -746,15 +683,18 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
   p.ident = p.wpack + wbytes;
   p.bias_x = reinterpret_cast<const uint16_t*>(bias_x);
   p.bias_a = reinterpret_cast<const uint16_t*>(bias_a);
-  p.neg8sp_bf = ws_min.neg8sp_bf;
-  p.reset_bits = ws_min.reset_bits;
+  p.neg8sp_bf = ws.neg8sp_bf;
+  p.reset_bits = ws.reset_bits;
   p.bits_bstride = seg_batch_stride == 0 ? 0 : words;
   p.words = words;
   p.h0 = h0; p.y = reinterpret_cast<uint16_t*>(y); p.last_h = last_h;
   p.epoch = ws.epoch; p.agg_p = ws.agg_p; p.agg_h = ws.agg_h; p.pref = ws.pref;
   p.gate_mul = reinterpret_cast<const uint16_t*>(gate_mul);
-  p.conv_flags = conv_flags;
-  p.conv_need = (E + 63) / 64;
+  p.x_lin = reinterpret_cast<const uint16_t*>(x);
+  p.conv_w = reinterpret_cast<const uint16_t*>(conv_w);
+  p.conv_b = reinterpret_cast<const uint16_t*>(conv_b);
+  p.conv_cache = reinterpret_cast<uint16_t*>(conv_cache_out);
+  p.mask_mode = mask_mode;
   p.dbg = reinterpret_cast<uint16_t*>(debug_out);
   p.err = ws.counter + 2;   // third word of the scratch header
   p.B = B; p.T = T; p.E = E;
@@ -763,8 +703,82 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, con
   const bool fast = (mode & CG_ARITH_FAST) != 0;
   const bool dbg = debug_out != nullptr;
   const bool mul = gate_mul != nullptr;
-  return bw == 256 ? dispatch_fused<4>(fast, dbg, mul, tmap, p, variant, stream)
-                   : dispatch_fused<2>(fast, dbg, mul, tmap, p, variant, stream);
+  if (conv)
+    return bw == 256 ? dispatch_fused<4, true>(fast, dbg, mul, tmap, p, variant, stream)
+                     : dispatch_fused<2, true>(fast, dbg, mul, tmap, p, variant, stream);
+  return bw == 256 ? dispatch_fused<4, false>(fast, dbg, mul, tmap, p, variant, stream)
+                   : dispatch_fused<2, false>(fast, dbg, mul, tmap, p, variant, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+int cg_rglru_fused_supported(int E, int H, int dtype) { return fused_shape_ok(E, H, dtype) ? 1 : 0; }
+
+size_t cg_rglru_gate_pack_bytes(int E, int H) {
+  if (!fused_shape_ok(E, H, CG_DTYPE_BF16)) return 0;
+  const size_t bw = (size_t)E / H;
+  // [E/128 families][2 gates][bw/64 K blocks][128 rows][128 B] + identity [2][128][128 B]
+  return (size_t)(E / 128) * 2 * (bw / 64) * cg::fused::kKBlockBytes + 2 * cg::fused::kKBlockBytes;
+}
+
+int cg_rglru_pack_gate_weights(const void* wx, const void* wa, void* wpack, int E, int H, int dtype,
+                               cg_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!wx || !wa || !wpack) return CG_ERR_NULL;
+  if (!fused_shape_ok(E, H, dtype)) return CG_ERR_UNSUPPORTED;
+  if (!aligned16(wpack)) return CG_ERR_ALIGN;
+  const int bw = E / H;
+  const size_t wbytes = cg_rglru_gate_pack_bytes(E, H) - 2 * cg::fused::kKBlockBytes;
+  const long long chunks = (long long)(wbytes / 16) + 2 * 128 * 8;
+  cg::fused::pack_gate_weights_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint16_t*>(wx), reinterpret_cast<const uint16_t*>(wa),
+      reinterpret_cast<unsigned char*>(wpack), reinterpret_cast<unsigned char*>(wpack) + wbytes, H, bw);
+  return (int)cudaGetLastError();
+}
+
+size_t cg_rglru_fused_workspace_bytes(int B, int T, int E) {
+  if (B < 1 || T < 1 || E < 1) return 0;
+  return carve(nullptr, B, T, E, cg::fused::kMch, cg::fused::kTile).total;
+}
+
+int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x, const void* bias_a,
+                       const void* a_param, const void* seg, int seg_is_i64, long long seg_batch_stride,
+                       const float* h0, void* y, float* last_h, void* workspace, size_t workspace_bytes,
+                       int B, int T, int E, int H, int dtype, int arith_mode, const void* gate_mul,
+                       cg_stream_t stream_) {
+  return fused_forward(x, nullptr, nullptr, nullptr, CG_MASK_FORK, wpack, bias_x, bias_a, a_param, seg,
+                       seg_is_i64, seg_batch_stride, h0, y, last_h, workspace, workspace_bytes, B, T, E, H,
+                       dtype, arith_mode, gate_mul, nullptr, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+int cg_recurrent_prefill_fwd(const void* x, const void* conv_w, const void* conv_b, const void* wpack,
+                             const void* bias_x, const void* bias_a, const void* a_param, const void* seg,
+                             int seg_is_i64, long long seg_batch_stride, const float* h0, const void* gate_mul,
+                             void* y, void* conv_cache_out, float* last_h, void* workspace,
+                             size_t workspace_bytes, int B, int T, int E, int H, int W, int dtype,
+                             int mask_mode, int arith_mode, cg_stream_t stream_) {
+  if (!conv_w || !conv_b) return CG_ERR_NULL;
+  if (W != 4) return CG_ERR_UNSUPPORTED;   // the temporal width of every Griffin preset
+  return fused_forward(x, conv_w, conv_b, conv_cache_out, mask_mode, wpack, bias_x, bias_a, a_param, seg,
+                       seg_is_i64, seg_batch_stride, h0, y, last_h, workspace, workspace_bytes, B, T, E, H,
+                       dtype, arith_mode, gate_mul, nullptr, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+/* experimental (include/cadence_b200_experimental.h): the same two entry points with a
+ * debug tap -- debug_out [3][B,T,E] receives the rounded gate pre-activations and the
+ * (convolved) x as the epilogue sees them.  Not part of the drop-in surface. */
+int cg_recurrent_prefill_debug(const void* x, const void* conv_w, const void* conv_b, const void* wpack,
+                               const void* bias_x, const void* bias_a, const void* a_param, const void* seg,
+                               int seg_is_i64, long long seg_batch_stride, const float* h0, void* y,
+                               void* conv_cache_out, float* last_h, void* workspace, size_t workspace_bytes,
+                               int B, int T, int E, int H, int dtype, int mask_mode, int arith_mode,
+                               void* debug_out, cg_stream_t stream_) {
+  if (!debug_out) return CG_ERR_NULL;
+  return fused_forward(x, conv_w, conv_b, conv_cache_out, mask_mode, wpack, bias_x, bias_a, a_param, seg,
+                       seg_is_i64, seg_batch_stride, h0, y, last_h, workspace, workspace_bytes, B, T, E, H,
+                       dtype, arith_mode, nullptr, debug_out, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 
@@ -803,14 +817,18 @@ int cg_recurrent_decode_step(const void* x, const void* conv_w, const void* conv
   dim3 grid(H * (p.bw / 64), (B + cg::kDecBT - 1) / cg::kDecBT);
   size_t smem = (size_t)2 * p.bw * 128;                  // both gates' [bw x 64] bf16 slice ...
   if (smem < 32768) smem = 32768;                        // ... later reused for the partial sums
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(cg::recurrent_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         2 * cg::kDecMaxBw * 128);
-    cudaFuncSetAttribute(cg::recurrent_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         2 * cg::kDecMaxBw * 128);
-    configured = true;
-  }
+  static DeviceSlot slots[kMaxDevices];
+  int dev = 0;
+  if (cudaError_t e = cudaGetDevice(&dev)) return (int)e;
+  if (dev < 0 || dev >= kMaxDevices) return (int)cudaErrorInvalidDevice;
+  std::call_once(slots[dev].once, [&] {
+    slots[dev].err = cudaFuncSetAttribute(cg::recurrent_decode_kernel<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * cg::kDecMaxBw * 128);
+    if (slots[dev].err == cudaSuccess)
+      slots[dev].err = cudaFuncSetAttribute(cg::recurrent_decode_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * cg::kDecMaxBw * 128);
+  });
+  if (slots[dev].err != cudaSuccess) return (int)slots[dev].err;
   if (arith_mode & CG_ARITH_FAST) cg::recurrent_decode_kernel<true><<<grid, 256, smem, stream>>>(p);
   else cg::recurrent_decode_kernel<false><<<grid, 256, smem, stream>>>(p);
   return (int)cudaGetLastError();

@@ -33,10 +33,8 @@ struct ConvParams {
 // the reference.  !EMUL (bf16 only): fp32 accumulation, one final rounding.
 // ---------------------------------------------------------------------------
 // One tile = 128 threads: channel tile `ctile` (8 lanes x 16 B), 16 time slots of
-// LC steps starting at slot block `tblock`, batch row b.  KEEP: plain stores (the
-// output is re-read from L2 right away by a concurrently running consumer)
-// instead of streaming (evict-first) ones.
-template <typename IO, bool EMUL, int LC, bool KEEP>
+// LC steps starting at slot block `tblock`, batch row b.
+template <typename IO, bool EMUL, int LC>
 __device__ __forceinline__ void conv1d_w4_tile(const ConvParams& p, int ctile, int tblock, int b) {
   constexpr int V = IoVec<IO>::V;
   constexpr bool BF = IoVec<IO>::kBf16;
@@ -126,8 +124,7 @@ __device__ __forceinline__ void conv1d_w4_tile(const ConvParams& p, int ctile, i
         o[i] = __float_as_uint(__fadd_rn(acc, __uint_as_float(bb[i])));
       }
     }
-    if constexpr (KEEP) *reinterpret_cast<uint4*>(yb + (size_t)t * p.E) = make_uint4(o[0], o[1], o[2], o[3]);
-    else stg_stream(yb + (size_t)t * p.E, make_uint4(o[0], o[1], o[2], o[3]));
+    stg_stream(yb + (size_t)t * p.E, make_uint4(o[0], o[1], o[2], o[3]));
   }
 
   // new cache = last 3 input rows, left zero padded (:542-543); written by the
@@ -152,30 +149,7 @@ conv1d_w4_kernel(const ConvParams p) {
   // PDL consumer (the RG-LRU prologue, then the fused kernel's set-up) may begin;
   // consumers order themselves after this grid's stores with griddepcontrol.wait
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  conv1d_w4_tile<IO, EMUL, LC, false>(p, blockIdx.x, blockIdx.y, blockIdx.z);
-}
-
-// Producer form for the overlapped Conv1D -> RG-LRU pipeline: few persistent
-// blocks (they share the SMs with the fused RG-LRU kernel, which runs at the same
-// time on another stream) walk the tiles in TIME-MAJOR order -- the order in which
-// the consumer needs them -- and count finished tiles per (128-step group, batch
-// row) in `flags`; the consumer's TMA producer waits until all `ctiles` channel
-// tiles of a group are there.  flags must be zeroed before the launch.
-template <typename IO, bool EMUL, int LC>
-__global__ void __launch_bounds__(128, 8)
-conv1d_w4_stream_kernel(const ConvParams p, int* flags, int ctiles, int tgroups) {
-  const int ntiles = tgroups * p.B * ctiles;
-  for (int id = blockIdx.x; id < ntiles; id += gridDim.x) {
-    const int ct = id % ctiles;
-    const int r = id / ctiles;
-    const int b = r % p.B, g = r / p.B;
-    conv1d_w4_tile<IO, EMUL, LC, true>(p, ct, g, b);
-    __syncthreads();                 // every thread's stores are issued ...
-    if (threadIdx.x == 0) {
-      __threadfence();               // ... and visible device-wide before the count moves
-      atomicAdd(flags + g * p.B + b, 1);
-    }
-  }
+  conv1d_w4_tile<IO, EMUL, LC>(p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 // ---------------------------------------------------------------------------

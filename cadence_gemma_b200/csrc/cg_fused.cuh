@@ -23,7 +23,7 @@
 //   with the decoupled look-back of cg_scan.cuh (tagged 64-bit words, folds are
 //   always left-to-right => bit-reproducible).
 //
-// Roles (576 threads, 1 CTA / SM, persistent):
+// Roles (640 threads, 1 CTA / SM, persistent):
 //   warps 0-15   four epilogue warpgroups in two pairs; pair p owns TMEM columns
 //                [256p, 256p+256): 192 accumulator + 2 x 32 state.  Warpgroup
 //                (p, h) works on half h (columns 32h..32h+31) of every MMA tile
@@ -32,6 +32,8 @@
 //                family, then two X boxes [32 steps x head width] per MMA tile
 //                through a 3-D tensor map (SWIZZLE_128B, zero fill beyond T)
 //   warp 17      MMA issuer (one thread), tcgen05.commit -> mbarriers
+//   warps 18-19  CONV kernels only: the temporal convolution, in place in the X
+//                stage, one warp per half of the stage (see conv_row below)
 // CTA i works on family i % families; the CTAs of one family take its tiles
 // two at a time, round-robin in time-major order, so look-back dependencies
 // always point to tiles that are already running (all CTAs are co-resident:
@@ -60,25 +62,24 @@
 #ifndef CGF_HINT_NS
 #define CGF_HINT_NS 20000
 #endif
-// CGF_INTERLEAVE: the replay pass of the previous tile runs inside the gate loop
-// of the current one (same basic block: the compiler fills the gate math's MUFU
-// latencies with the replay's FMA / store work) instead of before it
-#ifndef CGF_LATE_WAIT_ST
-#define CGF_LATE_WAIT_ST 0
+// register re-split between the roles (setmaxnreg): the 16 epilogue warps grow to
+// CGF_REG_EPI, the producer / MMA / convolution warpgroup shrinks to CGF_REG_AUX.
+// 20 warps x 96 registers are allocated at launch: 16 x 104 + 4 x 64 = 1920 warp-registers.
+#ifndef CGF_SETMAXNREG
+#define CGF_SETMAXNREG 1
 #endif
-#ifndef CGF_WAIT_LATE
-#define CGF_WAIT_LATE 0
+#ifndef CGF_REG_EPI
+#define CGF_REG_EPI 104
 #endif
-#ifndef CGF_INTERLEAVE
-#define CGF_INTERLEAVE 0   // measured: no gain (110.8 vs 109.8 us), the kernel is throughput-bound
+#ifndef CGF_REG_AUX
+#define CGF_REG_AUX 64
 #endif
-static_assert(!(CGF_LATE_WAIT_ST && CGF_INTERLEAVE), "the woven replay reads the state columns without that wait");
 // CGF_ABLATE (timing experiments only, results are WRONG): 1 = no look-back,
-// 2 = no y stores, 4 = no replay pass at all
+// 2 = no y stores, 4 = no replay pass at all, 8 = no in-kernel convolution arithmetic
 #ifndef CGF_ABLATE
 #define CGF_ABLATE 0
 #endif
-// CGF_TRACE: debug_out becomes a timeline buffer [6 roles][1024] of
+// CGF_TRACE: debug_out becomes a timeline buffer [7 roles][1024] of
 // (clock64 << 4 | event) words written by CTA 0 (scripts/fused_trace.py)
 #ifndef CGF_TRACE
 #define CGF_TRACE 0
@@ -104,7 +105,8 @@ constexpr int kMch = 128;         // channels per work column (UMMA M)
 constexpr int kPairCols = 256;    // TMEM columns per warpgroup pair: 3 x 64 accumulator + 2 x 32 state
 constexpr int kTmemCols = 512;
 constexpr int kEpiWarps = 16;     // four warpgroups
-constexpr int kThreads = (kEpiWarps + 2) * 32;
+constexpr int kAuxWarps = 4;      // fifth warpgroup: TMA producer, MMA issuer, two Conv1D warps
+constexpr int kThreads = (kEpiWarps + kAuxWarps) * 32;
 constexpr uint32_t kKBlockBytes = 128u * 128u;   // 128 rows x 64 bf16 (one swizzle-128B K block)
 
 struct FusedParams {
@@ -123,8 +125,13 @@ struct FusedParams {
   unsigned long long* agg_p;       // [families][ntt][B][128]
   unsigned long long* agg_h;
   unsigned long long* pref;
-  const int* conv_flags;           // optional [ceil(T/64)][B]: channel tiles of x the Conv1D producer kernel has finished
-  int conv_need;                   // ... out of this many (E / 64)
+  // in-kernel temporal convolution (CONV kernels): the tensor map then describes x_lin, the INPUT of
+  // Conv1D.forward, and the X stages are convolved in place before the MMAs read them
+  const uint16_t* x_lin;           // [B,T,E] (halo rows and the returned cache are read directly)
+  const uint16_t* conv_w;          // [4,E]
+  const uint16_t* conv_b;          // [E]
+  uint16_t* conv_cache;            // optional [B,3,E]: last three input rows, left zero padded (layers.py:542-543)
+  int mask_mode;                   // CG_MASK_FORK / CG_MASK_UPSTREAM
   const uint16_t* gate_mul;        // optional [B,T,E]: y <- round_bf16(y * gate_mul) (RecurrentBlock, modules.py:651)
   uint16_t* dbg;                   // optional [3][B][T][E]: rounded pre_x, pre_a, x^T
   int* err;                        // watchdog flag
@@ -159,15 +166,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"((unsigned)CGF_HINT_NS) : "memory");   // suspend-time hint (ns)
   return ok != 0;
 }
-// Bounded wait: a protocol bug must end the launch, never hang the device.  On
-// a timeout the wait raises the error flag (workspace header) and returns; once
-// the flag is up every later wait returns at once, so the kernel drains (with
-// garbage results) and the host finds the flag.
-constexpr long long kWatchdogCycles = 1000000000LL;   // ~0.5 s
+// Bounded wait: a protocol bug must end the launch, never hang the device, and
+// must never go unnoticed.  On a timeout the wait records which wait it was in
+// the workspace header (diagnosis under a debugger) and TRAPS: the launch fails
+// and the stream carries a sticky CUDA error that the host sees at its next
+// synchronisation -- no call can return garbage with status 0.
+constexpr long long kWatchdogCycles = 4000000000LL;   // ~2 s
 __device__ __forceinline__ bool watchdog_expired(long long t0, int* err, int code, unsigned& polls) {
   if ((++polls & 63u) != 0u) return false;
-  if (*reinterpret_cast<volatile int*>(err) != 0) return true;
-  if (clock64() - t0 > kWatchdogCycles) { atomicCAS(err, 0, code); return true; }
+  if (clock64() - t0 > kWatchdogCycles) {
+    atomicCAS(err, 0, code);
+    __threadfence_system();
+    __trap();
+  }
   return false;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
@@ -269,25 +280,21 @@ __device__ __forceinline__ uint32_t ld_u16(const uint16_t* p) {
   asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
   return v;
 }
-// y stores.  CGF_YST: 0 = default policy, 1 = .cs (streaming / evict-first), 2 = .wt
-// (write-through), 3 = L2::evict_first cache-hint policy.  The 84 MB of y a
-// config-2 launch writes would otherwise sit dirty in the 126 MB L2 and be
-// written back under the NEXT kernel, which then pays for it.
-#ifndef CGF_YST
-#define CGF_YST 0   // measured: no policy changes the step time (149-153 us for all four)
-#endif
 __device__ __forceinline__ void st_u16(uint16_t* p, uint32_t v) {
-#if CGF_YST == 1
-  asm volatile("st.global.cs.u16 [%0], %1;" :: "l"(p), "h"(static_cast<uint16_t>(v)) : "memory");
-#elif CGF_YST == 2
-  asm volatile("st.global.wt.u16 [%0], %1;" :: "l"(p), "h"(static_cast<uint16_t>(v)) : "memory");
-#elif CGF_YST == 3
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  asm volatile("st.global.L2::cache_hint.u16 [%0], %1, %2;" :: "l"(p), "h"(static_cast<uint16_t>(v)), "l"(pol) : "memory");
-#else
+  // (cache policies .cs / .wt / L2::evict_first were measured: no change of the step time)
   asm volatile("st.global.u16 [%0], %1;" :: "l"(p), "h"(static_cast<uint16_t>(v)) : "memory");
-#endif
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -311,7 +318,7 @@ struct FusedCfg {
   static constexpr uint32_t kXKBlock = kMmaN * 128u;               // one K block of an X stage: 64 rows x 128 B
   static constexpr uint32_t kXStageBytes = static_cast<uint32_t>(KB) * kXKBlock;
   static constexpr int kXStages = 2;                               // one per warpgroup pair
-  static constexpr int kBars = 2 + 2 * kXStages + 4;
+  static constexpr int kBars = 2 + 3 * kXStages + 4;
   static constexpr size_t kSmemBytes = 1024 + kWBytes + kIBytes + kXStages * kXStageBytes + kBars * 8 + 16;
   static_assert(KB % 2 == 0, "head width must be a multiple of 128");
 };
@@ -371,103 +378,85 @@ __global__ void pack_gate_weights_kernel(const uint16_t* __restrict__ wx, const 
 // works through SEGMENTS (family, first pair, stride, count), in order, and
 // reloads the gate weights when the family changes.
 //   G < families           CTA i takes families i, i+G, ... completely (test hook)
-//   G = d * families       d CTAs per family share its pairs round-robin
-//   G = d * families + r   (148 SMs, 20 families: d = 7, r = 8): round-robin with d or
-//       d + 1 CTAs per family, or, with CGF_BALANCE:
-//       d dedicated CTAs per family plus r FLOATERS.  The pair sequence of every
-//       family is cut into S equal parts; in h of them a floater joins as member
-//       d + 1 (S = families / gcd, h = r / gcd).  Floater k spends its s-th part
-//       on family (k*S + s) / h, so every CTA gets ~npairs * families / G pairs
-//       instead of npairs / d on the d-CTA families and npairs / (d+1) on the
-//       others (-5 % on the critical path at config 2).  Every CTA visits the
-//       parts in increasing order and a floater's part index equals the family's
-//       part index, so all look-back dependencies point to work that is running
-//       or done: no cycles.
+//   G = d * families + r   (148 SMs, 20 families: d = 7, r = 8): the d or d + 1 CTAs of
+//       a family share its pairs round-robin, so every look-back dependency points
+//       to a pair that is running or done.
+// (A balanced variant with "floater" CTAs that help several families was measured
+// slower -- 116 us vs 105.6 us at config 2: a floater couples the chains of the
+// families it visits -- and removed)
 // ---------------------------------------------------------------------------
-// Measured (config 2, A/B in one run): 116 us balanced vs 105.6 us round-robin.
-// The floater couples the families it visits: a family helped in part q reaches
-// part q+1 earlier than the family the floater goes to next, the round-robin
-// chain of the new family cannot pass the floater's pairs, and the lags add up.
-// Kept (off) with its coverage test; row-disjoint shares are the next thing to try.
-#ifndef CGF_BALANCE
-#define CGF_BALANCE 0
-#endif
 struct Seg { int fam, j0, stride, count; };
 struct Schedule {
-  int mode;        // 0 = whole families, 1 = round-robin, 2 = balanced with floaters
+  int mode;        // 0 = whole families, 1 = round-robin
   int cta, G, nfam, npairs;
-  int d, S, h;     // mode 2
-  __host__ __device__ __forceinline__ static int gcd(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
-  __host__ __device__ __forceinline__ Schedule(int cta_, int G_, int nfam_, int npairs_,
-                                              bool balance = CGF_BALANCE != 0)
-      : cta(cta_), G(G_), nfam(nfam_), npairs(npairs_), d(0), S(1), h(0) {
-    if (G < nfam) { mode = 0; return; }
-    mode = 1;
-    d = G / nfam;
-    const int r = G - d * nfam;
-    if (balance && r != 0) {
-      const int g = gcd(nfam, r);
-      S = nfam / g; h = r / g;
-      if (npairs >= 2 * S * (d + 1)) mode = 2;
-    }
+  __host__ __device__ __forceinline__ Schedule(int cta_, int G_, int nfam_, int npairs_)
+      : cta(cta_), G(G_), nfam(nfam_), npairs(npairs_) {
+    mode = G < nfam ? 0 : 1;
   }
   __host__ __device__ __forceinline__ int nseg() const {
     if (mode == 0) return cta < nfam ? (nfam - 1 - cta) / G + 1 : 0;
-    return mode == 1 ? 1 : S;
-  }
-  __host__ __device__ __forceinline__ static int count_from(int j0, int end, int stride) {
-    return j0 < end ? (end - j0 + stride - 1) / stride : 0;
+    return 1;
   }
   __host__ __device__ __forceinline__ Seg get(int s) const {
     Seg sg;
     if (mode == 0) {
       sg.fam = cta + s * G; sg.j0 = 0; sg.stride = 1; sg.count = npairs;
-    } else if (mode == 1) {
+    } else {
       sg.fam = cta % nfam;
       const int rank = cta / nfam;
       sg.stride = (G - 1 - sg.fam) / nfam + 1;
       sg.j0 = rank;
-      sg.count = count_from(rank, npairs, sg.stride);
-    } else {
-      const int b0 = (int)((long long)s * npairs / S), b1 = (int)((long long)(s + 1) * npairs / S);
-      if (cta < nfam * d) {                          // dedicated: member `rank` of its family
-        sg.fam = cta % nfam;
-        const int rank = cta / nfam;
-        // is a floater with this family in part q?  family f owns global slices [f*h, f*h + h)
-        auto members = [&](int q) {
-          bool helped = false;
-          for (int u = sg.fam * h; u < sg.fam * h + h; ++u) helped = helped || (u % S == q);
-          return d + (helped ? 1 : 0);
-        };
-        // the members that get one pair more than the others in a part (its length
-        // is not a multiple of the member count) rotate from part to part
-        int start = 0;
-        for (int q = 0; q < s; ++q) {
-          const int len = (int)((long long)(q + 1) * npairs / S) - (int)((long long)q * npairs / S);
-          start += len % members(q);
-        }
-        sg.stride = members(s);
-        sg.j0 = b0 + ((rank - start) % d + d) % d;
-      } else {                                       // floater: member d of family (k*S + s) / h
-        const int k = cta - nfam * d;
-        sg.fam = (k * S + s) / h;
-        sg.stride = d + 1;
-        sg.j0 = b0 + d;
-      }
-      sg.count = count_from(sg.j0, b1, sg.stride);
+      sg.count = rank < npairs ? (npairs - rank + sg.stride - 1) / sg.stride : 0;
     }
     return sg;
   }
 };
 
 // ---------------------------------------------------------------------------
+// In-kernel temporal convolution (CONV kernels; north star: "the width-4 Conv1D is
+// fused into the same pass").  The TMA producer loads the rows of x_lin -- the
+// INPUT of Conv1D.forward -- into the X stage; one warp per half of the stage
+// (32 steps x head width) then convolves the rows IN PLACE: lane l owns the
+// 16-byte chunk (K block l / 8, chunk l % 8) of every row, walks the rows forward
+// with a three-row register window (the three halo rows before the tile come
+// straight from global memory, requested before the wait for the TMA data), and
+// writes each output row over the input row it has just read -- a lane only ever
+// touches its own chunk, so there is no hazard inside or between the warps.
+// Arithmetic: the reference's accumulation order with one bf16 rounding per eager
+// op (layers.py:530-536: packed HMUL2 / HADD2, no contraction), bit-exact with
+// cg::conv1d_w4_kernel and the reference.  The conv output never reaches HBM.
+// ---------------------------------------------------------------------------
+struct ConvTaps { uint4 w0, w1, w2, w3, b; };   // w[k] multiplies x[t - (3 - k)] (layers.py:530)
+
+__device__ __forceinline__ uint4 conv_row(const ConvTaps& k, const uint4& x0, const uint4& x1, const uint4& x2,
+                                          const uint4& x3) {
+  const uint32_t s0[4] = {x0.x, x0.y, x0.z, x0.w}, s1[4] = {x1.x, x1.y, x1.z, x1.w};
+  const uint32_t s2[4] = {x2.x, x2.y, x2.z, x2.w}, s3[4] = {x3.x, x3.y, x3.z, x3.w};
+  const uint32_t k0[4] = {k.w0.x, k.w0.y, k.w0.z, k.w0.w}, k1[4] = {k.w1.x, k.w1.y, k.w1.z, k.w1.w};
+  const uint32_t k2[4] = {k.w2.x, k.w2.y, k.w2.z, k.w2.w}, k3[4] = {k.w3.x, k.w3.y, k.w3.z, k.w3.w};
+  const uint32_t bb[4] = {k.b.x, k.b.y, k.b.z, k.b.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t acc = bf2_mul(s0[i], k3[i]);                 // shift 0
+    acc = bf2_add(acc, bf2_mul(s1[i], k2[i]));            // shift 1
+    acc = bf2_add(acc, bf2_mul(s2[i], k1[i]));            // shift 2
+    acc = bf2_add(acc, bf2_mul(s3[i], k0[i]));            // shift 3
+    o[i] = bf2_add(acc, bb[i]);                           // + b, :536
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// ---------------------------------------------------------------------------
 // The fused kernel.  KB = head width / 64 (K blocks of the gate GEMMs).
 // ---------------------------------------------------------------------------
-// (registers are allocated in units of four warps: 18 warps count as 20, which
-// caps the kernel at 96 registers per thread)
+// 20 warps are allocated with 96 registers each; setmaxnreg then moves registers
+// from the producer / MMA / convolution warpgroup to the four epilogue warpgroups.
 // MUL: multiply the output by a second activation tensor on the way out (the
 // gating product of RecurrentBlock), SURVEY.md section 8(f) row F2.
-template <int KB, bool FAST, bool DBG, bool MUL>
+// CONV: the temporal convolution runs in the kernel (see above): `tmap_x` describes
+// x_lin and the kernel computes Conv1D.forward -> RGLRU.forward in one launch.
+template <int KB, bool FAST, bool DBG, bool MUL, bool CONV>
 __global__ void __launch_bounds__(kThreads, 1)
 rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams p) {
   using Cfg = FusedCfg<KB>;
@@ -483,11 +472,13 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Cfg::kWBytes + Cfg::kIBytes + XS * Cfg::kXStageBytes);
   uint64_t* w_full = bars;
   uint64_t* w_empty = bars + 1;
-  uint64_t* x_full = bars + 2;
-  uint64_t* x_empty = x_full + XS;
+  uint64_t* raw_full = bars + 2;            // [XS] the TMA boxes of the stage have landed
+  uint64_t* x_full = raw_full + XS;         // [XS] CONV: both halves of the stage are convolved
+  uint64_t* x_empty = x_full + XS;          // [XS] the MMAs that read the stage are complete
   uint64_t* t_full = x_empty + XS;          // [2] accumulators of pair p are complete
   uint64_t* t_empty = t_full + 2;           // [2] both warpgroups of pair p have read them
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* mma_ready = CONV ? x_full : raw_full;   // what the MMA warp waits for
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -495,7 +486,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
     mbar_init(w_empty, 1);
-    for (int i = 0; i < XS; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
+    for (int i = 0; i < XS; ++i) { mbar_init(raw_full + i, 1); mbar_init(x_full + i, 2); mbar_init(x_empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }
     fence_mbar_init();
   }
@@ -504,6 +495,12 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+
+#if CGF_SETMAXNREG
+  // all four warps of a warpgroup execute the same setmaxnreg (it is .aligned)
+  if (warp >= kEpiWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(CGF_REG_AUX));
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(CGF_REG_EPI));
+#endif
 
   // work schedule of this CTA (identical in every role), see Schedule above.
   // Ticket = tt * B + b (time-major); pair j = tickets 2j, 2j + 1 = one MMA tile.
@@ -552,26 +549,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           CGF_EVENT(0, 1);
           mbar_wait(x_empty + stage, (use & 1) ^ 1, p.err, 2);
           CGF_EVENT(0, 2);
-          if (p.conv_flags != nullptr) {
-            // x is being written right now by the Conv1D producer kernel on another
-            // stream (conv1d_w4_stream_kernel): wait until every channel tile of
-            // the 64-step group(s) of this MMA tile is there, then order the
-            // generic-proxy view before the async-proxy (TMA) reads.
-            for (int hf = 0; hf < nhalf; ++hf) {
-              const int ticket = t1st + hf;
-              const int tt = ticket / p.B, b = ticket - tt * p.B;
-              const int* flag = p.conv_flags + (tt >> 1) * p.B + b;
-              const long long t0w = clock64();
-              unsigned polls = 0;
-              while (ld_acquire(flag) < p.conv_need) {
-                __nanosleep(100);
-                polls += 15;
-                if (watchdog_expired(t0w, p.err, 8, polls)) break;
-              }
-            }
-            asm volatile("fence.proxy.async;" ::: "memory");
-          }
-          if (elect_one()) mbar_expect_tx(x_full + stage, nhalf * (Cfg::kXStageBytes / 2));
+          if (elect_one()) mbar_expect_tx(raw_full + stage, nhalf * (Cfg::kXStageBytes / 2));
           for (int hf = 0; hf < nhalf; ++hf) {
             const int ticket = t1st + hf;
             const int tt = ticket / p.B, b = ticket - tt * p.B;
@@ -579,7 +557,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
 #pragma unroll
               for (int kb = 0; kb < KB; ++kb)
                 tma_load_3d(sX + stage * Cfg::kXStageBytes + kb * Cfg::kXKBlock + hf * (kTile * 128), &tmap_x,
-                            x_full + stage, c_head + kb * 64, tt * kTile, b);
+                            raw_full + stage, c_head + kb * 64, tt * kTile, b);
             }
           }
           __syncwarp();
@@ -612,7 +590,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         for (int m = 0; m < sg.count; ++m, ++mq) {
           const uint32_t pr = mq & 1u, use = mq >> 1;      // warpgroup pair == X stage
           CGF_EVENT(1, 1);
-          mbar_wait(x_full + pr, use & 1, p.err, 4);
+          mbar_wait(mma_ready + pr, use & 1, p.err, 4);
           CGF_EVENT(1, 2);
           mbar_wait(t_empty + pr, (use & 1) ^ 1, p.err, 5);
           CGF_EVENT(1, 3);
@@ -644,6 +622,115 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           }
           __syncwarp();
           CGF_EVENT(1, 4);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kEpiWarps + 2) {
+    // ===================================================== Conv1D warps (CONV only)
+    if constexpr (CONV) {
+      const int hfc = warp - (kEpiWarps + 2);            // the half of every X stage this warp convolves
+      const bool active = lane < KB * 8;                 // 8 channels per lane; head width 128: 16 lanes
+      const int kbc = lane >> 3, chunk = lane & 7;
+      const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+      // reset bitmask (prologue kernel) and x_lin (whatever precedes on the stream)
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      uint32_t mq = 0;
+      int tn = 0; (void)tn;
+      int cur_head = -1;
+      ConvTaps taps{zero4, zero4, zero4, zero4, zero4};
+      int ch0 = 0;
+      for (int sgi = 0; sgi < nsegs; ++sgi) {
+        const Seg sg = sched.get(sgi);
+        if (sg.count == 0) continue;
+        const int fam = sg.fam;
+        const int head = fam / CBS;
+        if (head != cur_head) {                            // taps of this lane's 8 channels
+          cur_head = head;
+          ch0 = head * (KB * 64) + lane * 8;
+          if (active) {
+            taps.w0 = *reinterpret_cast<const uint4*>(p.conv_w + ch0);
+            taps.w1 = *reinterpret_cast<const uint4*>(p.conv_w + (size_t)p.E + ch0);
+            taps.w2 = *reinterpret_cast<const uint4*>(p.conv_w + 2 * (size_t)p.E + ch0);
+            taps.w3 = *reinterpret_cast<const uint4*>(p.conv_w + 3 * (size_t)p.E + ch0);
+            taps.b = *reinterpret_cast<const uint4*>(p.conv_b + ch0);
+          }
+        }
+        const bool cache_writer = p.conv_cache != nullptr && (fam % CBS) == 0;
+#pragma unroll 1
+        for (int m = 0; m < sg.count; ++m, ++mq) {
+          const uint32_t stage = mq & 1u, use = mq >> 1;
+          const int ticket = 2 * (sg.j0 + m * sg.stride) + hfc;
+          const bool valid = ticket < ntiles && active;
+          int tt = 0, b = 0;
+          uint4 h1 = zero4, h2 = zero4, h3 = zero4;        // x[t0-1], x[t0-2], x[t0-3]
+          unsigned long long nzw = ~0ull;                  // bit r: segment_pos[t0 + r - 2] != 0
+          if (valid) {
+            tt = ticket / p.B; b = ticket - tt * p.B;
+            const int t0 = tt * kTile;
+            // halo rows straight from global memory: the round trip hides behind the
+            // wait for the stage's TMA boxes (x[t < 0] = 0, layers.py:484-492)
+            const uint16_t* xb = p.x_lin + ((size_t)b * p.T) * p.E + ch0;
+            if (t0 >= 1) h1 = ldg_stream(xb + (size_t)(t0 - 1) * p.E);
+            if (t0 >= 2) h2 = ldg_stream(xb + (size_t)(t0 - 2) * p.E);
+            if (t0 >= 3) h3 = ldg_stream(xb + (size_t)(t0 - 3) * p.E);
+            const unsigned* rw = p.reset_bits + (long long)b * p.bits_bstride + tt;
+            const unsigned cur = rw[0];
+            const unsigned prev = tt > 0 ? rw[-1] : 0u;    // positions before 0 gate taps that are zero anyway
+            nzw = ((unsigned long long)(~cur) << 2) | (unsigned long long)((~prev) >> 30);
+          }
+          CGF_EVENT(6, 1);
+          mbar_wait(raw_full + stage, use & 1, p.err, 9);
+          CGF_EVENT(6, 2);
+          if (valid && !(CGF_ABLATE & 8)) {
+            uint32_t row = sX + stage * Cfg::kXStageBytes + kbc * Cfg::kXKBlock + (uint32_t)(hfc * kTile) * 128u;
+            const bool upstream = p.mask_mode != 0;
+            // no document start near the tile: every tap is live (the common case)
+            const bool plain = upstream ? (nzw & 0x3ffffffffull) == 0x3ffffffffull
+                                        : (nzw & 0xffffffffull) == 0xffffffffull;
+            if (plain) {
+#pragma unroll 8
+              for (int r = 0; r < kTile; ++r) {
+                const uint32_t addr = row + r * 128 + ((uint32_t)(chunk ^ (r & 7)) << 4);
+                const uint4 x0 = lds128(addr);
+                sts128(addr, conv_row(taps, x0, h1, h2, h3));
+                h3 = h2; h2 = h1; h1 = x0;
+              }
+            } else {
+#pragma unroll 1
+              for (int r = 0; r < kTile; ++r) {
+                const uint32_t addr = row + r * 128 + ((uint32_t)(chunk ^ (r & 7)) << 4);
+                const uint4 x0 = lds128(addr);
+                const unsigned w3 = (unsigned)(nzw >> r) & 7u;   // bit 0: seg[t-2], 1: seg[t-1], 2: seg[t]  (!= 0)
+                bool m1 = true, m2 = true, m3;
+                if (!upstream) {
+                  m3 = (w3 & 1u) != 0;                     // fork: only seg[t-2], layers.py:629-632
+                } else {
+                  m1 = (w3 & 4u) != 0;                     // upstream: seg[t-s+1 .. t] all != 0
+                  m2 = (w3 & 6u) == 6u;
+                  m3 = (w3 & 7u) == 7u;
+                }
+                sts128(addr, conv_row(taps, x0, m1 ? h1 : zero4, m2 ? h2 : zero4, m3 ? h3 : zero4));
+                h3 = h2; h2 = h1; h1 = x0;
+              }
+            }
+            // the convolution's returned cache: the last three INPUT rows of the
+            // sequence, left zero padded (layers.py:542-543, :650-662)
+            if (cache_writer && tt == p.ntt - 1) {
+              const uint16_t* xb = p.x_lin + ((size_t)b * p.T) * p.E + ch0;
+              uint16_t* cb = p.conv_cache + ((size_t)b * 3) * p.E + ch0;
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                const int ti = p.T - 3 + r;
+                *reinterpret_cast<uint4*>(cb + (size_t)r * p.E) = ti >= 0 ? ldg_stream(xb + (size_t)ti * p.E) : zero4;
+              }
+            }
+          }
+          // my stores to the stage (generic proxy) before the MMA's operand reads (async proxy)
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(x_full + stage);
+          CGF_EVENT(6, 3);
         }
       }
     }
@@ -807,9 +894,6 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         for (int i = 0; i < 8; ++i) gm[i] = i < pd.nvalid ? ld_u16(gmp + i * E) : 0u;
       }
       float h = resolve_carry(early);
-      // CGF_LATE_WAIT_ST: the tile's state stores are awaited here, right before they
-      // are read back, instead of right after they were issued
-      if (CGF_LATE_WAIT_ST) tmem_wait_st();
 #pragma unroll 1
       for (int c = 0; c < ((CGF_ABLATE & 4) ? 0 : kTile / 8); ++c) {
         uint32_t st[8];
@@ -854,10 +938,6 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         if (twarp) CGF_EVENT(trole, 8);
         const unsigned long long early = request_pred();
         if (twarp) CGF_EVENT(trole, 1);
-        // CGF_WAIT_LATE: the pending tile needs nothing from the new accumulators --
-        // finish it first, so that a late MMA costs no idle time in this warpgroup
-        const bool pend_first = CGF_WAIT_LATE && !CGF_INTERLEAVE && pd.on;
-        if (pend_first) finish(early);
         mbar_wait(t_full + pr, use & 1, p.err, 6);
         if (twarp) CGF_EVENT(trole, 2);
         tc_fence_after();
@@ -871,12 +951,8 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         const unsigned rbits = p.reset_bits[(long long)b * p.bits_bstride + tt];   // kTile == 32: one word
         const int nvalid = p.T - t0;                       // >= 1; >= kTile for a full tile
         const bool fast_tile = CGF_PRELOAD && rbits == 0u && nvalid >= kTile;
-        // F(k-1): before the new tile -- or, for a common-case tile, only the carry
-        // now and the replay inside the gate loop below
-        const bool weave = CGF_INTERLEAVE && !MUL && fast_tile && pd.on;
-        float ph = 0.0f;                                   // running state of the pending tile's replay
-        if (weave) ph = resolve_carry(early);
-        else if (pd.on) finish(early);
+        // F(k-1): before the new tile
+        if (pd.on) finish(early);
         float P = 1.0f, Hh = 0.0f;
         // gates for one bf16x2 pair of steps (t, t+1) -> (a, x~); the tile's
         // transform h -> P*h + H is accumulated on the way
@@ -945,14 +1021,6 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
               release_slot();
               if (twarp) CGF_EVENT(trole, 3);
             }
-            // the pending tile's (a, x~) of these 16 steps leave my state columns
-            // before this tile's take their place
-            uint32_t os[2][8];
-            if (weave) {
-              tmem_ld8(tm_state + hh * 16, os[0]);
-              tmem_ld8(tm_state + hh * 16 + 8, os[1]);
-              tmem_wait_ld();
-            }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
               uint32_t st[8];
@@ -960,10 +1028,8 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
               for (int i = 0; i < 4; ++i)
                 gate_step(xv[c * 4 + i], gx[c * 4 + i], ga[c * 4 + i], hh * 16 + c * 8 + 2 * i, FalseTag{}, st[i], st[4 + i]);
               tmem_st8(tm_state + hh * 16 + c * 8, st);
-              if (weave) replay_chunk(hh * 2 + c, os[c], ph, nullptr);
             }
           }
-          if (weave) retire_pending(ph);
         } else {
           // document starts or a ragged tail inside the tile (rare, warp-uniform):
           // gates chunk by chunk out of TMEM
@@ -985,7 +1051,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           }
           release_slot();
         }
-        if (!CGF_LATE_WAIT_ST) tmem_wait_st();
+        tmem_wait_st();
         if (twarp) CGF_EVENT(trole, 4);
         // publish the tile's aggregate (tile 0 publishes its state right away in
         // F instead) and queue the tile for F

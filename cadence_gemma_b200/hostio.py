@@ -17,6 +17,8 @@ from __future__ import annotations
 
 import torch
 
+from cadence_gemma_b200 import pipeline
+
 
 def bind_host_thread_to_device(device_index: int):
   """Binds the calling thread to the CPU cores next to GPU ``device_index`` (NVML's
@@ -165,10 +167,11 @@ class HostPrefill:
         self.s_run.wait_event(self.ev_in[k])
         if reuse:
           self.s_run.wait_event(self.ev_out[k])          # the slot's last results have been downloaded
-        self.conv.forward_into(self.x_dev[k], self.seg_dev[k], out=self.xc_dev[k],
-                               cache_out=self.c_dev[k])
-        self.lru.forward_into(self.xc_dev[k], self.seg_dev[k], out=self.y_dev[k],
-                              last_h_out=self.h_dev[k])
+        # ONE fused launch at RecurrentGemma shapes (pipeline.recurrent_hot_path);
+        # xc_dev is only touched by the two-kernel route
+        pipeline.recurrent_hot_path(self.conv, self.lru, self.x_dev[k], self.seg_dev[k],
+                                    out=self.y_dev[k], last_h_out=self.h_dev[k],
+                                    conv_out=self.xc_dev[k], conv_cache_out=self.c_dev[k])
         self.ev_run[k].record(self.s_run)
       with torch.cuda.stream(self.s_out):
         self.s_out.wait_event(self.ev_run[k])

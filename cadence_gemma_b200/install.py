@@ -8,7 +8,9 @@ modules, exactly the three entry points of the hot path:
   * ``layers.RGLRU.forward``   (reference layers.py:322-375)
   * ``layers.Conv1D.forward``  (reference layers.py:458-546)
 
-so an unmodified ``RecurrentBlock`` / ``ResidualBlock`` / ``Griffin`` built
+and, given ``ref_modules``, ``modules.RecurrentBlock.forward`` (reference
+modules.py:613-660), whose ``conv_1d -> rg_lru`` pair then runs as ONE fused
+kernel (``cg_recurrent_prefill_fwd``) -- so an unmodified ``RecurrentBlock`` / ``ResidualBlock`` / ``Griffin`` built
 from the reference classes (``examples/cadence_sampler.py`` included) runs the
 sm_100a kernels with its own parameters.  ``uninstall`` restores the originals.
 """
@@ -91,21 +93,24 @@ def _conv1d_forward(self, x, segment_pos, cache=None, return_cache=True):
 
 
 def _recurrent_block_forward(self, x, segment_pos, cache=None, return_cache=True):
-  """RecurrentBlock.forward (reference modules.py:613-660) with the gating product
-  ``x * y`` (:651) folded into the fused RG-LRU kernel when that kernel runs."""
+  """RecurrentBlock.forward (reference modules.py:613-660) with ``conv_1d -> rg_lru``
+  (:638-649) routed through the hot-path entry point: ONE fused kernel for a bf16
+  prefill at RecurrentGemma shapes (convolution inside the tcgen05 RG-LRU kernel),
+  one launch for a decode step (gating product ``x * y``, :651, folded in there)."""
+  from cadence_gemma_b200 import pipeline
   y = self.linear_y(x)
   h = self.linear_x(x)
-  h, conv1d_state = self.conv_1d(
-      x=h, segment_pos=segment_pos,
-      cache=None if cache is None else cache.conv1d_state, return_cache=return_cache)
+  conv_cache = None if cache is None else cache.conv1d_state
   lru_cache = None if cache is None else cache.rg_lru_state
-  if (cg_layers.fold_gate_enabled() and cg_layers.uses_fused_kernel(self.rg_lru, h) and
-      not cg_layers._wants_grad(h, y, lru_cache, *self.rg_lru.parameters())):
-    h, rg_lru_state = _rglru_forward(self.rg_lru, h, segment_pos, lru_cache, return_cache,
-                                     gate_mul=y)
-  else:
-    h, rg_lru_state = self.rg_lru(x=h, segment_pos=segment_pos, cache=lru_cache,
-                                  return_cache=return_cache)
+  grad = cg_layers._wants_grad(h, y, conv_cache, lru_cache, *self.conv_1d.parameters(),
+                               *self.rg_lru.parameters())
+  fold = not grad and (
+      (cg_layers.fold_gate_enabled() and cg_layers.uses_fused_kernel(self.rg_lru, h)) or
+      pipeline.can_fuse_decode(self.conv_1d, self.rg_lru, h, conv_cache))
+  h, conv1d_state, rg_lru_state = pipeline.recurrent_hot_path(
+      self.conv_1d, self.rg_lru, h, segment_pos, conv_cache=conv_cache, lru_cache=lru_cache,
+      return_cache=return_cache, gate_mul=y if fold else None)
+  if not fold:
     h = h * y
   out = self.linear_out(h)
   if not return_cache:

@@ -1,4 +1,4 @@
-"""Conv1D -> RG-LRU as ONE overlapped pipeline (prefill).
+"""Conv1D -> RG-LRU of one recurrent block: the hot-path entry point.
 
 ``recurrent_hot_path(conv, lru, x, segment_pos)`` computes what
 ``RecurrentBlock.forward`` computes between its projections (reference
@@ -7,20 +7,19 @@
     x, conv1d_state = conv_1d(x, segment_pos)
     x, rg_lru_state = rg_lru(x, segment_pos)
 
-By default the two kernels run one after the other on the caller's stream.
+Prefill at RecurrentGemma shapes (bf16, temporal width 4, head width 128 / 256,
+T > 1) is ONE kernel: ``cg_recurrent_prefill_fwd`` -- the temporal convolution
+runs inside the fused tcgen05 RG-LRU kernel (TMA-loaded rows convolved in place
+in shared memory), so neither the conv output nor the gate pre-activations
+reach HBM.  ``set_fused_conv(False)`` / ``CG_B200_FUSED_CONV=0`` runs the two
+kernels one after the other instead (Conv1D kernel, then the fused RG-LRU
+kernel); other shapes / fp32 take the Conv1D kernel + cuBLAS gate GEMM + scan
+kernel.  A decode step (T == 1, caches given) is one launch as well
+(``cg_recurrent_decode_step``).
 
-EXPERIMENTAL (``set_overlap(True)`` / ``CG_B200_OVERLAP=1``): the temporal
-convolution is HBM-bound while the fused tensor-core RG-LRU kernel is bound by
-the issue / MUFU rate of its gate math and leaves most of the HBM bandwidth idle,
-so the two can run AT THE SAME TIME: the convolution as a few persistent producer
-blocks on a side stream (``cg_conv1d_stream_fwd``, time-major order, a counter
-per 64-step group and batch row), the RG-LRU kernel on the caller's stream with
-its TMA producer waiting on those counters tile by tile (``conv_flags`` of
-``cg_rglru_fused_fwd``).  The protocol is correct (tested bit for bit against the
-sequential pair, with the intermediate poisoned) but on B200 it is SLOWER
-(287 us vs 137 us at config 2): the fused kernel's 576 threads x 96 registers
-leave room for one 128-thread convolution block per SM, far too few loads in
-flight for an HBM-bound producer.  Kept switched off; see DESIGN.md section 9.
+(A producer / consumer overlap of the two kernels on two streams was built and
+measured in round 1 -- 287 us vs 137 us at config 2 -- and removed; DESIGN.md
+section 9.)
 
 No CPU path.
 """
@@ -32,28 +31,19 @@ import torch
 
 from cadence_gemma_b200 import _abi, layers
 
-_overlap = os.environ.get("CG_B200_OVERLAP", "0") != "0"
+# Convolution inside the fused RG-LRU kernel (one launch per prefill step).
+_fused_conv = os.environ.get("CG_B200_FUSED_CONV", "1") != "0"
 # One-launch decode step (cg_recurrent_decode_step).  It more than halves the cost
 # of an EAGER decode step (30 us vs 76 us per block at B = 32: three launches and
 # their host overhead become one); inside a CUDA graph, where launch overhead is
 # gone, the three small kernels are ~5 us faster at B = 32 -- switch it off there.
 _fused_decode = os.environ.get("CG_B200_FUSED_DECODE", "1") != "0"
-_side_streams: dict = {}
-_flag_buffers: dict = {}
 
 
-def _side_stream(device) -> torch.cuda.Stream:
-  s = _side_streams.get(device)
-  if s is None:
-    s = torch.cuda.Stream(device)
-    _side_streams[device] = s
-  return s
-
-
-def set_overlap(enabled: bool) -> bool:
-  """Switches the experimental producer / consumer overlap; returns the old setting."""
-  global _overlap
-  old, _overlap = _overlap, bool(enabled)
+def set_fused_conv(enabled: bool) -> bool:
+  """Switches the in-kernel convolution of the prefill path; returns the old setting."""
+  global _fused_conv
+  old, _fused_conv = _fused_conv, bool(enabled)
   return old
 
 
@@ -73,10 +63,11 @@ def can_fuse_decode(conv, lru, x, conv_cache) -> bool:
           _abi.decode_supported(lru.width, lru.num_heads, conv.w.shape[0], x.dtype))
 
 
-def can_overlap(conv, lru, x, conv_cache=None) -> bool:
-  """True if ``recurrent_hot_path`` runs the convolution under the RG-LRU kernel."""
-  return (_overlap and layers.fused_enabled() and conv_cache is None and x.is_cuda and
-          conv.w.shape[0] == 4 and x.shape[-1] % 64 == 0 and
+def can_fuse_conv(conv, lru, x, conv_cache=None) -> bool:
+  """True if ``recurrent_hot_path`` runs Conv1D + RG-LRU as ONE kernel
+  (``cg_recurrent_prefill_fwd``)."""
+  return (_fused_conv and layers.fused_enabled() and conv_cache is None and x.is_cuda and
+          conv.w.shape[0] == 4 and conv.w.dtype == x.dtype and
           (layers.get_arith_mode() & _abi.ARITH_FP32) == 0 and
           layers.uses_fused_kernel(lru, x))
 
@@ -119,49 +110,32 @@ def _recurrent_hot_path_inference(conv, lru, x, segment_pos, conv_cache=None, lr
         lru.a_gate.b, lru.a_param, segment_pos, h0=lru_cache, gate_mul=gate_mul,
         return_cache=return_cache, arith_mode=layers.get_arith_mode())
     return y, conv_state, h
-  if not can_overlap(conv, lru, x, conv_cache):
-    xc, conv_state = conv(x, segment_pos, conv_cache, return_cache)
-    if gate_mul is not None and not layers.uses_fused_kernel(lru, xc):
-      y, h = lru(xc, segment_pos, lru_cache, return_cache)
-      return y * gate_mul, conv_state, h
-    if hasattr(lru, "forward_into"):
-      y, h = lru.forward_into(xc, segment_pos, lru_cache, return_cache, out=out,
-                              last_h_out=last_h_out, gate_mul=gate_mul)
-    else:   # a reference module patched by install()
-      y, h = lru(xc, segment_pos, lru_cache, return_cache) if gate_mul is None else \
-          type(lru).forward(lru, xc, segment_pos, lru_cache, return_cache, gate_mul=gate_mul)
+  if can_fuse_conv(conv, lru, x, conv_cache):
+    # prefill: convolution + gate GEMMs + gate math + scan in ONE launch
+    bsz, steps, _ = x.shape
+    if segment_pos.shape != (bsz, steps):
+      segment_pos = segment_pos[None, :]
+    assert segment_pos.shape == (bsz, steps)            # layers.py:344
+    if layers._empty_batch(x):
+      xc, conv_state = layers._empty_conv1d(x, 4, None, return_cache, conv_out, conv_cache_out)
+      y, h = layers._empty_rglru(xc, lru.width, return_cache, out, last_h_out)
+      return y, conv_state, h
+    y, conv_state, h = _abi.recurrent_prefill_fwd(
+        x, conv.w, conv.b, layers.packed_gate_weight(lru), lru.input_gate.b, lru.a_gate.b, lru.a_param,
+        segment_pos, lru.num_heads, h0=lru_cache, return_cache=return_cache,
+        mask_mode=getattr(conv, "mask_mode", _abi.MASK_FORK), arith_mode=layers.get_arith_mode(),
+        out=out, conv_cache_out=conv_cache_out, last_h_out=last_h_out, gate_mul=gate_mul)
     return y, conv_state, h
-
-  bsz, steps, width = x.shape
-  if segment_pos.shape != (bsz, steps):
-    segment_pos = segment_pos[None, :]
-  assert segment_pos.shape == (bsz, steps)            # layers.py:344
-  dev = x.device
-  cur = torch.cuda.current_stream(dev)
-  side = _side_stream(dev)
-  x = x.contiguous()
-  key = (dev, cur.cuda_stream, bsz, steps)
-  flags = _flag_buffers.get(key)
-  if flags is None:
-    n = _abi.load().cg_conv1d_stream_flags_bytes(bsz, steps) // 4
-    flags = torch.zeros(n, dtype=torch.int32, device=dev)
-    if len(_flag_buffers) > 64:
-      _flag_buffers.clear()
-    _flag_buffers[key] = flags
-  xc = torch.empty_like(x) if conv_out is None else conv_out
-  conv_state = None
-  if return_cache:
-    conv_state = (torch.empty((bsz, 3, width), dtype=x.dtype, device=dev)
-                  if conv_cache_out is None else conv_cache_out)
-  wpack = layers.packed_gate_weight(lru)               # (re)packs on the caller's stream if stale
-  flags.zero_()                                        # consumer's stream, before the fork
-  side.wait_stream(cur)
-  with torch.cuda.stream(side):                        # producer FIRST (it never waits for the consumer)
-    _abi.conv1d_stream_fwd(x, conv.w, conv.b, segment_pos, flags, out=xc, cache_out=conv_state,
-                           mask_mode=getattr(conv, "mask_mode", _abi.MASK_FORK))
-  y, h = _abi.rglru_fused_fwd(xc, wpack, lru.input_gate.b, lru.a_gate.b, lru.a_param, segment_pos,
-                              lru.num_heads, h0=lru_cache, return_cache=return_cache,
-                              arith_mode=layers.get_arith_mode(), out=out, last_h_out=last_h_out,
-                              gate_mul=gate_mul, conv_flags=flags)
-  cur.wait_stream(side)                                # join: conv_state / xc are complete on `cur`
+  xc, conv_state = (conv.forward_into(x, segment_pos, conv_cache, return_cache, out=conv_out,
+                                      cache_out=conv_cache_out)
+                    if hasattr(conv, "forward_into") else conv(x, segment_pos, conv_cache, return_cache))
+  if gate_mul is not None and not layers.uses_fused_kernel(lru, xc):
+    y, h = lru(xc, segment_pos, lru_cache, return_cache)
+    return y * gate_mul, conv_state, h
+  if hasattr(lru, "forward_into"):
+    y, h = lru.forward_into(xc, segment_pos, lru_cache, return_cache, out=out,
+                            last_h_out=last_h_out, gate_mul=gate_mul)
+  else:   # a reference module patched by install()
+    y, h = lru(xc, segment_pos, lru_cache, return_cache) if gate_mul is None else \
+        type(lru).forward(lru, xc, segment_pos, lru_cache, return_cache, gate_mul=gate_mul)
   return y, conv_state, h

@@ -35,7 +35,10 @@
 extern "C" {
 #endif
 
-#define CG_ABI_VERSION 1
+/* 2: cg_rglru_fused_fwd lost its conv_flags / debug_out parameters (round-1 experiments),
+ *    cg_recurrent_prefill_fwd added, cg_conv1d_stream_* and cg_rglru_fused_schedule removed.
+ * Bumped on EVERY signature change; binders must compare it with cg_abi_version(). */
+#define CG_ABI_VERSION 2
 
 /* activation dtype of x / y / gate GEMM outputs / parameters */
 #define CG_DTYPE_F32 0
@@ -220,9 +223,11 @@ int cg_rnn_scan_bwd(const void* gy, const float* g_last_h, const void* a, const 
  *                              (K-major, 128 B swizzle) the MMAs read.  Call once
  *                              per weight update.
  *   cg_rglru_fused_workspace_bytes  scratch size; zero-fill ONCE before first use
- *                              (same rules as cg_scan_workspace_bytes).  A non-zero
- *                              int32 at byte offset 8 of the scratch after a launch
- *                              means the kernel's watchdog fired (protocol error).
+ *                              (same rules as cg_scan_workspace_bytes).  Every wait inside
+ *                              the kernel is bounded by a clock watchdog; if one ever
+ *                              expires (a protocol error) the kernel TRAPS: the stream
+ *                              carries a sticky CUDA error and the next synchronising
+ *                              call of the host fails -- results are never silently wrong.
  *   cg_rglru_fused_fwd         x [B,T,E] Conv1D output; biases [E] or NULL;
  *                              h0 / last_h / y / seg as in cg_rglru_fwd.
  *                              arith_mode: CG_ARITH_REFERENCE or CG_ARITH_FAST
@@ -236,22 +241,11 @@ int cg_rnn_scan_bwd(const void* gy, const float* g_last_h, const void* a, const 
  *                              RecurrentBlock.forward (modules.py:651, `x = x * y`) folded
  *                              into the store; last_h is
  *                              unaffected.
- *                              conv_flags (nullable): see cg_conv1d_stream_fwd below.
- *                              debug_out (nullable): [3][B][T][E] bf16 -- the rounded
- *                              pre_x, pre_a and the transposed x the epilogue saw.
  */
 int cg_rglru_fused_supported(int E, int H, int dtype);
 size_t cg_rglru_gate_pack_bytes(int E, int H);
 int cg_rglru_pack_gate_weights(const void* wx, const void* wa, void* wpack,
                                int E, int H, int dtype, cg_stream_t stream);
-/* Introspection (host only, no GPU needed): the work schedule the fused kernel
- * uses for a grid of `ctas` CTAs, `families` 128-channel families and `pairs`
- * MMA tiles per family.  balance: 1 = with floater CTAs, 0 = plain round-robin,
- * -1 = what the kernel was built to use.  Writes up to max_segments rows
- * {family, first pair, stride, count} of CTA `cta` and returns its number of
- * segments (tests check that every pair is covered exactly once). */
-int cg_rglru_fused_schedule(int ctas, int families, int pairs, int cta, int balance,
-                            int* segments, int max_segments);
 size_t cg_rglru_fused_workspace_bytes(int B, int T, int E);
 int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x,
                        const void* bias_a, const void* a_param, const void* seg,
@@ -259,29 +253,36 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x,
                        const float* h0, void* y, float* last_h, void* workspace,
                        size_t workspace_bytes, int B, int T, int E, int H,
                        int dtype, int arith_mode, const void* gate_mul,
-                       const int* conv_flags, void* debug_out,
                        cg_stream_t stream);
 
 /*
- * Overlapped Conv1D -> RG-LRU (bf16, W = 4, E % 64 == 0): the producer form of
- * cg_conv1d_fwd.  A few persistent blocks walk x in time-major order and count
- * finished [64 steps x 64 channels] tiles per (64-step group, batch row) in
- * `flags` ([ceil(T/64)][B] int32, cg_conv1d_stream_flags_bytes); a
- * cg_rglru_fused_fwd call that is given the same `flags` as `conv_flags` and the
- * conv output `y` as its `x` may be enqueued on ANOTHER stream and runs at the
- * same time: its TMA producer waits per tile until the rows it needs are there.
- * The Conv1D traffic then hides under the (compute-bound) RG-LRU kernel.
- * Protocol: zero `flags` on the consumer's stream, fork (event) to the
- * producer's stream, enqueue cg_conv1d_stream_fwd there FIRST, then
- * cg_rglru_fused_fwd on the consumer's stream, join.  The producer never waits
- * for the consumer, so the pair cannot deadlock.
+ * Conv1D.forward -> RGLRU.forward of one recurrent block as ONE kernel (prefill,
+ * bf16, W == 4, head width 128 / 256): what RecurrentBlock.forward does between
+ * its projections (recurrentgemma/torch/modules.py:638-649) --
+ *     x, conv1d_state = conv_1d(x, segment_pos)       layers.py:458-546
+ *     x, rg_lru_state = rg_lru(x, segment_pos)        layers.py:322-375
+ * -- with the temporal convolution computed INSIDE the fused tensor-core kernel:
+ * TMA loads the rows of x (= linear_x output) into shared memory, two warps
+ * convolve them in place with the reference's rounding (bit-exact with
+ * cg_conv1d_fwd), the tcgen05 gate GEMMs read the result, gate math and scan
+ * follow in the epilogue.  Neither the conv output nor the gate pre-activations
+ * reach HBM: the step moves 2 x B*T*E*2 bytes (x in, y out).
+ *   x [B,T,E] Conv1D INPUT; conv_w [4,E]; conv_b [E];
+ *   conv_cache_out (nullable) [B,3,E] bf16: the last three rows of x, left zero
+ *        padded (layers.py:542-543);
+ *   everything else as cg_rglru_fused_fwd (wpack from cg_rglru_pack_gate_weights,
+ *   workspace of cg_rglru_fused_workspace_bytes, gate_mul nullable).
+ *   mask_mode: CG_MASK_FORK / CG_MASK_UPSTREAM.  W must be 4 (CG_ERR_UNSUPPORTED
+ *   otherwise: run cg_conv1d_fwd + cg_rglru_fused_fwd).
  */
-size_t cg_conv1d_stream_flags_bytes(int B, int T);
-int cg_conv1d_stream_fwd(const void* x, const void* w, const void* b,
-                         const void* seg, int seg_is_i64,
-                         long long seg_batch_stride, void* y, void* cache_out,
-                         int* flags, int B, int T, int E, int W, int dtype,
-                         int mask_mode, int arith_mode, cg_stream_t stream);
+int cg_recurrent_prefill_fwd(const void* x, const void* conv_w, const void* conv_b,
+                             const void* wpack, const void* bias_x, const void* bias_a,
+                             const void* a_param, const void* seg, int seg_is_i64,
+                             long long seg_batch_stride, const float* h0,
+                             const void* gate_mul, void* y, void* conv_cache_out,
+                             float* last_h, void* workspace, size_t workspace_bytes,
+                             int B, int T, int E, int H, int W, int dtype,
+                             int mask_mode, int arith_mode, cg_stream_t stream);
 
 /*
  * Fused decode step of the recurrent hot path (T == 1, caches given, bf16,

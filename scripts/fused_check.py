@@ -57,8 +57,7 @@ def run_case(B, T, E, H, mode, variant, use_h0=True, debug=True):
   out = _abi.rglru_fused_fwd(x, wpack, lru.input_gate.b, lru.a_gate.b, lru.a_param, seg, H,
                              h0=h0 if use_h0 else None, arith_mode=arith, debug=debug, workspace=ws)
   torch.cuda.synchronize()
-  res = {"case": [B, T, E, H], "mode": mode, "variant": variant,
-         "watchdog": _abi.fused_watchdog_code(ws)}
+  res = {"case": [B, T, E, H], "mode": mode, "variant": variant}
   y, last_h = out[0], out[1]
   # unfused reference: cuBLAS fused-gate GEMM + scan kernel, same arithmetic mode
   gates = lru.gate_gemm(x)
@@ -102,46 +101,52 @@ def time_case(mode, variant, iters=20, B=8, T=2048):
   us = sorted(a.elapsed_time(b) * 1e3 for a, b in evs)
   nelem = B * T * E
   res = {"time": [B, T], "mode": mode, "variant": variant, "us_median": us[len(us) // 2], "us_best": us[0],
-         "alg_GBps_8B_per_elem": 8 * nelem / (us[len(us) // 2] * 1e-6) / 1e9,
-         "watchdog": _abi.fused_watchdog_code(ws)}
+         "alg_GBps_8B_per_elem": 8 * nelem / (us[len(us) // 2] * 1e-6) / 1e9}
   print(json.dumps(res), flush=True)
 
 
-def overlap_case(B=8, T=2048, iters=30):
-  """Conv1D -> RG-LRU: sequential kernels vs the overlapped producer / consumer pipeline."""
+def _time(fn, iters):
+  for _ in range(5):
+    fn()
+  torch.cuda.synchronize()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(iters):
+    fn()
+  b.record()
+  torch.cuda.synchronize()
+  return a.elapsed_time(b) * 1e3 / iters
+
+
+def conv_case(B=8, T=2048, iters=40, check=True):
+  """Conv1D -> RG-LRU: the two kernels one after the other vs ONE fused launch
+  (cg_recurrent_prefill_fwd, convolution inside the tcgen05 kernel)."""
+  from cadence_gemma_b200 import pipeline
   E, H = 2560, 10
-  x, lru, seg, _ = make(B, T, E, H, resets=False)
+  x, lru, seg, _ = make(B, T, E, H, resets=check)
   conv = cg.Conv1D(E, 4, device=x.device, dtype=torch.bfloat16)
   with torch.no_grad():
     conv.w.normal_(0, 0.4); conv.b.normal_(0, 0.2)
+  y = torch.empty_like(x)
+  xc = torch.empty_like(x)
+  h = torch.empty((B, E), dtype=torch.float32, device=x.device)
+  cs = torch.empty((B, 3, E), dtype=x.dtype, device=x.device)
 
-  def seq():
-    xc, cs = conv(x, seg)
-    return lru(xc, seg)
+  def run():
+    return cg.recurrent_hot_path(conv, lru, x, seg, out=y, last_h_out=h, conv_out=xc, conv_cache_out=cs)
 
-  from cadence_gemma_b200 import pipeline
-  pipeline.set_overlap(True)
-
-  def ovl():
-    return cg.recurrent_hot_path(conv, lru, x, seg)
-
-  res = {"overlap": [B, T]}
+  res = {"conv_case": [B, T]}
   with torch.no_grad():
-    for name, fn in (("sequential_us", seq), ("overlapped_us", ovl)):
-      for _ in range(5):
-        fn()
-      torch.cuda.synchronize()
-      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      a.record()
-      for _ in range(iters):
-        fn()
-      b.record()
-      torch.cuda.synchronize()
-      res[name] = a.elapsed_time(b) * 1e3 / iters
-    y1, h1 = seq()
-    y2, _, h2 = ovl()
-    res["identical"] = bool(torch.equal(y1, y2) and torch.equal(h1, h2))
-  res["watchdog"] = [_abi.fused_watchdog_code(w) for w in _abi._fused_workspaces.values()]
+    old = pipeline.set_fused_conv(False)
+    res["two_kernels_us"] = _time(run, iters)
+    y1, c1, h1 = [t.clone() for t in run()]
+    pipeline.set_fused_conv(True)
+    res["one_launch_us"] = _time(run, iters)
+    y2, c2, h2 = [t.clone() for t in run()]
+    pipeline.set_fused_conv(old)
+    res["identical"] = bool(torch.equal(y1, y2) and torch.equal(h1, h2) and torch.equal(c1, c2))
+    if not res["identical"]:
+      res["y"] = stats(y2, y1); res["h"] = stats(h2, h1); res["cache_equal"] = bool(torch.equal(c1, c2))
   print(json.dumps(res), flush=True)
 
 
@@ -162,10 +167,12 @@ def main():
     run_case(8, 2048, 2560, 10, a.mode, a.variant, debug=False)
   elif a.case == "time":
     time_case(a.mode, a.variant)
-  elif a.case == "overlap":
-    overlap_case()
-    overlap_case(32, 768)
-    overlap_case(2, 8192)
+  elif a.case == "conv":
+    conv_case()
+    conv_case(check=False)
+  elif a.case == "conv_shapes":
+    for B, T in [(1, 2048), (2, 8192), (32, 768), (16, 8192)]:
+      conv_case(B, T, check=False)
   elif a.case == "time_shapes":
     for B, T in [(1, 2048), (2, 2048), (2, 8192), (32, 768), (8, 2048)]:
       time_case(a.mode, a.variant, B=B, T=T)

@@ -18,11 +18,11 @@ for _ in range(3):
   out = _abi.rglru_fused_fwd(x, wpack, lru.input_gate.b, lru.a_gate.b, lru.a_param, seg, H,
                              arith_mode=2, debug=True, workspace=ws)
 torch.cuda.synchronize()
-tr = out[2].view(-1).view(torch.int64)[: 6 * 1024].view(6, 1024).cpu()
-names = ["producer", "mma", "wg0", "wg1", "wg2", "wg3"]
+tr = out[2].view(-1).view(torch.int64)[: 7 * 1024].view(7, 1024).cpu()
+names = ["producer", "mma", "wg0", "wg1", "wg2", "wg3", "conv"]
 t0 = None
 res = {}
-for r in range(6):
+for r in range(7):
   ev = [(int(v) >> 4, int(v) & 15) for v in tr[r].tolist() if v != 0]
   if ev and (t0 is None or ev[0][0] < t0):
     t0 = ev[0][0]

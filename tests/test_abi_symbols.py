@@ -11,11 +11,22 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-  with open(os.path.join(ROOT, "include", "cadence_b200.h")) as f:
-    text = f.read()
-  text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-  return sorted(set(re.findall(r"\b(cg_[a-z0-9_]+)\s*\(", text)))
+def _header_text(name="cadence_b200.h"):
+  with open(os.path.join(ROOT, "include", name)) as f:
+    return re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+
+
+def _declared_symbols(name="cadence_b200.h"):
+  return sorted(set(re.findall(r"\b(cg_[a-z0-9_]+)\s*\(", _header_text(name))))
+
+
+def _declared_arg_counts(name="cadence_b200.h"):
+  """{symbol: number of parameters} parsed from the prototypes of a header."""
+  out = {}
+  for m in re.finditer(r"\b(cg_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", _header_text(name)):
+    args = m.group(2).strip()
+    out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+  return out
 
 
 def test_library_exports_every_declared_symbol():
@@ -27,8 +38,19 @@ def test_library_exports_every_declared_symbol():
   for name in declared:
     assert hasattr(lib, name), f"{name} declared in the header but not exported"
   assert sorted(_abi.SYMBOLS) == declared, "ctypes table out of sync with the header"
+  # ... argument for argument (a stale binder would pass the stream in the wrong slot)
+  counts = _declared_arg_counts()
+  for name, (_, argtypes) in _abi.SYMBOLS.items():
+    assert counts[name] == len(argtypes), (name, counts[name], len(argtypes))
+  # the experimental header (development taps) is bound separately and is NOT part of the surface
+  exp = _declared_symbols("cadence_b200_experimental.h")
+  assert sorted(_abi.EXPERIMENTAL_SYMBOLS) == exp
+  exp_counts = _declared_arg_counts("cadence_b200_experimental.h")
+  for name, (_, argtypes) in _abi.EXPERIMENTAL_SYMBOLS.items():
+    assert hasattr(lib, name) and exp_counts[name] == len(argtypes), name
   loaded = _abi.load()
-  assert loaded.cg_abi_version() == 1
+  version = int(re.search(r"#define CG_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "cadence_b200.h")).read()).group(1))
+  assert loaded.cg_abi_version() == version == _abi.ABI_VERSION
   assert b"workspace" in loaded.cg_status_string(-5)
   assert loaded.cg_scan_workspace_bytes(8, 2048, 2560, 1) > 0
   assert loaded.cg_scan_workspace_bytes(0, 1, 1, 1) == 0
@@ -102,47 +124,3 @@ def test_install_patches_reference_entry_points():
   finally:
     install.uninstall()
   assert (ref.layers.rnn_scan, ref.layers.RGLRU.forward, ref.layers.Conv1D.forward) == orig
-
-
-@pytest.mark.parametrize("ctas,families,pairs", [
-    (148, 20, 256),    # config 2: 7 dedicated CTAs per family + 8 floaters
-    (148, 20, 384),    # config 3 (B=32, T=768)
-    (148, 20, 2048),   # config 4 (B=16, T=8192)
-    (148, 20, 37),     # too few pairs to balance: plain round-robin
-    (148, 8, 300),     # 18 per family + 4 floaters, S = 2
-    (148, 4, 64),      # divides evenly
-    (132, 20, 256),    # another SM count
-    (3, 20, 10),       # fewer CTAs than families (test hook): whole families
-    (148, 32, 501),    # 9B shape (E = 4096), odd pair count
-])
-@pytest.mark.parametrize("balance", [0, 1, -1])
-def test_fused_schedule_covers_every_pair_once_and_is_balanced(ctas, families, pairs, balance):
-  """The fused kernel's work schedule (floater CTAs when the SM count is not a
-  multiple of the family count), evaluated on the host through the C ABI."""
-  import ctypes
-  from cadence_gemma_b200 import _abi
-  lib = _abi.load()
-  seen = [[0] * pairs for _ in range(families)]
-  load = []
-  for cta in range(ctas):
-    buf = (ctypes.c_int * (4 * 64))()
-    n = lib.cg_rglru_fused_schedule(ctas, families, pairs, cta, balance, ctypes.cast(buf, ctypes.c_void_p), 64)
-    assert 0 <= n <= 64
-    total, last = 0, (-1, -1)
-    for i in range(n):
-      fam, j0, stride, count = buf[4 * i:4 * i + 4]
-      assert 0 <= fam < families and stride >= 1 and count >= 0
-      for m in range(count):
-        j = j0 + m * stride
-        assert 0 <= j < pairs
-        seen[fam][j] += 1
-      if count:
-        # a CTA moves forward in time inside a family; it never returns to a family it left
-        assert (fam, j0) > last or fam != last[0]
-        last = (fam, j0 + (count - 1) * stride)
-      total += count
-    load.append(total)
-  assert all(c == 1 for row in seen for c in row)
-  if ctas >= families and balance == 1:
-    ideal = families * pairs / ctas
-    assert max(load) <= ideal + 3 or pairs < 80, (max(load), ideal)

@@ -658,7 +658,6 @@ def test_fused_rglru_golden(case, mode):
   y, h, dbg = abi.rglru_fused_fwd(cu(g["x"]), wpack, cu(g["input_gate_b"]), cu(g["a_gate_b"]),
                                   cu(g["a_param"]), cu(g["seg"]), heads, arith_mode=mode,
                                   debug=True, workspace=ws)
-  assert abi.fused_watchdog_code(ws) == 0
   # the debug planes hold round_bf16(x @ w) WITHOUT bias and the transposed x
   bx = g["input_gate_b"].reshape(-1).float()
   ba = g["a_gate_b"].reshape(-1).float()
@@ -757,8 +756,7 @@ def test_fused_rglru_full_size_properties(steps, bsz):
     xb[:, :cut] = torch.randn_like(xb[:, :cut]) * 3
     yb, _ = lru(xb, seg2)
     assert torch.equal(ya[:, cut:], yb[:, cut:])
-  for ws in abi._fused_workspaces.values():
-    assert abi.fused_watchdog_code(ws) == 0
+  torch.cuda.synchronize()   # a fired watchdog traps: the synchronisation would raise
 
 
 def test_fused_rglru_argument_errors():
@@ -884,8 +882,7 @@ def test_back_to_back_steps_with_programmatic_dependent_launch_are_ordered():
     assert torch.equal(y_bufs[k], want[k][0]) and torch.equal(h_bufs[k], want[k][1]), k
     assert torch.equal(c_bufs[k], want[k][2]), k
   abi = _abi()
-  for ws in abi._fused_workspaces.values():
-    assert abi.fused_watchdog_code(ws) == 0
+  torch.cuda.synchronize()   # a fired watchdog traps: the synchronisation would raise
 
 
 def test_fused_rglru_api_variants_and_cuda_graph():
@@ -932,8 +929,7 @@ def test_fused_rglru_api_variants_and_cuda_graph():
       torch.cuda.synchronize()
       y_ref, h_ref = lru(xn, seg32)
       assert torch.equal(ys, y_ref) and torch.equal(hs, h_ref), k
-  for ws in abi._fused_workspaces.values():
-    assert abi.fused_watchdog_code(ws) == 0
+  torch.cuda.synchronize()   # a fired watchdog traps: the synchronisation would raise
 
 
 @pytest.mark.parametrize("shape", [(2, 100, 512, 2), (3, 64, 256, 2), (1, 333, 2560, 10)])
@@ -958,16 +954,9 @@ def test_fused_gating_product(shape):
     assert torch.equal(hm, h)
 
 
-@pytest.mark.parametrize("shape", [(8, 2048, 2560, 10), (3, 200, 512, 2), (2, 33, 256, 2), (1, 1000, 2560, 10)])
-def test_overlapped_conv_rglru_pipeline_equals_sequential(shape):
-  """Conv1D as a producer kernel on a side stream under the fused RG-LRU kernel
-  (pipeline.recurrent_hot_path) == the two kernels one after the other, bit for
-  bit, run after run (the flag protocol must not let the consumer read rows that
-  are not there yet)."""
+def _conv_lru(width, heads, seed):
   import cadence_gemma_b200 as cg
-  from cadence_gemma_b200 import pipeline
-  bsz, steps, width, heads = shape
-  torch.manual_seed(sum(shape))
+  torch.manual_seed(seed)
   conv = cg.Conv1D(width, 4, device=DEV, dtype=torch.bfloat16)
   lru = cg.RGLRU(width, heads, device=DEV, dtype=torch.bfloat16)
   with torch.no_grad():
@@ -975,32 +964,86 @@ def test_overlapped_conv_rglru_pipeline_equals_sequential(shape):
     conv.b.normal_(0, 0.2)
     lru.input_gate.b.normal_()
     lru.a_gate.b.normal_()
+  return conv, lru
+
+
+@pytest.mark.parametrize("mask_mode", [0, 1])
+@pytest.mark.parametrize("shape", [(8, 2048, 2560, 10), (3, 200, 512, 2), (2, 33, 256, 2), (1, 1000, 2560, 10),
+                                   (5, 97, 1024, 4), (2, 3, 256, 2), (1, 2, 512, 2), (4, 64, 256, 1)])
+def test_fused_conv_prefill_equals_two_kernel_path(shape, mask_mode):
+  """cg_recurrent_prefill_fwd -- the temporal convolution INSIDE the fused tcgen05
+  RG-LRU kernel (ONE launch) -- against the Conv1D kernel followed by the fused
+  RG-LRU kernel: y, last_h and the returned conv cache bit for bit, the in-kernel
+  conv output (debug tap) bit-exact with cg_conv1d_fwd (itself bit-exact with the
+  reference, test_conv1d_golden); both document masks, ragged T, T < 4, head
+  widths 128 / 256, document starts at tile boundaries, h0, gate product."""
+  import cadence_gemma_b200 as cg
+  from cadence_gemma_b200 import pipeline
+  abi = _abi()
+  bsz, steps, width, heads = shape
+  conv, lru = _conv_lru(width, heads, sum(shape))
+  conv.mask_mode = mask_mode
+  with torch.no_grad():
     x = torch.randn(bsz, steps, width, device=DEV).to(torch.bfloat16)
     seg = torch.arange(steps, device=DEV, dtype=torch.int32)[None].repeat(bsz, 1)
-    seg[:, steps // 2:] -= steps // 2
+    g = torch.Generator().manual_seed(sum(shape) + mask_mode)
+    for b in range(bsz):                      # document starts, incl. next to 32-step tile edges
+      cuts = torch.randint(1, max(steps, 2), (3,), generator=g).tolist() + [31, 32, 33, 34, 64]
+      for cut in sorted(c for c in cuts[:3 + 2 * (b % 3)] if c < steps):
+        seg[b, cut:] = torch.arange(steps - cut, dtype=torch.int32, device=DEV)
     h0 = torch.randn(bsz, width, device=DEV)
-    xc, cs_ref = conv(x, seg)
-    y_ref, h_ref = lru(xc, seg, h0)
-    gate = torch.randn_like(x)
-    # default: sequential kernels through the same entry point
-    assert not pipeline.can_overlap(conv, lru, x)
-    y, cs, h = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0)
-    assert torch.equal(y, y_ref) and torch.equal(h, h_ref) and torch.equal(cs, cs_ref)
-    old = pipeline.set_overlap(True)
+    old = pipeline.set_fused_conv(False)
     try:
-      assert pipeline.can_overlap(conv, lru, x)
-      for it in range(12):
-        # poison what the producer is about to write, so that a premature read shows
-        y, cs, h = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0,
-                                         conv_out=torch.full_like(x, float("nan")))
-        assert torch.equal(y, y_ref) and torch.equal(h, h_ref) and torch.equal(cs, cs_ref), it
-      y, _, _ = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0, gate_mul=gate)
-      assert torch.equal(y, y_ref * gate)
+      assert not pipeline.can_fuse_conv(conv, lru, x)
+      xc_ref = torch.empty_like(x)
+      y_ref, cs_ref, h_ref = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0, conv_out=xc_ref)
     finally:
-      pipeline.set_overlap(old)
-  abi = _abi()
-  for ws in abi._fused_workspaces.values():
-    assert abi.fused_watchdog_code(ws) == 0
+      pipeline.set_fused_conv(old)
+    assert pipeline.can_fuse_conv(conv, lru, x)
+    for it in range(3):
+      y, cs, h = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0)
+      assert torch.equal(cs, cs_ref), (shape, it)
+      assert torch.equal(y, y_ref) and torch.equal(h, h_ref), (shape, it, identical_fraction(y, y_ref))
+    # the conv output as the epilogue saw it (identity-MMA transpose of the in-place conv)
+    _, _, _, dbg = abi.recurrent_prefill_fwd(x, conv.w, conv.b, cg.layers.packed_gate_weight(lru),
+                                             lru.input_gate.b, lru.a_gate.b, lru.a_param, seg, heads,
+                                             h0=h0, mask_mode=mask_mode, arith_mode=cg.get_arith_mode(),
+                                             debug=True)
+    assert_bitexact(dbg[2].cpu(), xc_ref.cpu(), f"{shape} in-kernel conv output")
+    # no caches requested / gating product folded in
+    y_n, cs_n, h_n = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0, return_cache=False)
+    assert cs_n is None and h_n is None and torch.equal(y_n, y_ref)
+    gate = torch.randn_like(x)
+    y_g, _, _ = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0, gate_mul=gate)
+    assert torch.equal(y_g, y_ref * gate)
+  torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("case", fixture_io.cases("recurrent_block_"))
+def test_fused_conv_prefill_recurrent_block_golden(case):
+  """The reference's own RecurrentBlock outputs (tests/golden) against the hot path
+  with the convolution inside the fused kernel, where the fixture's shape takes it."""
+  import cadence_gemma_b200 as cg
+  from cadence_gemma_b200 import pipeline
+  g = fixture_io.load(case)
+  if g["x"].dtype != torch.bfloat16:
+    pytest.skip("fp32 fixture: not on the fused path")
+  width = g["conv_in"].shape[-1]
+  heads = g["param.rg_lru.input_gate.w"].shape[0]
+  if width // heads not in (128, 256):
+    pytest.skip("head width not on the fused path")
+  conv = cg.Conv1D(width, 4, device=DEV, dtype=torch.bfloat16)
+  lru = cg.RGLRU(width, heads, device=DEV, dtype=torch.bfloat16)
+  with torch.no_grad():
+    conv.w.copy_(cu(g["param.conv_1d.w"])); conv.b.copy_(cu(g["param.conv_1d.b"]))
+    lru.a_param.copy_(cu(g["param.rg_lru.a_param"]))
+    lru.input_gate.w.copy_(cu(g["param.rg_lru.input_gate.w"])); lru.input_gate.b.copy_(cu(g["param.rg_lru.input_gate.b"]))
+    lru.a_gate.w.copy_(cu(g["param.rg_lru.a_gate.w"])); lru.a_gate.b.copy_(cu(g["param.rg_lru.a_gate.b"]))
+    assert pipeline.can_fuse_conv(conv, lru, cu(g["conv_in"]))
+    y, cs, h = cg.recurrent_hot_path(conv, lru, cu(g["conv_in"]), cu(g["seg"]))
+  assert_bitexact(cs.cpu(), g["conv1d_state"], case + " conv cache")
+  assert normwise(h.cpu(), g["rg_lru_state"]) <= 1e-2
+  assert_close_bf16(y.cpu(), g["rglru_out"], case + " rg_lru output", min_identical=0.98)
 
 
 @pytest.mark.parametrize("shape", [(32, 2560, 10), (5, 512, 2), (8, 256, 4), (1, 256, 2), (3, 1024, 4)])
@@ -1071,5 +1114,4 @@ def test_fused_rglru_family_loop_small_grid(ctas):
   y_ref, h_ref = abi.rglru_fused_fwd(x, wpack, bx, ba, ap, seg, heads, h0=h0, arith_mode=FAST, workspace=ws)
   y, h = abi.rglru_fused_fwd(x, wpack, bx, ba, ap, seg, heads, h0=h0, arith_mode=FAST | (ctas << 8),
                              workspace=ws)
-  assert abi.fused_watchdog_code(ws) == 0
   assert torch.equal(y, y_ref) and torch.equal(h, h_ref)
