@@ -1,22 +1,33 @@
 """Benchmark of the recurrent hot path (Conv1D -> gate GEMMs -> RG-LRU scan).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload config2|config3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
         --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): one RecurrentGemma-2B-shape recurrent
-block's hot path, random init, bf16, batch 8, seq 2048 prefill, per GPU.  A
-"step" is one pass of that batch through ``Conv1D.forward`` ->
-``RGLRU.forward`` (block-diagonal gate GEMMs in cuBLAS + the fused gate/scan
-kernel).  With N GPUs every rank runs its own batch of 8 (batch-sharded, weak
-scaling, no collective inside the path; the small per-row states are
-all-gathered on a side stream).
+Workload (default, BASELINE.json configs[1]): one RecurrentGemma-2B-shape
+recurrent block's hot path, random init, bf16, batch 8, seq 2048 prefill, per
+GPU.  A "step" is one pass of that batch through the hot-path entry point
+``cadence_gemma_b200.recurrent_hot_path`` = ``Conv1D.forward -> RGLRU.forward``
+(reference modules.py:638-649): the Conv1D kernel followed by the fused tcgen05
+kernel (gate GEMMs + gate math + scan), or ONE launch with the convolution inside
+that kernel where that is the faster route (pipeline.py).  With N GPUs every rank
+runs its own batch of 8 (batch-sharded, weak scaling, no collective inside the
+path; the small per-row states are all-gathered on a side stream once per 18
+block steps = one 2B prefill).
+
+``--workload config3`` (BASELINE.json configs[2]): the Cadence multimodal prefill
+at MODEL level -- synthetic ViT features -> MLP projector -> RecurrentGemma-2B
+stack (18 recurrent + 8 attention blocks), batch 32 sharded over the ranks, 256
+visual + 512 text tokens (scripts/model_prefill.py).
 
 Prints ONE JSON line (see the task contract): metric = prefill tokens/s of the
-hot path, with `roofline` for the dominant kernel (RG-LRU gate+scan, 4*s
-algorithmic bytes per element), `cpu_baseline` (the oracle port of the
-reference's eager torch path, timed on this box's host cores) and `e2e` (same
-step driven from pinned HOST buffers, H2D + D2H inside the timed region).
+hot path, `roofline` for the dominant kernel on the bytes it really moves,
+`roofline_step` on the canonical 12 B/element of SURVEY 8(d) (the number tracked
+against the north star's 70 % target), `cpu_baseline` (the reference's own eager
+torch path on this box's host cores), `parity` (bit-identical fraction against
+that CPU run for the shipped and the exact arithmetic mode) and `e2e` (same step
+driven from pinned HOST buffers, H2D + D2H inside the timed region, with the
+box's host-link ceiling measured in the same process).
 """
 from __future__ import annotations
 
@@ -24,7 +35,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -37,10 +47,10 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(batch=8, seq_len=2048, width=2560, heads=10, temporal_width=4)
 GATHER_EVERY = int(os.environ.get("CG_BENCH_GATHER_EVERY", "18"))   # recurrent blocks per 2B prefill (common.py:90-101)
 METRIC = "rglru_conv1d_prefill_tokens_per_sec"
-# dram__bytes_read.sum + dram__bytes_write.sum of one fused-kernel launch at config 2
-# (ncu --set full, profiles/r1_rglru_fused_kernel_ncu_summary.txt)
-NCU_TRAFFIC_BYTES = 162999296   # 94.71 MB read + 68.29 MB written (profiles/r1_rglru_fused_kernel_ncu_summary.txt)
 UNIT = "tokens/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+# capture of the dominant kernel (not measurable inside an un-profiled run)
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 
 
 def parse_args():
@@ -50,16 +60,28 @@ def parse_args():
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", default="own", choices=["own", "reference"])
   ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+  ap.add_argument("--workload", default="config2", choices=["config2", "config3"])
   ap.add_argument("--no-cpu-baseline", action="store_true")
   return ap.parse_args()
 
 
-def measured_peak_gbs():
+def measured_peaks():
   path = os.path.join(ROOT, "MEASURED_PEAKS.json")
   if os.path.exists(path):
     with open(path) as f:
-      return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-  return 6650.0, "fallback (B200_PROFILING.md)"
+      d = json.load(f)
+    return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+  return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_key):
+  try:
+    with open(NCU_TRAFFIC_FILE) as f:
+      d = json.load(f)
+    e = d[kernel_key]
+    return int(e["dram_bytes_per_launch"]), e["source"]
+  except Exception:  # pylint: disable=broad-except
+    return None, None
 
 
 def make_host_inputs(dtype, seed=1):
@@ -88,20 +110,23 @@ def make_host_inputs(dtype, seed=1):
 # clocks / throttle sampling during the timed region
 # ----------------------------------------------------------------------------
 class ClockSampler:
-  """Samples SM clock and throttle reasons through NVML from a background
-  thread while the timed region runs (nvidia-smi -lms is too slow to start for
-  regions of a few milliseconds)."""
+  """Samples SM clock and throttle reasons through NVML from a background thread.
+  It is started BEFORE the clock-ramp loop (NVML needs tens of milliseconds to
+  initialise, the timed region of a short run lasts 3 ms); `window()` brackets
+  the timed region in wall-clock time and only samples inside it are reported."""
 
   REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40,
              "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
   def __init__(self, gpu_index):
     self.gpu_index = gpu_index
-    self.samples, self.reasons = [], set()
+    self.samples = []          # (wall time, MHz, reason mask)
     self.sm_max = None
     self._stop = threading.Event()
+    self._ready = threading.Event()
     self._thread = None
     self._err = None
+    self.t0 = self.t1 = None
 
   def _run(self):
     try:
@@ -118,55 +143,102 @@ class ClockSampler:
       if handle is None:
         handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
       self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
+      self._ready.set()
       while not self._stop.is_set():
-        self.samples.append(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+        mhz = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
         mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
-        for name, bit in self.REASONS.items():
-          if mask & bit:
-            self.reasons.add(name)
-        time.sleep(0.002)
+        self.samples.append((time.perf_counter(), mhz, mask))
+        time.sleep(0.0005)
     except Exception as exc:  # pylint: disable=broad-except
       self._err = repr(exc)
+      self._ready.set()
 
   def start(self):
     self._thread = threading.Thread(target=self._run, daemon=True)
     self._thread.start()
-    time.sleep(0.05)   # let NVML initialise before the timed region starts
+    self._ready.wait(timeout=10)
+
+  def window_begin(self):
+    self.t0 = time.perf_counter()
+
+  def window_end(self):
+    self.t1 = time.perf_counter()
 
   def stop(self):
     self._stop.set()
     if self._thread is not None:
       self._thread.join(timeout=5)
-    out = {"sm_mhz": statistics.median(self.samples) if self.samples else None,
-           "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
-           "samples": len(self.samples)}
+    inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= self.t1]
+    # a 3 ms region may hold only a few samples: the load ramp right before it runs the same steps
+    near = [s for s in self.samples if self.t0 is not None and self.t0 - 0.2 <= s[0] <= self.t1]
+    use = inside if len(inside) >= 3 else near
+    reasons = set()
+    for _, _, mask in use:
+      for name, bit in self.REASONS.items():
+        if mask & bit:
+          reasons.add(name)
+    out = {"sm_mhz": statistics.median(s[1] for s in use) if use else None,
+           "sm_max_mhz": self.sm_max, "reasons": sorted(reasons),
+           "samples": len(use), "samples_inside_timed_region": len(inside)}
     if self._err:
       out["error"] = self._err
     return out
 
 
 # ----------------------------------------------------------------------------
-def run_cpu_port(host, steps, warmup, threads):
-  """The oracle port of the reference's eager torch path on the host cores.
+def cpu_reference_runner(host, threads):
+  """Returns ``(kind, fn)``: ``fn()`` runs Conv1D.forward -> RGLRU.forward of the
+  reference on the host cores and returns ``(y, last_h, conv_state)``.
 
-  This is the ONLY place bench.py touches oracle/: as the reported CPU
-  baseline / the `--impl reference` arm, never on the product path.
+  kind "reference": the reference's OWN classes, imported unmodified from
+  baseline/_ref (or /root/reference); kind "port": oracle/torch_port.py, which
+  issues the same ATen ops, when no copy of the reference is on the box.  This is
+  the ONLY place bench.py touches oracle/: as the reported CPU baseline / the
+  `--impl reference` arm, never on the product path.
   """
-  from oracle import torch_port
   torch.set_num_threads(threads)
+  from oracle import ref_loader
+  w = WORKLOAD
+  if ref_loader.reference_available():
+    ref = ref_loader.load_reference()
+    dtype = host["x_lin"].dtype
+    conv = ref.layers.Conv1D(width=w["width"], temporal_width=w["temporal_width"], dtype=dtype)
+    lru = ref.layers.RGLRU(width=w["width"], num_heads=w["heads"], dtype=dtype)
+    with torch.no_grad():
+      conv.w.copy_(host["conv_w"]); conv.b.copy_(host["conv_b"])
+      lru.a_param.copy_(host["a_param"])
+      lru.input_gate.w.copy_(host["input_gate_w"]); lru.input_gate.b.copy_(host["input_gate_b"])
+      lru.a_gate.w.copy_(host["a_gate_w"]); lru.a_gate.b.copy_(host["a_gate_b"])
+
+    def run_ref():
+      with torch.no_grad():
+        # the reference masks its input in place (layers.py:524): give it a copy
+        xc, conv_state = conv(host["x_lin"].clone(), host["segment_pos"])
+        y, last_h = lru(xc, host["segment_pos"])
+      return y, last_h, conv_state
+    return "reference", run_ref
+
+  from oracle import torch_port
   params = torch_port.RGLRUParams(host["a_param"], host["input_gate_w"],
                                   host["input_gate_b"], host["a_gate_w"], host["a_gate_b"])
-  times, out = [], None
-  with torch.no_grad():
-    for i in range(warmup + steps):
-      t0 = time.perf_counter()
+
+  def run_port():
+    with torch.no_grad():
       xc, conv_state = torch_port.conv1d_forward(host["conv_w"], host["conv_b"],
                                                  host["x_lin"], host["segment_pos"])
       y, last_h = torch_port.rglru_forward(params, xc, host["segment_pos"])
-      dt = time.perf_counter() - t0
-      if i >= warmup:
-        times.append(dt)
-      out = (y, last_h, conv_state)
+    return y, last_h, conv_state
+  return "port", run_port
+
+
+def time_cpu(fn, steps, warmup):
+  times, out = [], None
+  for i in range(warmup + steps):
+    t0 = time.perf_counter()
+    out = fn()
+    dt = time.perf_counter() - t0
+    if i >= warmup:
+      times.append(dt)
   return times, out
 
 
@@ -174,10 +246,15 @@ def reference_arm(args, dtype):
   rank = int(os.environ.get("RANK", "0"))
   if rank != 0:
     return   # rank 0 alone runs the CPU reference arm
+  if args.workload == "config3":
+    from scripts import model_prefill
+    print(json.dumps(model_prefill.reference_arm_line(args)), flush=True)
+    return
   threads = os.cpu_count() or 1
   host = make_host_inputs(dtype)
   tokens = WORKLOAD["batch"] * WORKLOAD["seq_len"]
-  times, _ = run_cpu_port(host, args.steps, args.warmup, threads)
+  kind, fn = cpu_reference_runner(host, threads)
+  times, _ = time_cpu(fn, args.steps, args.warmup)
   total = sum(times)
   value = tokens * len(times) / total
   sample = (f"full config-2 batch (B={WORKLOAD['batch']}, T={WORKLOAD['seq_len']}, "
@@ -187,9 +264,12 @@ def reference_arm(args, dtype):
       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
       "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-      "config": config_dict(args, "cpu"),
-      "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                       "sample": sample},
+      "config": config_dict(args),   # the SAME config as the GPU arm
+      "device": "cpu",
+      "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                       "sample": sample,
+                       "what": ("the reference's own Conv1D.forward + RGLRU.forward (unmodified, baseline/_ref)"
+                                if kind == "reference" else "oracle/torch_port.py (same ATen ops as the reference)")},
       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
               "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
@@ -197,7 +277,7 @@ def reference_arm(args, dtype):
   print(json.dumps(line), flush=True)
 
 
-def config_dict(args, where):
+def config_dict(args):
   w = WORKLOAD
   return {"workload": ("BASELINE configs[1]: RecurrentGemma-2B-shape RG-LRU+Conv1D block, "
                        f"random init, {args.dtype}, batch {w['batch']}, seq {w['seq_len']} prefill"),
@@ -207,15 +287,43 @@ def config_dict(args, where):
           "parallelism": (f"batch-sharded x{args.gpus}, no collective in the path; NCCL all-gather "
                           f"of last_h + conv cache once per {GATHER_EVERY} block steps (one 2B prefill)"),
           "l2": "working set 420 MB per step > 126 MB L2 (no explicit flush)",
-          "clock_ramp": "W warm-up steps plus 400 ms of untimed steps before the timed region",
-          "device": where}
+          "clock_ramp": "W warm-up steps plus 400 ms of untimed steps before the timed region"}
+
+
+def host_link_ceiling(dev, nbytes_up, nbytes_dn, reps=10):
+  """Plain pinned-memory copies of one step's bytes, up and down at the same time,
+  no kernels: the box's host-link ceiling for `e2e` (ms per step)."""
+  up_h = torch.empty(nbytes_up, dtype=torch.uint8).pin_memory()
+  dn_h = torch.empty(nbytes_dn, dtype=torch.uint8).pin_memory()
+  up_d = torch.empty(nbytes_up, dtype=torch.uint8, device=dev)
+  dn_d = torch.empty(nbytes_dn, dtype=torch.uint8, device=dev)
+  s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+  ms = None
+  for timed in (False, True):
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream(dev)
+    e0.record(cur)
+    s_up.wait_event(e0)
+    s_dn.wait_event(e0)
+    for _ in range(reps):
+      with torch.cuda.stream(s_up):
+        up_d.copy_(up_h, non_blocking=True)
+      with torch.cuda.stream(s_dn):
+        dn_h.copy_(dn_d, non_blocking=True)
+    cur.wait_stream(s_up)
+    cur.wait_stream(s_dn)
+    e1.record(cur)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+  return ms
 
 
 # ----------------------------------------------------------------------------
 def own_arm(args, dtype):
   import torch.distributed as dist
   import cadence_gemma_b200 as cg
-  from cadence_gemma_b200 import _abi
+  from cadence_gemma_b200 import _abi, pipeline
 
   world = int(os.environ.get("WORLD_SIZE", "1"))
   rank = int(os.environ.get("RANK", "0"))
@@ -234,6 +342,15 @@ def own_arm(args, dtype):
     # fail fast: a collective that does not complete is an error here, not a 10 minute wait
     dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
   _abi.load()
+
+  if args.workload == "config3":
+    from scripts import model_prefill
+    line = model_prefill.run(args, dev, world, rank)
+    if rank == 0:
+      print(json.dumps(line), flush=True)
+    if world > 1:
+      dist.destroy_process_group()
+    return
 
   w = WORKLOAD
   host = make_host_inputs(dtype, seed=1 + rank)   # every rank its own batch shard
@@ -257,6 +374,7 @@ def own_arm(args, dtype):
                 if world > 1 else None)
 
   fused = lru.uses_fused_kernel(x_dev)
+  one_launch = pipeline.can_fuse_conv(conv, lru, x_dev)
   k_events = {"conv1d": [], "gate_gemm": [], "rglru": []}
   step_no = [0]
 
@@ -266,7 +384,8 @@ def own_arm(args, dtype):
     return e
 
   def step(x, seg, record=False, gather=True):
-    if record:   # same calls as the module API makes, with events between the kernels
+    if record and not one_launch:
+      # the same kernels the hot-path entry point launches, with events between them
       e0 = ev()
       xc, conv_state = conv(x, seg)
       e1 = ev()
@@ -284,9 +403,12 @@ def own_arm(args, dtype):
       if e2 is not e1:
         k_events["gate_gemm"].append((e1, e2))
       k_events["rglru"].append((e2, e3))
+    elif record:
+      e0 = ev()
+      y, conv_state, last_h = cg.recurrent_hot_path(conv, lru, x, seg)
+      k_events["rglru"].append((e0, ev()))
     else:
-      xc, conv_state = conv(x, seg)
-      y, last_h = lru(xc, seg)
+      y, conv_state, last_h = cg.recurrent_hot_path(conv, lru, x, seg)
     step_no[0] += 1
     if gather and world > 1 and GATHER_EVERY > 0 and step_no[0] % GATHER_EVERY == 0:
       # merged cache for the host: one all-gather of the small per-row states
@@ -305,6 +427,29 @@ def own_arm(args, dtype):
       dist.barrier()
     torch.cuda.synchronize()
 
+  def timed_region(join_gather):
+    """EXACTLY K steps between two events on this rank's stream.  join_gather: the
+    side-stream all-gather is joined BEFORE the closing event (a consumer that needs
+    the merged cache right away) or after it (the merged cache is only needed before
+    the next decode step: SURVEY 8(e) asks for both figures)."""
+    step_no[0] = 0
+    sync_all()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    # per-kernel CUDA events bracket every CG_BENCH_EVENT_EVERY-th step of the timed
+    # region (each bracket costs ~1-2 us of stream time, so not every step)
+    ev_every = max(1, min(args.steps, int(os.environ.get("CG_BENCH_EVENT_EVERY", "5"))))
+    o = None
+    for i in range(args.steps):
+      o = step(x_dev, seg_dev, record=(not join_gather and i % ev_every == ev_every // 2))
+    if world > 1 and join_gather:
+      torch.cuda.current_stream().wait_stream(comm_stream)
+    t_end.record()
+    sync_all()
+    return t_start.elapsed_time(t_end), o
+
+  sampler = ClockSampler(local_rank)
+  sampler.start()
   with torch.no_grad():
     # W warm-up steps, then keep stepping until the GPU has been busy for
     # CG_BENCH_RAMP_MS: a step is ~0.15 ms, so W steps alone end before the SM
@@ -329,27 +474,15 @@ def own_arm(args, dtype):
       comm_stream.wait_stream(torch.cuda.current_stream())
       with torch.cuda.stream(comm_stream):
         dist.all_gather_into_tensor(gather_out, gather_in)
-    step_no[0] = 0
-    sync_all()
 
     # ---------------- device-resident timed region: EXACTLY K steps -------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = _abi.launch_count
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    # per-kernel CUDA events bracket every CG_BENCH_EVENT_EVERY-th step of the timed
-    # region (each bracket costs ~1-2 us of stream time, so not every step)
-    ev_every = max(1, min(args.steps, int(os.environ.get("CG_BENCH_EVENT_EVERY", "5"))))
-    for i in range(args.steps):
-      out = step(x_dev, seg_dev, record=(i % ev_every == ev_every // 2))
-    if world > 1:
-      torch.cuda.current_stream().wait_stream(comm_stream)
-    t_end.record()
-    sync_all()
+    sampler.window_begin()
+    ms_total, out = timed_region(join_gather=False)
+    sampler.window_end()
     launches = _abi.launch_count - launches0
     clocks = sampler.stop()
-    ms_total = t_start.elapsed_time(t_end)
+    ms_joined = timed_region(join_gather=True)[0] if world > 1 else ms_total
     k_us = {k: statistics.mean(a.elapsed_time(b) * 1e3 for a, b in v) if v else 0.0
             for k, v in k_events.items()}
 
@@ -393,8 +526,8 @@ def own_arm(args, dtype):
       step_no[0] += 1
 
     def e2e_join():                                      # results of every submitted step are on the host
-      for ev in e2e_done:
-        torch.cuda.current_stream().wait_event(ev)
+      for e in e2e_done:
+        torch.cuda.current_stream().wait_event(e)
       e2e_done.clear()
 
     e2e_steps = max(3, min(args.steps, 20))
@@ -412,63 +545,101 @@ def own_arm(args, dtype):
     e_end.record()
     sync_all()
     e2e_ms = e_start.elapsed_time(e_end)
+    # host-link ceiling of this box for the same bytes, all ranks copying at the same time
+    sync_all()
+    link_ms = host_link_ceiling(dev, h2d, d2h)
 
   # max over ranks (device time)
-  t = torch.tensor([ms_total, e2e_ms, k_us["rglru"], k_us["conv1d"], k_us["gate_gemm"]],
+  t = torch.tensor([ms_total, e2e_ms, k_us["rglru"], k_us["conv1d"], k_us["gate_gemm"], ms_joined, link_ms],
                    dtype=torch.float64, device=dev)
   if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  ms_total, e2e_ms, k2_mean_us, conv_us, gemm_us = t.tolist()
+  ms_total, e2e_ms, k2_mean_us, conv_us, gemm_us, ms_joined, link_ms = t.tolist()
 
   if rank == 0:
-    peak, peak_src = measured_peak_gbs()
-    k2_bytes = 4 * esize * nelem          # read x, gemm_x, gemm_a; write y
-    achieved = k2_bytes / (k2_mean_us * 1e-6) / 1e9
+    peak, peak_tf, peak_src = measured_peaks()
     value = world * tokens * args.steps / (ms_total * 1e-3)
     e2e_value = world * tokens * e2e_steps / (e2e_ms * 1e-3)
+    step_us = 1e3 * ms_total / args.steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": config_dict(args, "cuda"),
+        "config": config_dict(args),
+        "device": "cuda",
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": e2e_ms / e2e_steps,
                 "how": (f"HostPrefill: {e2e_chunks} row chunks pipelined over upload / kernel / download "
                         "streams" + ("; consecutive steps streamed with submit() (upload of step n+1 under "
-                                     "the download of step n)" if e2e_stream else ""))},
+                                     "the download of step n)" if e2e_stream else "")),
+                "ceiling": {"value": world * tokens / (link_ms * 1e-3), "unit": UNIT,
+                            "ms_per_step": link_ms,
+                            "what": ("host-link ceiling of THIS box measured in this process: plain pinned copies of "
+                                     "one step's H2D and D2H bytes at the same time on every rank, no kernels; e2e "
+                                     "cannot exceed it and its scaling over N is the box's host links, not the path"),
+                            "e2e_frac_of_ceiling": link_ms / (e2e_ms / e2e_steps)}},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm",
-                     "kernel": ("cg::fused::rglru_fused_kernel (tcgen05 gate GEMMs + gate math + scan in one "
-                                "launch; events bracket the cg_rglru_fused_fwd call incl. its small prologue "
-                                "launch)") if fused else
-                               ("cg::scan_kernel (RG-LRU gates + scan; events bracket the cg_rglru_fwd call "
-                                "incl. its small prologue launch)"),
-                     "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": k2_bytes,
-                     "algorithmic_bytes_note": ("SURVEY 8(d) K2 figure: 4 x 2 B per element (x, pre_x, pre_a "
-                                                "in, y out).  The fused kernel keeps pre_x / pre_a in TMEM, "
-                                                "so it moves only about half of that (see `traffic`) and is "
-                                                "bound by the SM-wide issue / MUFU throughput of the epilogue (gate math "
-                                                "+ scan: 51 instructions, 5 of them MUFU, per element; ablations in "
-                                                "DESIGN.md section 9), not HBM"
-                                                if fused else "SURVEY 8(d) K2 figure: 4 x s bytes per element"),
-                     "us_per_launch": k2_mean_us, "traffic": NCU_TRAFFIC_BYTES if fused else None},
-        "kernels_us": ({"conv1d": conv_us, "rglru_fused_tcgen05": k2_mean_us} if fused else
-                       {"conv1d": conv_us, "gate_gemm_cublas_fused": gemm_us, "rglru": k2_mean_us}),
-        "roofline_conv1d": {"bound": "hbm", "achieved": 2 * esize * nelem / (conv_us * 1e-6) / 1e9,
-                            "peak": peak, "unit": "GB/s",
-                            "frac": 2 * esize * nelem / (conv_us * 1e-6) / 1e9 / peak},
-        "roofline_conv1d_plus_rglru": {   # whole block incl. the gate GEMMs, canonical 6 x s bytes
-            "bound": "hbm", "achieved": 6 * esize * nelem / ((conv_us + gemm_us + k2_mean_us) * 1e-6) / 1e9,
-            "peak": peak, "unit": "GB/s",
-            "frac": 6 * esize * nelem / ((conv_us + gemm_us + k2_mean_us) * 1e-6) / 1e9 / peak},
+        "launches_per_step": launches / args.steps,
+        "route": ("one launch: conv inside the fused tcgen05 kernel (cg_recurrent_prefill_fwd)" if one_launch else
+                  "conv1d kernel + fused tcgen05 kernel (cg_conv1d_fwd, cg_rglru_fused_fwd)" if fused else
+                  "conv1d kernel + cuBLAS gate GEMM + scan kernel"),
         "arith_mode": cg.get_arith_mode(),
         "fused_tcgen05_rglru": bool(fused),
     }
+    if world > 1:
+      line["with_gather_joined"] = {
+          "value": world * tokens * args.steps / (ms_joined * 1e-3), "unit": UNIT,
+          "ms_per_step": ms_joined / args.steps,
+          "what": ("the same K steps with the side-stream all-gather of last_h + conv cache JOINED before the closing "
+                   "event; `value` enqueues the same gather but joins it after the closing event (the merged cache is "
+                   "only needed before the next decode step) -- SURVEY 8(e): both figures")}
+    # ---- roofline of the dominant kernel, on the bytes it really moves
+    if fused:
+      wbytes = 2 * w["width"] * (w["width"] // w["heads"]) * esize     # both gates' block-diagonal weights, once
+      io_elems = 2 if not one_launch else 2      # x in, y out (pre-activations stay in TMEM)
+      k_bytes = io_elems * esize * nelem + wbytes
+      flop = 2 * 2 * tokens * w["width"] * (w["width"] // w["heads"])  # two gate GEMMs
+      traffic, traffic_src = ncu_traffic("fused_conv" if one_launch else "fused")
+      line["roofline"] = {
+          "bound": "hbm",
+          "kernel": ("cg::fused::rglru_fused_kernel<CONV> (Conv1D + tcgen05 gate GEMMs + gate math + scan)"
+                     if one_launch else
+                     "cg::fused::rglru_fused_kernel (tcgen05 gate GEMMs + gate math + scan in one launch); events "
+                     "bracket the cg_rglru_fused_fwd call incl. its ~2 us prologue launch"),
+          "achieved": k_bytes / (k2_mean_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+          "frac": k_bytes / (k2_mean_us * 1e-6) / 1e9 / peak, "peak_source": peak_src,
+          "algorithmic_bytes_per_launch": k_bytes,
+          "algorithmic_bytes_note": ("what this kernel has to move: x in + y out = 2 x 2 B per element, plus the packed "
+                                     "gate weights once (the gate pre-activations never leave TMEM)"),
+          "us_per_launch": k2_mean_us, "traffic": traffic, "traffic_source": traffic_src,
+          "limiter": ("NOT HBM: the epilogue's issue / FMA-pipe / XU rate (gate math with every bf16 rounding point of "
+                      "the reference + scan; DESIGN.md section 9) and, close behind, the tensor side at N = 64"),
+          "tensor": {"useful_flop_per_launch": flop, "achieved": flop / (k2_mean_us * 1e-6) / 1e12,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": flop / (k2_mean_us * 1e-6) / 1e12 / peak_tf}}
+    else:
+      k_bytes = 4 * esize * nelem
+      line["roofline"] = {"bound": "hbm", "kernel": "cg::scan_kernel (RG-LRU gates + scan)",
+                          "achieved": k_bytes / (k2_mean_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": k_bytes / (k2_mean_us * 1e-6) / 1e9 / peak, "peak_source": peak_src,
+                          "algorithmic_bytes_per_launch": k_bytes, "us_per_launch": k2_mean_us, "traffic": None}
+    line["kernels_us"] = ({"recurrent_prefill_fused_tcgen05": k2_mean_us} if one_launch else
+                          {"conv1d": conv_us, "rglru_fused_tcgen05": k2_mean_us} if fused else
+                          {"conv1d": conv_us, "gate_gemm_cublas_fused": gemm_us, "rglru": k2_mean_us})
+    if conv_us > 0:
+      line["roofline_conv1d"] = {"bound": "hbm", "achieved": 2 * esize * nelem / (conv_us * 1e-6) / 1e9,
+                                 "peak": peak, "unit": "GB/s",
+                                 "frac": 2 * esize * nelem / (conv_us * 1e-6) / 1e9 / peak}
+    # ---- the number tracked against the north star: the whole step on the canonical bytes
+    canon = 6 * esize * nelem
+    line["roofline_step"] = {
+        "bound": "hbm", "what": ("Conv1D + gate GEMMs + RG-LRU on SURVEY 8(d)'s canonical 6 x s = 12 B per element "
+                                 "(read x_lin; write+read x_conv, pre_x, pre_a; write y) over ms_per_step"),
+        "algorithmic_bytes_per_step": canon, "achieved": canon / (step_us * 1e-6) / 1e9, "peak": peak,
+        "unit": "GB/s", "frac": canon / (step_us * 1e-6) / 1e9 / peak, "target_frac": 0.70,
+        "us_per_step": step_us, "us_at_target": canon / (0.70 * peak * 1e9) * 1e6}
     if world == 1 and not args.no_cpu_baseline:
       if prev_affinity is not None:     # the CPU baseline uses every host core again
         for tid in os.listdir("/proc/self/task"):       # worker threads inherit the bound mask
@@ -478,17 +649,37 @@ def own_arm(args, dtype):
             pass
       threads = os.cpu_count() or 1
       host0 = make_host_inputs(dtype, seed=1)
-      times, cpu_out = run_cpu_port(host0, 3, 1, threads)
+      kind, fn = cpu_reference_runner(host0, threads)
+      times, cpu_out = time_cpu(fn, 3, 1)
       best = min(times)
       line["cpu_baseline"] = {
-          "value": tokens / best, "unit": UNIT, "cores": threads, "kind": "port",
+          "value": tokens / best, "unit": UNIT, "cores": threads, "kind": kind,
           "sample": "full config-2 batch (16384 tokens), best of 3 after 1 warm-up",
           "ms_per_step": best * 1e3}
-      y_gpu = out[0].float().cpu()
-      y_cpu = cpu_out[0].float()
-      line["parity_vs_cpu_port"] = {
-          "normwise": ((y_gpu - y_cpu).abs().max() / y_cpu.abs().max()).item(),
-          "bit_identical_frac": (out[0].cpu() == cpu_out[0]).float().mean().item()}
+      # ---- parity of the whole step against that CPU run, shipped mode and exact mode
+      def parity_of(mode):
+        old = cg.set_arith_mode(mode)
+        try:
+          with torch.no_grad():
+            for _ in range(3):
+              y, _, h = cg.recurrent_hot_path(conv, lru, x_dev, seg_dev)
+            torch.cuda.synchronize()
+            e0 = ev()
+            for _ in range(10):
+              cg.recurrent_hot_path(conv, lru, x_dev, seg_dev)
+            e1 = ev()
+            torch.cuda.synchronize()
+        finally:
+          cg.set_arith_mode(old)
+        yg, yc = y.float().cpu(), cpu_out[0].float()
+        return {"arith_mode": mode, "us_per_step": e0.elapsed_time(e1) * 100.0,
+                "bit_identical_frac": (y.cpu() == cpu_out[0]).float().mean().item(),
+                "normwise": ((yg - yc).abs().max() / yc.abs().max()).item(),
+                "within_rtol1e-2_atol3e-2": bool(torch.allclose(yg, yc, rtol=1e-2, atol=3e-2)),
+                "last_h_normwise": ((h.cpu() - cpu_out[1]).abs().max() / cpu_out[1].abs().max()).item()}
+      line["parity"] = {"against": f"cpu_baseline ({kind}) on the same inputs, y of the whole step",
+                        "shipped": parity_of(cg.get_arith_mode()),
+                        "exact_reference": parity_of(_abi.ARITH_REFERENCE)}
     print(json.dumps(line), flush=True)
   if world > 1:
     dist.destroy_process_group()

@@ -49,6 +49,10 @@
 #ifndef CGF_SLEEP_NS
 #define CGF_SLEEP_NS 64
 #endif
+// back-off of the producer / MMA / convolution warps' waits (their wake-up latency has slack)
+#ifndef CGF_SLEEP_AUX_NS
+#define CGF_SLEEP_AUX_NS CGF_SLEEP_NS
+#endif
 #ifndef CGF_PRELOAD
 #define CGF_PRELOAD 1
 #endif
@@ -66,13 +70,16 @@
 // CGF_REG_EPI, the producer / MMA / convolution warpgroup shrinks to CGF_REG_AUX.
 // 20 warps x 96 registers are allocated at launch: 16 x 104 + 4 x 64 = 1920 warp-registers.
 #ifndef CGF_SETMAXNREG
-#define CGF_SETMAXNREG 1
+#define CGF_SETMAXNREG 0   // measured: 123 us vs 110 us (the 64-register side spills shared bookkeeping)
 #endif
 #ifndef CGF_REG_EPI
 #define CGF_REG_EPI 104
 #endif
 #ifndef CGF_REG_AUX
 #define CGF_REG_AUX 64
+#endif
+#ifndef CGF_CONV_BATCH
+#define CGF_CONV_BATCH 8    // rows of the in-kernel convolution held in registers at a time
 #endif
 // CGF_ABLATE (timing experiments only, results are WRONG): 1 = no look-back,
 // 2 = no y stores, 4 = no replay pass at all, 8 = no in-kernel convolution arithmetic
@@ -181,13 +188,24 @@ __device__ __forceinline__ bool watchdog_expired(long long t0, int* err, int cod
   }
   return false;
 }
+// NS: plain back-off between two polls.  The loop body is kept minimal (a waiting warp's
+// polls compete for issue slots with the warps of its scheduler that have work) and the
+// watchdog's clock is read once per 64 polls only.
+template <int NS = CGF_SLEEP_NS>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  unsigned polls = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (CGF_SLEEP_NS > 0) __nanosleep(CGF_SLEEP_NS);   // waiting warps must not eat the issue slots of the working ones
-    if (watchdog_expired(t0, err, code, polls)) return;
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+      if (NS > 0) __nanosleep(NS);
+      if (mbar_try_wait(bar, parity)) return;
+    }
+    if (clock64() - t0 > kWatchdogCycles) {
+      atomicCAS(err, 0, code);
+      __threadfence_system();
+      __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar,
@@ -285,12 +303,12 @@ __device__ __forceinline__ void st_u16(uint16_t* p, uint32_t v) {
   asm volatile("st.global.u16 [%0], %1;" :: "l"(p), "h"(static_cast<uint16_t>(v)) : "memory");
 }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 r;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+  uint4 r;   // volatile, no "memory" clobber: ordered against sts128, free against arithmetic
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -522,7 +540,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         const int fam = sg.fam;
         if (fam != cur_fam) {
         cur_fam = fam;
-        if (witer > 0) mbar_wait(w_empty, (witer - 1) & 1, p.err, 1);
+        if (witer > 0) mbar_wait<CGF_SLEEP_AUX_NS>(w_empty, (witer - 1) & 1, p.err, 1);
         const unsigned char* wsrc = p.wpack + (size_t)fam * Cfg::kWBytes;
         if (elect_one()) {
           mbar_expect_tx(w_full, Cfg::kWBytes + Cfg::kIBytes);
@@ -547,7 +565,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           const int nhalf = t1st + 1 < ntiles ? 2 : 1;
           const uint32_t stage = mq & 1u, use = mq >> 1;
           CGF_EVENT(0, 1);
-          mbar_wait(x_empty + stage, (use & 1) ^ 1, p.err, 2);
+          mbar_wait<CGF_SLEEP_AUX_NS>(x_empty + stage, (use & 1) ^ 1, p.err, 2);
           CGF_EVENT(0, 2);
           if (elect_one()) mbar_expect_tx(raw_full + stage, nhalf * (Cfg::kXStageBytes / 2));
           for (int hf = 0; hf < nhalf; ++hf) {
@@ -581,7 +599,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
             __syncwarp();
           }
           cur_fam = fam;
-          mbar_wait(w_full, witer & 1, p.err, 3);
+          mbar_wait<CGF_SLEEP_AUX_NS>(w_full, witer & 1, p.err, 3);
           tc_fence_after();
           ++witer;
         }
@@ -590,9 +608,9 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         for (int m = 0; m < sg.count; ++m, ++mq) {
           const uint32_t pr = mq & 1u, use = mq >> 1;      // warpgroup pair == X stage
           CGF_EVENT(1, 1);
-          mbar_wait(mma_ready + pr, use & 1, p.err, 4);
+          mbar_wait<CGF_SLEEP_AUX_NS>(mma_ready + pr, use & 1, p.err, 4);
           CGF_EVENT(1, 2);
-          mbar_wait(t_empty + pr, (use & 1) ^ 1, p.err, 5);
+          mbar_wait<CGF_SLEEP_AUX_NS>(t_empty + pr, (use & 1) ^ 1, p.err, 5);
           CGF_EVENT(1, 3);
           tc_fence_after();
           const uint32_t xs = sX + pr * Cfg::kXStageBytes;
@@ -680,7 +698,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
             nzw = ((unsigned long long)(~cur) << 2) | (unsigned long long)((~prev) >> 30);
           }
           CGF_EVENT(6, 1);
-          mbar_wait(raw_full + stage, use & 1, p.err, 9);
+          mbar_wait<CGF_SLEEP_AUX_NS>(raw_full + stage, use & 1, p.err, 9);
           CGF_EVENT(6, 2);
           if (valid && !(CGF_ABLATE & 8)) {
             uint32_t row = sX + stage * Cfg::kXStageBytes + kbc * Cfg::kXKBlock + (uint32_t)(hfc * kTile) * 128u;
@@ -688,31 +706,46 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
             // no document start near the tile: every tap is live (the common case)
             const bool plain = upstream ? (nzw & 0x3ffffffffull) == 0x3ffffffffull
                                         : (nzw & 0xffffffffull) == 0xffffffffull;
-            if (plain) {
-#pragma unroll 8
-              for (int r = 0; r < kTile; ++r) {
-                const uint32_t addr = row + r * 128 + ((uint32_t)(chunk ^ (r & 7)) << 4);
-                const uint4 x0 = lds128(addr);
-                sts128(addr, conv_row(taps, x0, h1, h2, h3));
-                h3 = h2; h2 = h1; h1 = x0;
-              }
-            } else {
+            // Rows go through registers in batches of kConvBatch: all loads of a batch are
+            // issued before its arithmetic, so the batch's 4 x kConvBatch independent
+            // bf16x2 chains overlap (a row-by-row in-place loop serialises on
+            // LDS -> 5 dependent packed ops -> STS: measured 8 000 cycles per tile).
+            constexpr int kConvBatch = CGF_CONV_BATCH;
 #pragma unroll 1
-              for (int r = 0; r < kTile; ++r) {
-                const uint32_t addr = row + r * 128 + ((uint32_t)(chunk ^ (r & 7)) << 4);
-                const uint4 x0 = lds128(addr);
-                const unsigned w3 = (unsigned)(nzw >> r) & 7u;   // bit 0: seg[t-2], 1: seg[t-1], 2: seg[t]  (!= 0)
-                bool m1 = true, m2 = true, m3;
-                if (!upstream) {
-                  m3 = (w3 & 1u) != 0;                     // fork: only seg[t-2], layers.py:629-632
-                } else {
-                  m1 = (w3 & 4u) != 0;                     // upstream: seg[t-s+1 .. t] all != 0
-                  m2 = (w3 & 6u) == 6u;
-                  m3 = (w3 & 7u) == 7u;
+            for (int r0 = 0; r0 < kTile; r0 += kConvBatch) {
+              uint4 xr[kConvBatch];
+#pragma unroll
+              for (int j = 0; j < kConvBatch; ++j)
+                xr[j] = lds128(row + (r0 + j) * 128 + ((uint32_t)(chunk ^ ((r0 + j) & 7)) << 4));
+              if (plain) {
+#pragma unroll
+                for (int j = 0; j < kConvBatch; ++j) {
+                  const uint4& a1 = j >= 1 ? xr[j - 1] : h1;
+                  const uint4& a2 = j >= 2 ? xr[j - 2] : (j == 1 ? h1 : h2);
+                  const uint4& a3 = j >= 3 ? xr[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
+                  sts128(row + (r0 + j) * 128 + ((uint32_t)(chunk ^ ((r0 + j) & 7)) << 4),
+                         (CGF_ABLATE & 16) ? xr[j] : conv_row(taps, xr[j], a1, a2, a3));
                 }
-                sts128(addr, conv_row(taps, x0, m1 ? h1 : zero4, m2 ? h2 : zero4, m3 ? h3 : zero4));
-                h3 = h2; h2 = h1; h1 = x0;
+              } else {
+#pragma unroll
+                for (int j = 0; j < kConvBatch; ++j) {
+                  const uint4& a1 = j >= 1 ? xr[j - 1] : h1;
+                  const uint4& a2 = j >= 2 ? xr[j - 2] : (j == 1 ? h1 : h2);
+                  const uint4& a3 = j >= 3 ? xr[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
+                  const unsigned w3 = (unsigned)(nzw >> (r0 + j)) & 7u;   // bit 0: seg[t-2], 1: seg[t-1], 2: seg[t]  (!= 0)
+                  bool m1 = true, m2 = true, m3;
+                  if (!upstream) {
+                    m3 = (w3 & 1u) != 0;                   // fork: only seg[t-2], layers.py:629-632
+                  } else {
+                    m1 = (w3 & 4u) != 0;                   // upstream: seg[t-s+1 .. t] all != 0
+                    m2 = (w3 & 6u) == 6u;
+                    m3 = (w3 & 7u) == 7u;
+                  }
+                  sts128(row + (r0 + j) * 128 + ((uint32_t)(chunk ^ ((r0 + j) & 7)) << 4),
+                         conv_row(taps, xr[j], m1 ? a1 : zero4, m2 ? a2 : zero4, m3 ? a3 : zero4));
+                }
               }
+              h3 = xr[kConvBatch - 3]; h2 = xr[kConvBatch - 2]; h1 = xr[kConvBatch - 1];
             }
             // the convolution's returned cache: the last three INPUT rows of the
             // sequence, left zero padded (layers.py:542-543, :650-662)
@@ -731,6 +764,30 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           __syncwarp();
           if (lane == 0) mbar_arrive(x_full + stage);
           CGF_EVENT(6, 3);
+#if (CGF_ABLATE & 32)
+          // timing experiment: the convolution arithmetic OFF the critical path (after the
+          // hand-over; results are wrong): separates latency in the stage loop from issue load
+          if (valid) {
+            const uint32_t row = sX + stage * Cfg::kXStageBytes + kbc * Cfg::kXKBlock + (uint32_t)(hfc * kTile) * 128u;
+#pragma unroll 1
+            for (int r0 = 0; r0 < kTile; r0 += 8) {
+              uint4 xr[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) xr[j] = lds128(row + (r0 + j) * 128 + ((uint32_t)(chunk ^ ((r0 + j) & 7)) << 4));
+              uint4 acc = zero4;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4& a1 = j >= 1 ? xr[j - 1] : h1;
+                const uint4& a2 = j >= 2 ? xr[j - 2] : (j == 1 ? h1 : h2);
+                const uint4& a3 = j >= 3 ? xr[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
+                const uint4 o = conv_row(taps, xr[j], a1, a2, a3);
+                acc.x ^= o.x; acc.y ^= o.y; acc.z ^= o.z; acc.w ^= o.w;
+              }
+              if (acc.x == 0x12345678u && acc.y == 0x9abcdef0u) sts128(row, acc);   // never true: keeps the math alive
+              h3 = xr[5]; h2 = xr[6]; h1 = xr[7];
+            }
+          }
+#endif
         }
       }
     }

@@ -8,13 +8,14 @@
     x, rg_lru_state = rg_lru(x, segment_pos)
 
 Prefill at RecurrentGemma shapes (bf16, temporal width 4, head width 128 / 256,
-T > 1) is ONE kernel: ``cg_recurrent_prefill_fwd`` -- the temporal convolution
-runs inside the fused tcgen05 RG-LRU kernel (TMA-loaded rows convolved in place
-in shared memory), so neither the conv output nor the gate pre-activations
-reach HBM.  ``set_fused_conv(False)`` / ``CG_B200_FUSED_CONV=0`` runs the two
-kernels one after the other instead (Conv1D kernel, then the fused RG-LRU
-kernel); other shapes / fp32 take the Conv1D kernel + cuBLAS gate GEMM + scan
-kernel.  A decode step (T == 1, caches given) is one launch as well
+T > 1) can run as ONE kernel: ``cg_recurrent_prefill_fwd`` -- the temporal
+convolution runs inside the fused tcgen05 RG-LRU kernel (TMA-loaded rows
+convolved in place in shared memory), so neither the conv output nor the gate
+pre-activations reach HBM.  ``set_fused_conv`` / ``CG_B200_FUSED_CONV`` select
+it: "auto" (default) takes the one-launch route for small, latency-bound
+problems and the Conv1D kernel followed by the fused RG-LRU kernel for large
+ones (see the measurements next to ``_fused_conv`` below); other shapes / fp32
+take the Conv1D kernel + cuBLAS gate GEMM + scan kernel.  A decode step (T == 1, caches given) is one launch as well
 (``cg_recurrent_decode_step``).
 
 (A producer / consumer overlap of the two kernels on two streams was built and
@@ -31,8 +32,16 @@ import torch
 
 from cadence_gemma_b200 import _abi, layers
 
-# Convolution inside the fused RG-LRU kernel (one launch per prefill step).
-_fused_conv = os.environ.get("CG_B200_FUSED_CONV", "1") != "0"
+# Convolution inside the fused RG-LRU kernel (one launch per prefill step):
+# "auto" (default) = where it is the faster route, "1" = whenever the shape allows, "0" = never.
+# The fused kernel is bound by the issue / FMA-pipe rate of its epilogue, so the
+# convolution's 8 packed bf16 ops per channel pair are not free inside it: at
+# config 2 (B=8, T=2048) one launch takes 165-172 us against 136 us for the
+# Conv1D kernel (HBM-bound, SMs otherwise idle) followed by the fused kernel,
+# while a small, latency-bound problem gains (B=1, T=2048: 53 us vs 80 us).
+# Measured crossover: see DESIGN.md section 4.0 / profiles/r2_fused_conv_ab.json.
+_fused_conv = os.environ.get("CG_B200_FUSED_CONV", "auto")
+FUSED_CONV_MAX_TILES = 256      # auto: B * ceil(T / 32) scan tiles per channel family at most
 # One-launch decode step (cg_recurrent_decode_step).  It more than halves the cost
 # of an EAGER decode step (30 us vs 76 us per block at B = 32: three launches and
 # their host overhead become one); inside a CUDA graph, where launch overhead is
@@ -40,10 +49,12 @@ _fused_conv = os.environ.get("CG_B200_FUSED_CONV", "1") != "0"
 _fused_decode = os.environ.get("CG_B200_FUSED_DECODE", "1") != "0"
 
 
-def set_fused_conv(enabled: bool) -> bool:
-  """Switches the in-kernel convolution of the prefill path; returns the old setting."""
+def set_fused_conv(mode):
+  """Selects the in-kernel convolution of the prefill path: ``"auto"``, ``True`` (always,
+  when the shape allows) or ``False`` (never); returns the old setting."""
   global _fused_conv
-  old, _fused_conv = _fused_conv, bool(enabled)
+  old = _fused_conv
+  _fused_conv = mode if mode == "auto" else ("1" if mode in (True, "1", 1) else "0")
   return old
 
 
@@ -66,7 +77,11 @@ def can_fuse_decode(conv, lru, x, conv_cache) -> bool:
 def can_fuse_conv(conv, lru, x, conv_cache=None) -> bool:
   """True if ``recurrent_hot_path`` runs Conv1D + RG-LRU as ONE kernel
   (``cg_recurrent_prefill_fwd``)."""
-  return (_fused_conv and layers.fused_enabled() and conv_cache is None and x.is_cuda and
+  if _fused_conv == "0":
+    return False
+  if _fused_conv == "auto" and x.shape[0] * ((x.shape[1] + 31) // 32) > FUSED_CONV_MAX_TILES:
+    return False
+  return (layers.fused_enabled() and conv_cache is None and x.is_cuda and
           conv.w.shape[0] == 4 and conv.w.dtype == x.dtype and
           (layers.get_arith_mode() & _abi.ARITH_FP32) == 0 and
           layers.uses_fused_kernel(lru, x))

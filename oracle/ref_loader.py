@@ -1,10 +1,16 @@
 """TEST INFRASTRUCTURE ONLY -- never imported by the product path.
 
 Imports the *unmodified* reference hot-path modules from ``/root/reference``
-(present in the build container only; it does not exist on the GPU box) so that
+(present in the build container only) or, where that does not exist -- the GPU
+box --, from the git-ignored copy ``baseline/_ref`` that
+``baseline/install_reference.py`` makes in the build container and that travels
+with the repo snapshot, so that
 
   * ``tests/golden/make_golden.py`` can generate golden input/output vectors,
-  * CPU tests can cross-check the oracle restatements against the real code.
+  * CPU tests can cross-check the oracle restatements against the real code,
+  * the ``-m gpu`` install tests can drive the reference's OWN ``RecurrentBlock`` /
+    ``ResidualBlock`` / ``Griffin`` classes with the kernels patched in,
+  * ``bench.py --impl reference`` can time the reference's own CPU path.
 
 ``import recurrentgemma`` itself fails here because
 ``recurrentgemma/__init__.py:18-20`` pulls in ``timm`` through
@@ -20,7 +26,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CADENCE_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+  env = os.environ.get("CADENCE_REFERENCE_ROOT")
+  if env:
+    return env
+  for cand in ("/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+    if os.path.isfile(os.path.join(cand, "recurrentgemma", "torch", "layers.py")):
+      return cand
+  return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

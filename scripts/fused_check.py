@@ -141,6 +141,7 @@ def conv_case(B=8, T=2048, iters=40, check=True):
     res["two_kernels_us"] = _time(run, iters)
     y1, c1, h1 = [t.clone() for t in run()]
     pipeline.set_fused_conv(True)
+    assert pipeline.can_fuse_conv(conv, lru, x)
     res["one_launch_us"] = _time(run, iters)
     y2, c2, h2 = [t.clone() for t in run()]
     pipeline.set_fused_conv(old)

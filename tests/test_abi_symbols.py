@@ -124,3 +124,28 @@ def test_install_patches_reference_entry_points():
   finally:
     install.uninstall()
   assert (ref.layers.rnn_scan, ref.layers.RGLRU.forward, ref.layers.Conv1D.forward) == orig
+
+
+def _integration_md_blocks():
+  with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+    text = f.read()
+  return re.findall(r"```python\n(.*?)```", text, flags=re.S)
+
+
+def test_integration_md_stubs_match_the_header():
+  """Every `argtypes` list a maintainer would paste from INTEGRATION.md has exactly
+  as many entries as the prototype in include/cadence_b200.h (round 1 shipped a
+  21-argument stub for a 23-argument function) and names the current ABI version."""
+  from cadence_gemma_b200 import _abi
+  counts = _declared_arg_counts()
+  code = "\n".join(_integration_md_blocks())
+  found = re.findall(r"_lib\.(cg_[a-z0-9_]+)\.argtypes\s*=\s*\[(.*?)\]", code, flags=re.S)
+  assert len(found) >= 6, [f[0] for f in found]
+  for name, body in found:
+    n = len([t for t in re.split(r"[,\s]+", body.split("#")[0].strip()) if t])
+    assert name in counts, name
+    assert n == counts[name] == len(_abi.SYMBOLS[name][1]), (name, n, counts[name])
+  assert f"cg_abi_version() == {_abi.ABI_VERSION}" in code
+  # every symbol the stubs call exists in the public header (nothing experimental)
+  for name in set(re.findall(r"_lib\.(cg_[a-z0-9_]+)", code)):
+    assert name in counts, f"INTEGRATION.md uses {name}, which include/cadence_b200.h does not declare"

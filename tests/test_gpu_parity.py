@@ -999,6 +999,7 @@ def test_fused_conv_prefill_equals_two_kernel_path(shape, mask_mode):
       y_ref, cs_ref, h_ref = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0, conv_out=xc_ref)
     finally:
       pipeline.set_fused_conv(old)
+    pipeline.set_fused_conv(True)
     assert pipeline.can_fuse_conv(conv, lru, x)
     for it in range(3):
       y, cs, h = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0)
@@ -1016,6 +1017,9 @@ def test_fused_conv_prefill_equals_two_kernel_path(shape, mask_mode):
     gate = torch.randn_like(x)
     y_g, _, _ = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0, gate_mul=gate)
     assert torch.equal(y_g, y_ref * gate)
+    pipeline.set_fused_conv(old)
+    # "auto": one launch for small problems only
+    assert pipeline.can_fuse_conv(conv, lru, x) == (bsz * ((steps + 31) // 32) <= pipeline.FUSED_CONV_MAX_TILES)
   torch.cuda.synchronize()
 
 
