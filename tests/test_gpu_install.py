@@ -151,7 +151,8 @@ def test_reference_recurrent_block_with_install_matches_golden():
     with _installed(ref), torch.no_grad():
       y, cache = block(g["x"].to(DEV), g["seg"].to(DEV), None, True)
       _compare(y.cpu(), g["y"], dtype, case + " y", floor=0.6)
-      assert torch.equal(cache.conv1d_state.cpu(), g["conv1d_state"]), case
+      # rows of linear_x's output: cuBLAS here, MKL in the fixture (not bit-comparable)
+      _compare(cache.conv1d_state.cpu(), g["conv1d_state"], dtype, case + " conv cache", floor=0.9)
       for i in range(2):
         ys, cache = block(g[f"step{i}_x"].to(DEV), (g["seg"][:, -1:] + 1 + i).to(DEV), cache, True)
         _compare(ys.cpu(), g[f"step{i}_y"], dtype, f"{case} step{i}", floor=0.6)
@@ -197,7 +198,8 @@ def test_tiny_griffin_with_install_config1(gradient_checkpointing):
     if hasattr(c, "rg_lru_state"):
       idx = key.split(".")[-1]
       assert normwise(c.rg_lru_state.cpu(), fx[f"blk{idx}_rg_lru_state"]) <= 5e-5
-      assert torch.equal(c.conv1d_state.cpu(), fx[f"blk{idx}_conv1d_state"])
+      # the conv cache holds rows of linear_x's output: cuBLAS here, MKL in the fixture
+      assert normwise(c.conv1d_state.cpu(), fx[f"blk{idx}_conv1d_state"]) <= 1e-5
   # config 1 proper: T = 512, two rows run one at a time
   steps = 512
   g2 = torch.Generator().manual_seed(5)
