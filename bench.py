@@ -36,7 +36,6 @@ import json
 import os
 import statistics
 import sys
-import threading
 import time
 
 import torch
@@ -110,30 +109,27 @@ def make_host_inputs(dtype, seed=1):
 # clocks / throttle sampling during the timed region
 # ----------------------------------------------------------------------------
 class ClockSampler:
-  """Samples SM clock and throttle reasons through NVML from a background thread.
-  It is started BEFORE the clock-ramp loop (NVML needs tens of milliseconds to
-  initialise, the timed region of a short run lasts 3 ms); `window()` brackets
-  the timed region in wall-clock time and only samples inside it are reported."""
+  """SM clock and throttle reasons through NVML, sampled by the MAIN thread at points
+  where the host has nothing to launch: between the batches of the clock-ramp loop and,
+  for the timed region, right after its last launch has been enqueued while the GPU is
+  still executing it (the host runs ahead of the GPU: `t_end.query()` is False for
+  another millisecond or more).  A background thread polling NVML was measured to slow
+  the launch loop itself (NVML queries serialise with kernel launches in the driver:
+  236 us per step instead of 145 us), i.e. to perturb exactly what is being timed."""
 
   REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40,
              "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
   def __init__(self, gpu_index):
-    self.gpu_index = gpu_index
-    self.samples = []          # (wall time, MHz, reason mask)
+    self.samples = []          # (tag, MHz, reason mask)
     self.sm_max = None
-    self._stop = threading.Event()
-    self._ready = threading.Event()
-    self._thread = None
     self._err = None
-    self.t0 = self.t1 = None
-
-  def _run(self):
+    self._nvml = self._handle = None
     try:
       import pynvml
       pynvml.nvmlInit()
       # CUDA_VISIBLE_DEVICES remapping: match by PCI bus id of the torch device
-      bus = torch.cuda.get_device_properties(self.gpu_index).pci_bus_id
+      bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id
       handle = None
       for i in range(pynvml.nvmlDeviceGetCount()):
         h = pynvml.nvmlDeviceGetHandleByIndex(i)
@@ -141,37 +137,33 @@ class ClockSampler:
           handle = h
           break
       if handle is None:
-        handle = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
       self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM)
-      self._ready.set()
-      while not self._stop.is_set():
-        mhz = pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
-        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle)
-        self.samples.append((time.perf_counter(), mhz, mask))
-        time.sleep(0.002)   # a faster poll steals the GIL from the launch loop (measured: +25 us per step at 0.5 ms)
+      self._nvml, self._handle = pynvml, handle
     except Exception as exc:  # pylint: disable=broad-except
       self._err = repr(exc)
-      self._ready.set()
 
-  def start(self):
-    self._thread = threading.Thread(target=self._run, daemon=True)
-    self._thread.start()
-    self._ready.wait(timeout=10)
+  def sample(self, tag):
+    if self._handle is None:
+      return
+    try:
+      mhz = self._nvml.nvmlDeviceGetClockInfo(self._handle, self._nvml.NVML_CLOCK_SM)
+      mask = self._nvml.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+      self.samples.append((tag, mhz, mask))
+    except Exception as exc:  # pylint: disable=broad-except
+      self._err = repr(exc)
 
-  def window_begin(self):
-    self.t0 = time.perf_counter()
+  def sample_until(self, event, tag, limit=64):
+    """Samples while `event` (recorded after the timed region's last launch) is pending."""
+    n = 0
+    while n < limit and not event.query():
+      self.sample(tag)
+      n += 1
 
-  def window_end(self):
-    self.t1 = time.perf_counter()
-
-  def stop(self):
-    self._stop.set()
-    if self._thread is not None:
-      self._thread.join(timeout=5)
-    inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= self.t1]
-    # a 3 ms region may hold only a few samples: the load ramp right before it runs the same steps
-    near = [s for s in self.samples if self.t0 is not None and self.t0 - 0.2 <= s[0] <= self.t1]
-    use = inside if len(inside) >= 3 else near
+  def summary(self):
+    inside = [s for s in self.samples if s[0] == "timed"]
+    ramp = [s for s in self.samples if s[0] == "ramp"]
+    use = inside + ramp[-8:]
     reasons = set()
     for _, _, mask in use:
       for name, bit in self.REASONS.items():
@@ -179,7 +171,10 @@ class ClockSampler:
           reasons.add(name)
     out = {"sm_mhz": statistics.median(s[1] for s in use) if use else None,
            "sm_max_mhz": self.sm_max, "reasons": sorted(reasons),
-           "samples": len(use), "samples_inside_timed_region": len(inside)}
+           "samples": len(use), "samples_inside_timed_region": len(inside),
+           "how": ("NVML from the main thread: ONE sample after the timed region's last launch while the GPU is "
+                   "still executing it (more polling slows the timed kernels: 186 vs 143 us per step), plus the "
+                   "last 8 samples of the clock-ramp loop, which runs the same steps right before it")}
     if self._err:
       out["error"] = self._err
     return out
@@ -445,11 +440,14 @@ def own_arm(args, dtype):
     if world > 1 and join_gather:
       torch.cuda.current_stream().wait_stream(comm_stream)
     t_end.record()
+    if not join_gather:
+      # ONE sample while the GPU is still inside the timed region: polling NVML for the whole
+      # region was measured to slow the GPU work itself (186 us per step vs 143 us unpolled)
+      sampler.sample_until(t_end, "timed", limit=1)
     sync_all()
     return t_start.elapsed_time(t_end), o
 
   sampler = ClockSampler(local_rank)
-  sampler.start()
   with torch.no_grad():
     # W warm-up steps, then keep stepping until the GPU has been busy for
     # CG_BENCH_RAMP_MS: a step is ~0.15 ms, so W steps alone end before the SM
@@ -464,6 +462,7 @@ def own_arm(args, dtype):
       # collective inside (a gather here once left two ranks in different collectives)
       for _ in range(20):
         out = step(x_dev, seg_dev, gather=False)
+      sampler.sample("ramp")     # under load, outside any timed region
       torch.cuda.synchronize()
     if world > 1:
       # exercise the whole gather path once outside the timed region: NCCL sets
@@ -477,11 +476,9 @@ def own_arm(args, dtype):
 
     # ---------------- device-resident timed region: EXACTLY K steps -------------
     launches0 = _abi.launch_count
-    sampler.window_begin()
     ms_total, out = timed_region(join_gather=False)
-    sampler.window_end()
     launches = _abi.launch_count - launches0
-    clocks = sampler.stop()
+    clocks = sampler.summary()
     ms_joined = timed_region(join_gather=True)[0] if world > 1 else ms_total
     k_us = {k: statistics.mean(a.elapsed_time(b) * 1e3 for a, b in v) if v else 0.0
             for k, v in k_events.items()}

@@ -236,7 +236,9 @@ def conv1d_bwd(gy, x, w, segment_pos, mask_mode=MASK_FORK):
   return dx, dw, db
 
 
-def conv1d_decode(x, w, b, cache, return_cache=True, arith_mode=ARITH_REFERENCE):
+def conv1d_decode(x, w, b, cache, return_cache=True, arith_mode=ARITH_REFERENCE, cache_out=None):
+  """``cache_out`` may be ``cache`` itself (in-place roll; the kernel reads a thread's rows
+  before it writes them -- include/cadence_b200.h)."""
   global launch_count
   _require_cuda(x, w, b, cache)
   bsz, steps, width = x.shape
@@ -245,7 +247,7 @@ def conv1d_decode(x, w, b, cache, return_cache=True, arith_mode=ARITH_REFERENCE)
   assert cache.shape == (bsz, tw - 1, width), "layers.py:565"
   x, w, b, cache = x.contiguous(), w.contiguous(), b.contiguous(), cache.contiguous()
   y = torch.empty_like(x)
-  new_cache = torch.empty_like(cache) if return_cache else None
+  new_cache = (torch.empty_like(cache) if cache_out is None else cache_out) if return_cache else None
   with _on_device(x.device):
     rc = load().cg_conv1d_decode(x.data_ptr(), w.data_ptr(), b.data_ptr(),
                                  cache.data_ptr(), dtype_code(cache.dtype),

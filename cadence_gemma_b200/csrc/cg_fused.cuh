@@ -78,6 +78,9 @@
 #ifndef CGF_REG_AUX
 #define CGF_REG_AUX 64
 #endif
+#ifndef CGF_DESC_LO
+#define CGF_DESC_LO 1       // MMA descriptors as base + small add (see umma_bf16_lo)
+#endif
 #ifndef CGF_CONV_BATCH
 #define CGF_CONV_BATCH 8    // rows of the in-kernel convolution held in registers at a time
 #endif
@@ -254,6 +257,26 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// The same MMA with the descriptors given as their LOW words (start address >> 4 | LBO): the high
+// word (SBO = 1024 B, version 1, SWIZZLE_128B) is the same constant for every operand of this
+// kernel, and advancing an operand by `bytes` is ONE 32-bit add of bytes >> 4 to the low word
+// (all of shared memory is below 256 KB, so the 14-bit address field cannot overflow).  Building
+// each 64-bit descriptor from the address (shift, mask, or, or) made the issue loop spend ~10
+// uniform-datapath instructions per MMA -- as long as the MMA itself takes.
+constexpr uint32_t kDescHi = 0x40004040u;   // (64 << 0) | (1 << 14) | (2 << 29)  ==  bits 32.. of umma_desc()
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr >> 4) & 0x3fffu) | (1u << 16);
+}
+__device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+      :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
@@ -586,6 +609,8 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   } else if (warp == kEpiWarps + 1) {
     // ===================================================== MMA issuer
     {
+      const uint32_t w_lo0 = umma_desc_lo(sW), i_lo0 = umma_desc_lo(sI), x_lo0 = umma_desc_lo(sX);
+      (void)w_lo0; (void)i_lo0; (void)x_lo0;
       uint32_t mq = 0, witer = 0;
       int tn = 0; (void)tn;
       int cur_fam = -1;
@@ -613,8 +638,32 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           mbar_wait<CGF_SLEEP_AUX_NS>(t_empty + pr, (use & 1) ^ 1, p.err, 5);
           CGF_EVENT(1, 3);
           tc_fence_after();
-          const uint32_t xs = sX + pr * Cfg::kXStageBytes;
           const uint32_t dcol = tmem_base + pr * kPairCols;
+#if CGF_DESC_LO
+          const uint32_t x_lo = x_lo0 + pr * (Cfg::kXStageBytes >> 4);
+          if (elect_one()) {
+#pragma unroll
+          for (int gate = 0; gate < 2; ++gate) {
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_lo(dcol + gate * kMmaN, w_lo0 + (((gate * KB + kb) * kKBlockBytes + k * 32) >> 4),
+                             x_lo + ((kb * Cfg::kXKBlock + k * 32) >> 4), IDESC, (kb | k) != 0);
+              }
+            }
+          }
+          const uint32_t xt_lo = x_lo + cb * ((2 * Cfg::kXKBlock) >> 4);
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16_lo(dcol + 2 * kMmaN, i_lo0 + ((kb * kKBlockBytes + k * 32) >> 4),
+                           xt_lo + ((kb * Cfg::kXKBlock + k * 32) >> 4), IDESC, (kb | k) != 0);
+            }
+          }
+#else
+          const uint32_t xs = sX + pr * Cfg::kXStageBytes;
           if (elect_one()) {
 #pragma unroll
           for (int gate = 0; gate < 2; ++gate) {
@@ -635,6 +684,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
                         umma_desc(xs + (2 * cb + kb) * Cfg::kXKBlock + k * 32), IDESC, (kb | k) != 0);
             }
           }
+#endif
           umma_commit(t_full + pr);
           umma_commit(x_empty + pr);
           }

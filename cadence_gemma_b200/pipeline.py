@@ -38,10 +38,12 @@ from cadence_gemma_b200 import _abi, layers
 # convolution's 8 packed bf16 ops per channel pair are not free inside it: at
 # config 2 (B=8, T=2048) one launch takes 165-172 us against 136 us for the
 # Conv1D kernel (HBM-bound, SMs otherwise idle) followed by the fused kernel,
-# while a small, latency-bound problem gains (B=1, T=2048: 53 us vs 80 us).
-# Measured crossover: see DESIGN.md section 4.0 / profiles/r2_fused_conv_ab.json.
+# while a small, latency-bound problem gains (B=2, T=2048: 51 us vs 77 us; B=8, T=512:
+# 52 us vs 93 us; B=16, T=256: 50 us vs 79 us).  Measured crossover at 128 scan tiles per
+# family: B=1, T=8192 (256 tiles) 94 vs 98 us, B=4, T=2048 91 vs 80 us, B=8, T=1024
+# 92 vs 84 us (profiles/r2_fused_conv_crossover.txt).
 _fused_conv = os.environ.get("CG_B200_FUSED_CONV", "auto")
-FUSED_CONV_MAX_TILES = 256      # auto: B * ceil(T / 32) scan tiles per channel family at most
+FUSED_CONV_MAX_TILES = 128      # auto: B * ceil(T / 32) scan tiles per channel family at most
 # One-launch decode step (cg_recurrent_decode_step).  It more than halves the cost
 # of an EAGER decode step (30 us vs 76 us per block at B = 32: three launches and
 # their host overhead become one); inside a CUDA graph, where launch overhead is

@@ -77,8 +77,9 @@ class BatchShardedHotPath:
     self._step_fn = step_fn or self._cuda_step
 
   def _cuda_step(self, x, segment_pos, conv_cache, lru_cache):
-    xc, conv_state = self.conv(x, segment_pos, conv_cache)
-    y, last_h = self.lru(xc, segment_pos, lru_cache)
+    from cadence_gemma_b200 import pipeline   # the hot-path entry point (one launch where that is faster)
+    y, conv_state, last_h = pipeline.recurrent_hot_path(self.conv, self.lru, x, segment_pos,
+                                                        conv_cache=conv_cache, lru_cache=lru_cache)
     return y, last_h, conv_state
 
   def forward(self, x_full, segment_pos_full, conv_cache_full=None,

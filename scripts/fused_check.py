@@ -172,7 +172,7 @@ def main():
     conv_case()
     conv_case(check=False)
   elif a.case == "conv_shapes":
-    for B, T in [(1, 2048), (2, 8192), (32, 768), (16, 8192)]:
+    for B, T in [(1, 2048), (2, 2048), (4, 2048), (1, 8192), (8, 512), (8, 1024), (16, 256), (2, 8192), (32, 768)]:
       conv_case(B, T, check=False)
   elif a.case == "time_shapes":
     for B, T in [(1, 2048), (2, 2048), (2, 8192), (32, 768), (8, 2048)]:
