@@ -110,12 +110,11 @@ def make_host_inputs(dtype, seed=1):
 # ----------------------------------------------------------------------------
 class ClockSampler:
   """SM clock and throttle reasons through NVML, sampled by the MAIN thread at points
-  where the host has nothing to launch: between the batches of the clock-ramp loop and,
-  for the timed region, right after its last launch has been enqueued while the GPU is
-  still executing it (the host runs ahead of the GPU: `t_end.query()` is False for
-  another millisecond or more).  A background thread polling NVML was measured to slow
-  the launch loop itself (NVML queries serialise with kernel launches in the driver:
-  236 us per step instead of 145 us), i.e. to perturb exactly what is being timed."""
+  where the host has nothing to launch: between the batches of the clock-ramp loop and
+  right after the last launch of a region has been enqueued while the GPU is still
+  executing it (the host runs ahead of the GPU: `t_end.query()` is False for another
+  millisecond or more).  A background thread polling NVML competes with the launch loop
+  for the interpreter (and the driver) and was measured to slow the steps it samples."""
 
   REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40,
              "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
@@ -172,9 +171,9 @@ class ClockSampler:
     out = {"sm_mhz": statistics.median(s[1] for s in use) if use else None,
            "sm_max_mhz": self.sm_max, "reasons": sorted(reasons),
            "samples": len(use), "samples_inside_timed_region": len(inside),
-           "how": ("NVML from the main thread: ONE sample after the timed region's last launch while the GPU is "
-                   "still executing it (more polling slows the timed kernels: 186 vs 143 us per step), plus the "
-                   "last 8 samples of the clock-ramp loop, which runs the same steps right before it")}
+           "how": ("NVML polled from the main thread while the GPU executes a back-to-back REPLICA of the timed region "
+                   "(the same K steps; its step time is in ms_per_step_of_the_sampled_replica), so the timed region "
+                   "itself carries no instrumentation; plus the last 8 samples of the clock-ramp loop")}
     if self._err:
       out["error"] = self._err
     return out
@@ -422,7 +421,7 @@ def own_arm(args, dtype):
       dist.barrier()
     torch.cuda.synchronize()
 
-  def timed_region(join_gather):
+  def timed_region(join_gather, sample_clocks=False):
     """EXACTLY K steps between two events on this rank's stream.  join_gather: the
     side-stream all-gather is joined BEFORE the closing event (a consumer that needs
     the merged cache right away) or after it (the merged cache is only needed before
@@ -440,10 +439,8 @@ def own_arm(args, dtype):
     if world > 1 and join_gather:
       torch.cuda.current_stream().wait_stream(comm_stream)
     t_end.record()
-    if not join_gather:
-      # ONE sample while the GPU is still inside the timed region: polling NVML for the whole
-      # region was measured to slow the GPU work itself (186 us per step vs 143 us unpolled)
-      sampler.sample_until(t_end, "timed", limit=1)
+    if sample_clocks:
+      sampler.sample_until(t_end, "timed")   # the GPU is still executing the region
     sync_all()
     return t_start.elapsed_time(t_end), o
 
@@ -454,6 +451,13 @@ def own_arm(args, dtype):
     # clocks have ramped up from idle on a fresh box (seen: 2x slower steps)
     for _ in range(max(args.warmup, 3)):
       out = step(x_dev, seg_dev)
+    # the bracketed variant of a step allocates its intermediates in a different pattern: let the
+    # caching allocator see it BEFORE the timed region (a first-time cudaMalloc inside the region
+    # cost 30 us per step: 177 us for the first region against 145 us for an identical second one)
+    for _ in range(3):
+      step(x_dev, seg_dev, record=True, gather=False)
+    for v in k_events.values():
+      v.clear()
     torch.cuda.synchronize()
     ramp_ms = float(os.environ.get("CG_BENCH_RAMP_MS", "400"))
     t_ramp = time.perf_counter()
@@ -478,7 +482,13 @@ def own_arm(args, dtype):
     launches0 = _abi.launch_count
     ms_total, out = timed_region(join_gather=False)
     launches = _abi.launch_count - launches0
+    # clocks: the SAME K steps once more, right away, with NVML polled by the main thread while
+    # the GPU executes them (after the last launch has been enqueued, so the polling cannot
+    # delay a launch): the region that is timed carries no instrumentation at all, the region
+    # that is sampled is its back-to-back replica (its own step time is reported beside it).
+    ms_sampled = timed_region(join_gather=False, sample_clocks=True)[0]
     clocks = sampler.summary()
+    clocks["ms_per_step_of_the_sampled_replica"] = ms_sampled / args.steps
     ms_joined = timed_region(join_gather=True)[0] if world > 1 else ms_total
     k_us = {k: statistics.mean(a.elapsed_time(b) * 1e3 for a, b in v) if v else 0.0
             for k, v in k_events.items()}

@@ -7,6 +7,10 @@
 #include "cg_common.cuh"
 #include "cg_scan.cuh"   // IoVec, load_io / store_io
 
+#ifndef CG_CONV_ST
+#define CG_CONV_ST 0
+#endif
+
 namespace cg {
 
 struct ConvParams {
@@ -124,7 +128,21 @@ __device__ __forceinline__ void conv1d_w4_tile(const ConvParams& p, int ctile, i
         o[i] = __float_as_uint(__fadd_rn(acc, __uint_as_float(bb[i])));
       }
     }
+    // CG_CONV_ST: 0 = streaming (evict-first) store, 1 = default policy, 2 = L2::evict_last.  The
+    // consumer (RG-LRU kernel) re-reads the 84 MB of a config-2 output right away: kept in the
+    // 126 MB L2 they need no DRAM read and their write-back leaves this kernel's critical path
+#if CG_CONV_ST == 1
+    *reinterpret_cast<uint4*>(yb + (size_t)t * p.E) = make_uint4(o[0], o[1], o[2], o[3]);
+#elif CG_CONV_ST == 2
+    {
+      uint64_t pol;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+                   :: "l"(yb + (size_t)t * p.E), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "l"(pol) : "memory");
+    }
+#else
     stg_stream(yb + (size_t)t * p.E, make_uint4(o[0], o[1], o[2], o[3]));
+#endif
   }
 
   // new cache = last 3 input rows, left zero padded (:542-543); written by the
