@@ -421,7 +421,7 @@ def own_arm(args, dtype):
       dist.barrier()
     torch.cuda.synchronize()
 
-  def timed_region(join_gather, sample_clocks=False):
+  def timed_region(join_gather, sample_clocks=False, brackets=False):
     """EXACTLY K steps between two events on this rank's stream.  join_gather: the
     side-stream all-gather is joined BEFORE the closing event (a consumer that needs
     the merged cache right away) or after it (the merged cache is only needed before
@@ -430,12 +430,9 @@ def own_arm(args, dtype):
     sync_all()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
-    # per-kernel CUDA events bracket every CG_BENCH_EVENT_EVERY-th step of the timed
-    # region (each bracket costs ~1-2 us of stream time, so not every step)
-    ev_every = max(1, min(args.steps, int(os.environ.get("CG_BENCH_EVENT_EVERY", "5"))))
     o = None
     for i in range(args.steps):
-      o = step(x_dev, seg_dev, record=(not join_gather and i % ev_every == ev_every // 2))
+      o = step(x_dev, seg_dev, record=brackets)
     if world > 1 and join_gather:
       torch.cuda.current_stream().wait_stream(comm_stream)
     t_end.record()
@@ -456,9 +453,9 @@ def own_arm(args, dtype):
     # cost 30 us per step: 177 us for the first region against 145 us for an identical second one)
     for _ in range(3):
       step(x_dev, seg_dev, record=True, gather=False)
+    torch.cuda.synchronize()
     for v in k_events.values():
       v.clear()
-    torch.cuda.synchronize()
     ramp_ms = float(os.environ.get("CG_BENCH_RAMP_MS", "400"))
     t_ramp = time.perf_counter()
     while (time.perf_counter() - t_ramp) * 1e3 < ramp_ms:
@@ -487,6 +484,10 @@ def own_arm(args, dtype):
     # delay a launch): the region that is timed carries no instrumentation at all, the region
     # that is sampled is its back-to-back replica (its own step time is reported beside it).
     ms_sampled = timed_region(join_gather=False, sample_clocks=True)[0]
+    # per-kernel times: the same K steps a third time with CUDA events between the kernels of
+    # every step (the brackets cost stream time and a different call sequence on the host, so
+    # they stay out of the region that is timed)
+    timed_region(join_gather=False, brackets=True)
     clocks = sampler.summary()
     clocks["ms_per_step_of_the_sampled_replica"] = ms_sampled / args.steps
     ms_joined = timed_region(join_gather=True)[0] if world > 1 else ms_total
