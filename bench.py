@@ -162,7 +162,7 @@ class ClockSampler:
   def summary(self):
     inside = [s for s in self.samples if s[0] == "timed"]
     ramp = [s for s in self.samples if s[0] == "ramp"]
-    use = inside + ramp[-8:]
+    use = inside + ramp[-8:]   # (no "ramp" samples are taken any more; kept for tools that add them)
     reasons = set()
     for _, _, mask in use:
       for name, bit in self.REASONS.items():
@@ -173,7 +173,7 @@ class ClockSampler:
            "samples": len(use), "samples_inside_timed_region": len(inside),
            "how": ("NVML polled from the main thread while the GPU executes a back-to-back REPLICA of the timed region "
                    "(the same K steps; its step time is in ms_per_step_of_the_sampled_replica), so the timed region "
-                   "itself carries no instrumentation; plus the last 8 samples of the clock-ramp loop")}
+                   "itself carries no instrumentation")}
     if self._err:
       out["error"] = self._err
     return out
@@ -369,6 +369,9 @@ def own_arm(args, dtype):
 
   fused = lru.uses_fused_kernel(x_dev)
   one_launch = pipeline.can_fuse_conv(conv, lru, x_dev)
+  bufs = dict(out=torch.empty_like(x_dev), conv_out=torch.empty_like(x_dev),
+              last_h_out=torch.empty((w["batch"], w["width"]), dtype=torch.float32, device=dev),
+              conv_cache_out=torch.empty((w["batch"], w["temporal_width"] - 1, w["width"]), dtype=dtype, device=dev))
   k_events = {"conv1d": [], "gate_gemm": [], "rglru": []}
   step_no = [0]
 
@@ -399,10 +402,12 @@ def own_arm(args, dtype):
       k_events["rglru"].append((e2, e3))
     elif record:
       e0 = ev()
-      y, conv_state, last_h = cg.recurrent_hot_path(conv, lru, x, seg)
+      y, conv_state, last_h = cg.recurrent_hot_path(conv, lru, x, seg, **bufs)
       k_events["rglru"].append((e0, ev()))
     else:
-      y, conv_state, last_h = cg.recurrent_hot_path(conv, lru, x, seg)
+      # caller-provided output buffers: no allocator traffic inside a step (a step that has to
+      # cudaMalloc a fresh 84 MB block stalls the launch loop for ~1 ms: measured)
+      y, conv_state, last_h = cg.recurrent_hot_path(conv, lru, x, seg, **bufs)
     step_no[0] += 1
     if gather and world > 1 and GATHER_EVERY > 0 and step_no[0] % GATHER_EVERY == 0:
       # merged cache for the host: one all-gather of the small per-row states
@@ -431,8 +436,12 @@ def own_arm(args, dtype):
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     o = None
+    host_t = [time.perf_counter()]
     for i in range(args.steps):
       o = step(x_dev, seg_dev, record=brackets)
+      host_t.append(time.perf_counter())
+    if os.environ.get("CG_BENCH_DEBUG"):
+      sys.stderr.write("host us per step: " + " ".join(f"{(b - a) * 1e6:.0f}" for a, b in zip(host_t, host_t[1:])) + "\n")
     if world > 1 and join_gather:
       torch.cuda.current_stream().wait_stream(comm_stream)
     t_end.record()
@@ -463,8 +472,8 @@ def own_arm(args, dtype):
       # collective inside (a gather here once left two ranks in different collectives)
       for _ in range(20):
         out = step(x_dev, seg_dev, gather=False)
-      sampler.sample("ramp")     # under load, outside any timed region
-      torch.cuda.synchronize()
+      torch.cuda.synchronize()   # (no NVML query in here: it idles the GPU for milliseconds and the
+                                 # first region after such a gap was measured at 263 us per step, the next at 136)
     if world > 1:
       # exercise the whole gather path once outside the timed region: NCCL sets
       # connections up lazily and CUDA loads the small copy/cast kernels lazily
@@ -670,11 +679,11 @@ def own_arm(args, dtype):
         try:
           with torch.no_grad():
             for _ in range(3):
-              y, _, h = cg.recurrent_hot_path(conv, lru, x_dev, seg_dev)
+              y, _, h = cg.recurrent_hot_path(conv, lru, x_dev, seg_dev, **bufs)
             torch.cuda.synchronize()
             e0 = ev()
             for _ in range(10):
-              cg.recurrent_hot_path(conv, lru, x_dev, seg_dev)
+              cg.recurrent_hot_path(conv, lru, x_dev, seg_dev, **bufs)
             e1 = ev()
             torch.cuda.synchronize()
         finally:
