@@ -30,7 +30,7 @@ constexpr int kMinSuperChunk = 64;  // smallest NW * 4 * L of any compiled geome
 // Per-device launch state: cudaFuncSetAttribute, occupancy and the SM count belong
 // to a device, not to the process (a process may drive several GPUs).
 constexpr int kMaxDevices = 64;
-struct DeviceSlot { std::once_flag once; int sms = 0; cudaError_t err = cudaSuccess; };
+struct DeviceSlot { std::once_flag once; int sms = 0; int resident = 0; cudaError_t err = cudaSuccess; };
 
 // scratch layout: [ticket, epoch | 256 B][agg_p][agg_h][pref][neg8sp]
 // The exchange arrays hold 64-bit {value, epoch} words; the scratch must be
@@ -582,7 +582,11 @@ int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int g
   if (sms < 1) return (int)cudaErrorLaunchOutOfResources;
   // one persistent CTA per SM; grid_limit > 0 (test hook) runs with fewer CTAs than
   // column families, which exercises the family loop (weight reload) of a CTA
-  const int grid = grid_limit > 0 && grid_limit < sms ? grid_limit : sms;
+  // CONV kernels at head width 256: the two CTAs of a head form a thread-block cluster
+  constexpr int CL = CONV ? KB / 2 : 1;
+  int grid = grid_limit > 0 && grid_limit < sms ? grid_limit : sms;
+  grid = grid / CL * CL;
+  if (grid < CL) grid = CL;
   // programmatic dependent launch behind the prologue kernel (see the
   // griddepcontrol.wait in the epilogue warps): set-up and operand loads start
   // while the prologue is still running
@@ -591,11 +595,24 @@ int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int g
   cfg.blockDim = dim3(cg::fused::kThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (CL > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = CL; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+    // every CTA waits on others (look-back): all clusters of the grid must be co-resident
+    if (slot.resident == 0) {
+      int ncl = 0;
+      if (cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg)) return (int)e;
+      slot.resident = ncl > 0 ? ncl : -1;
+    }
+    if (slot.resident < 1) return (int)cudaErrorLaunchOutOfResources;
+    if (grid > slot.resident * CL) { grid = slot.resident * CL; cfg.gridDim = dim3(grid); }
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmap, p);
   if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();

@@ -32,8 +32,9 @@
 //                family, then two X boxes [32 steps x head width] per MMA tile
 //                through a 3-D tensor map (SWIZZLE_128B, zero fill beyond T)
 //   warp 17      MMA issuer (one thread), tcgen05.commit -> mbarriers
-//   warps 18-19  CONV kernels only: the temporal convolution, in place in the X
-//                stage, one warp per half of the stage (see conv_row below)
+//   warps 18-19  idle (registers are allocated per four warps).  CONV kernels: the
+//                temporal convolution runs in the epilogue warpgroups, in place in
+//                the X stage (conv_tile)
 // CTA i works on family i % families; the CTAs of one family take its tiles
 // two at a time, round-robin in time-major order, so look-back dependencies
 // always point to tiles that are already running (all CTAs are co-resident:
@@ -338,6 +339,51 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- thread-block cluster helpers (CONV kernels at head width 256: the two CTAs that own the two
+// channel halves of a head form a cluster and exchange their halves of the convolved X stage)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// bulk copy local shared memory -> a peer CTA's shared memory, completing (bytes) on the PEER's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes,
+                                                  uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      :: "r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
+}
+// tcgen05.commit that arrives on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t r;   // volatile, no "memory" clobber: ordered against sts32, free against arithmetic
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v));
+}
+__device__ __forceinline__ uint32_t ldg32_nc(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start address >> 4 | LBO (ignored for swizzled K-major, 1) | SBO = 1024 B between
 // 8-row groups | version 1 (Blackwell) | layout type 2 (128 B swizzle).
@@ -456,38 +502,16 @@ struct Schedule {
 // ---------------------------------------------------------------------------
 // In-kernel temporal convolution (CONV kernels; north star: "the width-4 Conv1D is
 // fused into the same pass").  The TMA producer loads the rows of x_lin -- the
-// INPUT of Conv1D.forward -- into the X stage; one warp per half of the stage
-// (32 steps x head width) then convolves the rows IN PLACE: lane l owns the
-// 16-byte chunk (K block l / 8, chunk l % 8) of every row, walks the rows forward
-// with a three-row register window (the three halo rows before the tile come
-// straight from global memory, requested before the wait for the TMA data), and
-// writes each output row over the input row it has just read -- a lane only ever
-// touches its own chunk, so there is no hazard inside or between the warps.
-// Arithmetic: the reference's accumulation order with one bf16 rounding per eager
-// op (layers.py:530-536: packed HMUL2 / HADD2, no contraction), bit-exact with
-// cg::conv1d_w4_kernel and the reference.  The conv output never reaches HBM.
+// INPUT of Conv1D.forward -- into the X stage and the EPILOGUE warpgroups convolve
+// them in place before the MMA warp may read the stage (conv_tile in the kernel):
+// the convolution's issue load is spread over the SM's four sub-partitions, and at
+// head width 256 the two CTAs of a head (a 2-CTA cluster) each convolve their 128
+// channels and exchange the halves with bulk shared -> shared::cluster copies, so
+// the convolution is computed once per head.  Arithmetic: the reference's
+// accumulation order with one bf16 rounding per eager op (layers.py:530-536:
+// packed HMUL2 / HADD2, no contraction), bit-exact with cg::conv1d_w4_kernel and
+// the reference.  The conv output never reaches HBM.
 // ---------------------------------------------------------------------------
-struct ConvTaps { uint4 w0, w1, w2, w3, b; };   // w[k] multiplies x[t - (3 - k)] (layers.py:530)
-
-__device__ __forceinline__ uint4 conv_row(const ConvTaps& k, const uint4& x0, const uint4& x1, const uint4& x2,
-                                          const uint4& x3) {
-  const uint32_t s0[4] = {x0.x, x0.y, x0.z, x0.w}, s1[4] = {x1.x, x1.y, x1.z, x1.w};
-  const uint32_t s2[4] = {x2.x, x2.y, x2.z, x2.w}, s3[4] = {x3.x, x3.y, x3.z, x3.w};
-  const uint32_t k0[4] = {k.w0.x, k.w0.y, k.w0.z, k.w0.w}, k1[4] = {k.w1.x, k.w1.y, k.w1.z, k.w1.w};
-  const uint32_t k2[4] = {k.w2.x, k.w2.y, k.w2.z, k.w2.w}, k3[4] = {k.w3.x, k.w3.y, k.w3.z, k.w3.w};
-  const uint32_t bb[4] = {k.b.x, k.b.y, k.b.z, k.b.w};
-  uint32_t o[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint32_t acc = bf2_mul(s0[i], k3[i]);                 // shift 0
-    acc = bf2_add(acc, bf2_mul(s1[i], k2[i]));            // shift 1
-    acc = bf2_add(acc, bf2_mul(s2[i], k1[i]));            // shift 2
-    acc = bf2_add(acc, bf2_mul(s3[i], k0[i]));            // shift 3
-    o[i] = bf2_add(acc, bb[i]);                           // + b, :536
-  }
-  return make_uint4(o[0], o[1], o[2], o[3]);
-}
-
 // ---------------------------------------------------------------------------
 // The fused kernel.  KB = head width / 64 (K blocks of the gate GEMMs).
 // ---------------------------------------------------------------------------
@@ -501,9 +525,16 @@ template <int KB, bool FAST, bool DBG, bool MUL, bool CONV>
 __global__ void __launch_bounds__(kThreads, 1)
 rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams p) {
   using Cfg = FusedCfg<KB>;
-  constexpr int CBS = KB / 2;               // 128-channel halves per head
+  constexpr int CBS = KB / 2;               // 128-channel halves (families) per head
   constexpr int XS = Cfg::kXStages;
   constexpr uint32_t IDESC = umma_idesc(kMch, kMmaN);
+  // CONV: the CBS CTAs that own the families of one head form a thread-block cluster.  Each CTA loads
+  // and convolves only ITS 128 input channels (KBL = 2 K blocks of the X stage) and sends the result
+  // to its peer with one bulk shared->shared copy per K block, so the convolution is computed once per
+  // head, not once per family.
+  constexpr int CL = CONV ? CBS : 1;        // cluster size
+  constexpr int KBL = KB / CL;              // K blocks of an X stage this CTA loads (and convolves)
+  static_assert(!CONV || KBL == 2, "the in-kernel convolution maps one warp to one K block of a half stage");
 
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -527,15 +558,19 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
     mbar_init(w_empty, 1);
-    for (int i = 0; i < XS; ++i) { mbar_init(raw_full + i, 1); mbar_init(x_full + i, 2); mbar_init(x_empty + i, 1); }
+    // x_full: one arrival per warpgroup of the pair (+ the peer's bytes, CL == 2); x_empty: the MMAs of
+    // EVERY CTA of the cluster have read the stage (the peer writes into my stage too)
+    for (int i = 0; i < XS; ++i) { mbar_init(raw_full + i, 1); mbar_init(x_full + i, 2); mbar_init(x_empty + i, CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }
     fence_mbar_init();
   }
   if (warp == kEpiWarps) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();   // the peer's barriers exist before anything is sent to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
 
 #if CGF_SETMAXNREG
   // all four warps of a warpgroup execute the same setmaxnreg (it is .aligned)
@@ -548,8 +583,11 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   const int nfam = p.families;
   const int ntiles = p.ntt * p.B;
   const int npairs = (ntiles + 1) >> 1;
-  const Schedule sched(blockIdx.x, gridDim.x, nfam, npairs);
+  // CONV: the schedule hands out HEADS to clusters; CTA `crank` of the cluster takes family head * CBS + crank
+  const Schedule sched(CONV ? (int)blockIdx.x / CL : (int)blockIdx.x, CONV ? (int)gridDim.x / CL : (int)gridDim.x,
+                       CONV ? nfam / CBS : nfam, npairs);
   const int nsegs = sched.nseg();
+  auto seg_family = [&](const Seg& sg) -> int { return CONV ? sg.fam * CBS + (int)crank : sg.fam; };
 
   if (warp == kEpiWarps) {
     // ===================================================== TMA producer
@@ -560,7 +598,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       for (int sgi = 0; sgi < nsegs; ++sgi) {
         const Seg sg = sched.get(sgi);
         if (sg.count == 0) continue;
-        const int fam = sg.fam;
+        const int fam = seg_family(sg);
         if (fam != cur_fam) {
         cur_fam = fam;
         if (witer > 0) mbar_wait<CGF_SLEEP_AUX_NS>(w_empty, (witer - 1) & 1, p.err, 1);
@@ -590,15 +628,17 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           CGF_EVENT(0, 1);
           mbar_wait<CGF_SLEEP_AUX_NS>(x_empty + stage, (use & 1) ^ 1, p.err, 2);
           CGF_EVENT(0, 2);
-          if (elect_one()) mbar_expect_tx(raw_full + stage, nhalf * (Cfg::kXStageBytes / 2));
+          if (elect_one()) mbar_expect_tx(raw_full + stage, nhalf * (Cfg::kXStageBytes / 2 / CL));
           for (int hf = 0; hf < nhalf; ++hf) {
             const int ticket = t1st + hf;
             const int tt = ticket / p.B, b = ticket - tt * p.B;
             if (elect_one()) {
 #pragma unroll
-              for (int kb = 0; kb < KB; ++kb)
+              for (int kbl = 0; kbl < KBL; ++kbl) {
+                const int kb = (CL > 1 ? (int)crank * KBL : 0) + kbl;   // CONV: my channel half only
                 tma_load_3d(sX + stage * Cfg::kXStageBytes + kb * Cfg::kXKBlock + hf * (kTile * 128), &tmap_x,
                             raw_full + stage, c_head + kb * 64, tt * kTile, b);
+              }
             }
           }
           __syncwarp();
@@ -617,7 +657,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       for (int sgi = 0; sgi < nsegs; ++sgi) {
         const Seg sg = sched.get(sgi);
         if (sg.count == 0) continue;
-        const int fam = sg.fam;
+        const int fam = seg_family(sg);
         if (fam != cur_fam) {
           if (cur_fam >= 0) {                            // the old family's weights may be overwritten
             if (elect_one()) umma_commit(w_empty);
@@ -686,7 +726,8 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           }
 #endif
           umma_commit(t_full + pr);
-          umma_commit(x_empty + pr);
+          if constexpr (CL > 1) umma_commit_mc(x_empty + pr, (uint16_t)((1u << CL) - 1u));   // my stage AND the peer's copy target
+          else umma_commit(x_empty + pr);
           }
           __syncwarp();
           CGF_EVENT(1, 4);
@@ -695,153 +736,10 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     }
     __syncwarp();
   } else if (warp >= kEpiWarps + 2) {
-    // ===================================================== Conv1D warps (CONV only)
-    if constexpr (CONV) {
-      const int hfc = warp - (kEpiWarps + 2);            // the half of every X stage this warp convolves
-      const bool active = lane < KB * 8;                 // 8 channels per lane; head width 128: 16 lanes
-      const int kbc = lane >> 3, chunk = lane & 7;
-      const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-      // reset bitmask (prologue kernel) and x_lin (whatever precedes on the stream)
-      asm volatile("griddepcontrol.wait;" ::: "memory");
-      uint32_t mq = 0;
-      int tn = 0; (void)tn;
-      int cur_head = -1;
-      ConvTaps taps{zero4, zero4, zero4, zero4, zero4};
-      int ch0 = 0;
-      for (int sgi = 0; sgi < nsegs; ++sgi) {
-        const Seg sg = sched.get(sgi);
-        if (sg.count == 0) continue;
-        const int fam = sg.fam;
-        const int head = fam / CBS;
-        if (head != cur_head) {                            // taps of this lane's 8 channels
-          cur_head = head;
-          ch0 = head * (KB * 64) + lane * 8;
-          if (active) {
-            taps.w0 = *reinterpret_cast<const uint4*>(p.conv_w + ch0);
-            taps.w1 = *reinterpret_cast<const uint4*>(p.conv_w + (size_t)p.E + ch0);
-            taps.w2 = *reinterpret_cast<const uint4*>(p.conv_w + 2 * (size_t)p.E + ch0);
-            taps.w3 = *reinterpret_cast<const uint4*>(p.conv_w + 3 * (size_t)p.E + ch0);
-            taps.b = *reinterpret_cast<const uint4*>(p.conv_b + ch0);
-          }
-        }
-        const bool cache_writer = p.conv_cache != nullptr && (fam % CBS) == 0;
-#pragma unroll 1
-        for (int m = 0; m < sg.count; ++m, ++mq) {
-          const uint32_t stage = mq & 1u, use = mq >> 1;
-          const int ticket = 2 * (sg.j0 + m * sg.stride) + hfc;
-          const bool valid = ticket < ntiles && active;
-          int tt = 0, b = 0;
-          uint4 h1 = zero4, h2 = zero4, h3 = zero4;        // x[t0-1], x[t0-2], x[t0-3]
-          unsigned long long nzw = ~0ull;                  // bit r: segment_pos[t0 + r - 2] != 0
-          if (valid) {
-            tt = ticket / p.B; b = ticket - tt * p.B;
-            const int t0 = tt * kTile;
-            // halo rows straight from global memory: the round trip hides behind the
-            // wait for the stage's TMA boxes (x[t < 0] = 0, layers.py:484-492)
-            const uint16_t* xb = p.x_lin + ((size_t)b * p.T) * p.E + ch0;
-            if (t0 >= 1) h1 = ldg_stream(xb + (size_t)(t0 - 1) * p.E);
-            if (t0 >= 2) h2 = ldg_stream(xb + (size_t)(t0 - 2) * p.E);
-            if (t0 >= 3) h3 = ldg_stream(xb + (size_t)(t0 - 3) * p.E);
-            const unsigned* rw = p.reset_bits + (long long)b * p.bits_bstride + tt;
-            const unsigned cur = rw[0];
-            const unsigned prev = tt > 0 ? rw[-1] : 0u;    // positions before 0 gate taps that are zero anyway
-            nzw = ((unsigned long long)(~cur) << 2) | (unsigned long long)((~prev) >> 30);
-          }
-          CGF_EVENT(6, 1);
-          mbar_wait<CGF_SLEEP_AUX_NS>(raw_full + stage, use & 1, p.err, 9);
-          CGF_EVENT(6, 2);
-          if (valid && !(CGF_ABLATE & 8)) {
-            uint32_t row = sX + stage * Cfg::kXStageBytes + kbc * Cfg::kXKBlock + (uint32_t)(hfc * kTile) * 128u;
-            const bool upstream = p.mask_mode != 0;
-            // no document start near the tile: every tap is live (the common case)
-            const bool plain = upstream ? (nzw & 0x3ffffffffull) == 0x3ffffffffull
-                                        : (nzw & 0xffffffffull) == 0xffffffffull;
-            // Rows go through registers in batches of kConvBatch: all loads of a batch are
-            // issued before its arithmetic, so the batch's 4 x kConvBatch independent
-            // bf16x2 chains overlap (a row-by-row in-place loop serialises on
-            // LDS -> 5 dependent packed ops -> STS: measured 8 000 cycles per tile).
-            constexpr int kConvBatch = CGF_CONV_BATCH;
-#pragma unroll 1
-            for (int r0 = 0; r0 < kTile; r0 += kConvBatch) {
-              uint4 xr[kConvBatch];
-#pragma unroll
-              for (int j = 0; j < kConvBatch; ++j)
-                xr[j] = lds128(row + (r0 + j) * 128 + ((uint32_t)(chunk ^ ((r0 + j) & 7)) << 4));
-              if (plain) {
-#pragma unroll
-                for (int j = 0; j < kConvBatch; ++j) {
-                  const uint4& a1 = j >= 1 ? xr[j - 1] : h1;
-                  const uint4& a2 = j >= 2 ? xr[j - 2] : (j == 1 ? h1 : h2);
-                  const uint4& a3 = j >= 3 ? xr[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
-                  sts128(row + (r0 + j) * 128 + ((uint32_t)(chunk ^ ((r0 + j) & 7)) << 4),
-                         (CGF_ABLATE & 16) ? xr[j] : conv_row(taps, xr[j], a1, a2, a3));
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < kConvBatch; ++j) {
-                  const uint4& a1 = j >= 1 ? xr[j - 1] : h1;
-                  const uint4& a2 = j >= 2 ? xr[j - 2] : (j == 1 ? h1 : h2);
-                  const uint4& a3 = j >= 3 ? xr[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
-                  const unsigned w3 = (unsigned)(nzw >> (r0 + j)) & 7u;   // bit 0: seg[t-2], 1: seg[t-1], 2: seg[t]  (!= 0)
-                  bool m1 = true, m2 = true, m3;
-                  if (!upstream) {
-                    m3 = (w3 & 1u) != 0;                   // fork: only seg[t-2], layers.py:629-632
-                  } else {
-                    m1 = (w3 & 4u) != 0;                   // upstream: seg[t-s+1 .. t] all != 0
-                    m2 = (w3 & 6u) == 6u;
-                    m3 = (w3 & 7u) == 7u;
-                  }
-                  sts128(row + (r0 + j) * 128 + ((uint32_t)(chunk ^ ((r0 + j) & 7)) << 4),
-                         conv_row(taps, xr[j], m1 ? a1 : zero4, m2 ? a2 : zero4, m3 ? a3 : zero4));
-                }
-              }
-              h3 = xr[kConvBatch - 3]; h2 = xr[kConvBatch - 2]; h1 = xr[kConvBatch - 1];
-            }
-            // the convolution's returned cache: the last three INPUT rows of the
-            // sequence, left zero padded (layers.py:542-543, :650-662)
-            if (cache_writer && tt == p.ntt - 1) {
-              const uint16_t* xb = p.x_lin + ((size_t)b * p.T) * p.E + ch0;
-              uint16_t* cb = p.conv_cache + ((size_t)b * 3) * p.E + ch0;
-#pragma unroll
-              for (int r = 0; r < 3; ++r) {
-                const int ti = p.T - 3 + r;
-                *reinterpret_cast<uint4*>(cb + (size_t)r * p.E) = ti >= 0 ? ldg_stream(xb + (size_t)ti * p.E) : zero4;
-              }
-            }
-          }
-          // my stores to the stage (generic proxy) before the MMA's operand reads (async proxy)
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(x_full + stage);
-          CGF_EVENT(6, 3);
-#if (CGF_ABLATE & 32)
-          // timing experiment: the convolution arithmetic OFF the critical path (after the
-          // hand-over; results are wrong): separates latency in the stage loop from issue load
-          if (valid) {
-            const uint32_t row = sX + stage * Cfg::kXStageBytes + kbc * Cfg::kXKBlock + (uint32_t)(hfc * kTile) * 128u;
-#pragma unroll 1
-            for (int r0 = 0; r0 < kTile; r0 += 8) {
-              uint4 xr[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) xr[j] = lds128(row + (r0 + j) * 128 + ((uint32_t)(chunk ^ ((r0 + j) & 7)) << 4));
-              uint4 acc = zero4;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const uint4& a1 = j >= 1 ? xr[j - 1] : h1;
-                const uint4& a2 = j >= 2 ? xr[j - 2] : (j == 1 ? h1 : h2);
-                const uint4& a3 = j >= 3 ? xr[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
-                const uint4 o = conv_row(taps, xr[j], a1, a2, a3);
-                acc.x ^= o.x; acc.y ^= o.y; acc.z ^= o.z; acc.w ^= o.w;
-              }
-              if (acc.x == 0x12345678u && acc.y == 0x9abcdef0u) sts128(row, acc);   // never true: keeps the math alive
-              h3 = xr[5]; h2 = xr[6]; h1 = xr[7];
-            }
-          }
-#endif
-        }
-      }
-    }
-    __syncwarp();
+    // warps 18 / 19 complete the fifth warpgroup (registers are allocated per four warps) and idle.
+    // (Round 2's first version ran the in-kernel convolution here: two warps on two of the SM's four
+    // sub-partitions, the whole head's 256 channels per CTA -- 165-175 us at config 2 against 136 us for
+    // the two-kernel route.  It now runs in the epilogue warpgroups, see conv_tile below.)
   } else {
     // ===================================================== epilogue warpgroups
     // One warpgroup, tile after tile:
@@ -1025,159 +923,348 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
 
     int cur_fam = -1, ch = 0;
     uint32_t bx2 = 0, ba2 = 0, sp2 = 0;
-    for (int sgi = 0; sgi < nsegs; ++sgi) {
-      const Seg sg = sched.get(sgi);
-      if (sg.count == 0) continue;
-      const int fam = sg.fam;
-      if (fam != cur_fam) {                                // per-channel constants of the new family
-        cur_fam = fam;
-        ch = fam * kMch + chl;
-        bx2 = 0; ba2 = 0;
-        if (p.bias_x != nullptr) { const uint32_t v = p.bias_x[ch]; bx2 = v | (v << 16); }
-        if (p.bias_a != nullptr) { const uint32_t v = p.bias_a[ch]; ba2 = v | (v << 16); }
-        sp2 = p.neg8sp_bf[ch]; sp2 |= sp2 << 16;
-      }
+    auto load_family = [&](int fam) {                      // per-channel constants of a new family
+      if (fam == cur_fam) return;
+      cur_fam = fam;
+      ch = fam * kMch + chl;
+      bx2 = 0; ba2 = 0;
+      if (p.bias_x != nullptr) { const uint32_t v = p.bias_x[ch]; bx2 = v | (v << 16); }
+      if (p.bias_a != nullptr) { const uint32_t v = p.bias_a[ch]; ba2 = v | (v << 16); }
+      sp2 = p.neg8sp_bf[ch]; sp2 |= sp2 << 16;
+    };
+    // G(k): gates of one scan tile out of my half of the accumulators, aggregate published, tile queued for F
+    auto tile_body = [&](const int fam, const int tt, const int b, const unsigned rbits) {
+      const int t0 = tt * kTile;
+      const int nvalid = p.T - t0;                         // >= 1; >= kTile for a full tile
+      const bool fast_tile = CGF_PRELOAD && rbits == 0u && nvalid >= kTile;
+      float P = 1.0f, Hh = 0.0f;
+      // gates for one bf16x2 pair of steps (t, t+1) -> (a, x~); the tile's
+      // transform h -> P*h + H is accumulated on the way
+      auto gate_step = [&](uint32_t xc, uint32_t gxr, uint32_t gar, int tl, auto slow_tag,
+                           uint32_t& a2, uint32_t& n2) {
+        constexpr bool SLOW = decltype(slow_tag)::value;
+        gate_pair_emul<FAST, false>(xc, gxr, gar, bx2, ba2, sp2, a2, n2);
+        if constexpr (SLOW) {                            // tl = step of the low half inside the tile
+          const unsigned r2 = (rbits >> tl) & 3u;
+          if (r2 != 0u) {                                // document start inside the pair
+            uint32_t az, nr;
+            gate_pair_emul<FAST, true>(xc, gxr, gar, bx2, ba2, sp2, az, nr);
+            if (r2 & 1u) { a2 &= 0xffff0000u; n2 = (n2 & 0xffff0000u) | (nr & 0x0000ffffu); }
+            if (r2 & 2u) { a2 &= 0x0000ffffu; n2 = (n2 & 0x0000ffffu) | (nr & 0xffff0000u); }
+          }
+          if (tl + 1 >= nvalid) {                        // steps beyond T are identities
+            if (tl >= nvalid) { a2 = kOne2; n2 = 0u; }
+            else { a2 = (a2 & 0x0000ffffu) | 0x3f800000u; n2 &= 0x0000ffffu; }
+          }
+        }
+        if constexpr (DBG && !CGF_TRACE) {
+          const int tg = t0 + tl;
+          const size_t plane = (size_t)p.B * p.T * p.E;
+          const size_t o0 = ((size_t)b * p.T + tg) * p.E + ch;
+          if (tg < p.T) {
+            p.dbg[o0] = (uint16_t)(gxr & 0xffffu); p.dbg[plane + o0] = (uint16_t)(gar & 0xffffu);
+            p.dbg[2 * plane + o0] = (uint16_t)(xc & 0xffffu);
+          }
+          if (tg + 1 < p.T) {
+            p.dbg[o0 + p.E] = (uint16_t)(gxr >> 16); p.dbg[plane + o0 + p.E] = (uint16_t)(gar >> 16);
+            p.dbg[2 * plane + o0 + p.E] = (uint16_t)(xc >> 16);
+          }
+        }
+        const float al = bf_lo(a2), ah = bf_hi(a2);
+        Hh = add_bf_lo(n2, al * Hh);                     // mul then add, as the reference loop (:196)
+        Hh = add_bf_hi(n2, ah * Hh);
+        P *= al; P *= ah;
+      };
+      if (fast_tile) {
+        // ---- common case, half a tile (8 pairs) at a time: pull the
+        // accumulators out of TMEM, rounded to bf16 on the way (the GEMM output
+        // the reference materialises, :136-142), then the gate math from
+        // registers.  The slot goes back to the MMA warp as soon as the second
+        // half has been read.
 #pragma unroll 1
-      for (int m = 0; m < sg.count; ++m, ++mq) {
-        if ((mq & 1u) != pr) continue;
-        const uint32_t use = mq >> 1;
-        const int ticket = 2 * (sg.j0 + m * sg.stride) + (int)hf;
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t gx[8], ga[8], xv[8];
+          {
+            uint32_t dx[16], da[16], dt[16];
+            const uint32_t col = tm_acc + hh * 16;
+            tmem_ld8(col, *reinterpret_cast<uint32_t(*)[8]>(&dx[0]));
+            tmem_ld8(col + 8, *reinterpret_cast<uint32_t(*)[8]>(&dx[8]));
+            tmem_ld8(col + kMmaN, *reinterpret_cast<uint32_t(*)[8]>(&da[0]));
+            tmem_ld8(col + kMmaN + 8, *reinterpret_cast<uint32_t(*)[8]>(&da[8]));
+            tmem_ld8(col + 2 * kMmaN, *reinterpret_cast<uint32_t(*)[8]>(&dt[0]));
+            tmem_ld8(col + 2 * kMmaN + 8, *reinterpret_cast<uint32_t(*)[8]>(&dt[8]));
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              gx[i] = pack_bf2(__uint_as_float(dx[2 * i]), __uint_as_float(dx[2 * i + 1]));
+              ga[i] = pack_bf2(__uint_as_float(da[2 * i]), __uint_as_float(da[2 * i + 1]));
+              xv[i] = pack_bf2(__uint_as_float(dt[2 * i]), __uint_as_float(dt[2 * i + 1]));
+            }
+          }
+          if (hh == 1) {
+            release_slot();
+            if (twarp) CGF_EVENT(trole, 3);
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t st[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              gate_step(xv[c * 4 + i], gx[c * 4 + i], ga[c * 4 + i], hh * 16 + c * 8 + 2 * i, FalseTag{}, st[i], st[4 + i]);
+            tmem_st8(tm_state + hh * 16 + c * 8, st);
+          }
+        }
+      } else {
+        // document starts or a ragged tail inside the tile (rare, warp-uniform):
+        // gates chunk by chunk out of TMEM
+#pragma unroll 1
+        for (int c = 0; c < kTile / 8; ++c) {
+          uint32_t dx[8], da[8], dt[8], st[8];
+          tmem_ld8(tm_acc + c * 8, dx);
+          tmem_ld8(tm_acc + kMmaN + c * 8, da);
+          tmem_ld8(tm_acc + 2 * kMmaN + c * 8, dt);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t gxr = pack_bf2(__uint_as_float(dx[2 * i]), __uint_as_float(dx[2 * i + 1]));
+            const uint32_t gar = pack_bf2(__uint_as_float(da[2 * i]), __uint_as_float(da[2 * i + 1]));
+            const uint32_t xc = pack_bf2(__uint_as_float(dt[2 * i]), __uint_as_float(dt[2 * i + 1]));
+            gate_step(xc, gxr, gar, c * 8 + 2 * i, TrueTag{}, st[i], st[4 + i]);
+          }
+          tmem_st8(tm_state + c * 8, st);
+        }
+        release_slot();
+      }
+      tmem_wait_st();
+      if (twarp) CGF_EVENT(trole, 4);
+      // publish the tile's aggregate (tile 0 publishes its state right away in
+      // F instead) and queue the tile for F
+      pd.on = true; pd.tt = tt; pd.b = b; pd.nvalid = nvalid; pd.ch = ch; pd.P = P; pd.H = Hh;
+      pd.widx = (((size_t)fam * p.ntt + tt) * p.B + b) * kMch + chl;
+      pd.yp = p.y + ((size_t)b * p.T + t0) * p.E + ch;
+      if (tt > 0 && tt + 1 < p.ntt) {
+        st_relaxed_u64(p.agg_p + pd.widx, pack_tagged(P, epoch));
+        st_relaxed_u64(p.agg_h + pd.widx, pack_tagged(Hh, epoch));
+      }
+      if (twarp) CGF_EVENT(trole, 7);
+    };
+
+    if constexpr (!CONV) {
+      for (int sgi = 0; sgi < nsegs; ++sgi) {
+        const Seg sg = sched.get(sgi);
+        if (sg.count == 0) continue;
+        const int fam = sg.fam;
+        load_family(fam);
+#pragma unroll 1
+        for (int m = 0; m < sg.count; ++m, ++mq) {
+          if ((mq & 1u) != pr) continue;
+          const uint32_t use = mq >> 1;
+          const int ticket = 2 * (sg.j0 + m * sg.stride) + (int)hf;
+          if (twarp) CGF_EVENT(trole, 8);
+          const unsigned long long early = request_pred();
+          if (twarp) CGF_EVENT(trole, 1);
+          mbar_wait(t_full + pr, use & 1, p.err, 6);
+          if (twarp) CGF_EVENT(trole, 2);
+          tc_fence_after();
+          if (ticket >= ntiles) {                          // odd tile count: nothing in my half
+            release_slot();
+            if (pd.on) finish(early);
+            continue;
+          }
+          const int tt = ticket / p.B, b = ticket - tt * p.B;
+          const unsigned rbits = p.reset_bits[(long long)b * p.bits_bstride + tt];   // kTile == 32: one word
+          // F(k-1): before the new tile
+          if (pd.on) finish(early);
+          tile_body(fam, tt, b, rbits);
+        }
+      }
+    } else {
+      // ------------------------------------------------------------------------------------------
+      // CONV: this warpgroup also convolves ITS half (32 rows) of its pair's NEXT X stage, in place,
+      // between F(k-1) and G(k) -- the convolution's instructions are spread evenly over the SM's four
+      // sub-partitions (a warpgroup has one warp on each) and the TMA round trip of the next tile's raw
+      // rows hides behind F.  128 threads = 64 bf16x2 columns (this CTA's 128 input channels: warp ->
+      // K block, lane -> 4-byte word of the 128-byte row, conflict-free) x 2 row segments of 16 rows.
+      // A thread reads its 16 rows and its three halo rows (segment 0: the rows before the tile, straight
+      // from global memory, requested before the wait for the TMA data; segment 1: rows 13-15 of the
+      // half) BEFORE a warpgroup barrier and writes after it, so in-place is safe.  Arithmetic = the
+      // reference's accumulation order with one bf16 rounding per eager op (layers.py:530-536), bit-exact
+      // with cg::conv1d_w4_kernel.  CL == 2: the convolved half is then sent to the peer CTA (one bulk
+      // shared -> shared::cluster copy per K block, completing on the PEER's x_full), which needs it as
+      // the other half of the K range of its gate GEMMs -- the convolution is computed once per head.
+      // ------------------------------------------------------------------------------------------
+      struct Cur { int sgi, m; uint32_t mq; Seg sg; bool ok; };
+      auto step = [&](Cur& c) {                            // to the next MMA tile of my pair
+        for (;;) {
+          ++c.m; ++c.mq;
+          while (c.sgi < nsegs && c.m >= c.sg.count) {
+            ++c.sgi; c.m = 0;
+            if (c.sgi < nsegs) c.sg = sched.get(c.sgi);
+          }
+          if (c.sgi >= nsegs) { c.ok = false; return; }
+          if ((c.mq & 1u) == pr) return;
+        }
+      };
+      const int wq = warp & 3;
+      const int cseg = wq >> 1;                            // rows 16 * cseg .. + 15 of my half
+      const int ckb = (CL > 1 ? (int)crank * KBL : 0) + (wq & 1);   // my K block of the stage
+      const uint32_t lofs = (uint32_t)lane << 2;           // my word of a 128-byte row (16-byte chunk lane >> 2)
+      const uint32_t peer = crank ^ 1u;
+      auto conv_tile = [&](const Cur& c) {
+        const uint32_t use = c.mq >> 1;
+        const int head = c.sg.fam;                         // CONV schedules heads
+        const int ticket = 2 * (c.sg.j0 + c.m * c.sg.stride) + (int)hf;
+        const bool valid = ticket < ntiles;                // uniform over the warpgroup
+        const int chp = head * (KB * 64) + ckb * 64 + lane * 2;   // my two channels
+        uint32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0, kb_ = 0;  // w[k] multiplies x[t - (3 - k)] (layers.py:530)
+        uint32_t h1 = 0u, h2 = 0u, h3 = 0u;                // x[t0-1], x[t0-2], x[t0-3] of my segment
+        unsigned long long nzw = ~0ull;                    // bit r: segment_pos[t0 + r - 2] != 0
+        int tt = 0, b = 0;
+        if (valid) {
+          tt = ticket / p.B; b = ticket - tt * p.B;
+          const int t0 = tt * kTile;
+          k0 = ldg32_nc(p.conv_w + chp);
+          k1 = ldg32_nc(p.conv_w + (size_t)p.E + chp);
+          k2 = ldg32_nc(p.conv_w + 2 * (size_t)p.E + chp);
+          k3 = ldg32_nc(p.conv_w + 3 * (size_t)p.E + chp);
+          kb_ = ldg32_nc(p.conv_b + chp);
+          if (cseg == 0) {                                 // x[t < 0] = 0 (layers.py:484-492)
+            const uint16_t* xb = p.x_lin + ((size_t)b * p.T) * p.E + chp;
+            if (t0 >= 1) h1 = ldg32_nc(xb + (size_t)(t0 - 1) * p.E);
+            if (t0 >= 2) h2 = ldg32_nc(xb + (size_t)(t0 - 2) * p.E);
+            if (t0 >= 3) h3 = ldg32_nc(xb + (size_t)(t0 - 3) * p.E);
+          }
+          const unsigned* rw = p.reset_bits + (long long)b * p.bits_bstride + tt;
+          const unsigned cur = rw[0];
+          const unsigned prev = tt > 0 ? rw[-1] : 0u;      // positions before 0 gate taps that are zero anyway
+          nzw = ((unsigned long long)(~cur) << 2) | (unsigned long long)((~prev) >> 30);
+        }
+        if (twarp) CGF_EVENT(trole, 9);
+        mbar_wait(raw_full + pr, use & 1, p.err, 9);
+        if (twarp) CGF_EVENT(trole, 10);
+        const uint32_t half0 = sX + pr * Cfg::kXStageBytes + (uint32_t)ckb * Cfg::kXKBlock + (hf * kTile) * 128u;
+        const uint32_t row0 = half0 + (uint32_t)(cseg * 16) * 128u;     // (row & 7) == (j & 7) below
+        uint32_t xr[16];
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xr[j] = lds32(row0 + j * 128 + (lofs ^ ((uint32_t)(j & 7) << 4)));
+          if (cseg == 1) {
+            h1 = lds32(half0 + 15 * 128 + (lofs ^ (7u << 4)));
+            h2 = lds32(half0 + 14 * 128 + (lofs ^ (6u << 4)));
+            h3 = lds32(half0 + 13 * 128 + (lofs ^ (5u << 4)));
+          }
+        }
+        named_bar_sync(1 + wg, 128);                       // every read of the raw rows precedes every write
+        if (valid) {
+          const bool upstream = p.mask_mode != 0;
+          // no document start near the tile: every tap is live (the common case)
+          const bool plain = upstream ? (nzw & 0x3ffffffffull) == 0x3ffffffffull
+                                      : (nzw & 0xffffffffull) == 0xffffffffull;
+          if (plain) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t a1 = j >= 1 ? xr[j - 1] : h1;
+              const uint32_t a2 = j >= 2 ? xr[j - 2] : (j == 1 ? h1 : h2);
+              const uint32_t a3 = j >= 3 ? xr[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
+              uint32_t acc = bf2_mul(xr[j], k3);                   // shift 0
+              acc = bf2_add(acc, bf2_mul(a1, k2));                 // shift 1
+              acc = bf2_add(acc, bf2_mul(a2, k1));                 // shift 2
+              acc = bf2_add(acc, bf2_mul(a3, k0));                 // shift 3
+              sts32(row0 + j * 128 + (lofs ^ ((uint32_t)(j & 7) << 4)), bf2_add(acc, kb_));   // + b, :536
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t a1 = j >= 1 ? xr[j - 1] : h1;
+              const uint32_t a2 = j >= 2 ? xr[j - 2] : (j == 1 ? h1 : h2);
+              const uint32_t a3 = j >= 3 ? xr[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
+              const unsigned w3 = (unsigned)(nzw >> (cseg * 16 + j)) & 7u;   // bit 0: seg[t-2], 1: seg[t-1], 2: seg[t]  (!= 0)
+              bool m1 = true, m2 = true, m3;
+              if (!upstream) {
+                m3 = (w3 & 1u) != 0;                       // fork: only seg[t-2], layers.py:629-632
+              } else {
+                m1 = (w3 & 4u) != 0;                       // upstream: seg[t-s+1 .. t] all != 0
+                m2 = (w3 & 6u) == 6u;
+                m3 = (w3 & 7u) == 7u;
+              }
+              uint32_t acc = bf2_mul(xr[j], k3);
+              acc = bf2_add(acc, bf2_mul(m1 ? a1 : 0u, k2));
+              acc = bf2_add(acc, bf2_mul(m2 ? a2 : 0u, k1));
+              acc = bf2_add(acc, bf2_mul(m3 ? a3 : 0u, k0));
+              sts32(row0 + j * 128 + (lofs ^ ((uint32_t)(j & 7) << 4)), bf2_add(acc, kb_));
+            }
+          }
+          // the convolution's returned cache: the last three INPUT rows of the sequence, left zero
+          // padded (layers.py:542-543, :650-662)
+          if (p.conv_cache != nullptr && tt == p.ntt - 1 && cseg == 0) {
+            const uint16_t* xb = p.x_lin + ((size_t)b * p.T) * p.E + chp;
+            uint16_t* cb = p.conv_cache + ((size_t)b * 3) * p.E + chp;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const int ti = p.T - 3 + r;
+              *reinterpret_cast<uint32_t*>(cb + (size_t)r * p.E) = ti >= 0 ? ldg32_nc(xb + (size_t)ti * p.E) : 0u;
+            }
+          }
+        }
+        // my stores (generic proxy) before the MMA's operand reads and the bulk copy's source reads (async proxy)
+        fence_proxy_async_smem();
+        named_bar_sync(1 + wg, 128);
+        if (wq == 0 && lane == 0) {
+          if (CL > 1 && valid) {
+            // my two K blocks of this half: 32 rows x 128 B = 4 KB each, contiguous
+            const uint32_t src = sX + pr * Cfg::kXStageBytes + (crank * KBL) * Cfg::kXKBlock + (hf * kTile) * 128u;
+            const uint32_t bar_peer = mapa_u32(smem_u32(x_full + pr), peer);
+#pragma unroll
+            for (int kbl = 0; kbl < KBL; ++kbl)
+              bulk_copy_to_peer(mapa_u32(src + kbl * Cfg::kXKBlock, peer), src + kbl * Cfg::kXKBlock, kTile * 128u, bar_peer);
+            // my arrival, and the bytes the peer's warpgroup (pr, hf) sends into MY stage
+            mbar_expect_tx(x_full + pr, KBL * kTile * 128u);
+          } else {
+            mbar_arrive(x_full + pr);
+          }
+        }
+        if (twarp) CGF_EVENT(trole, 11);
+      };
+
+      Cur cur{0, -1, 0xffffffffu, Seg{0, 0, 1, 0}, nsegs > 0};
+      if (nsegs > 0) { cur.sg = sched.get(0); step(cur); }
+      if (cur.ok) conv_tile(cur);                          // the first tile of my pair
+      while (cur.ok) {
+        const uint32_t use = cur.mq >> 1;
+        const int fam = seg_family(cur.sg);
+        const int ticket = 2 * (cur.sg.j0 + cur.m * cur.sg.stride) + (int)hf;
+        load_family(fam);
         if (twarp) CGF_EVENT(trole, 8);
         const unsigned long long early = request_pred();
         if (twarp) CGF_EVENT(trole, 1);
         mbar_wait(t_full + pr, use & 1, p.err, 6);
         if (twarp) CGF_EVENT(trole, 2);
         tc_fence_after();
-        if (ticket >= ntiles) {                            // odd tile count: nothing in my half
-          release_slot();
-          if (pd.on) finish(early);
-          continue;
-        }
-        const int tt = ticket / p.B, b = ticket - tt * p.B;
-        const int t0 = tt * kTile;
-        const unsigned rbits = p.reset_bits[(long long)b * p.bits_bstride + tt];   // kTile == 32: one word
-        const int nvalid = p.T - t0;                       // >= 1; >= kTile for a full tile
-        const bool fast_tile = CGF_PRELOAD && rbits == 0u && nvalid >= kTile;
-        // F(k-1): before the new tile
-        if (pd.on) finish(early);
-        float P = 1.0f, Hh = 0.0f;
-        // gates for one bf16x2 pair of steps (t, t+1) -> (a, x~); the tile's
-        // transform h -> P*h + H is accumulated on the way
-        auto gate_step = [&](uint32_t xc, uint32_t gxr, uint32_t gar, int tl, auto slow_tag,
-                             uint32_t& a2, uint32_t& n2) {
-          constexpr bool SLOW = decltype(slow_tag)::value;
-          gate_pair_emul<FAST, false>(xc, gxr, gar, bx2, ba2, sp2, a2, n2);
-          if constexpr (SLOW) {                            // tl = step of the low half inside the tile
-            const unsigned r2 = (rbits >> tl) & 3u;
-            if (r2 != 0u) {                                // document start inside the pair
-              uint32_t az, nr;
-              gate_pair_emul<FAST, true>(xc, gxr, gar, bx2, ba2, sp2, az, nr);
-              if (r2 & 1u) { a2 &= 0xffff0000u; n2 = (n2 & 0xffff0000u) | (nr & 0x0000ffffu); }
-              if (r2 & 2u) { a2 &= 0x0000ffffu; n2 = (n2 & 0x0000ffffu) | (nr & 0xffff0000u); }
-            }
-            if (tl + 1 >= nvalid) {                        // steps beyond T are identities
-              if (tl >= nvalid) { a2 = kOne2; n2 = 0u; }
-              else { a2 = (a2 & 0x0000ffffu) | 0x3f800000u; n2 &= 0x0000ffffu; }
-            }
-          }
-          if constexpr (DBG && !CGF_TRACE) {
-            const int tg = t0 + tl;
-            const size_t plane = (size_t)p.B * p.T * p.E;
-            const size_t o0 = ((size_t)b * p.T + tg) * p.E + ch;
-            if (tg < p.T) {
-              p.dbg[o0] = (uint16_t)(gxr & 0xffffu); p.dbg[plane + o0] = (uint16_t)(gar & 0xffffu);
-              p.dbg[2 * plane + o0] = (uint16_t)(xc & 0xffffu);
-            }
-            if (tg + 1 < p.T) {
-              p.dbg[o0 + p.E] = (uint16_t)(gxr >> 16); p.dbg[plane + o0 + p.E] = (uint16_t)(gar >> 16);
-              p.dbg[2 * plane + o0 + p.E] = (uint16_t)(xc >> 16);
-            }
-          }
-          const float al = bf_lo(a2), ah = bf_hi(a2);
-          Hh = add_bf_lo(n2, al * Hh);                     // mul then add, as the reference loop (:196)
-          Hh = add_bf_hi(n2, ah * Hh);
-          P *= al; P *= ah;
-        };
-        if (fast_tile) {
-          // ---- common case, half a tile (8 pairs) at a time: pull the
-          // accumulators out of TMEM, rounded to bf16 on the way (the GEMM output
-          // the reference materialises, :136-142), then the gate math from
-          // registers.  The slot goes back to the MMA warp as soon as the second
-          // half has been read.
-#pragma unroll 1
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t gx[8], ga[8], xv[8];
-            {
-              uint32_t dx[16], da[16], dt[16];
-              const uint32_t col = tm_acc + hh * 16;
-              tmem_ld8(col, *reinterpret_cast<uint32_t(*)[8]>(&dx[0]));
-              tmem_ld8(col + 8, *reinterpret_cast<uint32_t(*)[8]>(&dx[8]));
-              tmem_ld8(col + kMmaN, *reinterpret_cast<uint32_t(*)[8]>(&da[0]));
-              tmem_ld8(col + kMmaN + 8, *reinterpret_cast<uint32_t(*)[8]>(&da[8]));
-              tmem_ld8(col + 2 * kMmaN, *reinterpret_cast<uint32_t(*)[8]>(&dt[0]));
-              tmem_ld8(col + 2 * kMmaN + 8, *reinterpret_cast<uint32_t(*)[8]>(&dt[8]));
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                gx[i] = pack_bf2(__uint_as_float(dx[2 * i]), __uint_as_float(dx[2 * i + 1]));
-                ga[i] = pack_bf2(__uint_as_float(da[2 * i]), __uint_as_float(da[2 * i + 1]));
-                xv[i] = pack_bf2(__uint_as_float(dt[2 * i]), __uint_as_float(dt[2 * i + 1]));
-              }
-            }
-            if (hh == 1) {
-              release_slot();
-              if (twarp) CGF_EVENT(trole, 3);
-            }
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              uint32_t st[8];
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                gate_step(xv[c * 4 + i], gx[c * 4 + i], ga[c * 4 + i], hh * 16 + c * 8 + 2 * i, FalseTag{}, st[i], st[4 + i]);
-              tmem_st8(tm_state + hh * 16 + c * 8, st);
-            }
-          }
+        const bool mine = ticket < ntiles;                 // odd tile count: nothing in my half of the last pair
+        int tt = 0, b = 0;
+        unsigned rbits = 0u;
+        if (mine) {
+          tt = ticket / p.B; b = ticket - tt * p.B;
+          rbits = p.reset_bits[(long long)b * p.bits_bstride + tt];
         } else {
-          // document starts or a ragged tail inside the tile (rare, warp-uniform):
-          // gates chunk by chunk out of TMEM
-#pragma unroll 1
-          for (int c = 0; c < kTile / 8; ++c) {
-            uint32_t dx[8], da[8], dt[8], st[8];
-            tmem_ld8(tm_acc + c * 8, dx);
-            tmem_ld8(tm_acc + kMmaN + c * 8, da);
-            tmem_ld8(tm_acc + 2 * kMmaN + c * 8, dt);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint32_t gxr = pack_bf2(__uint_as_float(dx[2 * i]), __uint_as_float(dx[2 * i + 1]));
-              const uint32_t gar = pack_bf2(__uint_as_float(da[2 * i]), __uint_as_float(da[2 * i + 1]));
-              const uint32_t xc = pack_bf2(__uint_as_float(dt[2 * i]), __uint_as_float(dt[2 * i + 1]));
-              gate_step(xc, gxr, gar, c * 8 + 2 * i, TrueTag{}, st[i], st[4 + i]);
-            }
-            tmem_st8(tm_state + c * 8, st);
-          }
           release_slot();
         }
-        tmem_wait_st();
-        if (twarp) CGF_EVENT(trole, 4);
-        // publish the tile's aggregate (tile 0 publishes its state right away in
-        // F instead) and queue the tile for F
-        pd.on = true; pd.tt = tt; pd.b = b; pd.nvalid = nvalid; pd.ch = ch; pd.P = P; pd.H = Hh;
-        pd.widx = (((size_t)fam * p.ntt + tt) * p.B + b) * kMch + chl;
-        pd.yp = p.y + ((size_t)b * p.T + t0) * p.E + ch;
-        if (tt > 0 && tt + 1 < p.ntt) {
-          st_relaxed_u64(p.agg_p + pd.widx, pack_tagged(P, epoch));
-          st_relaxed_u64(p.agg_h + pd.widx, pack_tagged(Hh, epoch));
-        }
-        if (twarp) CGF_EVENT(trole, 7);
+        if (pd.on) finish(early);                          // F(k-1)
+        Cur nxt = cur;
+        step(nxt);
+        if (nxt.ok) conv_tile(nxt);                        // the raw rows of my pair's next tile have landed under F
+        if (mine) tile_body(fam, tt, b, rbits);            // G(k)
+        cur = nxt;
       }
     }
-    if (pd.on) finish(request_pred());
+    if (pd.on) finish(request_pred());                     // the last tile of this warpgroup
   }
 
-  // teardown: every role is done with TMEM
+  // teardown: every role is done with TMEM; a CTA of a cluster must not exit while its peer may still
+  // signal its barriers (the multicast commit of the peer's last MMAs)
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();
   if (warp == kEpiWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

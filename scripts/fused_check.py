@@ -140,6 +140,7 @@ def conv_case(B=8, T=2048, iters=40, check=True):
     old = pipeline.set_fused_conv(False)
     res["two_kernels_us"] = _time(run, iters)
     y1, c1, h1 = [t.clone() for t in run()]
+    y.fill_(float("nan")); h.fill_(float("nan")); cs.fill_(float("nan"))   # nothing stale may pass as the second route's output
     pipeline.set_fused_conv(True)
     assert pipeline.can_fuse_conv(conv, lru, x)
     res["one_launch_us"] = _time(run, iters)
