@@ -717,6 +717,7 @@ int fused_forward(const void* x, const void* conv_w, const void* conv_b, void* c
   p.B = B; p.T = T; p.E = E;
   p.ntt = (T + tile_t - 1) / tile_t;
   p.families = E / cg::fused::kMch;
+  cg::fused::make_bdiv((uint32_t)B, p.bdiv_m, p.bdiv_s1, p.bdiv_s2);
   const bool fast = (mode & CG_ARITH_FAST) != 0;
   const bool dbg = debug_out != nullptr;
   const bool mul = gate_mul != nullptr;

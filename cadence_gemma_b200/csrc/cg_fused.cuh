@@ -149,7 +149,17 @@ struct FusedParams {
   int B, T, E;
   int ntt;                         // time tiles per batch row
   int families;                    // E / 128
+  // ticket / B without the ~25-instruction emulated division (Granlund-Montgomery, exact for every
+  // 32-bit ticket): q = (t + ((n - t) >> s1)) >> s2 with t = umulhi(m, n)   (make_bdiv on the host)
+  uint32_t bdiv_m, bdiv_s1, bdiv_s2;
 };
+__host__ __device__ __forceinline__ void make_bdiv(uint32_t d, uint32_t& m, uint32_t& s1, uint32_t& s2) {
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;                               // ceil(log2 d)
+  m = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  s1 = l < 1 ? l : 1;
+  s2 = l < 1 ? 0 : l - 1;
+}
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -406,7 +416,8 @@ struct FusedCfg {
   static constexpr uint32_t kXStageBytes = static_cast<uint32_t>(KB) * kXKBlock;
   static constexpr int kXStages = 2;                               // one per warpgroup pair
   static constexpr int kBars = 2 + 3 * kXStages + 4;
-  static constexpr size_t kSmemBytes = 1024 + kWBytes + kIBytes + kXStages * kXStageBytes + kBars * 8 + 16;
+  static constexpr uint32_t kTapBytes = 5u * 128u * 2u;             // CONV: w[0..3], b of this CTA's 128 input channels
+  static constexpr size_t kSmemBytes = 1024 + kWBytes + kIBytes + kXStages * kXStageBytes + kBars * 8 + 16 + kTapBytes;
   static_assert(KB % 2 == 0, "head width must be a multiple of 128");
 };
 
@@ -550,6 +561,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   uint64_t* t_full = x_empty + XS;          // [2] accumulators of pair p are complete
   uint64_t* t_empty = t_full + 2;           // [2] both warpgroups of pair p have read them
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(t_empty + 2);
+  const uint32_t sTap = smem_u32(tmem_holder) + 16u;   // [5][128] bf16: conv taps w[0..3], bias (CONV, one family per CTA)
   uint64_t* mma_ready = CONV ? x_full : raw_full;   // what the MMA warp waits for
 
   const int warp = threadIdx.x >> 5;
@@ -558,9 +570,9 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
     mbar_init(w_empty, 1);
-    // x_full: one arrival per warpgroup of the pair (+ the peer's bytes, CL == 2); x_empty: the MMAs of
+    // x_full: one arrival per warp of the pair's two warpgroups (+ the peer's bytes, CL == 2); x_empty: the MMAs of
     // EVERY CTA of the cluster have read the stage (the peer writes into my stage too)
-    for (int i = 0; i < XS; ++i) { mbar_init(raw_full + i, 1); mbar_init(x_full + i, 2); mbar_init(x_empty + i, CL); }
+    for (int i = 0; i < XS; ++i) { mbar_init(raw_full + i, 1); mbar_init(x_full + i, 8); mbar_init(x_empty + i, CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }
     fence_mbar_init();
   }
@@ -588,6 +600,10 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
                        CONV ? nfam / CBS : nfam, npairs);
   const int nsegs = sched.nseg();
   auto seg_family = [&](const Seg& sg) -> int { return CONV ? sg.fam * CBS + (int)crank : sg.fam; };
+  auto div_b = [&](int n) -> int {                           // n / p.B for 0 <= n
+    const uint32_t t = __umulhi(p.bdiv_m, (uint32_t)n);
+    return (int)((t + (((uint32_t)n - t) >> p.bdiv_s1)) >> p.bdiv_s2);
+  };
 
   if (warp == kEpiWarps) {
     // ===================================================== TMA producer
@@ -631,7 +647,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           if (elect_one()) mbar_expect_tx(raw_full + stage, nhalf * (Cfg::kXStageBytes / 2 / CL));
           for (int hf = 0; hf < nhalf; ++hf) {
             const int ticket = t1st + hf;
-            const int tt = ticket / p.B, b = ticket - tt * p.B;
+            const int tt = div_b(ticket), b = ticket - tt * p.B;
             if (elect_one()) {
 #pragma unroll
               for (int kbl = 0; kbl < KBL; ++kbl) {
@@ -1071,7 +1087,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
             if (pd.on) finish(early);
             continue;
           }
-          const int tt = ticket / p.B, b = ticket - tt * p.B;
+          const int tt = div_b(ticket), b = ticket - tt * p.B;
           const unsigned rbits = p.reset_bits[(long long)b * p.bits_bstride + tt];   // kTile == 32: one word
           // F(k-1): before the new tile
           if (pd.on) finish(early);
@@ -1110,6 +1126,21 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       const int ckb = (CL > 1 ? (int)crank * KBL : 0) + (wq & 1);   // my K block of the stage
       const uint32_t lofs = (uint32_t)lane << 2;           // my word of a 128-byte row (16-byte chunk lane >> 2)
       const uint32_t peer = crank ^ 1u;
+      // One family per CTA for the whole kernel (every production grid): the taps of this CTA's 128 input
+      // channels sit in shared memory, written once by warpgroup 0.  Several families per CTA (grids
+      // smaller than the head count): taps come from global memory per tile.
+      const bool taps_in_smem = sched.mode == 1;
+      if (taps_in_smem) {
+        if (wg == 0) {
+          const int cht = sched.get(0).fam * (KB * 64) + (CL > 1 ? (int)crank * 128 : 0) + (int)threadIdx.x;   // threads 0..127
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            asm volatile("st.shared.u16 [%0], %1;" :: "r"(sTap + k * 256 + threadIdx.x * 2), "h"(p.conv_w[(size_t)k * p.E + cht]));
+          asm volatile("st.shared.u16 [%0], %1;" :: "r"(sTap + 1024 + threadIdx.x * 2), "h"(p.conv_b[cht]));
+        }
+        named_bar_sync(1, kEpiWarps * 32);
+      }
+      unsigned rbits_next = 0u;                            // reset word of the tile convolved last (= the next G)
       auto conv_tile = [&](const Cur& c) {
         const uint32_t use = c.mq >> 1;
         const int head = c.sg.fam;                         // CONV schedules heads
@@ -1121,41 +1152,46 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         unsigned long long nzw = ~0ull;                    // bit r: segment_pos[t0 + r - 2] != 0
         int tt = 0, b = 0;
         if (valid) {
-          tt = ticket / p.B; b = ticket - tt * p.B;
-          const int t0 = tt * kTile;
-          k0 = ldg32_nc(p.conv_w + chp);
-          k1 = ldg32_nc(p.conv_w + (size_t)p.E + chp);
-          k2 = ldg32_nc(p.conv_w + 2 * (size_t)p.E + chp);
-          k3 = ldg32_nc(p.conv_w + 3 * (size_t)p.E + chp);
-          kb_ = ldg32_nc(p.conv_b + chp);
-          if (cseg == 0) {                                 // x[t < 0] = 0 (layers.py:484-492)
-            const uint16_t* xb = p.x_lin + ((size_t)b * p.T) * p.E + chp;
-            if (t0 >= 1) h1 = ldg32_nc(xb + (size_t)(t0 - 1) * p.E);
-            if (t0 >= 2) h2 = ldg32_nc(xb + (size_t)(t0 - 2) * p.E);
-            if (t0 >= 3) h3 = ldg32_nc(xb + (size_t)(t0 - 3) * p.E);
+          tt = div_b(ticket); b = ticket - tt * p.B;
+          const int ts = tt * kTile + cseg * 16;           // first step of my segment
+          if (!taps_in_smem) {                             // several families per CTA (small grids): per tile
+            k0 = ldg32_nc(p.conv_w + chp);
+            k1 = ldg32_nc(p.conv_w + (size_t)p.E + chp);
+            k2 = ldg32_nc(p.conv_w + 2 * (size_t)p.E + chp);
+            k3 = ldg32_nc(p.conv_w + 3 * (size_t)p.E + chp);
+            kb_ = ldg32_nc(p.conv_b + chp);
+          }
+          // the three rows before my segment, straight from global memory (L2: the TMA has just read
+          // them); x[t < 0] = 0 (layers.py:484-492)
+          const uint16_t* xb = p.x_lin + ((size_t)b * p.T + (size_t)ts) * p.E + chp;
+          if (ts >= 3 && ts <= p.T) {                      // interior (the common case)
+            const uint16_t* x3 = xb - 3 * (size_t)p.E;
+            h3 = ldg32_nc(x3); h2 = ldg32_nc(x3 + p.E); h1 = ldg32_nc(x3 + 2 * (size_t)p.E);
+          } else {
+            if (ts >= 1 && ts - 1 < p.T) h1 = ldg32_nc(xb - (size_t)p.E);
+            if (ts >= 2 && ts - 2 < p.T) h2 = ldg32_nc(xb - 2 * (size_t)p.E);
+            if (ts >= 3 && ts - 3 < p.T) h3 = ldg32_nc(xb - 3 * (size_t)p.E);
           }
           const unsigned* rw = p.reset_bits + (long long)b * p.bits_bstride + tt;
           const unsigned cur = rw[0];
           const unsigned prev = tt > 0 ? rw[-1] : 0u;      // positions before 0 gate taps that are zero anyway
           nzw = ((unsigned long long)(~cur) << 2) | (unsigned long long)((~prev) >> 30);
+          rbits_next = cur;
         }
         if (twarp) CGF_EVENT(trole, 9);
         mbar_wait(raw_full + pr, use & 1, p.err, 9);
         if (twarp) CGF_EVENT(trole, 10);
         const uint32_t half0 = sX + pr * Cfg::kXStageBytes + (uint32_t)ckb * Cfg::kXKBlock + (hf * kTile) * 128u;
         const uint32_t row0 = half0 + (uint32_t)(cseg * 16) * 128u;     // (row & 7) == (j & 7) below
-        uint32_t xr[16];
         if (valid) {
+          // a thread reads and writes only its own 16 words of the stage: no hazard, no barrier
+          uint32_t xr[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) xr[j] = lds32(row0 + j * 128 + (lofs ^ ((uint32_t)(j & 7) << 4)));
-          if (cseg == 1) {
-            h1 = lds32(half0 + 15 * 128 + (lofs ^ (7u << 4)));
-            h2 = lds32(half0 + 14 * 128 + (lofs ^ (6u << 4)));
-            h3 = lds32(half0 + 13 * 128 + (lofs ^ (5u << 4)));
+          if (taps_in_smem) {
+            const uint32_t ta = sTap + (uint32_t)((wq & 1) * 32 + lane) * 4u;
+            k0 = lds32(ta); k1 = lds32(ta + 256); k2 = lds32(ta + 512); k3 = lds32(ta + 768); kb_ = lds32(ta + 1024);
           }
-        }
-        named_bar_sync(1 + wg, 128);                       // every read of the raw rows precedes every write
-        if (valid) {
           const bool upstream = p.mask_mode != 0;
           // no document start near the tile: every tap is live (the common case)
           const bool plain = upstream ? (nzw & 0x3ffffffffull) == 0x3ffffffffull
@@ -1206,19 +1242,15 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
             }
           }
         }
-        // my stores (generic proxy) before the MMA's operand reads and the bulk copy's source reads (async proxy)
+        // my warp's stores (generic proxy) before the MMA's operand reads and the bulk copy's source reads
+        // (async proxy).  Every warp hands over ITS 16 rows x 128 B on its own: no warpgroup barrier.
         fence_proxy_async_smem();
-        named_bar_sync(1 + wg, 128);
-        if (wq == 0 && lane == 0) {
+        __syncwarp();
+        if (lane == 0) {
           if (CL > 1 && valid) {
-            // my two K blocks of this half: 32 rows x 128 B = 4 KB each, contiguous
-            const uint32_t src = sX + pr * Cfg::kXStageBytes + (crank * KBL) * Cfg::kXKBlock + (hf * kTile) * 128u;
-            const uint32_t bar_peer = mapa_u32(smem_u32(x_full + pr), peer);
-#pragma unroll
-            for (int kbl = 0; kbl < KBL; ++kbl)
-              bulk_copy_to_peer(mapa_u32(src + kbl * Cfg::kXKBlock, peer), src + kbl * Cfg::kXKBlock, kTile * 128u, bar_peer);
-            // my arrival, and the bytes the peer's warpgroup (pr, hf) sends into MY stage
-            mbar_expect_tx(x_full + pr, KBL * kTile * 128u);
+            bulk_copy_to_peer(mapa_u32(row0, peer), row0, 16u * 128u, mapa_u32(smem_u32(x_full + pr), peer));
+            // my arrival, and the bytes the peer's same warp sends into MY stage
+            mbar_expect_tx(x_full + pr, 16u * 128u);
           } else {
             mbar_arrive(x_full + pr);
           }
@@ -1244,8 +1276,8 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         int tt = 0, b = 0;
         unsigned rbits = 0u;
         if (mine) {
-          tt = ticket / p.B; b = ticket - tt * p.B;
-          rbits = p.reset_bits[(long long)b * p.bits_bstride + tt];
+          tt = div_b(ticket); b = ticket - tt * p.B;
+          rbits = rbits_next;                              // loaded by conv_tile for this very tile
         } else {
           release_slot();
         }

@@ -14,9 +14,17 @@ B, T, E, H = 8, 2048, 2560, 10
 x, lru, seg, _ = make(B, T, E, H, resets=False)
 wpack = _abi.pack_gate_weights(lru.input_gate.w, lru.a_gate.w)
 ws = _abi.fused_workspace(x.device, B, T, E)
+conv = "--conv" in sys.argv          # the one-launch route (convolution inside the kernel)
+cw = (torch.randn(4, E, device=x.device) * 0.4).to(torch.bfloat16)
+cb = (torch.randn(E, device=x.device) * 0.2).to(torch.bfloat16)
 for _ in range(3):
-  out = _abi.rglru_fused_fwd(x, wpack, lru.input_gate.b, lru.a_gate.b, lru.a_param, seg, H,
-                             arith_mode=2, debug=True, workspace=ws)
+  if conv:
+    out = _abi.recurrent_prefill_fwd(x, cw, cb, wpack, lru.input_gate.b, lru.a_gate.b, lru.a_param, seg, H,
+                                     arith_mode=2, debug=True, workspace=ws)
+    out = (out[0], out[2], out[3])
+  else:
+    out = _abi.rglru_fused_fwd(x, wpack, lru.input_gate.b, lru.a_gate.b, lru.a_param, seg, H,
+                               arith_mode=2, debug=True, workspace=ws)
 torch.cuda.synchronize()
 tr = out[2].view(-1).view(torch.int64)[: 7 * 1024].view(7, 1024).cpu()
 names = ["producer", "mma", "wg0", "wg1", "wg2", "wg3", "conv"]

@@ -1,0 +1,11 @@
+#!/bin/bash
+out=gpurun_out/r3_trace.log; : > $out
+V=$PWD/cadence_gemma_b200/csrc/variants
+echo "== trace, one launch (conv in the epilogue warpgroups)" >> $out
+CG_B200_LIB=$V/lib_trace.so timeout 120 python scripts/fused_trace.py --conv > /dev/null 2>>$out
+python scripts/trace_stats.py >> $out 2>&1
+cp gpurun_out/fused_trace.json gpurun_out/fused_trace_conv.json
+echo "== trace, plain fused kernel" >> $out
+CG_B200_LIB=$V/lib_trace.so timeout 120 python scripts/fused_trace.py > /dev/null 2>>$out
+python scripts/trace_stats.py >> $out 2>&1
+cat $out
