@@ -408,6 +408,24 @@ __host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// Per-tile bookkeeping, computed ONCE per CTA by the (otherwise idle) TMA producer warp and handed to
+// the sixteen epilogue warps through shared memory: scan tile (tt, b) of a ticket, the tile's document
+// starts, its element offset in the [B,T,E] tensors and its exchange-word index.  The epilogue warps
+// used to derive all of this themselves, every warp for every tile: ~200 of a warp's ~1 600 instructions
+// per tile at an IPC of ~0.1 (serial integer chains).  The descriptor of pair p's MMA tile with use
+// count u sits in slot [p][u & 1][half]; it is written before the producer's arrive on raw_full[p]
+// (release) and read after a wait on raw_full[p] / t_full[p] (acquire).
+struct TileDesc {
+  int tt;                 // time tile, -1: this half of the MMA tile is empty (odd tile count)
+  int b;                  // batch row
+  uint32_t rbits;         // document starts inside the tile (bit t % 32)
+  uint32_t rprev;         // ... of the previous tile of the row (0 before the first)
+  uint32_t eoff_lo, eoff_hi;   // element offset of (b, tt * 32, channel 0) in x / y
+  uint32_t widx;          // exchange-word index of (family, tt, b, channel 0 of the family)
+  int nvalid;             // T - tt * 32
+};
+static_assert(sizeof(TileDesc) == 32, "two 16-byte shared-memory accesses");
+
 template <int KB>
 struct FusedCfg {
   static constexpr uint32_t kWBytes = 2u * KB * kKBlockBytes;
@@ -417,7 +435,9 @@ struct FusedCfg {
   static constexpr int kXStages = 2;                               // one per warpgroup pair
   static constexpr int kBars = 2 + 3 * kXStages + 4;
   static constexpr uint32_t kTapBytes = 5u * 128u * 2u;             // CONV: w[0..3], b of this CTA's 128 input channels
-  static constexpr size_t kSmemBytes = 1024 + kWBytes + kIBytes + kXStages * kXStageBytes + kBars * 8 + 16 + kTapBytes;
+  static constexpr uint32_t kDescBytes = 2u * 2u * 2u * 32u;        // tile descriptors [pair][use & 1][half], see TileDesc
+  static constexpr size_t kSmemBytes = 1024 + kWBytes + kIBytes + kXStages * kXStageBytes + kBars * 8 + 16 + kTapBytes +
+                                       kDescBytes;
   static_assert(KB % 2 == 0, "head width must be a multiple of 128");
 };
 
@@ -562,6 +582,10 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   uint64_t* t_empty = t_full + 2;           // [2] both warpgroups of pair p have read them
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(t_empty + 2);
   const uint32_t sTap = smem_u32(tmem_holder) + 16u;   // [5][128] bf16: conv taps w[0..3], bias (CONV, one family per CTA)
+  const uint32_t sDesc = sTap + Cfg::kTapBytes;        // TileDesc [pair][use & 1][half]
+  auto desc_addr = [&](uint32_t pair, uint32_t use, uint32_t half) -> uint32_t {
+    return sDesc + (((pair * 2u + (use & 1u)) * 2u + half) << 5);
+  };
   uint64_t* mma_ready = CONV ? x_full : raw_full;   // what the MMA warp waits for
 
   const int warp = threadIdx.x >> 5;
@@ -641,9 +665,28 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           const int t1st = 2 * (sg.j0 + m * sg.stride);
           const int nhalf = t1st + 1 < ntiles ? 2 : 1;
           const uint32_t stage = mq & 1u, use = mq >> 1;
+          // lanes 0 / 1: the descriptor of half 0 / 1 (reset words requested before the wait below)
+          TileDesc td{-1, 0, 0u, 0u, 0u, 0u, 0u, 0};
+          if (lane < 2 && t1st + lane < ntiles) {
+            const int ticket = t1st + lane;
+            td.tt = div_b(ticket); td.b = ticket - td.tt * p.B;
+            const unsigned* rw = p.reset_bits + (long long)td.b * p.bits_bstride + td.tt;
+            td.rbits = rw[0];
+            td.rprev = td.tt > 0 ? rw[-1] : 0u;
+            const unsigned long long eo = ((unsigned long long)td.b * p.T + (unsigned long long)td.tt * kTile) * p.E;
+            td.eoff_lo = (uint32_t)eo; td.eoff_hi = (uint32_t)(eo >> 32);
+            td.widx = (uint32_t)((((size_t)fam * p.ntt + td.tt) * p.B + td.b) * kMch);
+            td.nvalid = p.T - td.tt * kTile;
+          }
           CGF_EVENT(0, 1);
           mbar_wait<CGF_SLEEP_AUX_NS>(x_empty + stage, (use & 1) ^ 1, p.err, 2);
           CGF_EVENT(0, 2);
+          if (lane < 2) {
+            const uint32_t da = desc_addr(stage, use, (uint32_t)lane);
+            sts128(da, make_uint4((uint32_t)td.tt, (uint32_t)td.b, td.rbits, td.rprev));
+            sts128(da + 16, make_uint4(td.eoff_lo, td.eoff_hi, td.widx, (uint32_t)td.nvalid));
+          }
+          __syncwarp();
           if (elect_one()) mbar_expect_tx(raw_full + stage, nhalf * (Cfg::kXStageBytes / 2 / CL));
           for (int hf = 0; hf < nhalf; ++hf) {
             const int ticket = t1st + hf;
@@ -937,6 +980,11 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       return (pd.on && pd.tt > 0) ? ld_relaxed_u64(p.pref + pd.widx - wstep) : 0ull;
     };
 
+    auto read_desc = [&](uint32_t use) -> TileDesc {         // my half of pair pr's MMA tile number `use`
+      const uint32_t da = desc_addr(pr, use, hf);
+      const uint4 q0 = lds128(da), q1 = lds128(da + 16);
+      return TileDesc{(int)q0.x, (int)q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, (int)q1.w};
+    };
     int cur_fam = -1, ch = 0;
     uint32_t bx2 = 0, ba2 = 0, sp2 = 0;
     auto load_family = [&](int fam) {                      // per-channel constants of a new family
@@ -949,9 +997,11 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       sp2 = p.neg8sp_bf[ch]; sp2 |= sp2 << 16;
     };
     // G(k): gates of one scan tile out of my half of the accumulators, aggregate published, tile queued for F
-    auto tile_body = [&](const int fam, const int tt, const int b, const unsigned rbits) {
-      const int t0 = tt * kTile;
-      const int nvalid = p.T - t0;                         // >= 1; >= kTile for a full tile
+    auto tile_body = [&](const TileDesc& td) {
+      const int tt = td.tt, b = td.b;
+      const unsigned rbits = td.rbits;
+      const int t0 = tt * kTile; (void)t0;
+      const int nvalid = td.nvalid;                        // >= 1; >= kTile for a full tile
       const bool fast_tile = CGF_PRELOAD && rbits == 0u && nvalid >= kTile;
       float P = 1.0f, Hh = 0.0f;
       // gates for one bf16x2 pair of steps (t, t+1) -> (a, x~); the tile's
@@ -1056,8 +1106,8 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       // publish the tile's aggregate (tile 0 publishes its state right away in
       // F instead) and queue the tile for F
       pd.on = true; pd.tt = tt; pd.b = b; pd.nvalid = nvalid; pd.ch = ch; pd.P = P; pd.H = Hh;
-      pd.widx = (((size_t)fam * p.ntt + tt) * p.B + b) * kMch + chl;
-      pd.yp = p.y + ((size_t)b * p.T + t0) * p.E + ch;
+      pd.widx = (size_t)td.widx + chl;
+      pd.yp = p.y + (((size_t)td.eoff_hi << 32) | td.eoff_lo) + ch;
       if (tt > 0 && tt + 1 < p.ntt) {
         st_relaxed_u64(p.agg_p + pd.widx, pack_tagged(P, epoch));
         st_relaxed_u64(p.agg_h + pd.widx, pack_tagged(Hh, epoch));
@@ -1075,23 +1125,21 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         for (int m = 0; m < sg.count; ++m, ++mq) {
           if ((mq & 1u) != pr) continue;
           const uint32_t use = mq >> 1;
-          const int ticket = 2 * (sg.j0 + m * sg.stride) + (int)hf;
           if (twarp) CGF_EVENT(trole, 8);
           const unsigned long long early = request_pred();
           if (twarp) CGF_EVENT(trole, 1);
           mbar_wait(t_full + pr, use & 1, p.err, 6);
           if (twarp) CGF_EVENT(trole, 2);
           tc_fence_after();
-          if (ticket >= ntiles) {                          // odd tile count: nothing in my half
+          const TileDesc td = read_desc(use);              // written by the producer before the TMA loads of this tile
+          if (td.tt < 0) {                                 // odd tile count: nothing in my half
             release_slot();
             if (pd.on) finish(early);
             continue;
           }
-          const int tt = div_b(ticket), b = ticket - tt * p.B;
-          const unsigned rbits = p.reset_bits[(long long)b * p.bits_bstride + tt];   // kTile == 32: one word
           // F(k-1): before the new tile
           if (pd.on) finish(early);
-          tile_body(fam, tt, b, rbits);
+          tile_body(td);
         }
       }
     } else {
@@ -1140,30 +1188,24 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         }
         named_bar_sync(1, kEpiWarps * 32);
       }
-      unsigned rbits_next = 0u;                            // reset word of the tile convolved last (= the next G)
+      const uint32_t row0 = sX + pr * Cfg::kXStageBytes + (uint32_t)ckb * Cfg::kXKBlock +
+                            (uint32_t)(hf * kTile + cseg * 16) * 128u;   // my 16 rows of the stage; (row & 7) == (j & 7)
+      const uint32_t tap_a = sTap + (uint32_t)((wq & 1) * 32 + lane) * 4u;
       auto conv_tile = [&](const Cur& c) {
         const uint32_t use = c.mq >> 1;
-        const int head = c.sg.fam;                         // CONV schedules heads
-        const int ticket = 2 * (c.sg.j0 + c.m * c.sg.stride) + (int)hf;
-        const bool valid = ticket < ntiles;                // uniform over the warpgroup
-        const int chp = head * (KB * 64) + ckb * 64 + lane * 2;   // my two channels
-        uint32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0, kb_ = 0;  // w[k] multiplies x[t - (3 - k)] (layers.py:530)
-        uint32_t h1 = 0u, h2 = 0u, h3 = 0u;                // x[t0-1], x[t0-2], x[t0-3] of my segment
-        unsigned long long nzw = ~0ull;                    // bit r: segment_pos[t0 + r - 2] != 0
-        int tt = 0, b = 0;
+        if (twarp) CGF_EVENT(trole, 9);
+        mbar_wait(raw_full + pr, use & 1, p.err, 9);       // the raw rows AND the tile's descriptor
+        if (twarp) CGF_EVENT(trole, 10);
+        const TileDesc td = read_desc(use);
+        const bool valid = td.tt >= 0;                     // uniform over the warpgroup
         if (valid) {
-          tt = div_b(ticket); b = ticket - tt * p.B;
-          const int ts = tt * kTile + cseg * 16;           // first step of my segment
-          if (!taps_in_smem) {                             // several families per CTA (small grids): per tile
-            k0 = ldg32_nc(p.conv_w + chp);
-            k1 = ldg32_nc(p.conv_w + (size_t)p.E + chp);
-            k2 = ldg32_nc(p.conv_w + 2 * (size_t)p.E + chp);
-            k3 = ldg32_nc(p.conv_w + 3 * (size_t)p.E + chp);
-            kb_ = ldg32_nc(p.conv_b + chp);
-          }
+          const int ts = td.tt * kTile + cseg * 16;        // first step of my segment
+          const int chp = c.sg.fam * (KB * 64) + ckb * 64 + lane * 2;   // my two channels (CONV schedules heads)
           // the three rows before my segment, straight from global memory (L2: the TMA has just read
-          // them); x[t < 0] = 0 (layers.py:484-492)
-          const uint16_t* xb = p.x_lin + ((size_t)b * p.T + (size_t)ts) * p.E + chp;
+          // them); x[t < 0] = 0 (layers.py:484-492).  Rows 3.. of the segment are convolved first, so
+          // this round trip hides behind them.
+          uint32_t h1 = 0u, h2 = 0u, h3 = 0u;              // x[ts-1], x[ts-2], x[ts-3]
+          const uint16_t* xb = p.x_lin + (((size_t)td.eoff_hi << 32) | td.eoff_lo) + (size_t)(cseg * 16) * p.E + chp;
           if (ts >= 3 && ts <= p.T) {                      // interior (the common case)
             const uint16_t* x3 = xb - 3 * (size_t)p.E;
             h3 = ldg32_nc(x3); h2 = ldg32_nc(x3 + p.E); h1 = ldg32_nc(x3 + 2 * (size_t)p.E);
@@ -1172,33 +1214,30 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
             if (ts >= 2 && ts - 2 < p.T) h2 = ldg32_nc(xb - 2 * (size_t)p.E);
             if (ts >= 3 && ts - 3 < p.T) h3 = ldg32_nc(xb - 3 * (size_t)p.E);
           }
-          const unsigned* rw = p.reset_bits + (long long)b * p.bits_bstride + tt;
-          const unsigned cur = rw[0];
-          const unsigned prev = tt > 0 ? rw[-1] : 0u;      // positions before 0 gate taps that are zero anyway
-          nzw = ((unsigned long long)(~cur) << 2) | (unsigned long long)((~prev) >> 30);
-          rbits_next = cur;
-        }
-        if (twarp) CGF_EVENT(trole, 9);
-        mbar_wait(raw_full + pr, use & 1, p.err, 9);
-        if (twarp) CGF_EVENT(trole, 10);
-        const uint32_t half0 = sX + pr * Cfg::kXStageBytes + (uint32_t)ckb * Cfg::kXKBlock + (hf * kTile) * 128u;
-        const uint32_t row0 = half0 + (uint32_t)(cseg * 16) * 128u;     // (row & 7) == (j & 7) below
-        if (valid) {
           // a thread reads and writes only its own 16 words of the stage: no hazard, no barrier
           uint32_t xr[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) xr[j] = lds32(row0 + j * 128 + (lofs ^ ((uint32_t)(j & 7) << 4)));
+          uint32_t k0, k1, k2, k3, kb_;                    // w[k] multiplies x[t - (3 - k)] (layers.py:530)
           if (taps_in_smem) {
-            const uint32_t ta = sTap + (uint32_t)((wq & 1) * 32 + lane) * 4u;
-            k0 = lds32(ta); k1 = lds32(ta + 256); k2 = lds32(ta + 512); k3 = lds32(ta + 768); kb_ = lds32(ta + 1024);
+            k0 = lds32(tap_a); k1 = lds32(tap_a + 256); k2 = lds32(tap_a + 512); k3 = lds32(tap_a + 768); kb_ = lds32(tap_a + 1024);
+          } else {                                         // several families per CTA (small grids): per tile
+            k0 = ldg32_nc(p.conv_w + chp);
+            k1 = ldg32_nc(p.conv_w + (size_t)p.E + chp);
+            k2 = ldg32_nc(p.conv_w + 2 * (size_t)p.E + chp);
+            k3 = ldg32_nc(p.conv_w + 3 * (size_t)p.E + chp);
+            kb_ = ldg32_nc(p.conv_b + chp);
           }
+          // bit r of nzw: segment_pos[t0 + r - 2] != 0
+          const unsigned long long nzw = ((unsigned long long)(~td.rbits) << 2) | (unsigned long long)((~td.rprev) >> 30);
           const bool upstream = p.mask_mode != 0;
           // no document start near the tile: every tap is live (the common case)
           const bool plain = upstream ? (nzw & 0x3ffffffffull) == 0x3ffffffffull
                                       : (nzw & 0xffffffffull) == 0xffffffffull;
           if (plain) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int jj = 0; jj < 16; ++jj) {
+              const int j = jj < 13 ? jj + 3 : jj - 13;    // rows 3..15, then the rows that need the halo
               const uint32_t a1 = j >= 1 ? xr[j - 1] : h1;
               const uint32_t a2 = j >= 2 ? xr[j - 2] : (j == 1 ? h1 : h2);
               const uint32_t a3 = j >= 3 ? xr[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
@@ -1210,7 +1249,8 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int jj = 0; jj < 16; ++jj) {
+              const int j = jj < 13 ? jj + 3 : jj - 13;
               const uint32_t a1 = j >= 1 ? xr[j - 1] : h1;
               const uint32_t a2 = j >= 2 ? xr[j - 2] : (j == 1 ? h1 : h2);
               const uint32_t a3 = j >= 3 ? xr[j - 3] : (j == 2 ? h1 : (j == 1 ? h2 : h3));
@@ -1232,13 +1272,13 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           }
           // the convolution's returned cache: the last three INPUT rows of the sequence, left zero
           // padded (layers.py:542-543, :650-662)
-          if (p.conv_cache != nullptr && tt == p.ntt - 1 && cseg == 0) {
-            const uint16_t* xb = p.x_lin + ((size_t)b * p.T) * p.E + chp;
-            uint16_t* cb = p.conv_cache + ((size_t)b * 3) * p.E + chp;
+          if (p.conv_cache != nullptr && td.tt == p.ntt - 1 && cseg == 0) {
+            const uint16_t* xq = p.x_lin + ((size_t)td.b * p.T) * p.E + chp;
+            uint16_t* cb = p.conv_cache + ((size_t)td.b * 3) * p.E + chp;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
               const int ti = p.T - 3 + r;
-              *reinterpret_cast<uint32_t*>(cb + (size_t)r * p.E) = ti >= 0 ? ldg32_nc(xb + (size_t)ti * p.E) : 0u;
+              *reinterpret_cast<uint32_t*>(cb + (size_t)r * p.E) = ti >= 0 ? ldg32_nc(xq + (size_t)ti * p.E) : 0u;
             }
           }
         }
@@ -1263,30 +1303,19 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       if (cur.ok) conv_tile(cur);                          // the first tile of my pair
       while (cur.ok) {
         const uint32_t use = cur.mq >> 1;
-        const int fam = seg_family(cur.sg);
-        const int ticket = 2 * (cur.sg.j0 + cur.m * cur.sg.stride) + (int)hf;
-        load_family(fam);
+        load_family(seg_family(cur.sg));
         if (twarp) CGF_EVENT(trole, 8);
         const unsigned long long early = request_pred();
         if (twarp) CGF_EVENT(trole, 1);
         mbar_wait(t_full + pr, use & 1, p.err, 6);
         if (twarp) CGF_EVENT(trole, 2);
         tc_fence_after();
-        const bool mine = ticket < ntiles;                 // odd tile count: nothing in my half of the last pair
-        int tt = 0, b = 0;
-        unsigned rbits = 0u;
-        if (mine) {
-          tt = div_b(ticket); b = ticket - tt * p.B;
-          rbits = rbits_next;                              // loaded by conv_tile for this very tile
-        } else {
-          release_slot();
-        }
+        const bool mine = (int)lds32(desc_addr(pr, use, hf)) >= 0;   // odd tile count: nothing in my half of the last pair
+        if (!mine) release_slot();
         if (pd.on) finish(early);                          // F(k-1)
-        Cur nxt = cur;
-        step(nxt);
-        if (nxt.ok) conv_tile(nxt);                        // the raw rows of my pair's next tile have landed under F
-        if (mine) tile_body(fam, tt, b, rbits);            // G(k)
-        cur = nxt;
+        step(cur);
+        if (cur.ok) conv_tile(cur);                        // the raw rows of my pair's next tile have landed under F
+        if (mine) tile_body(read_desc(use));               // G(k)  (the slot is rewritten two uses later)
       }
     }
     if (pd.on) finish(request_pred());                     // the last tile of this warpgroup
