@@ -413,8 +413,10 @@ __host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
 // starts, its element offset in the [B,T,E] tensors and its exchange-word index.  The epilogue warps
 // used to derive all of this themselves, every warp for every tile: ~200 of a warp's ~1 600 instructions
 // per tile at an IPC of ~0.1 (serial integer chains).  The descriptor of pair p's MMA tile with use
-// count u sits in slot [p][u & 1][half]; it is written before the producer's arrive on raw_full[p]
-// (release) and read after a wait on raw_full[p] / t_full[p] (acquire).
+// count u sits in slot [p][u & 3][half].  It is written ONE TILE AHEAD: before the producer's arrive
+// (release) on raw_full[p] for use u - 1 (u = 0: for use 0), so a warpgroup that has waited on
+// raw_full[p] for use u - 1 (acquire) may read it -- early enough to request the halo rows of the next
+// convolution a whole tile before they are needed.  A slot is rewritten four uses later.
 struct TileDesc {
   int tt;                 // time tile, -1: this half of the MMA tile is empty (odd tile count)
   int b;                  // batch row
@@ -435,7 +437,7 @@ struct FusedCfg {
   static constexpr int kXStages = 2;                               // one per warpgroup pair
   static constexpr int kBars = 2 + 3 * kXStages + 4;
   static constexpr uint32_t kTapBytes = 5u * 128u * 2u;             // CONV: w[0..3], b of this CTA's 128 input channels
-  static constexpr uint32_t kDescBytes = 2u * 2u * 2u * 32u;        // tile descriptors [pair][use & 1][half], see TileDesc
+  static constexpr uint32_t kDescBytes = 2u * 4u * 2u * 32u;        // tile descriptors [pair][use & 3][half], see TileDesc
   static constexpr size_t kSmemBytes = 1024 + kWBytes + kIBytes + kXStages * kXStageBytes + kBars * 8 + 16 + kTapBytes +
                                        kDescBytes;
   static_assert(KB % 2 == 0, "head width must be a multiple of 128");
@@ -584,7 +586,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   const uint32_t sTap = smem_u32(tmem_holder) + 16u;   // [5][128] bf16: conv taps w[0..3], bias (CONV, one family per CTA)
   const uint32_t sDesc = sTap + Cfg::kTapBytes;        // TileDesc [pair][use & 1][half]
   auto desc_addr = [&](uint32_t pair, uint32_t use, uint32_t half) -> uint32_t {
-    return sDesc + (((pair * 2u + (use & 1u)) * 2u + half) << 5);
+    return sDesc + (((pair * 4u + (use & 3u)) * 2u + half) << 5);
   };
   uint64_t* mma_ready = CONV ? x_full : raw_full;   // what the MMA warp waits for
 
@@ -665,24 +667,44 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           const int t1st = 2 * (sg.j0 + m * sg.stride);
           const int nhalf = t1st + 1 < ntiles ? 2 : 1;
           const uint32_t stage = mq & 1u, use = mq >> 1;
-          // lanes 0 / 1: the descriptor of half 0 / 1 (reset words requested before the wait below)
+          // Tile descriptors (TileDesc): lanes 0 / 1 = the halves of THIS tile (first use of the pair
+          // only), lanes 2 / 3 = the halves of the pair's NEXT tile (two MMA tiles ahead); the reset
+          // words are requested before the wait below.
           TileDesc td{-1, 0, 0u, 0u, 0u, 0u, 0u, 0};
-          if (lane < 2 && t1st + lane < ntiles) {
-            const int ticket = t1st + lane;
-            td.tt = div_b(ticket); td.b = ticket - td.tt * p.B;
-            const unsigned* rw = p.reset_bits + (long long)td.b * p.bits_bstride + td.tt;
-            td.rbits = rw[0];
-            td.rprev = td.tt > 0 ? rw[-1] : 0u;
-            const unsigned long long eo = ((unsigned long long)td.b * p.T + (unsigned long long)td.tt * kTile) * p.E;
-            td.eoff_lo = (uint32_t)eo; td.eoff_hi = (uint32_t)(eo >> 32);
-            td.widx = (uint32_t)((((size_t)fam * p.ntt + td.tt) * p.B + td.b) * kMch);
-            td.nvalid = p.T - td.tt * kTile;
+          if (lane < 4) {
+            int dfam = fam, dj = sg.j0 + m * sg.stride;
+            bool have = lane < 2;
+            if (lane >= 2) {                               // the tile two positions after (sgi, m)
+              int s2 = sgi, m2 = m + 2;
+              Seg g2 = sg;
+              have = true;
+              while (m2 >= g2.count) {
+                m2 -= g2.count;
+                do {
+                  ++s2;
+                  if (s2 < nsegs) g2 = sched.get(s2);
+                } while (s2 < nsegs && g2.count == 0);
+                if (s2 >= nsegs) { have = false; break; }
+              }
+              dfam = seg_family(g2); dj = g2.j0 + m2 * g2.stride;
+            }
+            const int ticket = 2 * dj + (lane & 1);
+            if (have && ticket < ntiles) {
+              td.tt = div_b(ticket); td.b = ticket - td.tt * p.B;
+              const unsigned* rw = p.reset_bits + (long long)td.b * p.bits_bstride + td.tt;
+              td.rbits = rw[0];
+              td.rprev = td.tt > 0 ? rw[-1] : 0u;
+              const unsigned long long eo = ((unsigned long long)td.b * p.T + (unsigned long long)td.tt * kTile) * p.E;
+              td.eoff_lo = (uint32_t)eo; td.eoff_hi = (uint32_t)(eo >> 32);
+              td.widx = (uint32_t)((((size_t)dfam * p.ntt + td.tt) * p.B + td.b) * kMch);
+              td.nvalid = p.T - td.tt * kTile;
+            }
           }
           CGF_EVENT(0, 1);
           mbar_wait<CGF_SLEEP_AUX_NS>(x_empty + stage, (use & 1) ^ 1, p.err, 2);
           CGF_EVENT(0, 2);
-          if (lane < 2) {
-            const uint32_t da = desc_addr(stage, use, (uint32_t)lane);
+          if (lane < 4 && (lane >= 2 || use == 0)) {
+            const uint32_t da = desc_addr(stage, use + (uint32_t)(lane >> 1), (uint32_t)(lane & 1));
             sts128(da, make_uint4((uint32_t)td.tt, (uint32_t)td.b, td.rbits, td.rprev));
             sts128(da + 16, make_uint4(td.eoff_lo, td.eoff_hi, td.widx, (uint32_t)td.nvalid));
           }
@@ -1191,29 +1213,40 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       const uint32_t row0 = sX + pr * Cfg::kXStageBytes + (uint32_t)ckb * Cfg::kXKBlock +
                             (uint32_t)(hf * kTile + cseg * 16) * 128u;   // my 16 rows of the stage; (row & 7) == (j & 7)
       const uint32_t tap_a = sTap + (uint32_t)((wq & 1) * 32 + lane) * 4u;
+      // The three rows before my segment of a tile come straight from global memory (L2: the TMA reads
+      // them at about the same time); x[t < 0] = 0 (layers.py:484-492).  They are requested a whole tile
+      // ahead -- the descriptor of the pair's next tile is readable as soon as this warpgroup has waited on
+      // raw_full for the current one (TileDesc) -- so the round trip never shows.
+      uint32_t hq1 = 0u, hq2 = 0u, hq3 = 0u;               // x[ts-1], x[ts-2], x[ts-3] of the next convolution
+      auto halo_request = [&](uint32_t use_n, int head_n) {
+        const uint32_t da = desc_addr(pr, use_n, hf);
+        const int tt_n = (int)lds32(da);
+        hq1 = 0u; hq2 = 0u; hq3 = 0u;
+        if (tt_n >= 0) {
+          const uint32_t e_lo = lds32(da + 16), e_hi = lds32(da + 20);
+          const int ts = tt_n * kTile + cseg * 16;         // first step of my segment
+          const int chp = head_n * (KB * 64) + ckb * 64 + lane * 2;
+          const uint16_t* xb = p.x_lin + (((size_t)e_hi << 32) | e_lo) + (size_t)(cseg * 16) * p.E + chp;
+          if (ts >= 3 && ts <= p.T) {                      // interior (the common case)
+            const uint16_t* x3 = xb - 3 * (size_t)p.E;
+            hq3 = ldg32_nc(x3); hq2 = ldg32_nc(x3 + p.E); hq1 = ldg32_nc(x3 + 2 * (size_t)p.E);
+          } else {
+            if (ts >= 1 && ts - 1 < p.T) hq1 = ldg32_nc(xb - (size_t)p.E);
+            if (ts >= 2 && ts - 2 < p.T) hq2 = ldg32_nc(xb - 2 * (size_t)p.E);
+            if (ts >= 3 && ts - 3 < p.T) hq3 = ldg32_nc(xb - 3 * (size_t)p.E);
+          }
+        }
+      };
       auto conv_tile = [&](const Cur& c) {
         const uint32_t use = c.mq >> 1;
         if (twarp) CGF_EVENT(trole, 9);
-        mbar_wait(raw_full + pr, use & 1, p.err, 9);       // the raw rows AND the tile's descriptor
+        mbar_wait(raw_full + pr, use & 1, p.err, 9);       // the raw rows of the tile
         if (twarp) CGF_EVENT(trole, 10);
         const TileDesc td = read_desc(use);
         const bool valid = td.tt >= 0;                     // uniform over the warpgroup
         if (valid) {
-          const int ts = td.tt * kTile + cseg * 16;        // first step of my segment
           const int chp = c.sg.fam * (KB * 64) + ckb * 64 + lane * 2;   // my two channels (CONV schedules heads)
-          // the three rows before my segment, straight from global memory (L2: the TMA has just read
-          // them); x[t < 0] = 0 (layers.py:484-492).  Rows 3.. of the segment are convolved first, so
-          // this round trip hides behind them.
-          uint32_t h1 = 0u, h2 = 0u, h3 = 0u;              // x[ts-1], x[ts-2], x[ts-3]
-          const uint16_t* xb = p.x_lin + (((size_t)td.eoff_hi << 32) | td.eoff_lo) + (size_t)(cseg * 16) * p.E + chp;
-          if (ts >= 3 && ts <= p.T) {                      // interior (the common case)
-            const uint16_t* x3 = xb - 3 * (size_t)p.E;
-            h3 = ldg32_nc(x3); h2 = ldg32_nc(x3 + p.E); h1 = ldg32_nc(x3 + 2 * (size_t)p.E);
-          } else {
-            if (ts >= 1 && ts - 1 < p.T) h1 = ldg32_nc(xb - (size_t)p.E);
-            if (ts >= 2 && ts - 2 < p.T) h2 = ldg32_nc(xb - 2 * (size_t)p.E);
-            if (ts >= 3 && ts - 3 < p.T) h3 = ldg32_nc(xb - 3 * (size_t)p.E);
-          }
+          const uint32_t h1 = hq1, h2 = hq2, h3 = hq3;
           // a thread reads and writes only its own 16 words of the stage: no hazard, no barrier
           uint32_t xr[16];
 #pragma unroll
@@ -1300,12 +1333,21 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
 
       Cur cur{0, -1, 0xffffffffu, Seg{0, 0, 1, 0}, nsegs > 0};
       if (nsegs > 0) { cur.sg = sched.get(0); step(cur); }
-      if (cur.ok) conv_tile(cur);                          // the first tile of my pair
+      if (cur.ok) {                                        // the first tile of my pair
+        mbar_wait(raw_full + pr, 0u, p.err, 9);            // its descriptor is written right before this arrive
+        halo_request(0u, cur.sg.fam);
+        conv_tile(cur);
+      }
       while (cur.ok) {
         const uint32_t use = cur.mq >> 1;
         load_family(seg_family(cur.sg));
         if (twarp) CGF_EVENT(trole, 8);
         const unsigned long long early = request_pred();
+        {   // halo rows of the NEXT convolution: its descriptor became readable with raw_full of this tile
+          Cur nxt = cur;
+          step(nxt);
+          if (nxt.ok) halo_request(nxt.mq >> 1, nxt.sg.fam);
+        }
         if (twarp) CGF_EVENT(trole, 1);
         mbar_wait(t_full + pr, use & 1, p.err, 6);
         if (twarp) CGF_EVENT(trole, 2);
