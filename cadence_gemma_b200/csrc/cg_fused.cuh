@@ -86,7 +86,8 @@
 #define CGF_CONV_BATCH 8    // rows of the in-kernel convolution held in registers at a time
 #endif
 // CGF_ABLATE (timing experiments only, results are WRONG): 1 = no look-back,
-// 2 = no y stores, 4 = no replay pass at all, 8 = no in-kernel convolution arithmetic
+// 2 = no y stores, 4 = no replay pass at all, 8 = no in-kernel convolution (loads, arithmetic, stores),
+// 16 = no exchange of the convolved halves between the CTAs of a cluster
 #ifndef CGF_ABLATE
 #define CGF_ABLATE 0
 #endif
@@ -1244,7 +1245,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         if (twarp) CGF_EVENT(trole, 10);
         const TileDesc td = read_desc(use);
         const bool valid = td.tt >= 0;                     // uniform over the warpgroup
-        if (valid) {
+        if (valid && !(CGF_ABLATE & 8)) {
           const int chp = c.sg.fam * (KB * 64) + ckb * 64 + lane * 2;   // my two channels (CONV schedules heads)
           const uint32_t h1 = hq1, h2 = hq2, h3 = hq3;
           // a thread reads and writes only its own 16 words of the stage: no hazard, no barrier
@@ -1320,7 +1321,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (CL > 1 && valid) {
+          if (CL > 1 && valid && !(CGF_ABLATE & 16)) {
             bulk_copy_to_peer(mapa_u32(row0, peer), row0, 16u * 128u, mapa_u32(smem_u32(x_full + pr), peer));
             // my arrival, and the bytes the peer's same warp sends into MY stage
             mbar_expect_tx(x_full + pr, 16u * 128u);

@@ -10,11 +10,12 @@
 Prefill at RecurrentGemma shapes (bf16, temporal width 4, head width 128 / 256,
 T > 1) can run as ONE kernel: ``cg_recurrent_prefill_fwd`` -- the temporal
 convolution runs inside the fused tcgen05 RG-LRU kernel (TMA-loaded rows
-convolved in place in shared memory), so neither the conv output nor the gate
-pre-activations reach HBM.  ``set_fused_conv`` / ``CG_B200_FUSED_CONV`` select
-it: "auto" (default) takes the one-launch route for small, latency-bound
-problems and the Conv1D kernel followed by the fused RG-LRU kernel for large
-ones (see the measurements next to ``_fused_conv`` below); other shapes / fp32
+convolved in place in shared memory by the epilogue warpgroups), so neither the
+conv output nor the gate pre-activations reach HBM.  ``set_fused_conv`` /
+``CG_B200_FUSED_CONV`` select it: "auto" (default) takes the one-launch route
+whenever the shape allows (it is the faster route at every measured size);
+``False`` / "0" runs the Conv1D kernel followed by the fused RG-LRU kernel; other
+shapes / fp32
 take the Conv1D kernel + cuBLAS gate GEMM + scan kernel.  A decode step (T == 1, caches given) is one launch as well
 (``cg_recurrent_decode_step``).
 
@@ -33,17 +34,15 @@ import torch
 from cadence_gemma_b200 import _abi, layers
 
 # Convolution inside the fused RG-LRU kernel (one launch per prefill step):
-# "auto" (default) = where it is the faster route, "1" = whenever the shape allows, "0" = never.
-# The fused kernel is bound by the issue / FMA-pipe rate of its epilogue, so the
-# convolution's 8 packed bf16 ops per channel pair are not free inside it: at
-# config 2 (B=8, T=2048) one launch takes 165-172 us against 136 us for the
-# Conv1D kernel (HBM-bound, SMs otherwise idle) followed by the fused kernel,
-# while a small, latency-bound problem gains (B=2, T=2048: 51 us vs 77 us; B=8, T=512:
-# 52 us vs 93 us; B=16, T=256: 50 us vs 79 us).  Measured crossover at 128 scan tiles per
-# family: B=1, T=8192 (256 tiles) 94 vs 98 us, B=4, T=2048 91 vs 80 us, B=8, T=1024
-# 92 vs 84 us (profiles/r2_fused_conv_crossover.txt).
+# "auto" (default) and "1" = whenever the shape allows, "0" = never (Conv1D kernel, then the fused
+# RG-LRU kernel).  The convolution runs in the epilogue warpgroups of the tcgen05 kernel, once per
+# head (the two CTAs of a head form a cluster and exchange their halves), and is the faster route at
+# every measured shape (profiles/r3_fused_conv_shapes.txt: B=8, T=2048 125 us vs 130 us; B=2, T=8192
+# 146 vs 154; B=16, T=8192 873 vs 890; B=32, T=768 177 vs 180; B=1, T=2048 53 vs 79; B=16, T=256
+# 42 vs 83).  (Round 2's first version -- two dedicated warps, the whole head per CTA -- lost above
+# 128 scan tiles per family: 165-175 us at B=8, T=2048; `FUSED_CONV_MAX_TILES` was its crossover.)
 _fused_conv = os.environ.get("CG_B200_FUSED_CONV", "auto")
-FUSED_CONV_MAX_TILES = 128      # auto: B * ceil(T / 32) scan tiles per channel family at most
+FUSED_CONV_MAX_TILES = None     # auto: no limit any more (kept for callers that read it)
 # One-launch decode step (cg_recurrent_decode_step).  It more than halves the cost
 # of an EAGER decode step (30 us vs 76 us per block at B = 32: three launches and
 # their host overhead become one); inside a CUDA graph, where launch overhead is
@@ -81,7 +80,8 @@ def can_fuse_conv(conv, lru, x, conv_cache=None) -> bool:
   (``cg_recurrent_prefill_fwd``)."""
   if _fused_conv == "0":
     return False
-  if _fused_conv == "auto" and x.shape[0] * ((x.shape[1] + 31) // 32) > FUSED_CONV_MAX_TILES:
+  if (_fused_conv == "auto" and FUSED_CONV_MAX_TILES is not None and
+      x.shape[0] * ((x.shape[1] + 31) // 32) > FUSED_CONV_MAX_TILES):
     return False
   return (layers.fused_enabled() and conv_cache is None and x.is_cuda and
           conv.w.shape[0] == 4 and conv.w.dtype == x.dtype and
