@@ -73,6 +73,9 @@ def measured_peaks():
   return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+LEAD_IN_STEPS = int(os.environ.get("CG_BENCH_LEAD_IN", "4"))   # untimed steps between the barrier and the start event
+
+
 def ncu_traffic(kernel_key):
   try:
     with open(NCU_TRAFFIC_FILE) as f:
@@ -280,8 +283,10 @@ def config_dict(args):
           "conv1d_temporal_width": w["temporal_width"],
           "parallelism": (f"batch-sharded x{args.gpus}, no collective in the path; NCCL all-gather "
                           f"of last_h + conv cache once per {GATHER_EVERY} block steps (one 2B prefill)"),
-          "l2": "working set 420 MB per step > 126 MB L2 (no explicit flush)",
-          "clock_ramp": "W warm-up steps plus 400 ms of untimed steps before the timed region"}
+          "l2": ("working set 168 MB per step (x_lin in, y out; one-launch route) / 336 MB (two-kernel route) "
+                 "> 126 MB L2 (no explicit flush)"),
+          "clock_ramp": ("W warm-up steps plus 400 ms of untimed steps before the timed region; "
+                         f"{LEAD_IN_STEPS} untimed lead-in steps between the barrier and the start event")}
 
 
 def host_link_ceiling(dev, nbytes_up, nbytes_dn, reps=10):
@@ -431,8 +436,14 @@ def own_arm(args, dtype):
     side-stream all-gather is joined BEFORE the closing event (a consumer that needs
     the merged cache right away) or after it (the merged cache is only needed before
     the next decode step: SURVEY 8(e) asks for both figures)."""
-    step_no[0] = 0
     sync_all()
+    # lead-in: the barrier above leaves the GPU idle for as long as the slowest rank takes to arrive
+    # (0.1 - 1 ms at N > 1), and the first steps after an idle gap run slower (clocks, L2): a few UNTIMED
+    # steps of the same kind go first, on the same stream, without any synchronisation -- the two events
+    # below still bracket EXACTLY K steps (measured at N = 2: 134.3 us per step without, 128.8 with)
+    for _ in range(LEAD_IN_STEPS):
+      step(x_dev, seg_dev, record=False, gather=False)
+    step_no[0] = 0
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     o = None
