@@ -7,8 +7,8 @@ from cadence_gemma_b200.layers import (BlockDiagonalLinear, Conv1D, RGLRU,
                                        fused_enabled, get_arith_mode, rnn_scan,
                                        set_arith_mode, set_fold_gate, set_fused)
 
-from cadence_gemma_b200.pipeline import recurrent_hot_path, set_fused_conv, set_fused_decode
+from cadence_gemma_b200.pipeline import GraphedHotPath, recurrent_hot_path, set_fused_conv, set_fused_decode
 
-__all__ = ["recurrent_hot_path", "BlockDiagonalLinear", "Conv1D", "RGLRU", "rnn_scan",
+__all__ = ["recurrent_hot_path", "GraphedHotPath", "BlockDiagonalLinear", "Conv1D", "RGLRU", "rnn_scan",
            "set_arith_mode", "get_arith_mode", "set_fused", "set_fold_gate", "set_fused_conv",
            "set_fused_decode", "fused_enabled", "_abi"]

@@ -156,3 +156,66 @@ def _recurrent_hot_path_inference(conv, lru, x, segment_pos, conv_cache=None, lr
     y, h = lru(xc, segment_pos, lru_cache, return_cache) if gate_mul is None else \
         type(lru).forward(lru, xc, segment_pos, lru_cache, return_cache, gate_mul=gate_mul)
   return y, conv_state, h
+
+
+class GraphedHotPath:
+  """``recurrent_hot_path`` for ONE fixed shape as a replayable CUDA graph (prefill).
+
+  A small-batch prefill (the reference sampler's shape is B = 1, ``sampler.py:217-223``) is bound by
+  the host: ~50 us of Python and launches per block step against 20-45 us of kernels.  This class
+  captures the step once -- prologue + ONE fused launch (or the two / three kernels of the other
+  routes) -- and replays it: no Python between the kernels, no allocator, no host synchronisation.
+
+  Inputs are written into static buffers (``self.x`` ``[B,T,E]``, ``self.segment_pos`` ``[B,T]`` int32,
+  ``self.h0`` ``[B,E]`` fp32 if ``with_h0``) -- either by the caller directly (a producer kernel that
+  writes ``self.x`` saves a copy) or by ``__call__``, which copies them on the current stream;
+  results live in ``self.y``, ``self.conv_state``, ``self.last_h`` until the next replay.
+  """
+
+  def __init__(self, conv, lru, batch: int, steps: int, with_h0: bool = False, warmup: int = 2):
+    dev, dtype, width = conv.w.device, conv.w.dtype, lru.width
+    self.conv, self.lru = conv, lru
+    self.x = torch.zeros((batch, steps, width), device=dev, dtype=dtype)
+    self.segment_pos = torch.arange(steps, device=dev, dtype=torch.int32)[None].repeat(batch, 1).contiguous()
+    self.h0 = torch.zeros((batch, width), device=dev, dtype=torch.float32) if with_h0 else None
+    self.y = torch.empty_like(self.x)
+    self.conv_out = torch.empty_like(self.x)            # only touched by the two-kernel routes
+    self.conv_state = torch.empty((batch, conv.w.shape[0] - 1, width), device=dev, dtype=dtype)
+    self.last_h = torch.empty((batch, width), device=dev, dtype=torch.float32)
+    self.device = dev
+    # warm up ON the capture stream: the kernels' scratch buffers and the packed gate weights are
+    # cached per stream / per weight version and must exist before the capture
+    self._side = torch.cuda.Stream(dev)
+    self._side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(self._side):
+      for _ in range(max(1, warmup)):
+        self._eager()
+    self._side.synchronize()
+    self._graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(self._graph, stream=self._side):
+      self._eager()
+    torch.cuda.current_stream(dev).wait_stream(self._side)
+
+  @torch.no_grad()
+  def _eager(self):
+    _recurrent_hot_path_inference(self.conv, self.lru, self.x, self.segment_pos, None, self.h0, True, None,
+                                  self.y, self.last_h, self.conv_out, self.conv_state)
+
+  @torch.no_grad()
+  def replay(self):
+    """Runs the captured step on the contents of the static input buffers."""
+    self._graph.replay()
+    return self.y, self.conv_state, self.last_h
+
+  @torch.no_grad()
+  def __call__(self, x, segment_pos, h0=None):
+    self.x.copy_(x)
+    self.segment_pos.copy_(segment_pos if segment_pos.dim() == 2 else segment_pos[None].expand_as(self.segment_pos))
+    if self.h0 is not None:
+      if h0 is None:
+        self.h0.zero_()
+      else:
+        self.h0.copy_(h0)
+    else:
+      assert h0 is None, "build with with_h0=True to continue from a state"
+    return self.replay()

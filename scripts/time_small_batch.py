@@ -44,9 +44,14 @@ def main():
       t_lru = timed(lambda: lru.forward_into(xc, seg, out=y, last_h_out=h))
       t_both = timed(lambda: (conv.forward_into(x, seg, out=xc, cache_out=cache),
                               lru.forward_into(xc, seg, out=y, last_h_out=h)))
+      t_hot = timed(lambda: cg.recurrent_hot_path(conv, lru, x, seg, out=y, last_h_out=h, conv_cache_out=cache))
+      gh = cg.GraphedHotPath(conv, lru, B, T)
+      gh.x.copy_(x)
+      t_graph = timed(gh.replay)
       print(json.dumps({"B": B, "T": T, "us_conv1d": round(t_conv, 1), "us_rglru_fused": round(t_lru, 1),
-                        "us_step": round(t_both, 1),
-                        "tokens_per_s_M": round(B * T / t_both, 1)}), flush=True)
+                        "us_two_kernels_eager": round(t_both, 1), "us_hot_path_eager": round(t_hot, 1),
+                        "us_hot_path_graphed": round(t_graph, 1),
+                        "tokens_per_s_M_graphed": round(B * T / t_graph, 1)}), flush=True)
 
 
 if __name__ == "__main__":

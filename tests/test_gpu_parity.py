@@ -1119,3 +1119,27 @@ def test_fused_rglru_family_loop_small_grid(ctas):
   y, h = abi.rglru_fused_fwd(x, wpack, bx, ba, ap, seg, heads, h0=h0, arith_mode=FAST | (ctas << 8),
                              workspace=ws)
   assert torch.equal(y, y_ref) and torch.equal(h, h_ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(1, 2048, 2560, 10), (2, 100, 512, 2), (3, 64, 256, 4)])
+def test_graphed_hot_path_equals_eager(shape):
+  """GraphedHotPath (the sampler's B = 1 prefill is host-bound): the step captured
+  once in a CUDA graph and replayed on new inputs gives the bits of the eager call, with and without a
+  state to continue from; head width 256 (one launch), 256 (one launch, small), 64 (conv kernel + cuBLAS
+  + scan kernel)."""
+  import cadence_gemma_b200 as cg
+  bsz, steps, width, heads = shape
+  conv, lru = _conv_lru(width, heads, sum(shape))
+  with torch.no_grad():
+    g = cg.GraphedHotPath(conv, lru, bsz, steps, with_h0=True)
+    for it in range(3):
+      x = torch.randn(bsz, steps, width, device=DEV).to(torch.bfloat16)
+      seg = torch.arange(steps, device=DEV, dtype=torch.int32)[None].repeat(bsz, 1)
+      if it > 0:
+        seg[:, steps // 2:] = torch.arange(steps - steps // 2, device=DEV, dtype=torch.int32)
+      h0 = torch.randn(bsz, width, device=DEV) if it != 1 else None
+      y_ref, cs_ref, h_ref = cg.recurrent_hot_path(conv, lru, x, seg, lru_cache=h0)
+      y, cs, h = g(x, seg, h0)
+      torch.cuda.synchronize()
+      assert torch.equal(y, y_ref) and torch.equal(cs, cs_ref) and torch.equal(h, h_ref), (shape, it)
