@@ -563,11 +563,11 @@ bool fused_shape_ok(int E, int H, int dtype) {
   return bw == 128 || bw == 256;
 }
 
-template <int KB, bool FAST, bool DBG, bool MUL, bool CONV>
+template <int KB, bool FAST, bool DBG, bool MUL, bool CONV, int LOOK = 2>
 int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int grid_limit,
                  cudaStream_t stream) {
   using Cfg = cg::fused::FusedCfg<KB>;
-  auto kernel = cg::fused::rglru_fused_kernel<KB, FAST, DBG, MUL, CONV>;
+  auto kernel = cg::fused::rglru_fused_kernel<KB, FAST, DBG, MUL, CONV, LOOK>;
   static DeviceSlot slots[kMaxDevices];
   int dev = 0;
   if (cudaError_t e = cudaGetDevice(&dev)) return (int)e;
@@ -625,6 +625,9 @@ int dispatch_fused(bool fast, bool dbg, bool mul, const CUtensorMap& tmap,
                        : launch_fused<KB, false, true, false, CONV>(tmap, p, grid_limit, stream);
   if (mul) return fast ? launch_fused<KB, true, false, true, CONV>(tmap, p, grid_limit, stream)
                        : launch_fused<KB, false, false, true, CONV>(tmap, p, grid_limit, stream);
+  // look-back depth 2 where the carry chain is the bound (small batches), 1 elsewhere (cg_fused.cuh)
+  if (p.B > CGF_LOOK_SPLIT) return fast ? launch_fused<KB, true, false, false, CONV, 1>(tmap, p, grid_limit, stream)
+                           : launch_fused<KB, false, false, false, CONV, 1>(tmap, p, grid_limit, stream);
   return fast ? launch_fused<KB, true, false, false, CONV>(tmap, p, grid_limit, stream)
               : launch_fused<KB, false, false, false, CONV>(tmap, p, grid_limit, stream);
 }

@@ -57,12 +57,16 @@
 #ifndef CGF_PRELOAD
 #define CGF_PRELOAD 1
 #endif
-// look-back depth per round trip: 2 = the predecessor's state word plus the aggregates /
-// state of the tile before it in ONE round trip.  Measured (us, fused kernel alone):
-// B=2,T=8192 141.6 -> 129.4; B=8,T=2048 107.0 -> 107.0; B=32,T=768 144.3 -> 144.0-145.9;
-// depth 4: 131.4 / 111.1 / 146.0 (more loads per poll than the chain is long)
+// look-back depth per round trip (template parameter LOOK of the kernel; this is its default):
+// 2 = the predecessor's state word plus the aggregates / state of the tile before it in ONE round trip.
+// Measured (us, fused kernel alone, round 1): B=2,T=8192 141.6 -> 129.4; B=8,T=2048 107.0 -> 107.0;
+// depth 4: 131.4 / 111.1 (more loads per poll than the chain is long).  Round 2, one-launch kernel at
+// config 2 (B=8): depth 1 123.7 us vs depth 2 125.3 us -> the host picks 2 for B <= 3, else 1.
 #ifndef CGF_LOOK
 #define CGF_LOOK 2
+#endif
+#ifndef CGF_LOOK_SPLIT
+#define CGF_LOOK_SPLIT 3    // batch sizes up to this use look-back depth 2, larger ones depth 1
 #endif
 #ifndef CGF_HINT_NS
 #define CGF_HINT_NS 20000
@@ -555,7 +559,9 @@ struct Schedule {
 // gating product of RecurrentBlock), SURVEY.md section 8(f) row F2.
 // CONV: the temporal convolution runs in the kernel (see above): `tmap_x` describes
 // x_lin and the kernel computes Conv1D.forward -> RGLRU.forward in one launch.
-template <int KB, bool FAST, bool DBG, bool MUL, bool CONV>
+// LOOK: look-back depth per round trip (see resolve_carry): 2 for small batches, where the carry chain
+// is the bound; 1 where the chain has slack (fewer loads per poll).
+template <int KB, bool FAST, bool DBG, bool MUL, bool CONV, int LOOK = CGF_LOOK>
 __global__ void __launch_bounds__(kThreads, 1)
 rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams p) {
   using Cfg = FusedCfg<KB>;
@@ -876,7 +882,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         // aggregates passed on the way one by one, left to right -- exactly the
         // expression each of those tiles evaluates for its own state, so the
         // carry does not depend on timing (bit-reproducible).
-        constexpr int kLook = CGF_LOOK;
+        constexpr int kLook = LOOK;
         int end = tt;                                    // tiles [end, tt): aggregate seen
         const long long t_start = clock64();
         unsigned polls = 0;
@@ -949,6 +955,9 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       }
       uint16_t* yc = pd.yp + (size_t)(c * 8) * E;
       if ((CGF_ABLATE & 2) && o[0] != 0x12345678u) return;
+      // (lane pairs swapping halves through a shuffle so that every lane writes ONE 4-byte word per pair
+      // of steps -- half the stores and address arithmetic -- was measured SLOWER: 126.7 vs 125.4 us at
+      // config 2, 879 vs 873 us at B=16, T=8192; profiles/r3_ab_look_shfl.txt)
       if (c * 8 + 8 <= pd.nvalid) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
