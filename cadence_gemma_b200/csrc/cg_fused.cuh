@@ -71,24 +71,6 @@
 #ifndef CGF_HINT_NS
 #define CGF_HINT_NS 20000
 #endif
-// register re-split between the roles (setmaxnreg): the 16 epilogue warps grow to
-// CGF_REG_EPI, the producer / MMA / convolution warpgroup shrinks to CGF_REG_AUX.
-// 20 warps x 96 registers are allocated at launch: 16 x 104 + 4 x 64 = 1920 warp-registers.
-#ifndef CGF_SETMAXNREG
-#define CGF_SETMAXNREG 0   // measured: 123 us vs 110 us (the 64-register side spills shared bookkeeping)
-#endif
-#ifndef CGF_REG_EPI
-#define CGF_REG_EPI 104
-#endif
-#ifndef CGF_REG_AUX
-#define CGF_REG_AUX 64
-#endif
-#ifndef CGF_DESC_LO
-#define CGF_DESC_LO 1       // MMA descriptors as base + small add (see umma_bf16_lo)
-#endif
-#ifndef CGF_CONV_BATCH
-#define CGF_CONV_BATCH 8    // rows of the in-kernel convolution held in registers at a time
-#endif
 // CGF_ABLATE (timing experiments only, results are WRONG): 1 = no look-back,
 // 2 = no y stores, 4 = no replay pass at all, 8 = no in-kernel convolution (loads, arithmetic, stores),
 // 16 = no exchange of the convolved halves between the CTAs of a cluster
@@ -617,11 +599,6 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   const uint32_t tmem_base = *tmem_holder;
   const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
 
-#if CGF_SETMAXNREG
-  // all four warps of a warpgroup execute the same setmaxnreg (it is .aligned)
-  if (warp >= kEpiWarps) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(CGF_REG_AUX));
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(CGF_REG_EPI));
-#endif
 
   // work schedule of this CTA (identical in every role), see Schedule above.
   // Ticket = tt * B + b (time-major); pair j = tickets 2j, 2j + 1 = one MMA tile.
@@ -738,7 +715,6 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     // ===================================================== MMA issuer
     {
       const uint32_t w_lo0 = umma_desc_lo(sW), i_lo0 = umma_desc_lo(sI), x_lo0 = umma_desc_lo(sX);
-      (void)w_lo0; (void)i_lo0; (void)x_lo0;
       uint32_t mq = 0, witer = 0;
       int tn = 0; (void)tn;
       int cur_fam = -1;
@@ -767,7 +743,6 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           CGF_EVENT(1, 3);
           tc_fence_after();
           const uint32_t dcol = tmem_base + pr * kPairCols;
-#if CGF_DESC_LO
           const uint32_t x_lo = x_lo0 + pr * (Cfg::kXStageBytes >> 4);
           if (elect_one()) {
 #pragma unroll
@@ -790,29 +765,6 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
                            xt_lo + ((kb * Cfg::kXKBlock + k * 32) >> 4), IDESC, (kb | k) != 0);
             }
           }
-#else
-          const uint32_t xs = sX + pr * Cfg::kXStageBytes;
-          if (elect_one()) {
-#pragma unroll
-          for (int gate = 0; gate < 2; ++gate) {
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16(dcol + gate * kMmaN, umma_desc(sW + (gate * KB + kb) * kKBlockBytes + k * 32),
-                          umma_desc(xs + kb * Cfg::kXKBlock + k * 32), IDESC, (kb | k) != 0);
-              }
-            }
-          }
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16(dcol + 2 * kMmaN, umma_desc(sI + kb * kKBlockBytes + k * 32),
-                        umma_desc(xs + (2 * cb + kb) * Cfg::kXKBlock + k * 32), IDESC, (kb | k) != 0);
-            }
-          }
-#endif
           umma_commit(t_full + pr);
           if constexpr (CL > 1) umma_commit_mc(x_empty + pr, (uint16_t)((1u << CL) - 1u));   // my stage AND the peer's copy target
           else umma_commit(x_empty + pr);
