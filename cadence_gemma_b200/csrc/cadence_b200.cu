@@ -6,6 +6,7 @@
 #include "../../include/cadence_b200.h"
 
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 
 #include <mutex>
@@ -563,6 +564,14 @@ bool fused_shape_ok(int E, int H, int dtype) {
   return bw == 128 || bw == 256;
 }
 
+// CG_B200_STEAL=0 switches the tail stealing of the fused kernels' schedule off (A/B runs)
+// (CG_B200_STEAL=n, n >= 2: steal exactly n pairs per poor unit -- tuning runs)
+int fused_steal_override() {
+  static const int v = [] { const char* e = getenv("CG_B200_STEAL"); return e ? atoi(e) : 1; }();
+  return v;
+}
+bool fused_steal_enabled() { return fused_steal_override() != 0; }
+
 template <int KB, bool FAST, bool DBG, bool MUL, bool CONV, int LOOK = 2>
 int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int grid_limit,
                  cudaStream_t stream) {
@@ -613,7 +622,32 @@ int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int g
     if (slot.resident < 1) return (int)cudaErrorLaunchOutOfResources;
     if (grid > slot.resident * CL) { grid = slot.resident * CL; cfg.gridDim = dim3(grid); }
   }
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmap, p);
+  // Tail stealing (cg::fused::Schedule): G = d * units + r work groups; the d + 1 CTAs of a rich unit end
+  // after npairs / (d + 1) tiles, reload weights and refill their pipeline (~2.3 tile times, measured) and
+  // take x * npoor / nrich tiles of the poor units' tails; a poor unit's d CTAs end after (npairs - x) / d.
+  // Equal ends:  x = (npairs / (d (d + 1)) - 2.3) / (npoor / nrich + 1 / d).  The stolen tiles are the END of
+  // a time line: a helper cannot finish them before the unit's own CTAs have produced the state they start
+  // from, so more than ~1.5 tiles per helper only queue up behind that point (measured: B=16, T=8192 with
+  // 18 tiles per helper 882 us, with 2 863 us, without stealing 869 us; config 2: 124.3 -> 121.8 us,
+  // profiles/r3_tail_stealing.txt) -- the real fix for the 7 % imbalance is a dynamic ticket per unit
+  // (DESIGN.md section 9).
+  cg::fused::FusedParams q = p;
+  {
+    const int units = CONV ? p.families / CL : p.families;
+    const int G = grid / CL, d = G / units, r = G % units;
+    const int ntiles = p.ntt * p.B, npairs = (ntiles + 1) / 2;
+    q.steal = 0;
+    if (d >= 1 && r > 0 && r * (d + 1) >= units - r && fused_steal_enabled()) {
+      const double npoor = units - r, nrich = (double)r * (d + 1);
+      double x = ((double)npairs / ((double)d * (d + 1)) - 2.3) / (npoor / nrich + 1.0 / d);
+      const double cap = 1.5 * nrich / npoor;
+      if (x > cap) x = cap;
+      if (x >= 1.0) q.steal = (int)(x + 0.5);
+      if (fused_steal_override() >= 2) q.steal = fused_steal_override();
+      if (q.steal > npairs / 4) q.steal = npairs / 4;
+    }
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmap, q);
   if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();
 }
@@ -721,6 +755,7 @@ int fused_forward(const void* x, const void* conv_w, const void* conv_b, void* c
   p.ntt = (T + tile_t - 1) / tile_t;
   p.families = E / cg::fused::kMch;
   cg::fused::make_bdiv((uint32_t)B, p.bdiv_m, p.bdiv_s1, p.bdiv_s2);
+  p.steal = -1;   // launch_fused: depends on the grid
   const bool fast = (mode & CG_ARITH_FAST) != 0;
   const bool dbg = debug_out != nullptr;
   const bool mul = gate_mul != nullptr;

@@ -139,6 +139,7 @@ struct FusedParams {
   // ticket / B without the ~25-instruction emulated division (Granlund-Montgomery, exact for every
   // 32-bit ticket): q = (t + ((n - t) >> s1)) >> s2 with t = umulhi(m, n)   (make_bdiv on the host)
   uint32_t bdiv_m, bdiv_s1, bdiv_s2;
+  int steal;                       // pairs a poor family hands to helper CTAs (Schedule), 0 = none
 };
 __host__ __device__ __forceinline__ void make_bdiv(uint32_t d, uint32_t& m, uint32_t& s1, uint32_t& s2) {
   uint32_t l = 0;
@@ -493,27 +494,49 @@ __global__ void pack_gate_weights_kernel(const uint16_t* __restrict__ wx, const 
 // families it visits -- and removed)
 // ---------------------------------------------------------------------------
 struct Seg { int fam, j0, stride, count; };
+// Round-robin mode with TAIL STEALING (steal > 0).  G = d * nfam + r: families f < r ("rich") have d + 1
+// CTAs, the others ("poor") d -- at config 2 (148 CTAs, 20 families; one launch: 74 clusters, 10 heads)
+// 32 vs 37 MMA tiles per CTA, and the poor ones set the kernel's time.  Each poor family therefore hands
+// its LAST `steal` pairs to CTAs of rich families: rich CTA number rho (of nrich) helps poor family
+// r + rho % npoor as helper rho / npoor and takes every nh-th of those pairs, after its own work and a
+// weight reload.  The stolen tiles are the end of the poor family's time line: nobody but their own
+// successors waits for them, so a late helper delays only that tail (the static "floater" of round 1, which
+// joined a family in the MIDDLE of its time line, stalled seven other CTAs whenever it was late).  The
+// host picks `steal` so that both kinds of CTA end at the same time (fused_forward).
 struct Schedule {
   int mode;        // 0 = whole families, 1 = round-robin
-  int cta, G, nfam, npairs;
-  __host__ __device__ __forceinline__ Schedule(int cta_, int G_, int nfam_, int npairs_)
-      : cta(cta_), G(G_), nfam(nfam_), npairs(npairs_) {
+  int cta, G, nfam, npairs, steal;
+  __host__ __device__ __forceinline__ Schedule(int cta_, int G_, int nfam_, int npairs_, int steal_ = 0)
+      : cta(cta_), G(G_), nfam(nfam_), npairs(npairs_), steal(steal_) {
     mode = G < nfam ? 0 : 1;
+    const int r = G % nfam, d = G / nfam;
+    if (mode == 0 || r == 0 || steal < 0 || steal > npairs || r * (d + 1) < nfam - r) steal = 0;
   }
+  __host__ __device__ __forceinline__ bool rich() const { return cta % nfam < G % nfam; }
   __host__ __device__ __forceinline__ int nseg() const {
     if (mode == 0) return cta < nfam ? (nfam - 1 - cta) / G + 1 : 0;
-    return 1;
+    return steal > 0 && rich() ? 2 : 1;
   }
   __host__ __device__ __forceinline__ Seg get(int s) const {
     Seg sg;
     if (mode == 0) {
       sg.fam = cta + s * G; sg.j0 = 0; sg.stride = 1; sg.count = npairs;
-    } else {
+    } else if (s == 0) {
       sg.fam = cta % nfam;
       const int rank = cta / nfam;
+      const int own = rich() ? npairs : npairs - steal;    // a poor family's own CTAs stop before its tail
       sg.stride = (G - 1 - sg.fam) / nfam + 1;
       sg.j0 = rank;
-      sg.count = rank < npairs ? (npairs - rank + sg.stride - 1) / sg.stride : 0;
+      sg.count = rank < own ? (own - rank + sg.stride - 1) / sg.stride : 0;
+    } else {
+      const int r = G % nfam, d = G / nfam, npoor = nfam - r, nrich = r * (d + 1);
+      const int rho = (cta / nfam) * r + cta % nfam;       // 0 .. nrich - 1
+      const int pf = rho % npoor, hi = rho / npoor;        // poor family r + pf, helper number hi
+      const int nh = (nrich - pf + npoor - 1) / npoor;     // helpers of that family
+      sg.fam = r + pf;
+      sg.stride = nh;
+      sg.j0 = npairs - steal + hi;
+      sg.count = hi < steal ? (steal - hi + nh - 1) / nh : 0;
     }
     return sg;
   }
@@ -582,6 +605,13 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+#if CGF_TRACE
+  if (threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    reinterpret_cast<unsigned long long*>(p.dbg)[7 * 1024 + 256 + blockIdx.x] = t;
+  }
+#endif
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
     mbar_init(w_empty, 1);
@@ -607,7 +637,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   const int npairs = (ntiles + 1) >> 1;
   // CONV: the schedule hands out HEADS to clusters; CTA `crank` of the cluster takes family head * CBS + crank
   const Schedule sched(CONV ? (int)blockIdx.x / CL : (int)blockIdx.x, CONV ? (int)gridDim.x / CL : (int)gridDim.x,
-                       CONV ? nfam / CBS : nfam, npairs);
+                       CONV ? nfam / CBS : nfam, npairs, p.steal);
   const int nsegs = sched.nseg();
   auto seg_family = [&](const Seg& sg) -> int { return CONV ? sg.fam * CBS + (int)crank : sg.fam; };
   auto div_b = [&](int n) -> int {                           // n / p.B for 0 <= n
@@ -1158,9 +1188,9 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       const int ckb = (CL > 1 ? (int)crank * KBL : 0) + (wq & 1);   // my K block of the stage
       const uint32_t lofs = (uint32_t)lane << 2;           // my word of a 128-byte row (16-byte chunk lane >> 2)
       const uint32_t peer = crank ^ 1u;
-      // One family per CTA for the whole kernel (every production grid): the taps of this CTA's 128 input
-      // channels sit in shared memory, written once by warpgroup 0.  Several families per CTA (grids
-      // smaller than the head count): taps come from global memory per tile.
+      // Round-robin schedule (every production grid): the taps of the 128 input channels of this CTA's
+      // home family sit in shared memory, written once by warpgroup 0.  Other families of a CTA (grids
+      // smaller than the head count; the stolen tail of another head): taps come from global memory per tile.
       const bool taps_in_smem = sched.mode == 1;
       if (taps_in_smem) {
         if (wg == 0) {
@@ -1214,7 +1244,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
 #pragma unroll
           for (int j = 0; j < 16; ++j) xr[j] = lds32(row0 + j * 128 + (lofs ^ ((uint32_t)(j & 7) << 4)));
           uint32_t k0, k1, k2, k3, kb_;                    // w[k] multiplies x[t - (3 - k)] (layers.py:530)
-          if (taps_in_smem) {
+          if (taps_in_smem && c.sgi == 0) {
             k0 = lds32(tap_a); k1 = lds32(tap_a + 256); k2 = lds32(tap_a + 512); k3 = lds32(tap_a + 768); kb_ = lds32(tap_a + 1024);
           } else {                                         // several families per CTA (small grids): per tile
             k0 = ldg32_nc(p.conv_w + chp);
@@ -1325,6 +1355,14 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     if (pd.on) finish(request_pred());                     // the last tile of this warpgroup
   }
 
+#if CGF_TRACE
+  // per-CTA end time (ns, %globaltimer) behind the role time lines: [7 * 1024 + blockIdx.x]
+  if (threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    reinterpret_cast<unsigned long long*>(p.dbg)[7 * 1024 + blockIdx.x] = t;
+  }
+#endif
   // teardown: every role is done with TMEM; a CTA of a cluster must not exit while its peer may still
   // signal its barriers (the multicast commit of the peer's last MMAs)
   tc_fence_before();

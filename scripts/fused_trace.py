@@ -40,3 +40,17 @@ for k, ev in res.items():
 json.dump(res, open("gpurun_out/fused_trace.json", "w"))
 for k, ev in res.items():
   print(k, len(ev), ev[:40])
+
+# per-CTA start / end times (ns): which CTAs set the kernel's time?
+tt = out[2].view(-1).view(torch.int64)[7 * 1024: 7 * 1024 + 512].cpu()
+end, start = tt[:148].tolist(), tt[256:256 + 148].tolist()
+t0g = min(start)
+dur = [(e - t0g) / 1e3 for e in end]
+fam = lambda i: (i // 2) % 10 if conv else i % 20
+import collections
+by = collections.defaultdict(list)
+for i, d in enumerate(dur):
+  by[fam(i)].append(d)
+print("kernel span us", round(max(dur), 1), "start skew us", round((max(start) - t0g) / 1e3, 1))
+for f in sorted(by):
+  print("unit", f, "ctas", len(by[f]), "end us min/max", round(min(by[f]), 1), round(max(by[f]), 1))
