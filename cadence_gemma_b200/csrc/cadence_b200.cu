@@ -647,6 +647,19 @@ int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int g
       if (q.steal > npairs / 4) q.steal = npairs / 4;
     }
   }
+  // CONV kernels: long kernels hand the last 10 % of every head's tiles out through ticket counters (no
+  // cluster idles while tiles are left: B=16, T=8192 867 -> 831 us); short ones keep the static schedule
+  // (dynamic tickets scramble the order in which the tiles of a chain are processed, the look-back waits
+  // longer: config 2 121.8 static vs 126.0 us).  CG_B200_DYNAMIC=<pct static> forces either (0 = static).
+  q.static_pct = 0;
+  if (CONV) {
+    const int units = p.families / CL, G = grid / CL;
+    const long long per_cluster = (long long)((p.ntt * p.B + 1) / 2) * units / (G > 0 ? G : 1);
+    if (G >= units && per_cluster >= 48) q.static_pct = 90;
+    static const int forced = [] { const char* e = getenv("CG_B200_DYNAMIC"); return e ? atoi(e) : -1; }();
+    if (forced >= 0 && forced <= 100 && G >= units) q.static_pct = forced;
+    if (q.static_pct > 0) q.steal = 0;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmap, q);
   if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();
@@ -756,6 +769,8 @@ int fused_forward(const void* x, const void* conv_w, const void* conv_b, void* c
   p.families = E / cg::fused::kMch;
   cg::fused::make_bdiv((uint32_t)B, p.bdiv_m, p.bdiv_s1, p.bdiv_s2);
   p.steal = -1;   // launch_fused: depends on the grid
+  p.tickets = ws.counter + 8;   // words 8 .. 63 of the scratch header, zeroed by the prologue kernel
+  if (conv && H > 32) return CG_ERR_UNSUPPORTED;   // one lane per head in the ticket draw
   const bool fast = (mode & CG_ARITH_FAST) != 0;
   const bool dbg = debug_out != nullptr;
   const bool mul = gate_mul != nullptr;

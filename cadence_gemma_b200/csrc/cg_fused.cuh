@@ -140,6 +140,9 @@ struct FusedParams {
   // 32-bit ticket): q = (t + ((n - t) >> s1)) >> s2 with t = umulhi(m, n)   (make_bdiv on the host)
   uint32_t bdiv_m, bdiv_s1, bdiv_s2;
   int steal;                       // pairs a poor family hands to helper CTAs (Schedule), 0 = none
+  int* tickets;                    // CONV kernels: one ticket counter per head, zeroed by the prologue kernel
+  int static_pct;                  // CONV kernels: 0 = static schedule (Schedule, with `steal`); 1..100 = that share of a
+                                   // head's tiles round-robin among its home clusters, the rest through the tickets
 };
 __host__ __device__ __forceinline__ void make_bdiv(uint32_t d, uint32_t& m, uint32_t& s1, uint32_t& s2) {
   uint32_t l = 0;
@@ -406,13 +409,13 @@ __host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
 // raw_full[p] for use u - 1 (acquire) may read it -- early enough to request the halo rows of the next
 // convolution a whole tile before they are needed.  A slot is rewritten four uses later.
 struct TileDesc {
-  int tt;                 // time tile, -1: this half of the MMA tile is empty (odd tile count)
+  int tt;                 // time tile, -1: this half of the MMA tile is empty (odd tile count), -2: STOP (no more tiles)
   int b;                  // batch row
   uint32_t rbits;         // document starts inside the tile (bit t % 32)
   uint32_t rprev;         // ... of the previous tile of the row (0 before the first)
   uint32_t eoff_lo, eoff_hi;   // element offset of (b, tt * 32, channel 0) in x / y
   uint32_t widx;          // exchange-word index of (family, tt, b, channel 0 of the family)
-  int nvalid;             // T - tt * 32
+  int fam;                // family (the dynamic schedule of the CONV kernels hands out tiles of several)
 };
 static_assert(sizeof(TileDesc) == 32, "two 16-byte shared-memory accesses");
 
@@ -427,7 +430,7 @@ struct FusedCfg {
   static constexpr uint32_t kTapBytes = 5u * 128u * 2u;             // CONV: w[0..3], b of this CTA's 128 input channels
   static constexpr uint32_t kDescBytes = 2u * 4u * 2u * 32u;        // tile descriptors [pair][use & 3][half], see TileDesc
   static constexpr size_t kSmemBytes = 1024 + kWBytes + kIBytes + kXStages * kXStageBytes + kBars * 8 + 16 + kTapBytes +
-                                       kDescBytes;
+                                       kDescBytes + 32;   // + dsc_full[2][2] (CONV clusters)
   static_assert(KB % 2 == 0, "head width must be a multiple of 128");
 };
 
@@ -596,7 +599,11 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   uint64_t* t_empty = t_full + 2;           // [2] both warpgroups of pair p have read them
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(t_empty + 2);
   const uint32_t sTap = smem_u32(tmem_holder) + 16u;   // [5][128] bf16: conv taps w[0..3], bias (CONV, one family per CTA)
-  const uint32_t sDesc = sTap + Cfg::kTapBytes;        // TileDesc [pair][use & 1][half]
+  const uint32_t sDesc = sTap + Cfg::kTapBytes;        // TileDesc [pair][use & 3][half]
+  // dsc_full[pair][use & 1] (CONV clusters): the leader CTA's producer has written the descriptors of
+  // pair `pair`'s tile number `use` into THIS CTA's ring (see the producer)
+  uint64_t* dsc_full = reinterpret_cast<uint64_t*>(sm + Cfg::kWBytes + Cfg::kIBytes + XS * Cfg::kXStageBytes +
+                                                   Cfg::kBars * 8 + 16 + Cfg::kTapBytes + Cfg::kDescBytes);
   auto desc_addr = [&](uint32_t pair, uint32_t use, uint32_t half) -> uint32_t {
     return sDesc + (((pair * 4u + (use & 3u)) * 2u + half) << 5);
   };
@@ -619,6 +626,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     // EVERY CTA of the cluster have read the stage (the peer writes into my stage too)
     for (int i = 0; i < XS; ++i) { mbar_init(raw_full + i, 1); mbar_init(x_full + i, 8); mbar_init(x_empty + i, CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 8); }
+    for (int i = 0; i < 4; ++i) mbar_init(dsc_full + i, 1);
     fence_mbar_init();
   }
   if (warp == kEpiWarps) tmem_alloc(smem_u32(tmem_holder), kTmemCols);
@@ -647,7 +655,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
 
   if (warp == kEpiWarps) {
     // ===================================================== TMA producer
-    {
+    if constexpr (!CONV) {
       uint32_t mq = 0, witer = 0;
       int tn = 0; (void)tn;
       int cur_fam = -1;
@@ -711,8 +719,8 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
               const unsigned long long eo = ((unsigned long long)td.b * p.T + (unsigned long long)td.tt * kTile) * p.E;
               td.eoff_lo = (uint32_t)eo; td.eoff_hi = (uint32_t)(eo >> 32);
               td.widx = (uint32_t)((((size_t)dfam * p.ntt + td.tt) * p.B + td.b) * kMch);
-              td.nvalid = p.T - td.tt * kTile;
             }
+            td.fam = dfam;
           }
           CGF_EVENT(0, 1);
           mbar_wait<CGF_SLEEP_AUX_NS>(x_empty + stage, (use & 1) ^ 1, p.err, 2);
@@ -720,7 +728,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           if (lane < 4 && (lane >= 2 || use == 0)) {
             const uint32_t da = desc_addr(stage, use + (uint32_t)(lane >> 1), (uint32_t)(lane & 1));
             sts128(da, make_uint4((uint32_t)td.tt, (uint32_t)td.b, td.rbits, td.rprev));
-            sts128(da + 16, make_uint4(td.eoff_lo, td.eoff_hi, td.widx, (uint32_t)td.nvalid));
+            sts128(da + 16, make_uint4(td.eoff_lo, td.eoff_hi, td.widx, (uint32_t)td.fam));
           }
           __syncwarp();
           if (elect_one()) mbar_expect_tx(raw_full + stage, nhalf * (Cfg::kXStageBytes / 2 / CL));
@@ -739,42 +747,252 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           __syncwarp();
         }
       }
+    } else {
+      // ---------------------------------------------------------------------------------------------
+      // CONV kernels: DYNAMIC schedule.  The tiles of a head are handed out in time-major order by a
+      // ticket counter per head in global memory (zeroed by the prologue kernel): a cluster draws from its
+      // home head until that is exhausted and then from the other heads, so no cluster idles while tiles
+      // are left -- the static round-robin leaves the clusters of the heads that own one cluster more
+      // (74 clusters, 10 heads) idle for the last 11 % of the kernel.  A ticket's predecessors in time were
+      // drawn earlier, i.e. are running or done, whoever holds them: the look-back cannot deadlock.  Only
+      // the LEADER CTA of a cluster draws (lane 0 of this warp); it writes the tile descriptors into its own
+      // ring AND into the peer's (st.shared::cluster), two tiles ahead, and arrives on the peer's dsc_full;
+      // every other role of both CTAs just follows the descriptors, a descriptor with tt == -2 ends them.
+      // ---------------------------------------------------------------------------------------------
+      const int nheads = nfam / CBS;
+      const int cluster = (int)blockIdx.x / CL, nclusters = (int)gridDim.x / CL;
+      const int home = cluster % nheads;
+      // static schedule: both CTAs of a cluster derive the same tile sequence on their own (nothing to
+      // forward); dynamic tickets: the leader CTA draws and forwards the descriptors to its peer
+      const bool forward = CL > 1 && p.static_pct != 0;
+      const bool leader = crank == 0 || !forward;
+      uint32_t witer = 0;
+      int tn = 0; (void)tn;
+      int cur_head = -1;
+      auto load_weights = [&](int head) {
+        cur_head = head;
+        if (witer > 0) mbar_wait<CGF_SLEEP_AUX_NS>(w_empty, (witer - 1) & 1, p.err, 1);
+        const unsigned char* wsrc = p.wpack + (size_t)(head * CBS + (int)crank) * Cfg::kWBytes;
+        if (elect_one()) {
+          mbar_expect_tx(w_full, Cfg::kWBytes + Cfg::kIBytes);
+#pragma unroll 1
+          for (uint32_t off = 0; off < Cfg::kWBytes; off += kKBlockBytes)
+            bulk_load(sW + off, wsrc + off, kKBlockBytes, w_full);
+#pragma unroll 1
+          for (uint32_t off = 0; off < Cfg::kIBytes; off += kKBlockBytes)
+            bulk_load(sI + off, p.ident + off, kKBlockBytes, w_full);
+        }
+        __syncwarp();
+        // x_lin and the prologue's outputs (ticket counters, reset bitmask): see the static producer
+        if (witer == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+        ++witer;
+      };
+      load_weights(home);                                  // the first tiles are the home head's
+      // ---- tickets (leader): (head, pair index) or head < 0 = STOP
+      // HYBRID: the first CGF_STATIC_PCT % of a head's pairs are dealt round-robin among its home clusters
+      // (clusters in lock-step: a tile's predecessors are processed half a round earlier, the look-back
+      // rarely waits); only the rest goes through the counter -- purely dynamic tickets, drawn two tiles
+      // ahead, scramble the order in which the tiles of a chain are processed (133 vs 122 us at config 2).
+      auto n_home = [&](int head) -> int { return head < nclusters ? (nclusters - 1 - head) / nheads + 1 : 0; };
+      auto j_static = [&](int head) -> int {
+        const int nh = n_home(head);
+        return nh > 0 ? (int)((long long)npairs * p.static_pct / 100 / nh) * nh : 0;
+      };
+      const int my_rank = cluster / nheads, my_nh = n_home(home), my_js = j_static(home);
+      int own_k = 0;
+      int fails = 0;
+      bool dry = false;
+      int s_sgi = 0, s_m = 0;                              // p.static_pct == 0: cursor over the static schedule
+      Seg s_sg = nsegs > 0 ? sched.get(0) : Seg{0, 0, 1, 0};
+      auto draw = [&](int& head_out, int& j_out) {
+        head_out = -1; j_out = 0;
+        if (p.static_pct == 0) {
+          // the STATIC schedule (round-robin + tail stealing, cg::fused::Schedule) through the same machinery:
+          // the better choice for short kernels (config 2: 121.8 us vs 126.0 us with 10 % dynamic tickets)
+          while (s_sgi < nsegs) {
+            if (s_m < s_sg.count) { head_out = s_sg.fam; j_out = s_sg.j0 + s_m * s_sg.stride; ++s_m; return; }
+            ++s_sgi; s_m = 0;
+            if (s_sgi < nsegs) s_sg = sched.get(s_sgi);
+          }
+          return;
+        }
+        if (own_k >= 0) {                                  // static share of the home head
+          const int j = my_rank + own_k * my_nh;
+          if (j < my_js) { ++own_k; head_out = home; j_out = j; return; }
+          own_k = -1;
+        }
+        while (!dry) {
+          // which heads still have tickets: one relaxed load per lane (a failed atomicAdd per exhausted head
+          // costs a round trip each -- ~10 us at the end of the kernel when every cluster runs dry at once)
+          int left = 0;
+          if (lane < nheads) {
+            int taken;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(taken) : "l"(p.tickets + lane) : "memory");
+            left = npairs - j_static(lane) - taken;
+          }
+          const unsigned avail = __ballot_sync(0xffffffffu, left > 0);
+          if (avail == 0u) { dry = true; break; }
+          // the home head first, then the others starting at a cluster-specific offset (the clusters of
+          // one head fan out over the other heads)
+          int pick = home;
+          if (!((avail >> home) & 1u)) {
+            const int start = (home + 1 + my_rank) % nheads;
+            const unsigned rot = ((avail >> start) | (avail << (nheads - start))) & (nheads < 32 ? (1u << nheads) - 1u : ~0u);
+            pick = (start + (__ffs(rot) - 1)) % nheads;
+          }
+          int j = 0;
+          if (lane == 0) j = atomicAdd(p.tickets + pick, 1);
+          j = __shfl_sync(0xffffffffu, j, 0) + j_static(pick);
+          if (j < npairs) { head_out = pick; j_out = j; return; }
+          if (++fails > 4 * nheads) { dry = true; break; }   // (cannot happen: every failure exhausts a head for good)
+        }
+      };
+      int h0 = -1, j0 = 0, h1 = -1, j1 = 0;              // tickets of tiles mq, mq + 1
+      if (leader) { draw(h0, j0); draw(h1, j1); }
+      uint32_t nstop = 0;
+      const uint32_t peer = crank ^ 1u;
+#pragma unroll 1
+      for (uint32_t mq = 0;; ++mq) {
+        const uint32_t stage = mq & 1u, use = mq >> 1;
+        if (leader) {
+          int h2, j2;
+          draw(h2, j2);                                    // tile mq + 2
+          // descriptors: lanes 0 / 1 = the halves of THIS tile (first use of a pair only), lanes 2 / 3 =
+          // the halves of tile mq + 2; the reset words are requested before the wait below
+          TileDesc td{-2, 0, 0u, 0u, 0u, 0u, 0u, 0};
+          if (lane < 4 && (lane >= 2 || use == 0)) {
+            const int dh = lane < 2 ? h0 : h2, dj = lane < 2 ? j0 : j2;
+            if (dh >= 0) {
+              td.tt = -1;
+              td.fam = dh * CBS + (int)crank;              // my family; a forwarded copy gets the peer's
+              const int ticket = 2 * dj + (lane & 1);
+              if (ticket < ntiles) {
+                td.tt = div_b(ticket); td.b = ticket - td.tt * p.B;
+                const unsigned* rw = p.reset_bits + (long long)td.b * p.bits_bstride + td.tt;
+                td.rbits = rw[0];
+                td.rprev = td.tt > 0 ? rw[-1] : 0u;
+                const unsigned long long eo = ((unsigned long long)td.b * p.T + (unsigned long long)td.tt * kTile) * p.E;
+                td.eoff_lo = (uint32_t)eo; td.eoff_hi = (uint32_t)(eo >> 32);
+                td.widx = (uint32_t)((((size_t)td.fam * p.ntt + td.tt) * p.B + td.b) * kMch);
+              }
+            }
+          }
+          // The ring slot of tile use + 1 held tile use - 3: every reader of that one is done once the MMAs
+          // of use - 2 are complete in both CTAs, which this warp saw two iterations ago -- so the
+          // descriptors (and the signal to the peer) go out BEFORE the wait for the stage, off the critical path
+          if (lane < 4 && (lane >= 2 || use == 0)) {
+            const uint32_t da = desc_addr(stage, use + (uint32_t)(lane >> 1), (uint32_t)(lane & 1));
+            sts128(da, make_uint4((uint32_t)td.tt, (uint32_t)td.b, td.rbits, td.rprev));
+            sts128(da + 16, make_uint4(td.eoff_lo, td.eoff_hi, td.widx, (uint32_t)td.fam));
+            if (forward) {                                 // the peer's copy: its family is the next one
+              const uint32_t dr = mapa_u32(da, peer);
+              const uint32_t wpeer = td.widx + (uint32_t)p.ntt * (uint32_t)p.B * kMch;
+              asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(dr), "r"((uint32_t)td.tt),
+                           "r"((uint32_t)td.b), "r"(td.rbits), "r"(td.rprev) : "memory");
+              asm volatile("st.shared::cluster.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(dr + 16), "r"(td.eoff_lo),
+                           "r"(td.eoff_hi), "r"(wpeer), "r"((uint32_t)(td.fam + 1)) : "memory");
+            }
+          }
+          __syncwarp();
+          if (forward) {
+            if (lane == 0) {                               // the peer's producer may read them now
+              asm volatile("fence.acq_rel.cluster;" ::: "memory");
+              if (use == 0)
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
+                             :: "r"(mapa_u32(smem_u32(dsc_full + stage * 2), peer)) : "memory");
+              asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];"
+                           :: "r"(mapa_u32(smem_u32(dsc_full + stage * 2 + ((use + 1) & 1)), peer)) : "memory");
+            }
+            __syncwarp();
+          }
+          h0 = h1; j0 = j1; h1 = h2; j1 = j2;
+          CGF_EVENT(0, 1);
+          mbar_wait<CGF_SLEEP_AUX_NS>(x_empty + stage, (use & 1) ^ 1, p.err, 2);
+          CGF_EVENT(0, 2);
+        } else {
+          // the peer: the descriptors arrive from the leader -- this tile's (first use of a pair) and the
+          // look-ahead tile's (the epilogue warpgroups read it as soon as raw_full of THIS tile completes)
+          auto wait_desc = [&](uint32_t u) {
+            uint64_t* bar = dsc_full + stage * 2 + (u & 1);
+            const uint32_t parity = (u >> 1) & 1;
+            uint32_t ok = 0;
+            const long long t0c = clock64();
+            unsigned polls = 0;
+            for (;;) {
+              asm volatile("{\n\t.reg .pred p;\n\t"
+                           "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                           "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+              if (ok) break;
+              __nanosleep(CGF_SLEEP_AUX_NS);
+              (void)watchdog_expired(t0c, p.err, 10, polls);
+            }
+          };
+          if (use == 0) wait_desc(0u);
+          wait_desc(use + 1);
+          CGF_EVENT(0, 1);
+          mbar_wait<CGF_SLEEP_AUX_NS>(x_empty + stage, (use & 1) ^ 1, p.err, 2);
+          CGF_EVENT(0, 2);
+        }
+        // ---- both CTAs: follow the descriptor of this tile
+        const uint4 q0 = lds128(desc_addr(stage, use, 0u));
+        const int tt0 = (int)q0.x, b0 = (int)q0.y;
+        if (tt0 == -2) {                                   // STOP: wake the roles behind me, twice (one per pair)
+          if (elect_one()) mbar_arrive(raw_full + stage);
+          __syncwarp();
+          if (++nstop == 2) break;
+          continue;
+        }
+        const int fam = (int)lds32(desc_addr(stage, use, 0u) + 28);
+        const uint4 r0 = lds128(desc_addr(stage, use, 1u));
+        const int tt1 = (int)r0.x, b1 = (int)r0.y;
+        const int head = fam / CBS;
+        const int c_head = head * (KB * 64);
+        const int nhalf = tt1 >= 0 ? 2 : 1;
+        if (elect_one()) mbar_expect_tx(raw_full + stage, nhalf * (Cfg::kXStageBytes / 2 / CL));
+        for (int hf = 0; hf < nhalf; ++hf) {
+          const int tt = hf == 0 ? tt0 : tt1, b = hf == 0 ? b0 : b1;
+          if (elect_one()) {
+#pragma unroll
+            for (int kbl = 0; kbl < KBL; ++kbl) {
+              const int kb = (CL > 1 ? (int)crank * KBL : 0) + kbl;   // my channel half only
+              tma_load_3d(sX + stage * Cfg::kXStageBytes + kb * Cfg::kXKBlock + hf * (kTile * 128), &tmap_x,
+                          raw_full + stage, c_head + kb * 64, tt * kTile, b);
+            }
+          }
+        }
+        __syncwarp();
+        // A tile of another head: its weights, AFTER its X loads -- the MMA warp learns the family from the
+        // descriptor once x_full of this tile completes and only then releases the old weights (w_empty)
+        if (head != cur_head) load_weights(head);
+      }
+      (void)nclusters;
     }
     __syncwarp();
   } else if (warp == kEpiWarps + 1) {
     // ===================================================== MMA issuer
     {
       const uint32_t w_lo0 = umma_desc_lo(sW), i_lo0 = umma_desc_lo(sI), x_lo0 = umma_desc_lo(sX);
-      uint32_t mq = 0, witer = 0;
+      uint32_t witer = 0;
       int tn = 0; (void)tn;
       int cur_fam = -1;
-      for (int sgi = 0; sgi < nsegs; ++sgi) {
-        const Seg sg = sched.get(sgi);
-        if (sg.count == 0) continue;
-        const int fam = seg_family(sg);
-        if (fam != cur_fam) {
-          if (cur_fam >= 0) {                            // the old family's weights may be overwritten
-            if (elect_one()) umma_commit(w_empty);
-            __syncwarp();
-          }
-          cur_fam = fam;
-          mbar_wait<CGF_SLEEP_AUX_NS>(w_full, witer & 1, p.err, 3);
-          tc_fence_after();
-          ++witer;
+      auto family_change = [&](int fam) {
+        if (cur_fam >= 0) {                              // the old family's weights may be overwritten
+          if (elect_one()) umma_commit(w_empty);
+          __syncwarp();
         }
-        const int cb = fam % CBS;
-#pragma unroll 1
-        for (int m = 0; m < sg.count; ++m, ++mq) {
-          const uint32_t pr = mq & 1u, use = mq >> 1;      // warpgroup pair == X stage
-          CGF_EVENT(1, 1);
-          mbar_wait<CGF_SLEEP_AUX_NS>(mma_ready + pr, use & 1, p.err, 4);
-          CGF_EVENT(1, 2);
-          mbar_wait<CGF_SLEEP_AUX_NS>(t_empty + pr, (use & 1) ^ 1, p.err, 5);
-          CGF_EVENT(1, 3);
-          tc_fence_after();
-          const uint32_t dcol = tmem_base + pr * kPairCols;
-          const uint32_t x_lo = x_lo0 + pr * (Cfg::kXStageBytes >> 4);
-          if (elect_one()) {
+        cur_fam = fam;
+        mbar_wait<CGF_SLEEP_AUX_NS>(w_full, witer & 1, p.err, 3);
+        tc_fence_after();
+        ++witer;
+      };
+      // the 40 MMAs of one tile of pair pr (= X stage pr): D_x, D_a, D_t
+      auto issue_tile = [&](uint32_t pr, uint32_t use, int cb) {
+        mbar_wait<CGF_SLEEP_AUX_NS>(t_empty + pr, (use & 1) ^ 1, p.err, 5);
+        CGF_EVENT(1, 3);
+        tc_fence_after();
+        const uint32_t dcol = tmem_base + pr * kPairCols;
+        const uint32_t x_lo = x_lo0 + pr * (Cfg::kXStageBytes >> 4);
+        if (elect_one()) {
 #pragma unroll
           for (int gate = 0; gate < 2; ++gate) {
 #pragma unroll
@@ -798,9 +1016,45 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           umma_commit(t_full + pr);
           if constexpr (CL > 1) umma_commit_mc(x_empty + pr, (uint16_t)((1u << CL) - 1u));   // my stage AND the peer's copy target
           else umma_commit(x_empty + pr);
+        }
+        __syncwarp();
+        CGF_EVENT(1, 4);
+      };
+      if constexpr (!CONV) {
+        uint32_t mq = 0;
+        for (int sgi = 0; sgi < nsegs; ++sgi) {
+          const Seg sg = sched.get(sgi);
+          if (sg.count == 0) continue;
+          const int fam = seg_family(sg);
+          if (fam != cur_fam) family_change(fam);
+          const int cb = fam % CBS;
+#pragma unroll 1
+          for (int m = 0; m < sg.count; ++m, ++mq) {
+            const uint32_t pr = mq & 1u, use = mq >> 1;    // warpgroup pair == X stage
+            CGF_EVENT(1, 1);
+            mbar_wait<CGF_SLEEP_AUX_NS>(mma_ready + pr, use & 1, p.err, 4);
+            CGF_EVENT(1, 2);
+            issue_tile(pr, use, cb);
           }
-          __syncwarp();
-          CGF_EVENT(1, 4);
+        }
+      } else {
+        // dynamic schedule (see the producer): follow the descriptors until both pairs have seen STOP
+        family_change((((int)blockIdx.x / CL) % (nfam / CBS)) * CBS + (int)crank);   // the producer's first load: the home family
+        uint32_t nstop = 0;
+#pragma unroll 1
+        for (uint32_t mq = 0;; ++mq) {
+          const uint32_t pr = mq & 1u, use = mq >> 1;
+          CGF_EVENT(1, 1);
+          mbar_wait<CGF_SLEEP_AUX_NS>(mma_ready + pr, use & 1, p.err, 4);   // x_full: the convolution warps have seen the tile
+          CGF_EVENT(1, 2);
+          const uint32_t da = desc_addr(pr, use, 0u);
+          if ((int)lds32(da) == -2) {
+            if (++nstop == 2) break;
+            continue;
+          }
+          const int fam = (int)lds32(da + 28);
+          if (fam != cur_fam) family_change(fam);
+          issue_tile(pr, use, fam % CBS);
         }
       }
     }
@@ -1014,8 +1268,8 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     auto tile_body = [&](const TileDesc& td) {
       const int tt = td.tt, b = td.b;
       const unsigned rbits = td.rbits;
-      const int t0 = tt * kTile; (void)t0;
-      const int nvalid = td.nvalid;                        // >= 1; >= kTile for a full tile
+      const int t0 = tt * kTile;
+      const int nvalid = p.T - t0;                         // >= 1; >= kTile for a full tile
       const bool fast_tile = CGF_PRELOAD && rbits == 0u && nvalid >= kTile;
       float P = 1.0f, Hh = 0.0f;
       // gates for one bf16x2 pair of steps (t, t+1) -> (a, x~); the tile's
@@ -1171,30 +1425,18 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       // shared -> shared::cluster copy per K block, completing on the PEER's x_full), which needs it as
       // the other half of the K range of its gate GEMMs -- the convolution is computed once per head.
       // ------------------------------------------------------------------------------------------
-      struct Cur { int sgi, m; uint32_t mq; Seg sg; bool ok; };
-      auto step = [&](Cur& c) {                            // to the next MMA tile of my pair
-        for (;;) {
-          ++c.m; ++c.mq;
-          while (c.sgi < nsegs && c.m >= c.sg.count) {
-            ++c.sgi; c.m = 0;
-            if (c.sgi < nsegs) c.sg = sched.get(c.sgi);
-          }
-          if (c.sgi >= nsegs) { c.ok = false; return; }
-          if ((c.mq & 1u) == pr) return;
-        }
-      };
       const int wq = warp & 3;
       const int cseg = wq >> 1;                            // rows 16 * cseg .. + 15 of my half
       const int ckb = (CL > 1 ? (int)crank * KBL : 0) + (wq & 1);   // my K block of the stage
       const uint32_t lofs = (uint32_t)lane << 2;           // my word of a 128-byte row (16-byte chunk lane >> 2)
       const uint32_t peer = crank ^ 1u;
-      // Round-robin schedule (every production grid): the taps of the 128 input channels of this CTA's
-      // home family sit in shared memory, written once by warpgroup 0.  Other families of a CTA (grids
-      // smaller than the head count; the stolen tail of another head): taps come from global memory per tile.
-      const bool taps_in_smem = sched.mode == 1;
-      if (taps_in_smem) {
+      // The taps of the 128 input channels of this CTA's HOME head sit in shared memory, written once by
+      // warpgroup 0; tiles of other heads (drawn once the home head is exhausted) take theirs from global
+      // memory per tile.
+      const int home_head = ((int)blockIdx.x / CL) % (nfam / CBS);
+      {
         if (wg == 0) {
-          const int cht = sched.get(0).fam * (KB * 64) + (CL > 1 ? (int)crank * 128 : 0) + (int)threadIdx.x;   // threads 0..127
+          const int cht = home_head * (KB * 64) + (CL > 1 ? (int)crank * 128 : 0) + (int)threadIdx.x;   // threads 0..127
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             asm volatile("st.shared.u16 [%0], %1;" :: "r"(sTap + k * 256 + threadIdx.x * 2), "h"(p.conv_w[(size_t)k * p.E + cht]));
@@ -1210,12 +1452,13 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       // ahead -- the descriptor of the pair's next tile is readable as soon as this warpgroup has waited on
       // raw_full for the current one (TileDesc) -- so the round trip never shows.
       uint32_t hq1 = 0u, hq2 = 0u, hq3 = 0u;               // x[ts-1], x[ts-2], x[ts-3] of the next convolution
-      auto halo_request = [&](uint32_t use_n, int head_n) {
+      auto halo_request = [&](uint32_t use_n) {
         const uint32_t da = desc_addr(pr, use_n, hf);
         const int tt_n = (int)lds32(da);
         hq1 = 0u; hq2 = 0u; hq3 = 0u;
         if (tt_n >= 0) {
           const uint32_t e_lo = lds32(da + 16), e_hi = lds32(da + 20);
+          const int head_n = (int)lds32(da + 28) / CBS;
           const int ts = tt_n * kTile + cseg * 16;         // first step of my segment
           const int chp = head_n * (KB * 64) + ckb * 64 + lane * 2;
           const uint16_t* xb = p.x_lin + (((size_t)e_hi << 32) | e_lo) + (size_t)(cseg * 16) * p.E + chp;
@@ -1229,22 +1472,23 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           }
         }
       };
-      auto conv_tile = [&](const Cur& c) {
-        const uint32_t use = c.mq >> 1;
+      // convolves my half of pair pr's tile number `use`; false: that tile is the STOP marker
+      auto conv_tile = [&](const uint32_t use) -> bool {
         if (twarp) CGF_EVENT(trole, 9);
         mbar_wait(raw_full + pr, use & 1, p.err, 9);       // the raw rows of the tile
         if (twarp) CGF_EVENT(trole, 10);
         const TileDesc td = read_desc(use);
         const bool valid = td.tt >= 0;                     // uniform over the warpgroup
         if (valid && !(CGF_ABLATE & 8)) {
-          const int chp = c.sg.fam * (KB * 64) + ckb * 64 + lane * 2;   // my two channels (CONV schedules heads)
+          const int head = td.fam / CBS;
+          const int chp = head * (KB * 64) + ckb * 64 + lane * 2;   // my two channels
           const uint32_t h1 = hq1, h2 = hq2, h3 = hq3;
           // a thread reads and writes only its own 16 words of the stage: no hazard, no barrier
           uint32_t xr[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) xr[j] = lds32(row0 + j * 128 + (lofs ^ ((uint32_t)(j & 7) << 4)));
           uint32_t k0, k1, k2, k3, kb_;                    // w[k] multiplies x[t - (3 - k)] (layers.py:530)
-          if (taps_in_smem && c.sgi == 0) {
+          if (head == home_head) {
             k0 = lds32(tap_a); k1 = lds32(tap_a + 256); k2 = lds32(tap_a + 512); k3 = lds32(tap_a + 768); kb_ = lds32(tap_a + 1024);
           } else {                                         // several families per CTA (small grids): per tile
             k0 = ldg32_nc(p.conv_w + chp);
@@ -1321,25 +1565,19 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           }
         }
         if (twarp) CGF_EVENT(trole, 11);
+        return td.tt != -2;
       };
 
-      Cur cur{0, -1, 0xffffffffu, Seg{0, 0, 1, 0}, nsegs > 0};
-      if (nsegs > 0) { cur.sg = sched.get(0); step(cur); }
-      if (cur.ok) {                                        // the first tile of my pair
-        mbar_wait(raw_full + pr, 0u, p.err, 9);            // its descriptor is written right before this arrive
-        halo_request(0u, cur.sg.fam);
-        conv_tile(cur);
-      }
-      while (cur.ok) {
-        const uint32_t use = cur.mq >> 1;
-        load_family(seg_family(cur.sg));
+      // prologue: the first tile of my pair (its descriptor is written right before the arrive on raw_full)
+      mbar_wait(raw_full + pr, 0u, p.err, 9);
+      halo_request(0u);
+      bool alive = conv_tile(0u);
+#pragma unroll 1
+      for (uint32_t use = 0; alive; ++use) {
         if (twarp) CGF_EVENT(trole, 8);
         const unsigned long long early = request_pred();
-        {   // halo rows of the NEXT convolution: its descriptor became readable with raw_full of this tile
-          Cur nxt = cur;
-          step(nxt);
-          if (nxt.ok) halo_request(nxt.mq >> 1, nxt.sg.fam);
-        }
+        // halo rows of the NEXT convolution: its descriptor became readable with raw_full of this tile
+        halo_request(use + 1);
         if (twarp) CGF_EVENT(trole, 1);
         mbar_wait(t_full + pr, use & 1, p.err, 6);
         if (twarp) CGF_EVENT(trole, 2);
@@ -1347,9 +1585,12 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
         const bool mine = (int)lds32(desc_addr(pr, use, hf)) >= 0;   // odd tile count: nothing in my half of the last pair
         if (!mine) release_slot();
         if (pd.on) finish(early);                          // F(k-1)
-        step(cur);
-        if (cur.ok) conv_tile(cur);                        // the raw rows of my pair's next tile have landed under F
-        if (mine) tile_body(read_desc(use));               // G(k)  (the slot is rewritten two uses later)
+        alive = conv_tile(use + 1);                        // the raw rows of my pair's next tile have landed under F
+        if (mine) {                                        // G(k)  (the slot is rewritten four uses later)
+          const TileDesc td = read_desc(use);
+          load_family(td.fam);
+          tile_body(td);
+        }
       }
     }
     if (pd.on) finish(request_pred());                     // the last tile of this warpgroup

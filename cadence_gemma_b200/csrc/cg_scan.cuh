@@ -822,6 +822,8 @@ __global__ void scan_prologue_kernel(const PrologueParams q) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && q.counter != nullptr) { *q.counter = 0; *q.epoch = *q.epoch + 1u; }
+  // per-head ticket counters of the fused kernel's dynamic schedule: words 8 .. 63 of the scratch header
+  if (i >= 8 && i < 64 && q.counter != nullptr) q.counter[i] = 0;
   if (q.a_param != nullptr && i < q.E) {
     float ap = q.is_bf16 ? __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(q.a_param)[i] << 16)
                          : reinterpret_cast<const float*>(q.a_param)[i];
