@@ -73,7 +73,7 @@ def measured_peaks():
   return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-LEAD_IN_STEPS = int(os.environ.get("CG_BENCH_LEAD_IN", "4"))   # untimed steps between the barrier and the start event
+LEAD_IN_STEPS = int(os.environ.get("CG_BENCH_LEAD_IN", "16"))   # untimed steps between the barrier and the start event
 
 
 def ncu_traffic(kernel_key):
