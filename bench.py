@@ -431,6 +431,8 @@ def own_arm(args, dtype):
       dist.barrier()
     torch.cuda.synchronize()
 
+  region_launches = [0]
+
   def timed_region(join_gather, sample_clocks=False, brackets=False):
     """EXACTLY K steps between two events on this rank's stream.  join_gather: the
     side-stream all-gather is joined BEFORE the closing event (a consumer that needs
@@ -444,6 +446,7 @@ def own_arm(args, dtype):
     for _ in range(LEAD_IN_STEPS):
       step(x_dev, seg_dev, record=False, gather=False)
     step_no[0] = 0
+    region_launches[0] = _abi.launch_count                 # kernels launched between the two events only
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     o = None
@@ -456,6 +459,7 @@ def own_arm(args, dtype):
     if world > 1 and join_gather:
       torch.cuda.current_stream().wait_stream(comm_stream)
     t_end.record()
+    region_launches[0] = _abi.launch_count - region_launches[0]
     if sample_clocks:
       sampler.sample_until(t_end, "timed")   # the GPU is still executing the region
     sync_all()
@@ -496,9 +500,8 @@ def own_arm(args, dtype):
         dist.all_gather_into_tensor(gather_out, gather_in)
 
     # ---------------- device-resident timed region: EXACTLY K steps -------------
-    launches0 = _abi.launch_count
     ms_total, out = timed_region(join_gather=False)
-    launches = _abi.launch_count - launches0
+    launches = region_launches[0]
     # clocks: the SAME K steps once more, right away, with NVML polled by the main thread while
     # the GPU executes them (after the last launch has been enqueued, so the polling cannot
     # delay a launch): the region that is timed carries no instrumentation at all, the region

@@ -572,11 +572,11 @@ int fused_steal_override() {
 }
 bool fused_steal_enabled() { return fused_steal_override() != 0; }
 
-template <int KB, bool FAST, bool DBG, bool MUL, bool CONV, int LOOK = 2>
+template <int KB, bool FAST, bool DBG, bool MUL, bool CONV, int LOOK = 2, int EFIX = 0>
 int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int grid_limit,
                  cudaStream_t stream) {
   using Cfg = cg::fused::FusedCfg<KB>;
-  auto kernel = cg::fused::rglru_fused_kernel<KB, FAST, DBG, MUL, CONV, LOOK>;
+  auto kernel = cg::fused::rglru_fused_kernel<KB, FAST, DBG, MUL, CONV, LOOK, EFIX>;
   static DeviceSlot slots[kMaxDevices];
   int dev = 0;
   if (cudaError_t e = cudaGetDevice(&dev)) return (int)e;
@@ -673,6 +673,15 @@ int dispatch_fused(bool fast, bool dbg, bool mul, const CUtensorMap& tmap,
   if (mul) return fast ? launch_fused<KB, true, false, true, CONV>(tmap, p, grid_limit, stream)
                        : launch_fused<KB, false, false, true, CONV>(tmap, p, grid_limit, stream);
   // look-back depth 2 where the carry chain is the bound (small batches), 1 elsewhere (cg_fused.cuh)
+  // RecurrentGemma-2B's / 9B's width with the row pitch as a compile-time constant (the shipped arithmetic
+  // only): immediate offsets instead of 64-bit address arithmetic per row in the y stores and the halo loads
+  // (config 2 one launch 121.7 -> 118.0 us, B=16 T=8192 856 -> 837 us; profiles/r3_ab_efix.txt)
+  if (CGF_EFIX && KB == 4 && fast && p.E == 2560)
+    return p.B > CGF_LOOK_SPLIT ? launch_fused<KB, true, false, false, CONV, 1, 2560>(tmap, p, grid_limit, stream)
+                                : launch_fused<KB, true, false, false, CONV, 2, 2560>(tmap, p, grid_limit, stream);
+  if (CGF_EFIX && KB == 4 && fast && p.E == 4096)
+    return p.B > CGF_LOOK_SPLIT ? launch_fused<KB, true, false, false, CONV, 1, 4096>(tmap, p, grid_limit, stream)
+                                : launch_fused<KB, true, false, false, CONV, 2, 4096>(tmap, p, grid_limit, stream);
   if (p.B > CGF_LOOK_SPLIT) return fast ? launch_fused<KB, true, false, false, CONV, 1>(tmap, p, grid_limit, stream)
                            : launch_fused<KB, false, false, false, CONV, 1>(tmap, p, grid_limit, stream);
   return fast ? launch_fused<KB, true, false, false, CONV>(tmap, p, grid_limit, stream)

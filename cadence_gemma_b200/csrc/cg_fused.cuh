@@ -68,6 +68,9 @@
 #ifndef CGF_LOOK_SPLIT
 #define CGF_LOOK_SPLIT 3    // batch sizes up to this use look-back depth 2, larger ones depth 1
 #endif
+#ifndef CGF_EFIX
+#define CGF_EFIX 1          // specialised instances with a compile-time row pitch for E = 2560
+#endif
 #ifndef CGF_HINT_NS
 #define CGF_HINT_NS 20000
 #endif
@@ -569,9 +572,12 @@ struct Schedule {
 // x_lin and the kernel computes Conv1D.forward -> RGLRU.forward in one launch.
 // LOOK: look-back depth per round trip (see resolve_carry): 2 for small batches, where the carry chain
 // is the bound; 1 where the chain has slack (fewer loads per poll).
-template <int KB, bool FAST, bool DBG, bool MUL, bool CONV, int LOOK = CGF_LOOK>
+// EFIX: the row pitch E as a compile-time constant (0 = p.E): the y stores of the replay pass and the halo
+// loads of the convolution then use immediate offsets instead of 64-bit address arithmetic per row.
+template <int KB, bool FAST, bool DBG, bool MUL, bool CONV, int LOOK = CGF_LOOK, int EFIX = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams p) {
+  const int rowE = EFIX > 0 ? EFIX : p.E;
   using Cfg = FusedCfg<KB>;
   constexpr int CBS = KB / 2;               // 128-channel halves (families) per head
   constexpr int XS = Cfg::kXStages;
@@ -1178,7 +1184,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     // then add as the reference loop (:196); y leaves as bf16 (2-byte stores: a
     // warp writes 64 contiguous bytes per row)
     auto replay_chunk = [&](int c, const uint32_t (&st)[8], float& h, const uint32_t* gm) {
-      const int E = p.E;
+      const int E = rowE;
       uint32_t o[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -1215,7 +1221,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     };
     // F: carry chain + the whole replay pass of the pending tile
     auto finish = [&](unsigned long long early) {
-      const int E = p.E;
+      const int E = rowE;
       // gating-product operand of the first 8 steps, requested before the
       // look-back so that its latency hides behind it
       uint32_t gm[8], gn[8];
@@ -1461,10 +1467,10 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
           const int head_n = (int)lds32(da + 28) / CBS;
           const int ts = tt_n * kTile + cseg * 16;         // first step of my segment
           const int chp = head_n * (KB * 64) + ckb * 64 + lane * 2;
-          const uint16_t* xb = p.x_lin + (((size_t)e_hi << 32) | e_lo) + (size_t)(cseg * 16) * p.E + chp;
+          const uint16_t* xb = p.x_lin + (((size_t)e_hi << 32) | e_lo) + (size_t)(cseg * 16) * rowE + chp;
           if (ts >= 3 && ts <= p.T) {                      // interior (the common case)
-            const uint16_t* x3 = xb - 3 * (size_t)p.E;
-            hq3 = ldg32_nc(x3); hq2 = ldg32_nc(x3 + p.E); hq1 = ldg32_nc(x3 + 2 * (size_t)p.E);
+            const uint16_t* x3 = xb - 3 * (size_t)rowE;
+            hq3 = ldg32_nc(x3); hq2 = ldg32_nc(x3 + rowE); hq1 = ldg32_nc(x3 + 2 * (size_t)rowE);
           } else {
             if (ts >= 1 && ts - 1 < p.T) hq1 = ldg32_nc(xb - (size_t)p.E);
             if (ts >= 2 && ts - 2 < p.T) hq2 = ldg32_nc(xb - 2 * (size_t)p.E);

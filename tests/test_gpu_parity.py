@@ -969,7 +969,8 @@ def _conv_lru(width, heads, seed):
 
 @pytest.mark.parametrize("mask_mode", [0, 1])
 @pytest.mark.parametrize("shape", [(8, 2048, 2560, 10), (3, 200, 512, 2), (2, 33, 256, 2), (1, 1000, 2560, 10),
-                                   (5, 97, 1024, 4), (2, 3, 256, 2), (1, 2, 512, 2), (4, 64, 256, 1)])
+                                   (5, 97, 1024, 4), (2, 3, 256, 2), (1, 2, 512, 2), (4, 64, 256, 1),
+                                   (2, 100, 4096, 16), (4, 3000, 2560, 10)])
 def test_fused_conv_prefill_equals_two_kernel_path(shape, mask_mode):
   """cg_recurrent_prefill_fwd -- the temporal convolution INSIDE the fused tcgen05
   RG-LRU kernel (ONE launch) -- against the Conv1D kernel followed by the fused
