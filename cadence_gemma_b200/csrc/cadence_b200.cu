@@ -572,11 +572,26 @@ int fused_steal_override() {
 }
 bool fused_steal_enabled() { return fused_steal_override() != 0; }
 
-template <int KB, bool FAST, bool DBG, bool MUL, bool CONV, int LOOK = 2, int EFIX = 0>
+// MMA tiles per cluster from which the one-launch kernel hands tiles out through ticket counters
+constexpr long long kDynamicMinTilesPerCluster = 48;
+
+// tiles per work group (cluster / CTA) of a full-device grid: the schedule decision of launch_fused, available
+// before the kernel instance is chosen
+long long fused_tiles_per_group(const cg::fused::FusedParams& p, int CL, bool conv) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1)
+    return 0;
+  const int units = conv ? p.families / CL : p.families;
+  const int G = sms / CL;
+  return (long long)((p.ntt * p.B + 1) / 2) * units / (G > 0 ? G : 1);
+}
+
+template <int KB, bool FAST, bool DBG, bool MUL, bool CONV, int LOOK = 2, int EFIX = 0, bool UNI = false>
 int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int grid_limit,
                  cudaStream_t stream) {
   using Cfg = cg::fused::FusedCfg<KB>;
-  auto kernel = cg::fused::rglru_fused_kernel<KB, FAST, DBG, MUL, CONV, LOOK, EFIX>;
+  auto kernel = cg::fused::rglru_fused_kernel<KB, FAST, DBG, MUL, CONV, LOOK, EFIX, UNI>;
   static DeviceSlot slots[kMaxDevices];
   int dev = 0;
   if (cudaError_t e = cudaGetDevice(&dev)) return (int)e;
@@ -655,7 +670,7 @@ int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int g
   if (CONV) {
     const int units = p.families / CL, G = grid / CL;
     const long long per_cluster = (long long)((p.ntt * p.B + 1) / 2) * units / (G > 0 ? G : 1);
-    if (G >= units && per_cluster >= 48) q.static_pct = 90;
+    if (G >= units && per_cluster >= kDynamicMinTilesPerCluster) q.static_pct = 90;
     static const int forced = [] { const char* e = getenv("CG_B200_DYNAMIC"); return e ? atoi(e) : -1; }();
     if (forced >= 0 && forced <= 100 && G >= units) q.static_pct = forced;
     if (q.static_pct > 0) q.steal = 0;
@@ -676,12 +691,22 @@ int dispatch_fused(bool fast, bool dbg, bool mul, const CUtensorMap& tmap,
   // RecurrentGemma-2B's / 9B's width with the row pitch as a compile-time constant (the shipped arithmetic
   // only): immediate offsets instead of 64-bit address arithmetic per row in the y stores and the halo loads
   // (config 2 one launch 121.7 -> 118.0 us, B=16 T=8192 856 -> 837 us; profiles/r3_ab_efix.txt)
-  if (CGF_EFIX && KB == 4 && fast && p.E == 2560)
-    return p.B > CGF_LOOK_SPLIT ? launch_fused<KB, true, false, false, CONV, 1, 2560>(tmap, p, grid_limit, stream)
-                                : launch_fused<KB, true, false, false, CONV, 2, 2560>(tmap, p, grid_limit, stream);
-  if (CGF_EFIX && KB == 4 && fast && p.E == 4096)
-    return p.B > CGF_LOOK_SPLIT ? launch_fused<KB, true, false, false, CONV, 1, 4096>(tmap, p, grid_limit, stream)
-                                : launch_fused<KB, true, false, false, CONV, 2, 4096>(tmap, p, grid_limit, stream);
+  if (CGF_EFIX && KB == 4 && fast && (p.E == 2560 || p.E == 4096)) {
+    // one-launch kernel: warp-uniform role branches (UNI) except for static schedules at B >= 6 (see the kernel)
+    const bool uni = CONV && grid_limit == 0 &&
+                     !(fused_tiles_per_group(p, CONV ? KB / 2 : 1, CONV) < kDynamicMinTilesPerCluster && p.B >= 6);
+    const bool deep = p.B <= CGF_LOOK_SPLIT;
+#define CG_EFIX_CASE(EV)                                                                                     \
+    if (p.E == EV) {                                                                                           \
+      if (uni) return deep ? launch_fused<KB, true, false, false, CONV, 2, EV, CONV>(tmap, p, grid_limit, stream) \
+                           : launch_fused<KB, true, false, false, CONV, 1, EV, CONV>(tmap, p, grid_limit, stream); \
+      return deep ? launch_fused<KB, true, false, false, CONV, 2, EV, false>(tmap, p, grid_limit, stream)        \
+                  : launch_fused<KB, true, false, false, CONV, 1, EV, false>(tmap, p, grid_limit, stream);       \
+    }
+    CG_EFIX_CASE(2560)
+    CG_EFIX_CASE(4096)
+#undef CG_EFIX_CASE
+  }
   if (p.B > CGF_LOOK_SPLIT) return fast ? launch_fused<KB, true, false, false, CONV, 1>(tmap, p, grid_limit, stream)
                            : launch_fused<KB, false, false, false, CONV, 1>(tmap, p, grid_limit, stream);
   return fast ? launch_fused<KB, true, false, false, CONV>(tmap, p, grid_limit, stream)

@@ -574,7 +574,10 @@ struct Schedule {
 // is the bound; 1 where the chain has slack (fewer loads per poll).
 // EFIX: the row pitch E as a compile-time constant (0 = p.E): the y stores of the replay pass and the halo
 // loads of the convolution then use immediate offsets instead of 64-bit address arithmetic per row.
-template <int KB, bool FAST, bool DBG, bool MUL, bool CONV, int LOOK = CGF_LOOK, int EFIX = 0>
+// UNI: the warp index goes through a shuffle, which tells the compiler that the role branches are
+// warp-uniform (see below): 2.6 instructions per element fewer, 2-7 % faster for dynamic schedules and small
+// batches, 4-9 % SLOWER for static schedules at B >= 6 (profiles/r3_ab_uniform_warp_index.txt) -- the host picks.
+template <int KB, bool FAST, bool DBG, bool MUL, bool CONV, int LOOK = CGF_LOOK, int EFIX = 0, bool UNI = false>
 __global__ void __launch_bounds__(kThreads, 1)
 rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams p) {
   const int rowE = EFIX > 0 ? EFIX : p.E;
@@ -615,7 +618,11 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
   };
   uint64_t* mma_ready = CONV ? x_full : raw_full;   // what the MMA warp waits for
 
-  const int warp = threadIdx.x >> 5;
+  // (UNI: through a shuffle -- the compiler then knows that the role branches below are warp-uniform and may
+  // keep uniform registers, e.g. the global-memory descriptor of every LDG / STG, live across them; with
+  // threadIdx.x >> 5 it re-materialises that descriptor with two R2UR before each access: 2.6 instructions
+  // per element)
+  const int warp = UNI ? __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) : (int)(threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
 
 #if CGF_TRACE
@@ -1272,6 +1279,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
     };
     // G(k): gates of one scan tile out of my half of the accumulators, aggregate published, tile queued for F
     auto tile_body = [&](const TileDesc& td) {
+      // (descriptor fields are the same in every lane; the shuffles tell the compiler so)
       const int tt = td.tt, b = td.b;
       const unsigned rbits = td.rbits;
       const int t0 = tt * kTile;
