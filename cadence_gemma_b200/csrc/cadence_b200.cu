@@ -674,6 +674,10 @@ int launch_fused(const CUtensorMap& tmap, const cg::fused::FusedParams& p, int g
     static const int forced = [] { const char* e = getenv("CG_B200_DYNAMIC"); return e ? atoi(e) : -1; }();
     if (forced >= 0 && forced <= 100 && G >= units) q.static_pct = forced;
     if (q.static_pct > 0) q.steal = 0;
+    static const int fwd = [] { const char* e = getenv("CG_B200_FORWARD"); return e ? atoi(e) : -1; }();
+    // (the UNI instances are 5 % slower when both CTAs of a cluster derive a static schedule on their own
+    // than when the peer follows the leader's descriptors: profiles/r3_ab_uniform_warp_index.txt)
+    q.forward = fwd >= 0 ? (q.static_pct != 0 || fwd == 1) : (q.static_pct != 0 || UNI);
   }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tmap, q);
   if (e != cudaSuccess) return (int)e;
@@ -692,9 +696,12 @@ int dispatch_fused(bool fast, bool dbg, bool mul, const CUtensorMap& tmap,
   // only): immediate offsets instead of 64-bit address arithmetic per row in the y stores and the halo loads
   // (config 2 one launch 121.7 -> 118.0 us, B=16 T=8192 856 -> 837 us; profiles/r3_ab_efix.txt)
   if (CGF_EFIX && KB == 4 && fast && (p.E == 2560 || p.E == 4096)) {
-    // one-launch kernel: warp-uniform role branches (UNI) except for static schedules at B >= 6 (see the kernel)
+    // one-launch kernel: warp-uniform role branches (UNI) except for static schedules at B >= 8 (see the kernel)
+    static const int uni_forced = [] { const char* e = getenv("CG_B200_UNI"); return e ? atoi(e) : -1; }();
     const bool uni = CONV && grid_limit == 0 &&
-                     !(fused_tiles_per_group(p, CONV ? KB / 2 : 1, CONV) < kDynamicMinTilesPerCluster && p.B >= 6);
+                     (uni_forced >= 0 ? uni_forced != 0
+                                      : !(fused_tiles_per_group(p, CONV ? KB / 2 : 1, CONV) < kDynamicMinTilesPerCluster &&
+                                          p.B >= 8));
     const bool deep = p.B <= CGF_LOOK_SPLIT;
 #define CG_EFIX_CASE(EV)                                                                                     \
     if (p.E == EV) {                                                                                           \

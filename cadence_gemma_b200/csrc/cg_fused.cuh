@@ -144,6 +144,8 @@ struct FusedParams {
   uint32_t bdiv_m, bdiv_s1, bdiv_s2;
   int steal;                       // pairs a poor family hands to helper CTAs (Schedule), 0 = none
   int* tickets;                    // CONV kernels: one ticket counter per head, zeroed by the prologue kernel
+  int forward;                     // CONV clusters: the leader CTA's producer forwards the tile descriptors to its peer
+                                   // (required for static_pct != 0; a static schedule may also be derived by both CTAs)
   int static_pct;                  // CONV kernels: 0 = static schedule (Schedule, with `steal`); 1..100 = that share of a
                                    // head's tiles round-robin among its home clusters, the rest through the tickets
 };
@@ -576,7 +578,7 @@ struct Schedule {
 // loads of the convolution then use immediate offsets instead of 64-bit address arithmetic per row.
 // UNI: the warp index goes through a shuffle, which tells the compiler that the role branches are
 // warp-uniform (see below): 2.6 instructions per element fewer, 2-7 % faster for dynamic schedules and small
-// batches, 4-9 % SLOWER for static schedules at B >= 6 (profiles/r3_ab_uniform_warp_index.txt) -- the host picks.
+// batches, 1.5 % slower for static schedules at B >= 8 (profiles/r3_ab_uniform_warp_index.txt) -- the host picks.
 template <int KB, bool FAST, bool DBG, bool MUL, bool CONV, int LOOK = CGF_LOOK, int EFIX = 0, bool UNI = false>
 __global__ void __launch_bounds__(kThreads, 1)
 rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams p) {
@@ -777,7 +779,7 @@ rglru_fused_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedParams
       const int home = cluster % nheads;
       // static schedule: both CTAs of a cluster derive the same tile sequence on their own (nothing to
       // forward); dynamic tickets: the leader CTA draws and forwards the descriptors to its peer
-      const bool forward = CL > 1 && p.static_pct != 0;
+      const bool forward = CL > 1 && p.forward != 0;
       const bool leader = crank == 0 || !forward;
       uint32_t witer = 0;
       int tn = 0; (void)tn;
