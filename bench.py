@@ -73,6 +73,7 @@ def measured_peaks():
   return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+SAMPLE_REPLICAS = int(os.environ.get("CG_BENCH_SAMPLE_REPLICAS", "10"))   # the clock-sampled region is this many x K steps
 LEAD_IN_STEPS = int(os.environ.get("CG_BENCH_LEAD_IN", "16"))   # untimed steps between the barrier and the start event
 
 
@@ -175,7 +176,7 @@ class ClockSampler:
            "sm_max_mhz": self.sm_max, "reasons": sorted(reasons),
            "samples": len(use), "samples_inside_timed_region": len(inside),
            "how": ("NVML polled from the main thread while the GPU executes a back-to-back REPLICA of the timed region "
-                   "(the same K steps; its step time is in ms_per_step_of_the_sampled_replica), so the timed region "
+                   "(the same steps, SAMPLE_REPLICAS x K of them; its step time is in ms_per_step_of_the_sampled_replica), so the timed region "
                    "itself carries no instrumentation")}
     if self._err:
       out["error"] = self._err
@@ -433,7 +434,7 @@ def own_arm(args, dtype):
 
   region_launches = [0]
 
-  def timed_region(join_gather, sample_clocks=False, brackets=False):
+  def timed_region(join_gather, sample_clocks=False, brackets=False, nsteps=None):
     """EXACTLY K steps between two events on this rank's stream.  join_gather: the
     side-stream all-gather is joined BEFORE the closing event (a consumer that needs
     the merged cache right away) or after it (the merged cache is only needed before
@@ -451,7 +452,7 @@ def own_arm(args, dtype):
     t_start.record()
     o = None
     host_t = [time.perf_counter()]
-    for i in range(args.steps):
+    for i in range(args.steps if nsteps is None else nsteps):
       o = step(x_dev, seg_dev, record=brackets)
       host_t.append(time.perf_counter())
     if os.environ.get("CG_BENCH_DEBUG"):
@@ -506,13 +507,16 @@ def own_arm(args, dtype):
     # the GPU executes them (after the last launch has been enqueued, so the polling cannot
     # delay a launch): the region that is timed carries no instrumentation at all, the region
     # that is sampled is its back-to-back replica (its own step time is reported beside it).
-    ms_sampled = timed_region(join_gather=False, sample_clocks=True)[0]
+    # (SAMPLE_REPLICAS x K steps: an NVML query takes 1-2 ms, K steps only ~2.4 ms -- one sample; the replica is
+    # long enough for a dozen)
+    ms_sampled = timed_region(join_gather=False, sample_clocks=True, nsteps=args.steps * SAMPLE_REPLICAS)[0]
     # per-kernel times: the same K steps a third time with CUDA events between the kernels of
     # every step (the brackets cost stream time and a different call sequence on the host, so
     # they stay out of the region that is timed)
     timed_region(join_gather=False, brackets=True)
     clocks = sampler.summary()
-    clocks["ms_per_step_of_the_sampled_replica"] = ms_sampled / args.steps
+    clocks["ms_per_step_of_the_sampled_replica"] = ms_sampled / (args.steps * SAMPLE_REPLICAS)
+    clocks["steps_of_the_sampled_replica"] = args.steps * SAMPLE_REPLICAS
     ms_joined = timed_region(join_gather=True)[0] if world > 1 else ms_total
     k_us = {k: statistics.mean(a.elapsed_time(b) * 1e3 for a, b in v) if v else 0.0
             for k, v in k_events.items()}
