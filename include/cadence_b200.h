@@ -262,11 +262,14 @@ int cg_rglru_fused_fwd(const void* x, const void* wpack, const void* bias_x,
  *     x, conv1d_state = conv_1d(x, segment_pos)       layers.py:458-546
  *     x, rg_lru_state = rg_lru(x, segment_pos)        layers.py:322-375
  * -- with the temporal convolution computed INSIDE the fused tensor-core kernel:
- * TMA loads the rows of x (= linear_x output) into shared memory, two warps
- * convolve them in place with the reference's rounding (bit-exact with
- * cg_conv1d_fwd), the tcgen05 gate GEMMs read the result, gate math and scan
- * follow in the epilogue.  Neither the conv output nor the gate pre-activations
- * reach HBM: the step moves 2 x B*T*E*2 bytes (x in, y out).
+ * TMA loads the rows of x (= linear_x output) into shared memory, the epilogue
+ * warpgroups convolve them in place with the reference's rounding (bit-exact with
+ * cg_conv1d_fwd; at head width 256 once per head: the two CTAs of a head form a
+ * cluster and exchange their halves), the tcgen05 gate GEMMs read the result,
+ * gate math and scan follow in the epilogue.  Neither the conv output nor the gate
+ * pre-activations reach HBM: the step moves 2 x B*T*E*2 bytes (x in, y out).
+ * Faster than cg_conv1d_fwd + cg_rglru_fused_fwd at every measured shape; same bits.
+ * H <= 32 (CG_ERR_UNSUPPORTED otherwise).
  *   x [B,T,E] Conv1D INPUT; conv_w [4,E]; conv_b [E];
  *   conv_cache_out (nullable) [B,3,E] bf16: the last three rows of x, left zero
  *        padded (layers.py:542-543);
