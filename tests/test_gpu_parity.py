@@ -1122,6 +1122,37 @@ def test_fused_rglru_family_loop_small_grid(ctas):
   assert torch.equal(y, y_ref) and torch.equal(h, h_ref)
 
 
+@pytest.mark.parametrize("ctas", [2, 4, 6])
+@pytest.mark.parametrize("heads,width", [(4, 1024), (8, 1024)])
+def test_fused_conv_prefill_small_grid(ctas, heads, width):
+  """The one-launch kernel (convolution inside) with fewer clusters / CTAs than heads, as on a device with
+  few SMs: a cluster then walks several heads in turn -- weight reload, convolution taps of the other heads
+  from global memory, tile descriptors with changing families -- and gives the bits of the full grid."""
+  abi = _abi()
+  torch.manual_seed(ctas + heads)
+  bsz, steps = 3, 150
+  bw = width // heads
+  wx = (torch.randn(heads, bw, bw, device=DEV) / bw ** 0.5).to(torch.bfloat16)
+  wa = (torch.randn(heads, bw, bw, device=DEV) / bw ** 0.5).to(torch.bfloat16)
+  bx = torch.randn(width, device=DEV).to(torch.bfloat16)
+  ba = torch.randn(width, device=DEV).to(torch.bfloat16)
+  ap = torch.randn(width, device=DEV).to(torch.bfloat16)
+  cw = (torch.randn(4, width, device=DEV) * 0.4).to(torch.bfloat16)
+  cb = (torch.randn(width, device=DEV) * 0.2).to(torch.bfloat16)
+  x = torch.randn(bsz, steps, width, device=DEV).to(torch.bfloat16)
+  seg = torch.arange(steps, device=DEV, dtype=torch.int32)[None].repeat(bsz, 1)
+  seg[:, 70:] -= 70
+  h0 = torch.randn(bsz, width, device=DEV)
+  wpack = abi.pack_gate_weights(wx, wa)
+  ws = abi.fused_workspace(torch.device(DEV), bsz, steps, width)
+  ref = abi.recurrent_prefill_fwd(x, cw, cb, wpack, bx, ba, ap, seg, heads, h0=h0, arith_mode=FAST, workspace=ws)
+  got = abi.recurrent_prefill_fwd(x, cw, cb, wpack, bx, ba, ap, seg, heads, h0=h0, arith_mode=FAST | (ctas << 8),
+                                  workspace=ws)
+  torch.cuda.synchronize()
+  for a, b in zip(got, ref):
+    assert torch.equal(a, b)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(1, 2048, 2560, 10), (2, 100, 512, 2), (3, 64, 256, 4)])
 def test_graphed_hot_path_equals_eager(shape):
