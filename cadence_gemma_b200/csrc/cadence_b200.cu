@@ -573,7 +573,10 @@ int fused_steal_override() {
 bool fused_steal_enabled() { return fused_steal_override() != 0; }
 
 // MMA tiles per cluster from which the one-launch kernel hands tiles out through ticket counters
-constexpr long long kDynamicMinTilesPerCluster = 48;
+// (profiles/r3_dynamic_tickets.txt: 52-69 tiles per cluster: static 0-1 % better; 277: tickets 1.7 % better)
+constexpr long long kDynamicMinTilesPerCluster = 128;
+// ... and below which (at B >= 8) the plain kernel instance beats the UNI one (r3_ab_uniform_warp_index.txt)
+constexpr long long kPlainInstanceMaxTilesPerCluster = 48;
 
 // tiles per work group (cluster / CTA) of a full-device grid: the schedule decision of launch_fused, available
 // before the kernel instance is chosen
@@ -700,7 +703,7 @@ int dispatch_fused(bool fast, bool dbg, bool mul, const CUtensorMap& tmap,
     static const int uni_forced = [] { const char* e = getenv("CG_B200_UNI"); return e ? atoi(e) : -1; }();
     const bool uni = CONV && grid_limit == 0 &&
                      (uni_forced >= 0 ? uni_forced != 0
-                                      : !(fused_tiles_per_group(p, CONV ? KB / 2 : 1, CONV) < kDynamicMinTilesPerCluster &&
+                                      : !(fused_tiles_per_group(p, CONV ? KB / 2 : 1, CONV) < kPlainInstanceMaxTilesPerCluster &&
                                           p.B >= 8));
     const bool deep = p.B <= CGF_LOOK_SPLIT;
 #define CG_EFIX_CASE(EV)                                                                                     \

@@ -1,6 +1,6 @@
 #!/bin/bash
 out=gpurun_out/r3_ab7.log; : > $out
-for dy in auto 0 85 90 95; do
+for dy in auto 0 auto; do
 echo "== dynamic $dy" >> $out
 if [ $dy = auto ]; then unset CG_B200_DYNAMIC; else export CG_B200_DYNAMIC=$dy; fi
 timeout 300 python - >> $out 2>&1 <<'P'
