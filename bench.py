@@ -73,7 +73,7 @@ def measured_peaks():
   return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-SAMPLE_REPLICAS = int(os.environ.get("CG_BENCH_SAMPLE_REPLICAS", "10"))   # the clock-sampled region is this many x K steps
+SAMPLE_REPLICAS = int(os.environ.get("CG_BENCH_SAMPLE_REPLICAS", "30"))   # the clock-sampled region is this many x K steps
 LEAD_IN_STEPS = int(os.environ.get("CG_BENCH_LEAD_IN", "16"))   # untimed steps between the barrier and the start event
 
 
@@ -454,6 +454,8 @@ def own_arm(args, dtype):
     host_t = [time.perf_counter()]
     for i in range(args.steps if nsteps is None else nsteps):
       o = step(x_dev, seg_dev, record=brackets)
+      if sample_clocks and i % 64 == 63:
+        sampler.sample("timed")    # (the replica region only: the GPU has a queue of launched steps to work on meanwhile)
       host_t.append(time.perf_counter())
     if os.environ.get("CG_BENCH_DEBUG"):
       sys.stderr.write("host us per step: " + " ".join(f"{(b - a) * 1e6:.0f}" for a, b in zip(host_t, host_t[1:])) + "\n")

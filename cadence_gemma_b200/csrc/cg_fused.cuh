@@ -61,12 +61,12 @@
 // 2 = the predecessor's state word plus the aggregates / state of the tile before it in ONE round trip.
 // Measured (us, fused kernel alone, round 1): B=2,T=8192 141.6 -> 129.4; B=8,T=2048 107.0 -> 107.0;
 // depth 4: 131.4 / 111.1 (more loads per poll than the chain is long).  Round 2, one-launch kernel at
-// config 2 (B=8): depth 1 123.7 us vs depth 2 125.3 us -> the host picks 2 for B <= 3, else 1.
+// config 2 (B=8): depth 1 123.7 us vs depth 2 125.3 us -> the host picks 2 for B <= CGF_LOOK_SPLIT, else 1.
 #ifndef CGF_LOOK
 #define CGF_LOOK 2
 #endif
 #ifndef CGF_LOOK_SPLIT
-#define CGF_LOOK_SPLIT 3    // batch sizes up to this use look-back depth 2, larger ones depth 1
+#define CGF_LOOK_SPLIT 6    // batch sizes up to this use look-back depth 2 (B = 4: -4 %, B = 5, 6: neutral), larger ones depth 1
 #endif
 #ifndef CGF_EFIX
 #define CGF_EFIX 1          // specialised instances with a compile-time row pitch for E = 2560
