@@ -28,9 +28,12 @@
 //                [256p, 256p+256): 192 accumulator + 2 x 32 state.  Warpgroup
 //                (p, h) works on half h (columns 32h..32h+31) of every MMA tile
 //                issued for pair p; MMA tiles alternate between the pairs.
-//   warp 16      TMA producer: packed, pre-swizzled gate weights once per
-//                family, then two X boxes [32 steps x head width] per MMA tile
-//                through a 3-D tensor map (SWIZZLE_128B, zero fill beyond T)
+//   warp 16      TMA producer and scheduler: packed, pre-swizzled gate weights once
+//                per family, then two X boxes [32 steps x head width] per MMA tile
+//                through a 3-D tensor map (SWIZZLE_128B, zero fill beyond T); writes
+//                the tile descriptors (TileDesc) every other role follows; CONV
+//                kernels: draws the tiles of long kernels from per-head ticket
+//                counters and forwards the descriptors to the peer CTA of its cluster
 //   warp 17      MMA issuer (one thread), tcgen05.commit -> mbarriers
 //   warps 18-19  idle (registers are allocated per four warps).  CONV kernels: the
 //                temporal convolution runs in the epilogue warpgroups, in place in
@@ -38,7 +41,9 @@
 // CTA i works on family i % families; the CTAs of one family take its tiles
 // two at a time, round-robin in time-major order, so look-back dependencies
 // always point to tiles that are already running (all CTAs are co-resident:
-// grid <= #SMs, 1 CTA / SM).
+// grid <= #SMs, 1 CTA / SM).  CONV kernels: the two CTAs that own the families of a
+// head form a 2-CTA cluster (the convolution is computed once per head and the
+// halves are exchanged); see Schedule (tail stealing) and the producer (tickets).
 #pragma once
 
 #include <cuda.h>
